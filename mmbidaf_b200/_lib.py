@@ -1,0 +1,75 @@
+"""ctypes binding of libmmbidaf_b200.so (the C ABI declared in include/mmbidaf_b200.h).
+
+There is no fallback: if the shared library is missing, or the device is not sm_100, every
+op raises.  torch is used only for device memory and streams; all pointers handed to the
+library are raw ``data_ptr()`` values of contiguous CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmmbidaf_b200.so")
+
+_lib: Optional[ctypes.CDLL] = None
+_device_ok = False
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/mmbidaf_b200.h
+SIGNATURES = {
+    "mmb_version": [],
+    "mmb_last_error": [],
+    "mmb_device_supported": [],
+    "mmb_bidaf_fwd": [c_void_p] * 10 + [c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
+}
+_RESTYPES = {"mmb_last_error": ctypes.c_char_p}
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m mmbidaf_b200.build` "
+                               "(there is no CPU or PyTorch fallback for the mmbidaf_b200 kernels)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)            # AttributeError if the .so is stale
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def lib() -> ctypes.CDLL:
+    """The library, after checking once that a B200 is the current device."""
+    global _device_ok
+    handle = load()
+    if not _device_ok:
+        if not torch.cuda.is_available():
+            raise RuntimeError("mmbidaf_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU path")
+        if not handle.mmb_device_supported():
+            raise RuntimeError(handle.mmb_last_error().decode())
+        _device_ok = True
+    return handle
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {load().mmb_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "mmbidaf_b200 ops take contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,27 @@
+// C-ABI entry points for BiDAF attention (validation + precision dispatch).
+#include "common.cuh"
+
+namespace mmb {
+int bidaf_fwd_f32(const float*, const float*, const uint8_t*, const uint8_t*, const float*, const float*, const float*,
+                  const float*, const uint8_t*, const uint8_t*, float, float*, float*, float*, float*, int, int, int, int,
+                  cudaStream_t);
+}
+
+extern "C" int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_t* text_mask,
+                             const uint8_t* modality_mask, const float* w_text, const float* w_modality,
+                             const float* w_cross, const float* bias, const uint8_t* keep_text,
+                             const uint8_t* keep_modality, float keep_scale, float* out, float* q2c, float* lse_row,
+                             float* lse_col, int B, int Lc, int Lq, int d, int precision, mmb_stream_t stream) {
+  MMB_REQUIRE(text && modality && text_mask && modality_mask && w_text && w_modality && w_cross && bias && out && q2c &&
+                  lse_row && lse_col,
+              MMB_ERR_INVALID, "mmb_bidaf_fwd: null pointer");
+  MMB_REQUIRE(B > 0 && Lc > 0 && Lq > 0 && d > 0, MMB_ERR_INVALID, "mmb_bidaf_fwd: B=%d Lc=%d Lq=%d d=%d", B, Lc, Lq, d);
+  MMB_REQUIRE(d % 4 == 0 && d <= 256, MMB_ERR_UNSUPPORTED, "mmb_bidaf_fwd: d=%d (need d %% 4 == 0, d <= 256)", d);
+  MMB_REQUIRE(B <= 65535, MMB_ERR_UNSUPPORTED, "mmb_bidaf_fwd: B=%d > 65535", B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == MMB_PREC_FP32)
+    return mmb::bidaf_fwd_f32(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias, keep_text,
+                              keep_modality, keep_scale, out, q2c, lse_row, lse_col, B, Lc, Lq, d, st);
+  mmb::set_error("mmb_bidaf_fwd: precision %d not available", precision);
+  return MMB_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,56 @@
+"""Thin Python wrappers over the C ABI: allocate outputs with torch, pass raw pointers + stream.
+
+Every function here launches hand-written sm_100a kernels from libmmbidaf_b200.so and raises
+if the library or a B200 is missing.  ``launch_count`` counts kernel launches issued through
+this module (bench.py reports it as ``gpu_launches``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+PREC_FP32, PREC_BF16 = 0, 1
+launch_count = 0
+
+
+def _count(n: int) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return mask.to(torch.uint8).contiguous()
+
+
+def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tensor, modality_mask: torch.Tensor,
+              w_text: torch.Tensor, w_modality: torch.Tensor, w_cross: torch.Tensor, bias: torch.Tensor,
+              keep_text: Optional[torch.Tensor] = None, keep_modality: Optional[torch.Tensor] = None,
+              keep_scale: float = 1.0, precision: int = PREC_FP32
+              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused BiDAF forward (attention.py:37-75).  Returns (out (B,Lc,4d), q2c (B,Lq,d),
+    lse_row (B,Lc), lse_col (B,Lq)); the last three are what the backward pass needs."""
+    L = _lib.lib()
+    assert text.dtype == torch.float32 and modality.dtype == torch.float32
+    B, Lc, d = text.shape
+    Lq = modality.shape[1]
+    text, modality = text.contiguous(), modality.contiguous()
+    tm, mm = _u8(text_mask.reshape(B, Lc)), _u8(modality_mask.reshape(B, Lq))
+    kt, km = _u8(keep_text), _u8(keep_modality)
+    wt, wm, wc = (w.detach().reshape(-1).contiguous() for w in (w_text, w_modality, w_cross))
+    out = torch.empty(B, Lc, 4 * d, device=text.device, dtype=torch.float32)
+    q2c = torch.empty(B, Lq, d, device=text.device, dtype=torch.float32)
+    lse_row = torch.empty(B, Lc, device=text.device, dtype=torch.float32)
+    lse_col = torch.empty(B, Lq, device=text.device, dtype=torch.float32)
+    p = _lib.ptr
+    _lib.check(L.mmb_bidaf_fwd(p(text), p(modality), p(tm), p(mm), p(wt), p(wm), p(wc), p(bias.detach().contiguous()),
+                               p(kt), p(km), float(keep_scale), p(out), p(q2c), p(lse_row), p(lse_col),
+                               B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
+    _count(2)
+    return out, q2c, lse_row, lse_col

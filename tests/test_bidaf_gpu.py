@@ -1,0 +1,98 @@
+"""GPU parity: fused BiDAF kernels (through the C ABI) vs the oracle and the reference's golden vectors."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import mmbidaf_oracle as O
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-5       # north_star: rel <= 1e-5 on the fp32 path
+
+
+def _run(g_state, text, modality, tmask, mmask, keep_c=None, keep_q=None, p=0.0, precision=0):
+    from mmbidaf_b200 import ops
+    dev = "cuda"
+    cu = lambda t: None if t is None else t.to(dev)
+    out, q2c, lse_r, lse_c = ops.bidaf_fwd(cu(text), cu(modality), cu(tmask), cu(mmask), cu(g_state["text_weight"]),
+                                           cu(g_state["modality_weight"]), cu(g_state["text_modality_weight"]),
+                                           cu(g_state["bias"]), cu(keep_c), cu(keep_q), 1.0 / (1.0 - p), precision)
+    torch.cuda.synchronize()
+    return out.cpu(), q2c.cpu(), lse_r.cpu(), lse_c.cpu()
+
+
+@pytest.mark.parametrize("name", ["bidaf_small.pt", "bidaf_d200.pt"])
+def test_forward_matches_reference_golden(name):
+    g = load_golden(name)
+    out, q2c, lse_r, lse_c = _run(g["state"], g["text"], g["modality"], g["text_mask"], g["modality_mask"])
+    assert rel_err(out, g["out"]) < FP32_TOL
+    # saved statistics against the reference's own similarity matrix
+    s = g["similarity"]
+    neg = torch.full_like(s, -1e30)
+    lse_row = torch.logsumexp(torch.where(g["modality_mask"].unsqueeze(1), s, neg), dim=2)
+    lse_col = torch.logsumexp(torch.where(g["text_mask"].unsqueeze(2), s, neg), dim=1)
+    assert rel_err(lse_r, lse_row) < FP32_TOL and rel_err(lse_c, lse_col) < FP32_TOL
+    # exact structure of the output: block 0 is the text itself, bit for bit
+    d = g["text"].shape[2]
+    assert torch.equal(out[:, :, :d], g["text"])
+
+
+@pytest.mark.parametrize("name", ["bidaf_small.pt", "bidaf_d200.pt"])
+def test_forward_training_dropout_matches_reference_golden(name):
+    import torch.nn.functional as F
+    g = load_golden(name)
+    pr = g["train_drop_prob"]
+    torch.manual_seed(g["train_seed"])
+    keep_c = F.dropout(torch.ones_like(g["text"]), pr, True) != 0
+    keep_q = F.dropout(torch.ones_like(g["modality"]), pr, True) != 0
+    out, *_ = _run(g["state"], g["text"], g["modality"], g["text_mask"], g["modality_mask"], keep_c, keep_q, pr)
+    assert rel_err(out, g["train_out"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 4), (2, 5, 3, 8), (3, 64, 32, 200), (2, 65, 33, 200), (2, 130, 257, 200),
+                                   (4, 100, 70, 64), (2, 40, 50, 256), (2, 31, 95, 12)])
+def test_forward_matches_oracle_ragged(shape):
+    bsz, lc, lq, d = shape
+    gen = torch.Generator().manual_seed(1000 + lc * 7 + lq)
+    p = {"text_weight": torch.randn(d, 1, generator=gen) * 0.2, "modality_weight": torch.randn(d, 1, generator=gen) * 0.2,
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen) * 0.2, "bias": torch.tensor([0.3])}
+    text = torch.randn(bsz, lc, d, generator=gen)
+    modality = torch.randn(bsz, lq, d, generator=gen)
+    c_len = torch.randint(1, lc + 1, (bsz,), generator=gen).tolist()
+    q_len = torch.randint(1, lq + 1, (bsz,), generator=gen).tolist()
+    c_len[0], q_len[0] = lc, lq
+    tmask, mmask = O.length_mask(lc, c_len), O.length_mask(lq, q_len)
+    want = O.bidaf_attention(p, text.double(), modality.double(), tmask, mmask)       # fp64 oracle
+    out, q2c, *_ = _run(p, text, modality, tmask, mmask)
+    assert rel_err(out, want) < FP32_TOL
+    # exact zeros in blocks 0, 2, 3 of rows whose text is zero padding
+    text_z = text.clone()
+    for b, n in enumerate(c_len):
+        text_z[b, n:] = 0
+    out_z, *_ = _run(p, text_z, modality, tmask, mmask)
+    for b, n in enumerate(c_len):
+        if n < lc:
+            assert (out_z[b, n:, :d] == 0).all() and (out_z[b, n:, 2 * d:] == 0).all()
+            assert out_z[b, n:, d:2 * d].abs().max() > 0
+
+
+def test_fully_masked_softmax_is_uniform_like_reference():
+    """attention.py:94 uses -1e30, not -inf: an all-masked soft-max is uniform, not NaN."""
+    gen = torch.Generator().manual_seed(5)
+    d, lc, lq = 8, 6, 5
+    p = {"text_weight": torch.randn(d, 1, generator=gen), "modality_weight": torch.randn(d, 1, generator=gen),
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen), "bias": torch.tensor([0.0])}
+    text, modality = torch.randn(2, lc, d, generator=gen), torch.randn(2, lq, d, generator=gen)
+    tmask = O.length_mask(lc, [6, 0])
+    mmask = O.length_mask(lq, [0, 5])
+    want = O.bidaf_attention(p, text, modality, tmask, mmask)
+    out, *_ = _run(p, text, modality, tmask, mmask)
+    assert torch.isfinite(out).all() and rel_err(out, want) < FP32_TOL
+
+
+def test_unsupported_shape_raises():
+    from mmbidaf_b200 import ops
+    t = torch.randn(1, 4, 6, device="cuda")
+    m = torch.ones(1, 4, dtype=torch.bool, device="cuda")
+    w = torch.randn(6, device="cuda")
+    with pytest.raises(RuntimeError, match="d=6"):
+        ops.bidaf_fwd(t, t, m, m, w, w, w, torch.zeros(1, device="cuda"))

@@ -73,6 +73,28 @@ MMB_API int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_
                   float* out, float* q2c, float* lse_row, float* lse_col,
                   int B, int Lc, int Lq, int d, int precision, mmb_stream_t stream);
 
+/* --------------------------------------------------------------------------------------
+ * Length-aware LSTM recurrence of one layer, 1 or 2 directions.  Replaces the nn.LSTM call of
+ * encoding.py:96 together with the sort / pack / pad / unsort gathers of encoding.py:91-101.
+ *   gates (B,L,ndir,4H): on entry x W_ih^T + b_ih + b_hh (gate order i,f,g,o; a plain GEMM done
+ *     by the caller); with save != 0 it holds the ACTIVATED gates on exit (for the backward pass)
+ *   w_hh (ndir,4H,H)   lengths (B) int32   order (B) int32 permutation, longest first, or NULL
+ *   out (B,L,ndir*H): hidden states, exact zeros past each length (pad_packed_sequence)
+ *   h_n, c_n (B,ndir,H): state after each sample's last valid step, in BATCH order
+ *   cell (B,L,ndir,H): cell states, written when save != 0 (may be NULL otherwise).  H <= 128.
+ */
+MMB_API int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out,
+                           float* h_n, float* c_n, float* cell, int B, int L, int H, int ndir, int save,
+                           mmb_stream_t stream);
+
+/* Backward through time of the same layer.  `gates` (activated gates from the forward pass) is
+ * overwritten with d(loss)/d(pre-activation) (zeros past each length); dout (B,L,ndir*H);
+ * dh_n / dc_n (B,ndir,H) may be NULL.  dW_ih, dx, db and dW_hh are GEMMs over `gates` for the caller.
+ */
+MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, const int32_t* lengths,
+                           const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, int B, int L,
+                           int H, int ndir, mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,8 @@ SIGNATURES = {
     "mmb_last_error": [],
     "mmb_device_supported": [],
     "mmb_bidaf_fwd": [c_void_p] * 10 + [c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
+    "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
+    "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
 }
 _RESTYPES = {"mmb_last_error": ctypes.c_char_p}
 

@@ -54,3 +54,38 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
                                B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
     _count(2)
     return out, q2c, lse_row, lse_col
+
+
+def lstm_layer_fwd(gates: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Tensor],
+                   B: int, L: int, H: int, ndir: int, save: bool
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Persistent LSTM recurrence of one layer (encoding.py:96).  ``gates`` (B,L,ndir,4H) holds the input
+    projection on entry and, when ``save``, the activated gates on exit.  Returns (out (B,L,ndir*H),
+    h_n (B,ndir,H), c_n (B,ndir,H), cell (B,L,ndir,H) or None)."""
+    lib = _lib.lib()
+    assert gates.dtype == torch.float32 and gates.numel() == B * L * ndir * 4 * H
+    assert lengths.dtype == torch.int32 and (order is None or order.dtype == torch.int32)
+    dev = gates.device
+    out = torch.empty(B, L, ndir * H, device=dev, dtype=torch.float32)
+    h_n = torch.empty(B, ndir, H, device=dev, dtype=torch.float32)
+    c_n = torch.empty(B, ndir, H, device=dev, dtype=torch.float32)
+    cell = torch.empty(B, L, ndir, H, device=dev, dtype=torch.float32) if save else None
+    p = _lib.ptr
+    _lib.check(lib.mmb_bilstm_fwd(p(gates), p(w_hh), p(lengths), p(order), p(out), p(h_n), p(c_n), p(cell),
+                                  B, L, H, ndir, int(save), _lib.stream()), "mmb_bilstm_fwd")
+    _count(1)
+    return out, h_n, c_n, cell
+
+
+def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor,
+                   order: Optional[torch.Tensor], dout: torch.Tensor, dh_n: Optional[torch.Tensor],
+                   dc_n: Optional[torch.Tensor], B: int, L: int, H: int, ndir: int) -> torch.Tensor:
+    """BPTT of :func:`lstm_layer_fwd`; overwrites ``gates`` with d(pre-activation) and returns it."""
+    lib = _lib.lib()
+    p = _lib.ptr
+    _lib.check(lib.mmb_bilstm_bwd(p(gates), p(cell), p(w_hh), p(lengths), p(order), p(dout.contiguous()),
+                                  p(None if dh_n is None else dh_n.contiguous()),
+                                  p(None if dc_n is None else dc_n.contiguous()), B, L, H, ndir, _lib.stream()),
+               "mmb_bilstm_bwd")
+    _count(1)
+    return gates

@@ -61,7 +61,7 @@ def test_forward_matches_oracle_ragged(shape):
     q_len = torch.randint(1, lq + 1, (bsz,), generator=gen).tolist()
     c_len[0], q_len[0] = lc, lq
     tmask, mmask = O.length_mask(lc, c_len), O.length_mask(lq, q_len)
-    want = O.bidaf_attention(p, text.double(), modality.double(), tmask, mmask)       # fp64 oracle
+    want = O.bidaf_attention({k: v.double() for k, v in p.items()}, text.double(), modality.double(), tmask, mmask)  # fp64 oracle
     out, q2c, *_ = _run(p, text, modality, tmask, mmask)
     assert rel_err(out, want) < FP32_TOL
     # exact zeros in blocks 0, 2, 3 of rows whose text is zero padding

@@ -95,6 +95,43 @@ MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, c
                            const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, int B, int L,
                            int H, int ndir, mmb_stream_t stream);
 
+/* --------------------------------------------------------------------------------------
+ * Multimodal attention decoder, one step.  Replaces attention.py:145-186.
+ * Device pointers to the module's parameters, named as in attention.py:119-142 (weights are
+ * nn.Linear layout (out,in); *b are the biases).
+ */
+typedef struct mmb_decoder_weights {
+  const float *W2, *b2, *Wc1, *bc1, *v1, *v1b;           /* text-audio additive attention (W1 is pre-applied) */
+  const float *W4, *b4, *Wc2, *bc2, *v2, *v2b;           /* text-image additive attention (W3 is pre-applied) */
+  const float *Wb1, *bb1, *Wb2, *bb2, *Wb3, *bb3, *Wb4, *bb4, *vb1, *vb1b, *vb2, *vb2b;   /* W_beta_1..4, v_beta_1..2 */
+  const float *lstm_w_ih, *lstm_w_hh, *lstm_b_ih, *lstm_b_hh;   /* lstm.weight_ih_l0 (4H, 2H+E) ... */
+  const float *out_w, *out_b;                            /* out: Linear(H -> M) */
+} mmb_decoder_weights;
+
+/*   proj_a = W1(enc_a) + b1, proj_i = W3(enc_i) + b3 (B,Lt,2H): step-invariant GEMMs done once by the caller
+ *   enc_a, enc_i (B,Lt,2H)   sent_embed (B,E)   h, cell (B,H)   coverage (B,Lt)   mask (B,M)
+ * Outputs: probs (B,M) = masked_softmax(out(h')) (attention.py:184); h_out, cell_out (B,H);
+ *   att_cov, cov_out (B,Lt) (attention.py:167,177); argmax (B) int64 first-max index of probs (nullable);
+ *   ctx (B,2H) the attended context (also a workspace); alpha (B,2,Lt), beta (B,2), gates (B,4H): nullable,
+ *   saved for a backward pass.  `w` is a HOST pointer to the struct.
+ */
+MMB_API int mmb_decoder_step_fwd(const mmb_decoder_weights* w, const float* proj_a, const float* proj_i,
+                                 const float* enc_a, const float* enc_i, const float* sent_embed, const float* h,
+                                 const float* cell, const float* coverage, const uint8_t* mask, float* probs,
+                                 float* h_out, float* cell_out, float* att_cov, float* cov_out, long long* argmax,
+                                 float* ctx, float* alpha, float* beta, float* gates, int B, int Lt, int H, int E,
+                                 int M, mmb_stream_t stream);
+
+/* --------------------------------------------------------------------------------------
+ * masked_softmax over the last axis (attention.py:78-98): y = softmax(mask ? x : -1e30), or
+ * log_softmax when log_mode != 0.  x, y (rows,n); mask (rows,n) bytes.  Backward returns
+ * dx = mask * dsoftmax (the reference's d(mask*x)/dx = mask).
+ */
+MMB_API int mmb_masked_softmax_fwd(const float* x, const uint8_t* mask, float* y, long long rows, int n, int log_mode,
+                                   mmb_stream_t stream);
+MMB_API int mmb_masked_softmax_bwd(const float* y, const float* dy, const uint8_t* mask, float* dx, long long rows,
+                                   int n, int log_mode, mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,8 +28,21 @@ SIGNATURES = {
     "mmb_bidaf_fwd": [c_void_p] * 10 + [c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
+    "mmb_decoder_step_fwd": [c_void_p] * 20 + [c_int] * 5 + [c_void_p],
+    "mmb_masked_softmax_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p],
+    "mmb_masked_softmax_bwd": [c_void_p] * 4 + [ctypes.c_longlong, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"mmb_last_error": ctypes.c_char_p}
+
+
+DECODER_WEIGHT_FIELDS = ("W2", "b2", "Wc1", "bc1", "v1", "v1b", "W4", "b4", "Wc2", "bc2", "v2", "v2b",
+                         "Wb1", "bb1", "Wb2", "bb2", "Wb3", "bb3", "Wb4", "bb4", "vb1", "vb1b", "vb2", "vb2b",
+                         "lstm_w_ih", "lstm_w_hh", "lstm_b_ih", "lstm_b_hh", "out_w", "out_b")
+
+
+class DecoderWeights(ctypes.Structure):
+    """struct mmb_decoder_weights: device pointers to the decoder's parameters."""
+    _fields_ = [(name, c_void_p) for name in DECODER_WEIGHT_FIELDS]
 
 
 def load() -> ctypes.CDLL:

@@ -65,3 +65,89 @@ def lstm_layer(x: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Ten
     Returns (out (B,L,ndir*H), h_n (B,ndir,H)) in batch order."""
     out, h_n, _ = _LstmLayer.apply(x.contiguous(), lengths, order, *weights)
     return out, h_n
+
+
+class _BidafAttention(torch.autograd.Function):
+    """Fused BiDAF attention (attention.py:37-75).  Forward = the fused kernels (S never materialised).
+    Backward (INTERIM, round 1): the closed-form gradient evaluated with cuBLAS batched GEMMs and ATen
+    element-wise ops on the GPU from the saved soft-max statistics; a fused recompute-S kernel replaces it
+    next (DESIGN.md, "BiDAF backward")."""
+
+    @staticmethod
+    def forward(ctx, text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
+                keep_text, keep_modality, keep_scale, precision):
+        out, q2c, lse_row, lse_col = ops.bidaf_fwd(text, modality, text_mask, modality_mask, w_text, w_modality,
+                                                   w_cross, bias, keep_text, keep_modality, keep_scale, precision)
+        ctx.save_for_backward(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
+                              keep_text, keep_modality, out, q2c, lse_row, lse_col)
+        ctx.keep_scale = keep_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (c, q, c_mask, q_mask, w_c, w_q, w_cq, bias, keep_c, keep_q, out, q2c, lse_row, lse_col) = ctx.saved_tensors
+        B, Lc, d = c.shape
+        scale = ctx.keep_scale
+        cd = c if keep_c is None else c * keep_c.to(c.dtype) * scale
+        qd = q if keep_q is None else q * keep_q.to(q.dtype) * scale
+        wc, wq, wx = w_c.reshape(d), w_q.reshape(d), w_cq.reshape(d)
+        cm, qm = c_mask.reshape(B, Lc, 1), q_mask.reshape(B, 1, -1)
+        s = torch.baddbmm((cd @ wc).unsqueeze(2) + (qd @ wq).unsqueeze(1) + bias, cd * wx, qd.transpose(1, 2))
+        neg = s.new_full((), -1e30)
+        p = torch.exp(torch.where(qm, s, neg) - lse_row.unsqueeze(2))      # row soft-max s1
+        r = torch.exp(torch.where(cm, s, neg) - lse_col.unsqueeze(1))      # column soft-max s2
+        g0, g1, g2, g3 = grad.split(d, dim=2)
+        a = out[:, :, d:2 * d]
+        bm = torch.bmm(p, q2c)
+        d_a = g1 + c * g2
+        d_bm = c * g3
+        dc = g0 + a * g2 + bm * g3
+        d_p = torch.bmm(d_a, q.transpose(1, 2)) + torch.bmm(d_bm, q2c.transpose(1, 2))
+        dq = torch.bmm(p.transpose(1, 2), d_a)
+        d_t = torch.bmm(p.transpose(1, 2), d_bm)
+        d_r = torch.bmm(c, d_t.transpose(1, 2))
+        dc = dc + torch.bmm(r, d_t)
+        ds = (p * (d_p - (d_p * p).sum(dim=2, keepdim=True))) * qm + (r * (d_r - (d_r * r).sum(dim=1, keepdim=True))) * cm
+        rows, cols = ds.sum(dim=2), ds.sum(dim=1)
+        ds_q = torch.bmm(ds, qd)
+        dcd = rows.unsqueeze(2) * wc + ds_q * wx
+        dqd = cols.unsqueeze(2) * wq + torch.bmm(ds.transpose(1, 2), cd * wx)
+        dw_c = (cd * rows.unsqueeze(2)).sum(dim=(0, 1)).reshape(w_c.shape)
+        dw_q = (qd * cols.unsqueeze(2)).sum(dim=(0, 1)).reshape(w_q.shape)
+        dw_cq = (cd * ds_q).sum(dim=(0, 1)).reshape(w_cq.shape)
+        dbias = ds.sum().reshape(bias.shape)
+        dc = dc + (dcd if keep_c is None else dcd * keep_c.to(c.dtype) * scale)
+        dq = dq + (dqd if keep_q is None else dqd * keep_q.to(q.dtype) * scale)
+        return dc, dq, None, None, dw_c, dw_q, dw_cq, dbias, None, None, None, None
+
+
+def bidaf_attention(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
+                    keep_text=None, keep_modality=None, keep_scale: float = 1.0, precision: int = ops.PREC_FP32):
+    return _BidafAttention.apply(text.contiguous(), modality.contiguous(), text_mask, modality_mask, w_text,
+                                 w_modality, w_cross, bias, keep_text, keep_modality, keep_scale, precision)
+
+
+class _MaskedSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, mask2d, log_mode):
+        y = ops.masked_softmax_fwd(x2d, mask2d, log_mode)
+        ctx.save_for_backward(y, mask2d)
+        ctx.log_mode = log_mode
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, mask2d = ctx.saved_tensors
+        return ops.masked_softmax_bwd(y, dy, mask2d, ctx.log_mode), None, None
+
+
+def masked_softmax(logits: torch.Tensor, mask: torch.Tensor, dim: int = -1, log_softmax: bool = False) -> torch.Tensor:
+    """attention.py:78-98 for any ``dim``: the axis is moved last, rows go through the CUDA kernel."""
+    if not logits.is_cuda:
+        raise RuntimeError("mmbidaf_b200 masked_softmax runs on a B200 only (no CPU fallback)")
+    dim = dim % logits.dim()
+    x = logits.float().movedim(dim, -1)
+    m = (mask != 0).expand_as(logits).movedim(dim, -1).contiguous().view(torch.uint8)
+    shape = x.shape
+    y = _MaskedSoftmax.apply(x.contiguous().view(-1, shape[-1]), m.view(-1, shape[-1]), bool(log_softmax))
+    return y.view(shape).movedim(-1, dim)

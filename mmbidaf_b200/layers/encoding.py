@@ -1,0 +1,137 @@
+"""Encoders of the MMBiDAF hot path on B200.
+
+Same public surface as the reference's layers/encoding.py (``Embedding``, ``HighwayEncoder``,
+``RNNEncoder``, ``ImageEmbedding``): identical constructor and ``forward`` signatures and identical
+parameter names / shapes, so a reference checkpoint loads with ``load_state_dict``.  The recurrent
+part runs in the persistent LSTM kernels of csrc/bilstm.cu; there is no cuDNN / CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as Fn
+
+__all__ = ["Embedding", "HighwayEncoder", "RNNEncoder", "ImageEmbedding"]
+
+
+class HighwayEncoder(nn.Module):
+    """``num_layers`` highway layers x <- g*relu(T x) + (1-g)*x  (reference encoding.py:45-59).
+    Adjacent to the hot path: plain cuBLAS GEMMs + ATen element-wise for now."""
+
+    def __init__(self, num_layers, hidden_size):
+        super().__init__()
+        self.transforms = nn.ModuleList(nn.Linear(hidden_size, hidden_size) for _ in range(num_layers))
+        self.gates = nn.ModuleList(nn.Linear(hidden_size, hidden_size) for _ in range(num_layers))
+
+    def forward(self, x):
+        for gate, transform in zip(self.gates, self.transforms):
+            g = torch.sigmoid(gate(x))
+            x = g * F.relu(transform(x)) + (1 - g) * x
+        return x
+
+
+class Embedding(nn.Module):
+    """dropout -> Linear(E -> H, no bias) -> 2-layer highway  (reference encoding.py:19-30)."""
+
+    def __init__(self, embedding_size, hidden_size, drop_prob):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.proj = nn.Linear(embedding_size, hidden_size, bias=False)
+        self.hwy = HighwayEncoder(2, hidden_size)
+
+    def forward(self, x):
+        return self.hwy(self.proj(F.dropout(x, self.drop_prob, self.training)))
+
+
+class _LengthCache:
+    """Host list of lengths -> (int32 device lengths, int32 device order, int64 device sort index).
+
+    The sort index is computed exactly as the reference does (encoding.py:85,91: a CPU float tensor
+    sorted with torch.sort descending) because the rows of the returned hidden state keep that order."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, lengths, device):
+        key = (tuple(int(v) for v in lengths), str(device))
+        hit = self._store.get(key)
+        if hit is None:
+            if len(self._store) > 64:
+                self._store.clear()
+            sort_idx = torch.Tensor(list(key[0])).sort(0, descending=True)[1]
+            packed = torch.stack([torch.tensor(key[0], dtype=torch.int64), sort_idx]).to(device, non_blocking=True)
+            hit = (packed[0].to(torch.int32), packed[1].to(torch.int32), packed[1])
+            self._store[key] = hit
+        return hit
+
+
+_lengths = _LengthCache()
+
+
+class RNNEncoder(nn.Module):
+    """Length-aware bidirectional LSTM encoder (reference encoding.py:62-108).
+
+    ``self.rnn`` is an ``nn.LSTM`` used purely as the parameter container (names
+    ``rnn.weight_ih_l{k}[_reverse]`` ... and default init identical to the reference); its own forward is
+    never called.  No sort / pack / unpack gathers: the kernel walks each sample up to its own length and
+    writes exact zeros past it.  Returns ``(x, x_hidden)`` with ``x_hidden`` (B, 2*layers, H) left in
+    descending-length row order, as the reference leaves it (quirk Q3, encoding.py:99-106)."""
+
+    def __init__(self, input_size, hidden_size, num_layers, drop_prob=0.):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.num_layers = num_layers
+        self.rnn = nn.LSTM(input_size, hidden_size, num_layers, batch_first=True, bidirectional=True,
+                           dropout=drop_prob if num_layers > 1 else 0.)
+
+    def _layer_weights(self, k):
+        return [getattr(self.rnn, f"{kind}_l{k}{suffix}") for suffix in ("", "_reverse")
+                for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+
+    def forward(self, x, lengths):
+        if not x.is_cuda:
+            raise RuntimeError("mmbidaf_b200.layers.RNNEncoder runs on a B200 only (no CPU fallback)")
+        len_dev, order_dev, sort_idx = _lengths.get(lengths, x.device)
+        finals = []
+        for k in range(self.num_layers):
+            x, h_n = Fn.lstm_layer(x, len_dev, order_dev, self._layer_weights(k))
+            finals.append(h_n)
+            if k + 1 < self.num_layers:                       # nn.LSTM's inter-layer dropout
+                x = F.dropout(x, self.rnn.dropout, self.training)
+        x = F.dropout(x, self.drop_prob, self.training)       # encoding.py:104
+        x_hidden = torch.cat(finals, dim=1).index_select(0, sort_idx)
+        return x, x_hidden
+
+
+class ImageEmbedding(nn.Module):
+    """Key-frame encoder (reference encoding.py:111-154): a frozen ImageNet ResNet-101 giving 1000-d
+    logits per frame.  The CNN is outside the hot path; it is built lazily on first use with real images
+    so that constructing the model needs no weight download.  Pre-extracted features shaped
+    (N, E, 1, 1) pass straight through (north_star feeds "image 1000-d")."""
+
+    def __init__(self):
+        super().__init__()
+        self.resnet = None                 # registered lazily under the reference's attribute name
+
+    def _build(self, pretrained, device=None):
+        import torchvision
+        weights = torchvision.models.ResNet101_Weights.IMAGENET1K_V1 if pretrained else None
+        net = torchvision.models.resnet101(weights=weights)
+        for p in net.parameters():         # fine_tune(False), reference encoding.py:141-154
+            p.requires_grad = False
+        self.resnet = net.to(device) if device is not None else net
+        return self.resnet
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # a reference checkpoint carries image_keyframes_emb.resnet.*: materialise the CNN to receive it
+        if self.resnet is None and any(k.startswith(prefix + "resnet.") for k in state_dict):
+            self._build(pretrained=False)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def forward(self, images):
+        if images.dim() == 4 and images.shape[2] == 1 and images.shape[3] == 1:
+            return images.flatten(1)
+        net = self.resnet if self.resnet is not None else self._build(pretrained=True, device=images.device)
+        return net(images)

@@ -1,0 +1,102 @@
+"""MMBiDAF on B200: the reference's ``models.MMBiDAF`` module surface over the fused kernels.
+
+Constructor and ``forward`` signatures, sub-module names and every parameter name / shape equal the
+reference's (models.py:29-83, :94), so ``train.py`` / ``evaluate.py`` style drivers and reference
+checkpoints (with or without the DataParallel ``module.`` prefix) work unchanged.  Differences are all
+inside ``forward``: masks are built on the device, and the decode loop gathers target probabilities and
+next inputs with device-side indexing instead of ``B x T`` ``int(tensor)`` host round trips
+(reference models.py:166-173, :186-193).  The value of every returned quantity is the reference's.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .layers import BiDAFAttention, Embedding, ImageEmbedding, MultimodalAttentionDecoder, RNNEncoder
+
+__all__ = ["MMBiDAF"]
+
+
+class MMBiDAF(nn.Module):
+    """Embedding -> bi-LSTM encoders -> BiDAF (text<->audio, text<->image) -> modality-aware 2-layer
+    bi-LSTMs -> multimodal attention decoder with coverage -> distribution over source sentences."""
+
+    def __init__(self, hidden_size, text_embedding_size, audio_embedding_size, image_embedding_size, device,
+                 drop_prob=0., max_transcript_length=405):
+        super().__init__()
+        self.device = device
+        self.max_transcript_length = max_transcript_length
+        self.emb = Embedding(embedding_size=text_embedding_size, hidden_size=hidden_size, drop_prob=drop_prob)
+        self.a_emb = Embedding(embedding_size=audio_embedding_size, hidden_size=hidden_size, drop_prob=drop_prob)
+        self.i_emb = Embedding(embedding_size=image_embedding_size, hidden_size=hidden_size, drop_prob=drop_prob)
+        self.text_enc = RNNEncoder(input_size=hidden_size, hidden_size=hidden_size, num_layers=1, drop_prob=drop_prob)
+        self.audio_enc = RNNEncoder(input_size=hidden_size, hidden_size=hidden_size, num_layers=1, drop_prob=drop_prob)
+        self.image_enc = RNNEncoder(input_size=hidden_size, hidden_size=hidden_size, num_layers=1, drop_prob=drop_prob)
+        self.image_keyframes_emb = ImageEmbedding()
+        self.bidaf_att_audio = BiDAFAttention(2 * hidden_size, drop_prob=drop_prob)
+        self.bidaf_att_image = BiDAFAttention(2 * hidden_size, drop_prob=drop_prob)
+        self.mod_t_a = RNNEncoder(input_size=8 * hidden_size, hidden_size=hidden_size, num_layers=2, drop_prob=drop_prob)
+        self.mod_t_i = RNNEncoder(input_size=8 * hidden_size, hidden_size=hidden_size, num_layers=2, drop_prob=drop_prob)
+        self.multimodal_att_decoder = MultimodalAttentionDecoder(text_embedding_size, hidden_size,
+                                                                 max_transcript_length, num_layers=1)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts reference checkpoints saved from ``nn.DataParallel`` (keys prefixed ``module.``)."""
+        if state_dict and all(k.startswith("module.") for k in state_dict):
+            state_dict = {k[len("module."):]: v for k, v in state_dict.items()}
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def get_mask(self, X, X_len):
+        """bool (B, L): position < length, on X's device (reference models.py:86-92 builds it on the CPU)."""
+        lens = torch.as_tensor(list(X_len), dtype=torch.long).to(X.device, non_blocking=True)
+        return torch.arange(X.size(1), device=X.device).unsqueeze(0) < lens.unsqueeze(1)
+
+    def forward(self, embedded_text, original_text_lengths, embedded_audio, original_audio_lengths, transformed_images,
+                original_image_lengths, batch_target_indices, original_target_len, max_dec_len):
+        B, Lt = embedded_text.size(0), embedded_text.size(1)
+        text_emb = self.emb(embedded_text)
+        text_encoded, _ = self.text_enc(text_emb, original_text_lengths)
+        audio_encoded, _ = self.audio_enc(self.a_emb(embedded_audio), original_audio_lengths)
+        img = transformed_images.reshape(-1, *transformed_images.shape[2:])
+        image_emb = self.image_keyframes_emb(img).reshape(B, transformed_images.size(1), -1)
+        image_encoded, _ = self.image_enc(self.i_emb(image_emb), original_image_lengths)
+
+        text_mask = self.get_mask(embedded_text, original_text_lengths)
+        audio_mask = self.get_mask(embedded_audio, original_audio_lengths)
+        image_mask = self.get_mask(image_emb, original_image_lengths)
+        decoder_mask = torch.zeros(B, self.max_transcript_length, dtype=torch.bool, device=text_mask.device)
+        decoder_mask[:, :Lt] = text_mask                                   # models.py:121-123
+
+        text_audio_att = self.bidaf_att_audio(text_encoded, audio_encoded, text_mask, audio_mask)
+        text_image_att = self.bidaf_att_image(text_encoded, image_encoded, text_mask, image_mask)
+        mod_text_audio, text_audio_hidden = self.mod_t_a(text_audio_att, original_text_lengths)
+        mod_text_image, text_img_hidden = self.mod_t_i(text_image_att, original_text_lengths)
+
+        # models.py:143-149 (the hidden-state rows are in descending-length order: reference quirk Q3)
+        decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)
+        decoder_cell_state = text_emb.new_zeros(1, B, decoder_hidden.size(-1))
+        decoder_input = embedded_text.new_zeros(B, 1, embedded_text.size(-1))
+        coverage_vec = text_emb.new_zeros(B, Lt, 1)
+
+        eps = 1e-12
+        rows = torch.arange(B, device=embedded_text.device)
+        targets = batch_target_indices.reshape(B, -1).to(embedded_text.device).long()      # int(tensor), models.py:168
+        loss = text_emb.new_zeros(())
+        out_distributions = []
+        steps = batch_target_indices.size(1) if self.training else max_dec_len
+        att_cov_dist = None
+        for idx in range(steps):
+            out_distribution, decoder_hidden, decoder_cell_state, att_cov_dist, coverage_vec = \
+                self.multimodal_att_decoder(decoder_input, decoder_hidden, decoder_cell_state, mod_text_audio,
+                                            mod_text_image, coverage_vec, decoder_mask)
+            tgt = targets[:, idx]
+            loss = loss - torch.log(out_distribution[rows, tgt] + eps).sum()                # models.py:168-170
+            nxt = tgt if self.training else out_distribution.max(dim=1)[1]                  # models.py:173 / :184,:193
+            decoder_input = embedded_text[rows, nxt].unsqueeze(1)
+            out_distributions.append(out_distribution)
+            if self.training:                                                               # models.py:177-178
+                loss = loss + torch.min(att_cov_dist, coverage_vec).sum()
+        if not self.training:                                                               # models.py:197-198
+            loss = loss + torch.min(att_cov_dist, coverage_vec).sum()
+        loss = loss / steps
+        return torch.stack(out_distributions).transpose(0, 1), loss

@@ -89,3 +89,61 @@ def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, 
                "mmb_bilstm_bwd")
     _count(1)
     return gates
+
+
+def decoder_weights(params: dict) -> "_lib.DecoderWeights":
+    """Pack device pointers of the decoder parameters (keys = _lib.DECODER_WEIGHT_FIELDS)."""
+    w = _lib.DecoderWeights()
+    for name in _lib.DECODER_WEIGHT_FIELDS:
+        t = params[name]
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, name
+        setattr(w, name, t.data_ptr())
+    return w
+
+
+def decoder_step_fwd(w, proj_a, proj_i, enc_a, enc_i, sent_embed, h, cell, coverage, mask_u8, M: int,
+                     want_argmax: bool = False, save: bool = False):
+    """One fused decoder step (attention.py:145-186).  All tensors 2-D/3-D contiguous fp32 CUDA:
+    proj_*/enc_* (B,Lt,2H), sent_embed (B,E), h/cell (B,H), coverage (B,Lt), mask_u8 (B,M) uint8.
+    Returns (probs, h', cell', att_cov, coverage', argmax|None, saved) with saved = (ctx, alpha, beta, gates)."""
+    import ctypes
+    lib = _lib.lib()
+    B, Lt, D = enc_a.shape
+    H, E = D // 2, sent_embed.shape[1]
+    dev = enc_a.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    probs = torch.empty(B, M, **f32)
+    h_out, cell_out = torch.empty(B, H, **f32), torch.empty(B, H, **f32)
+    att_cov, cov_out = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32)
+    ctx = torch.empty(B, D, **f32)
+    argmax = torch.empty(B, device=dev, dtype=torch.int64) if want_argmax else None
+    alpha = torch.empty(B, 2, Lt, **f32) if save else None
+    beta = torch.empty(B, 2, **f32) if save else None
+    gates = torch.empty(B, 4 * H, **f32) if save else None
+    p = _lib.ptr
+    _lib.check(lib.mmb_decoder_step_fwd(ctypes.addressof(w), p(proj_a), p(proj_i), p(enc_a), p(enc_i), p(sent_embed),
+                                        p(h), p(cell), p(coverage), p(mask_u8), p(probs), p(h_out), p(cell_out),
+                                        p(att_cov), p(cov_out), p(argmax), p(ctx), p(alpha), p(beta), p(gates),
+                                        B, Lt, H, E, M, _lib.stream()), "mmb_decoder_step_fwd")
+    _count(3)
+    return probs, h_out, cell_out, att_cov, cov_out, argmax, (ctx, alpha, beta, gates)
+
+
+def masked_softmax_fwd(x2d: torch.Tensor, mask2d_u8: torch.Tensor, log_mode: bool) -> torch.Tensor:
+    lib = _lib.lib()
+    rows, n = x2d.shape
+    y = torch.empty_like(x2d)
+    _lib.check(lib.mmb_masked_softmax_fwd(_lib.ptr(x2d), _lib.ptr(mask2d_u8), _lib.ptr(y), rows, n, int(log_mode),
+                                          _lib.stream()), "mmb_masked_softmax_fwd")
+    _count(1)
+    return y
+
+
+def masked_softmax_bwd(y2d: torch.Tensor, dy2d: torch.Tensor, mask2d_u8: torch.Tensor, log_mode: bool) -> torch.Tensor:
+    lib = _lib.lib()
+    rows, n = y2d.shape
+    dx = torch.empty_like(y2d)
+    _lib.check(lib.mmb_masked_softmax_bwd(_lib.ptr(y2d), _lib.ptr(dy2d.contiguous()), _lib.ptr(mask2d_u8), _lib.ptr(dx),
+                                          rows, n, int(log_mode), _lib.stream()), "mmb_masked_softmax_bwd")
+    _count(1)
+    return dx

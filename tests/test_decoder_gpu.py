@@ -1,0 +1,83 @@
+"""GPU parity: fused decoder step vs the reference's golden vectors and the oracle."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import mmbidaf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+FIELD_TO_PARAM = {
+    "W2": "W2.weight", "b2": "W2.bias", "Wc1": "Wc1.weight", "bc1": "Wc1.bias", "v1": "v1.weight", "v1b": "v1.bias",
+    "W4": "W4.weight", "b4": "W4.bias", "Wc2": "Wc2.weight", "bc2": "Wc2.bias", "v2": "v2.weight", "v2b": "v2.bias",
+    "Wb1": "W_beta_1.weight", "bb1": "W_beta_1.bias", "Wb2": "W_beta_2.weight", "bb2": "W_beta_2.bias",
+    "Wb3": "W_beta_3.weight", "bb3": "W_beta_3.bias", "Wb4": "W_beta_4.weight", "bb4": "W_beta_4.bias",
+    "vb1": "v_beta_1.weight", "vb1b": "v_beta_1.bias", "vb2": "v_beta_2.weight", "vb2b": "v_beta_2.bias",
+    "lstm_w_ih": "lstm.weight_ih_l0", "lstm_w_hh": "lstm.weight_hh_l0", "lstm_b_ih": "lstm.bias_ih_l0",
+    "lstm_b_hh": "lstm.bias_hh_l0", "out_w": "out.weight", "out_b": "out.bias"}
+
+
+def _step_fn(state):
+    from mmbidaf_b200 import ops
+    dev = "cuda"
+    held = {f: state[p].to(dev).contiguous() for f, p in FIELD_TO_PARAM.items()}
+    w = ops.decoder_weights(held)
+    W1, b1 = state["W1.weight"].to(dev), state["W1.bias"].to(dev)
+    W3, b3 = state["W3.weight"].to(dev), state["W3.bias"].to(dev)
+
+    def run(sent, h, cell, enc_a, enc_i, cov, mask, M):
+        enc_a, enc_i = enc_a.to(dev).contiguous(), enc_i.to(dev).contiguous()
+        B, Lt, D = enc_a.shape
+        proj_a = torch.addmm(b1, enc_a.view(B * Lt, D), W1.t()).view(B, Lt, D)
+        proj_i = torch.addmm(b3, enc_i.view(B * Lt, D), W3.t()).view(B, Lt, D)
+        out = ops.decoder_step_fwd(w, proj_a, proj_i, enc_a, enc_i, sent.to(dev).reshape(B, -1).contiguous(),
+                                   h.to(dev).reshape(B, -1).contiguous(), cell.to(dev).reshape(B, -1).contiguous(),
+                                   cov.to(dev).reshape(B, Lt).contiguous(), mask.to(dev).to(torch.uint8).contiguous(),
+                                   M, want_argmax=True, save=True)
+        torch.cuda.synchronize()
+        _ = held                                     # keep parameters alive while kernels run
+        return out
+    return run
+
+
+def test_decoder_steps_match_reference_golden():
+    g = load_golden("decoder_small.pt")
+    run = _step_fn(g["state"])
+    h, cell, cov = g["h0"], g["cell0"], g["cov0"]
+    M = g["mask"].shape[1]
+    for k, want in enumerate(g["steps"]):
+        probs, h, cell, att, cov, amax, _ = run(g["sent"][k], h, cell, g["enc_a"], g["enc_i"], cov, g["mask"], M)
+        assert rel_err(probs, want["probs"]) < TOL
+        assert rel_err(h, want["h"].squeeze(1)) < TOL and rel_err(cell, want["cell"].squeeze(0)) < TOL
+        assert rel_err(att, want["att_cov"].squeeze(2)) < TOL and rel_err(cov, want["coverage"].squeeze(2)) < TOL
+        assert (probs.cpu()[~g["mask"]] == 0).all()
+        assert torch.equal(amax.cpu(), want["probs"].argmax(dim=1))          # selected index: bit-exact
+
+
+@pytest.mark.parametrize("cfg", [(3, 24, 100, 300, 409), (32, 409, 100, 300, 409), (2, 700, 100, 300, 1024),
+                                 (5, 13, 6, 10, 17), (1, 1, 4, 3, 2)])
+def test_decoder_step_matches_oracle(cfg):
+    bsz, lt, hid, e, m = cfg
+    m = max(m, lt)
+    gen = torch.Generator().manual_seed(77 + lt)
+    shapes = O.param_shapes(hid, e, 4, 4, m)
+    state = {k[len("multimodal_att_decoder."):]: (torch.rand(v, generator=gen) - 0.5) * 0.4
+             for k, v in shapes.items() if k.startswith("multimodal_att_decoder.")}
+    enc_a = torch.randn(bsz, lt, 2 * hid, generator=gen)
+    enc_i = torch.randn(bsz, lt, 2 * hid, generator=gen)
+    h = torch.randn(bsz, 1, hid, generator=gen)
+    cell = torch.randn(1, bsz, hid, generator=gen)
+    cov = torch.rand(bsz, lt, 1, generator=gen)
+    sent = torch.randn(bsz, 1, e, generator=gen)
+    lens = torch.randint(1, lt + 1, (bsz,), generator=gen).tolist()
+    mask = O.decoder_mask(O.length_mask(lt, lens), m)
+    d64 = lambda t: t.double()
+    want = O.decoder_step({k: d64(v) for k, v in state.items()}, d64(sent), d64(h), d64(cell), d64(enc_a), d64(enc_i),
+                          d64(cov), mask)
+    probs, h1, c1, att, cov1, amax, saved = _step_fn(state)(sent, h, cell, enc_a, enc_i, cov, mask, m)
+    assert rel_err(probs, want[0]) < TOL
+    assert rel_err(h1, want[1].squeeze(1)) < TOL and rel_err(c1, want[2].squeeze(0)) < TOL
+    assert rel_err(att, want[3].squeeze(2)) < TOL and rel_err(cov1, want[4].squeeze(2)) < TOL
+    assert torch.equal(amax.cpu(), want[0].argmax(dim=1))
+    assert abs(float(probs.sum(dim=1).min()) - 1) < 1e-5

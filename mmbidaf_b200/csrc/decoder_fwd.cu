@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = ATT_THREADS / 32;
   extern __shared__ __align__(16) float smem[];
-  float* h_s = smem;                       // [H]
+  const bool vec4 = (D & 3) == 0;
+  const int n_groups = vec4 ? ATT_THREADS / (D >> 2) : ATT_THREADS / D;
+  float* part = smem;                      // [groups][2][D]  (first: 16-byte aligned for the float4 path)
+  float* h_s = part + n_groups * 2 * D;    // [H]
   float* hw = h_s + H;                     // [4][D]  W2 h + b2 + bc1 | W4 h + b4 + bc2 | Wb2 h + bb2 | Wb4 h + bb4
   float* vec = hw + 4 * D;                 // [4][D]  v1 | wc1 | v2 | wc2
   float* ctx1 = vec + 4 * D;               // [D]
@@ -51,7 +54,6 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   float* red = ctx2 + D;                   // [32]
   float* e1 = red + 32;                    // [Lt]
   float* e2 = e1 + Lt;                     // [Lt]
-  float* part = e2 + Lt;                   // [groups][2][D]
 
   for (int i = tid; i < H; i += ATT_THREADS) h_s[i] = a.h[(size_t)b * H + i];
   for (int i = tid; i < D; i += ATT_THREADS) {
@@ -120,10 +122,9 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   // ---- contexts c_k = sum_t alpha_k[t] enc_k[t] --------------------------------------------------------
   const float* ea = a.enc_a + (size_t)b * Lt * D;
   const float* ei = a.enc_i + (size_t)b * Lt * D;
-  int groups;
-  if ((D & 3) == 0 && D / 4 <= ATT_THREADS) {
+  const int groups = n_groups;
+  if (vec4) {
     const int dv4 = D >> 2;
-    groups = ATT_THREADS / dv4;
     const int g = tid / dv4, c4 = tid - g * dv4;
     if (g < groups) {
       float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
@@ -139,7 +140,6 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
       *reinterpret_cast<float4*>(part + (g * 2 + 1) * D + c4 * 4) = s2;
     }
   } else {
-    groups = ATT_THREADS / D;
     const int g = tid / D, d = tid - g * D;
     if (g < groups) {
       float s1 = 0.f, s2 = 0.f;

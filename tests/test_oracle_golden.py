@@ -165,7 +165,7 @@ def test_model_readme_sizes_match_reference():
     for k, v in g["train_grads_sample"].items():
         assert grad_err(p[k].grad, v, k) < 2e-4, k
     for k, v in g["train_grad_norms"].items():
-        assert abs(float(p[k].grad.double().norm()) - v) <= 2e-3 * max(v, 1e-5), k
+        assert abs(float(p[k].grad.double().norm()) - v) <= 2e-3 * max(v, 1e-3), k
     with torch.no_grad():
         out_e, loss_e = O.mmbidaf_forward(params, b.text, b.text_len, b.audio, b.audio_len, img, b.image_len,
                                           b.targets, b.max_dec_len, m, training=False, fast_lstm=True)

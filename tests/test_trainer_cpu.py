@@ -1,0 +1,94 @@
+"""CPU: the data-parallel training step logic (sharding, flat-bucket SUM all-reduce, global-norm clip,
+Adadelta) under gloo with world_size 2, on a small stand-in model with the MMBiDAF call signature."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mmbidaf_b200.synth import make_batch
+from mmbidaf_b200.trainer import FlatGrads, Trainer, shard_batch, shard_range
+
+
+class TinyModel(torch.nn.Module):
+    """Same forward signature / loss convention as MMBiDAF (loss summed over the batch)."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.t = torch.nn.Linear(300, 4)
+        self.a = torch.nn.Linear(128, 4)
+
+    def forward(self, text, text_len, audio, audio_len, images, image_len, targets, target_len, max_dec_len):
+        loss = text.new_zeros(())
+        for b, (n, m) in enumerate(zip(text_len, audio_len)):          # per-video terms, padding never visited
+            loss = loss + self.t(text[b, :n]).tanh().sum() + self.a(audio[b, :m]).sigmoid().sum()
+        return None, loss
+
+
+def test_shard_range_is_a_partition():
+    for n in (1, 7, 32, 33):
+        for world in (1, 2, 4, 8):
+            seen = [i for r in range(world) for i in shard_range(n, r, world)]
+            assert seen == list(range(n))
+            sizes = [len(shard_range(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_batch_repads_to_local_max():
+    batch = make_batch(5, 12, 20, 4, 3, seed=9)
+    parts = [shard_batch(batch, r, 2) for r in range(2)]
+    assert sum(len(p.text_len) for p in parts) == 5
+    for p in parts:
+        assert p.text.shape[1] == max(p.text_len) and p.audio.shape[1] == max(p.audio_len)
+    assert torch.equal(parts[1].text[0, :parts[1].text_len[0]], batch.text[3, :batch.text_len[3]])
+
+
+def test_flat_grads_clip_matches_torch():
+    model = TinyModel()
+    ref = TinyModel()
+    fg = FlatGrads(model.parameters())
+    batch = make_batch(3, 6, 7, 2, 2, seed=2)
+    for m in (model, ref):
+        m(batch.text, batch.text_len, batch.audio, batch.audio_len, None, None, None, None, None)[1].backward()
+    want = torch.nn.utils.clip_grad_norm_(ref.parameters(), 2.0)
+    got = fg.clip_(2.0)
+    assert torch.allclose(got, want)
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-6, atol=1e-8)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    model = TinyModel()
+    if rank == 1:                                       # replicas must be re-synchronised from rank 0
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    trainer = Trainer(model)
+    batch = make_batch(5, 12, 20, 4, 3, seed=9)
+    for _ in range(2):
+        trainer.step(shard_batch(batch, rank, world))
+    out[rank] = [p.detach().clone() for p in model.parameters()] + [trainer.last_grad_norm.clone()]
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process_global_batch():
+    world, port = 2, 29000 + os.getpid() % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        results = {r: out[r] for r in range(world)}
+    single = TinyModel()
+    trainer = Trainer(single)
+    batch = make_batch(5, 12, 20, 4, 3, seed=9)
+    for _ in range(2):
+        trainer.step(batch)
+    want = [p.detach() for p in single.parameters()] + [trainer.last_grad_norm]
+    for r in range(world):
+        for got, w in zip(results[r], want):
+            assert torch.allclose(got, w, rtol=1e-5, atol=1e-7)
+    for a, b in zip(results[0], results[1]):
+        assert torch.equal(a, b)                         # replicas bit-identical after the update

@@ -81,7 +81,7 @@ MMB_API int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_
  *   w_hh (ndir,4H,H)   lengths (B) int32   order (B) int32 permutation, longest first, or NULL
  *   out (B,L,ndir*H): hidden states, exact zeros past each length (pad_packed_sequence)
  *   h_n, c_n (B,ndir,H): state after each sample's last valid step, in BATCH order
- *   cell (B,L,ndir,H): cell states, written when save != 0 (may be NULL otherwise).  H <= 128.
+ *   cell (B,L,ndir,H): cell states, written when save != 0 (may be NULL otherwise).  H <= 104.
  */
 MMB_API int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out,
                            float* h_n, float* c_n, float* cell, int B, int L, int H, int ndir, int save,
@@ -119,8 +119,30 @@ MMB_API int mmb_decoder_step_fwd(const mmb_decoder_weights* w, const float* proj
                                  const float* enc_a, const float* enc_i, const float* sent_embed, const float* h,
                                  const float* cell, const float* coverage, const uint8_t* mask, float* probs,
                                  float* h_out, float* cell_out, float* att_cov, float* cov_out, long long* argmax,
-                                 float* ctx, float* alpha, float* beta, float* gates, int B, int Lt, int H, int E,
-                                 int M, mmb_stream_t stream);
+                                 float* ctx, float* alpha, float* beta, float* gates, float* ctx12, int B, int Lt,
+                                 int H, int E, int M, mmb_stream_t stream);
+
+/* Backward of one decoder step (two launches: output layer + LSTM cell, then the attentions).
+ * Inputs: the step's saved forward tensors (probs, h_out, cell_out, gates, alpha, beta, ctx12, and the
+ * step inputs h, cell, coverage, proj_*, enc_*) and the incoming gradients d_probs (B,M), d_h_out,
+ * d_cell_out (B,H), d_att_cov, d_cov_out (B,Lt).
+ * Outputs
+ *   d_h, d_cell (B,H), d_cov (B,Lt): gradients of the step inputs
+ *   d_proj_a, d_proj_i (B,Lt,2H): ACCUMULATED in place (+=) across the steps of one sequence
+ *   per-step rows for the deferred weight-gradient GEMMs:
+ *     d_logits (B,M), d_gates (B,4H), d_ctx12 (B,2,2H) = d(loss)/d(c1), d(c2),
+ *     d_pre (B,4,2H) = d tanh-argument sums [W2-side, W4-side, W_beta_1/2-side, W_beta_3/4-side]
+ *   vec_acc (B,6,2H) += [dWc1, dWc2, dv1, dv2, dv_beta_1, dv_beta_2];  scal_acc (B,4) += their biases.
+ */
+MMB_API int mmb_decoder_step_bwd(const mmb_decoder_weights* w, const float* proj_a, const float* proj_i,
+                                 const float* enc_a, const float* enc_i, const float* h, const float* cell,
+                                 const float* coverage, const float* probs, const float* h_out, const float* cell_out,
+                                 const float* gates, const float* alpha, const float* beta, const float* ctx12,
+                                 const float* d_probs, const float* d_h_out, const float* d_cell_out,
+                                 const float* d_att_cov, const float* d_cov_out, float* d_h, float* d_cell, float* d_cov,
+                                 float* d_proj_a, float* d_proj_i, float* d_logits, float* d_gates, float* d_ctx12,
+                                 float* d_pre, float* vec_acc, float* scal_acc, float* d_ctx, int B, int Lt, int H,
+                                 int E, int M, mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
  * masked_softmax over the last axis (attention.py:78-98): y = softmax(mask ? x : -1e30), or

@@ -28,7 +28,8 @@ SIGNATURES = {
     "mmb_bidaf_fwd": [c_void_p] * 10 + [c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
-    "mmb_decoder_step_fwd": [c_void_p] * 20 + [c_int] * 5 + [c_void_p],
+    "mmb_decoder_step_fwd": [c_void_p] * 21 + [c_int] * 5 + [c_void_p],
+    "mmb_decoder_step_bwd": [c_void_p] * 32 + [c_int] * 5 + [c_void_p],
     "mmb_masked_softmax_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p],
     "mmb_masked_softmax_bwd": [c_void_p] * 4 + [ctypes.c_longlong, c_int, c_int, c_void_p],
 }

@@ -4,13 +4,15 @@
 // gathers around it, encoding.py:91-101) for one layer, both directions.  The input projection
 // x W_ih^T + b_ih + b_hh is a plain GEMM done by the caller; this kernel owns the serial part.
 //
-// One CTA = one direction x NB sequences, alive for the whole sequence.  Thread (j, kp), with
-// j = hidden unit and kp = 0..3, keeps in REGISTERS the recurrent weights of the four gate rows of
-// unit j restricted to a quarter of the k range (4 x KS floats), so W_hh never leaves the
-// register file between time steps.  Per step: 4 x KS FMAs against h (broadcast float4 reads from
-// shared memory), a 3-shuffle reduce-scatter over the 4 kp lanes (lane kp ends with gate kp),
-// one activation per lane, a 4-shuffle exchange, the cell update, one __syncthreads.
-// Input pre-activations are prefetched RING-1 steps ahead with cp.async.
+// One CTA = one direction x NB sequences, alive for the whole sequence.  Two lanes share a hidden
+// unit j: lane kp (0/1) keeps in REGISTERS the recurrent weights of all four gate rows of unit j
+// restricted to half of the k range (4 x KS floats, KS = 52 at H = 100), so W_hh never leaves the
+// register file between time steps and the CTA is only 2H threads (7 warps at H = 100: <= 2 warps per
+// scheduler, 255 registers each -- no spills).  Per step: 4 x KS FMAs against h (broadcast float4
+// reads from shared memory), a 2-shuffle reduce-scatter (lane 0 ends with gates i,f; lane 1 with g,o),
+// two branch-free activations per lane, a 2-shuffle exchange, the cell update, one __syncthreads.
+// Input pre-activations are prefetched RING-1 steps ahead with cp.async; all addressing is by running
+// pointers (one add per step).
 //
 // Semantics follow torch.nn.LSTM on a PackedSequence: gate order i,f,g,o; zero initial state;
 // the reverse direction starts at each sample's own last valid step; outputs past a sample's
@@ -21,7 +23,7 @@
 namespace mmb {
 namespace {
 
-constexpr int RING = 8;
+constexpr int RING = 8;          // power of two
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -46,18 +48,20 @@ struct LstmArgs {
   int B, L, H, ndir, save;
 };
 
+constexpr int threads_for(int KS) { return (4 * KS + 31) / 32 * 32 < 64 ? 64 : (4 * KS + 31) / 32 * 32; }
+
 template <int KS, int NB>
-__global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_fwd_kernel(const LstmArgs a) {
-  constexpr int HP = 4 * KS;                       // padded hidden size
+__global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmArgs a) {
+  constexpr int HP = 2 * KS;                       // padded hidden size
   const int H = a.H, L = a.L, ndir = a.ndir;
   const int dir = blockIdx.y;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int j = tid >> 2, kp = tid & 3;
+  const int j = tid >> 1, kp = tid & 1;
   const bool live = j < H;
 
   extern __shared__ __align__(16) float smem[];
   float* h_s = smem;                               // [2][NB][HP]
-  float* ring = h_s + 2 * NB * HP;                 // [RING][NB][nthr]
+  float* ring = h_s + 2 * NB * HP;                 // [RING][NB][2][nthr]
 
   int seq[NB], len[NB];
   int max_len = 0;
@@ -83,33 +87,53 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_f
   }
   for (int i = tid; i < 2 * NB * HP; i += nthr) h_s[i] = 0.f;
 
-  auto gate_ptr = [&](int n, int s) -> float* {    // this lane's pre-activation of sequence n at step s
-    const int t = dir ? len[n] - 1 - s : s;
-    return a.gates + (((size_t)seq[n] * L + t) * ndir + dir) * 4 * H + kp * H + j;
-  };
-  auto prefetch = [&](int s) {
+  // Running pointers: this lane's two pre-activation / saved-gate slots (gates 2kp, 2kp+1 of unit j), the
+  // output slot and the cell slot of sequence n at the current step, and the prefetch pointer RING-1
+  // steps ahead.  Forward walks t = 0.., the reverse direction t = len-1 ...
+  const long sign = dir ? -1 : 1;
+  const long g_stride = sign * (long)ndir * 4 * H, o_stride = sign * (long)ndir * H;
+  float *gp[NB], *op[NB], *cp[NB];
+  const float* pf[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    const size_t bt0 = (size_t)max(seq[n], 0) * L + (dir ? max(len[n] - 1, 0) : 0);
+    gp[n] = a.gates + (bt0 * ndir + dir) * 4 * H + (2 * kp) * H + j;
+    op[n] = a.out + bt0 * ndir * H + dir * H + j;
+    cp[n] = a.cell ? a.cell + (bt0 * ndir + dir) * H + j : nullptr;
+    pf[n] = gp[n];
+  }
+  float* ring_t = ring + tid;
+  auto prefetch = [&](int s, int slot) {
     if (live) {
 #pragma unroll
-      for (int n = 0; n < NB; ++n)
-        if (s < len[n]) cp_async4(ring + ((s % RING) * NB + n) * nthr + tid, gate_ptr(n, s));
+      for (int n = 0; n < NB; ++n) {
+        if (s < len[n]) {
+          cp_async4(ring_t + ((slot * NB + n) * 2 + 0) * nthr, pf[n]);
+          cp_async4(ring_t + ((slot * NB + n) * 2 + 1) * nthr, pf[n] + H);
+        }
+        pf[n] += g_stride;
+      }
     }
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int s = 0; s < RING - 1; ++s) prefetch(s);
+  for (int s = 0; s < RING - 1; ++s) prefetch(s, s);
   __syncthreads();
 
   float c_reg[NB], h_reg[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) c_reg[n] = h_reg[n] = 0.f;
-  const int quad = (tid & 31) & ~3;
+  const float k_first = kp ? 2.0f : 1.0f;          // lane 0: (i, f) both sigmoid; lane 1: (g = tanh, o = sigmoid)
+  const bool save = a.save != 0;
+  const float* hc = h_s;
+  float* hn = h_s + NB * HP;
+  int slot = 0;
 
 #pragma unroll 1
   for (int s = 0; s < max_len; ++s) {
-    prefetch(s + RING - 1);
+    prefetch(s + RING - 1, (slot + RING - 1) & (RING - 1));
     cp_async_wait<RING - 1>();
-    const float* hc = h_s + (s & 1) * NB * HP;
-    float* hn = h_s + ((s + 1) & 1) * NB * HP;
+    const float* hk = hc + kp * KS;
 
     float acc[NB][4];
 #pragma unroll
@@ -120,7 +144,7 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_f
     for (int k4 = 0; k4 < KS / 4; ++k4) {
 #pragma unroll
       for (int n = 0; n < NB; ++n) {
-        const float4 hv = *reinterpret_cast<const float4*>(hc + n * HP + kp * KS + k4 * 4);
+        const float4 hv = *reinterpret_cast<const float4*>(hk + n * HP + k4 * 4);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           acc[n][g] = fmaf(w[g][k4 * 4 + 0], hv.x, acc[n][g]);
@@ -132,35 +156,39 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_f
     }
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
-      // reduce-scatter over the 4 kp lanes: lane kp ends with the full sum of gate kp
-      const bool hi = kp & 2, odd = kp & 1;
-      float k0 = hi ? acc[n][2] : acc[n][0], k1 = hi ? acc[n][3] : acc[n][1];
-      const float s0 = hi ? acc[n][0] : acc[n][2], s1 = hi ? acc[n][1] : acc[n][3];
-      k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      float mine = odd ? k1 : k0;
-      mine += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
-      const bool active = s < len[n];                               // uniform over the CTA
-      const float pre = mine + ((active && live) ? ring[((s % RING) * NB + n) * nthr + tid] : 0.f);
-      const float act = kp == 2 ? tanhf(pre) : sigmoidf_acc(pre);
-      const float gi = __shfl_sync(0xffffffffu, act, quad + 0);
-      const float gf = __shfl_sync(0xffffffffu, act, quad + 1);
-      const float gg = __shfl_sync(0xffffffffu, act, quad + 2);
-      const float go = __shfl_sync(0xffffffffu, act, quad + 3);
-      if (active && live) {
+      // reduce-scatter over the lane pair: lane 0 keeps gates (i, f), lane 1 keeps (g, o)
+      float m0 = kp ? acc[n][2] : acc[n][0], m1 = kp ? acc[n][3] : acc[n][1];
+      m0 += __shfl_xor_sync(0xffffffffu, kp ? acc[n][0] : acc[n][2], 1);
+      m1 += __shfl_xor_sync(0xffffffffu, kp ? acc[n][1] : acc[n][3], 1);
+      const bool on = live && s < len[n];                           // s < len[n] is uniform over the CTA
+      const float* rs = ring_t + (slot * NB + n) * 2 * nthr;
+      const float a0 = gate_act(m0 + (on ? rs[0] : 0.f), k_first);   // i | g
+      const float a1 = gate_act(m1 + (on ? rs[nthr] : 0.f), 1.0f);   // f | o
+      const float b0 = __shfl_xor_sync(0xffffffffu, a0, 1);
+      const float b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
+      const float gi = kp ? b0 : a0, gf = kp ? b1 : a1, gg = kp ? a0 : b0, go = kp ? a1 : b1;
+      if (on) {
         c_reg[n] = fmaf(gf, c_reg[n], gi * gg);
-        h_reg[n] = go * tanhf(c_reg[n]);
-        const int t = dir ? len[n] - 1 - s : s;
-        const size_t bt = (size_t)seq[n] * L + t;
+        h_reg[n] = go * tanh_fast(c_reg[n]);
         if (kp == 0) {
           hn[n * HP + j] = h_reg[n];
-          a.out[bt * ndir * H + dir * H + j] = h_reg[n];
+          *op[n] = h_reg[n];
         }
-        if (a.save) {
-          a.gates[(bt * ndir + dir) * 4 * H + kp * H + j] = act;
-          if (kp == 1) a.cell[(bt * ndir + dir) * H + j] = c_reg[n];
+        if (save) {
+          gp[n][0] = a0;
+          gp[n][H] = a1;
+          if (kp == 1) *cp[n] = c_reg[n];
         }
       }
+      gp[n] += g_stride;
+      op[n] += o_stride;
+      if (save) cp[n] += o_stride;
+    }
+    slot = (slot + 1) & (RING - 1);
+    {                                                               // swap the double-buffered hidden state
+      const float* t = hc;
+      hc = hn;
+      hn = const_cast<float*>(t);
     }
     __syncthreads();
   }
@@ -181,18 +209,20 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_f
 
 // Backward through time.  `gates` holds the activated gates on entry and d(pre-activation) on exit
 // (zeros past each length), so dW_ih / dx / db / dW_hh are plain GEMMs for the caller.
+// Lane kp of unit j owns gates (2kp, 2kp+1): it loads and differentiates those two gates and keeps the
+// matching 2 x H slice of W_hh^T (column j) in registers for the recurrent product dh = W_hh^T da.
 template <int KS, int NB>
-__global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_bwd_kernel(const LstmArgs a) {
-  constexpr int HP = 4 * KS;
+__global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmArgs a) {
+  constexpr int HP = 2 * KS;                       // >= H, multiple of 4
   const int H = a.H, L = a.L, ndir = a.ndir;
   const int dir = blockIdx.y;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int j = tid >> 2, kp = tid & 3;
+  const int j = tid >> 1, kp = tid & 1;
   const bool live = j < H;
 
   extern __shared__ __align__(16) float smem[];
   float* da_s = smem;                              // [2][NB][4][HP]
-  float* ring = da_s + 2 * NB * 4 * HP;            // [RING][NB][2][nthr]
+  float* ring = da_s + 2 * NB * 4 * HP;            // [RING][NB][4][nthr]
 
   int seq[NB], len[NB];
   int max_len = 0;
@@ -204,38 +234,54 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_b
     max_len = max(max_len, len[n]);
   }
 
-  // transposed recurrent weights: rows of gate kp, column j
-  float wt[HP];
+  float wt[2][HP];                                 // W_hh[(2kp+gg)*H + r][j]
   {
     const float* wd = a.w_hh + (size_t)dir * 4 * H * H;
 #pragma unroll
-    for (int r = 0; r < HP; ++r) wt[r] = (live && r < H) ? wd[(size_t)(kp * H + r) * H + j] : 0.f;
+    for (int gg = 0; gg < 2; ++gg)
+#pragma unroll
+      for (int r = 0; r < HP; ++r) wt[gg][r] = (live && r < H) ? wd[(size_t)((2 * kp + gg) * H + r) * H + j] : 0.f;
   }
   for (int i = tid; i < 2 * NB * 4 * HP; i += nthr) da_s[i] = 0.f;
 
-  // backward step s visits forward step fs = len-1-s, i.e. time t = dir ? s : len-1-s
-  auto time_of = [&](int n, int s) { return dir ? s : len[n] - 1 - s; };
-  auto prefetch = [&](int s) {
+  // Backward step s visits the forward steps in reverse: time t = dir ? s : len-1-s.
+  const long sign = dir ? 1 : -1;
+  const long g_stride = sign * (long)ndir * 4 * H, o_stride = sign * (long)ndir * H;
+  float* gp[NB];
+  const float *pg[NB], *pc[NB], *pd[NB];           // prefetch pointers: gates, cell, dout
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    const size_t bt0 = (size_t)max(seq[n], 0) * L + (dir ? 0 : max(len[n] - 1, 0));
+    gp[n] = a.gates + (bt0 * ndir + dir) * 4 * H + (2 * kp) * H + j;
+    pg[n] = gp[n];
+    pc[n] = a.cell + (bt0 * ndir + dir) * H + j;
+    pd[n] = a.dout + bt0 * ndir * H + dir * H + j;
+  }
+  float* ring_t = ring + tid;
+  auto prefetch = [&](int s, int slot) {
     if (live) {
 #pragma unroll
-      for (int n = 0; n < NB; ++n)
+      for (int n = 0; n < NB; ++n) {
         if (s < len[n]) {
-          const int t = time_of(n, s);
-          const size_t bt = (size_t)seq[n] * L + t;
-          float* slot = ring + (((s % RING) * NB + n) * 2) * nthr + tid;
-          cp_async4(slot, a.gates + (bt * ndir + dir) * 4 * H + kp * H + j);
-          if (kp == 0) cp_async4(slot + nthr, a.cell + (bt * ndir + dir) * H + j);
-          if (kp == 1) cp_async4(slot + nthr, a.dout + bt * ndir * H + dir * H + j);
-          if (kp == 2 && s + 1 < len[n]) {           // cell state of the previous forward step
-            const int tp = time_of(n, s + 1);
-            cp_async4(slot + nthr, a.cell + (((size_t)seq[n] * L + tp) * ndir + dir) * H + j);
+          float* dst = ring_t + (slot * NB + n) * 4 * nthr;
+          cp_async4(dst, pg[n]);
+          cp_async4(dst + nthr, pg[n] + H);
+          if (kp == 0) {
+            cp_async4(dst + 2 * nthr, pc[n]);                                 // c_t
+            if (s + 1 < len[n]) cp_async4(dst + 3 * nthr, pc[n] + o_stride);  // c of the previous forward step
+          } else {
+            cp_async4(dst + 2 * nthr, pd[n]);                                 // d out
           }
         }
+        pg[n] += g_stride;
+        pc[n] += o_stride;
+        pd[n] += o_stride;
+      }
     }
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int s = 0; s < RING - 1; ++s) prefetch(s);
+  for (int s = 0; s < RING - 1; ++s) prefetch(s, s);
 
   float dh_rec[NB], dc[NB];
 #pragma unroll
@@ -243,66 +289,73 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_b
     dh_rec[n] = (live && seq[n] >= 0 && a.dh_n) ? a.dh_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
     dc[n] = (live && seq[n] >= 0 && a.dc_n) ? a.dc_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
   }
-  const int quad = (tid & 31) & ~3;
   __syncthreads();
+  float* dcur = da_s;
+  float* dnxt = da_s + NB * 4 * HP;
+  int slot = 0;
 
 #pragma unroll 1
   for (int s = 0; s < max_len; ++s) {
-    prefetch(s + RING - 1);
+    prefetch(s + RING - 1, (slot + RING - 1) & (RING - 1));
     cp_async_wait<RING - 1>();
-    float* dcur = da_s + (s & 1) * NB * 4 * HP;
 
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
-      const bool active = s < len[n];
-      const float* slot = ring + (((s % RING) * NB + n) * 2) * nthr + tid;
-      const float v1 = (active && live) ? slot[0] : 0.f;
-      const float v2 = (active && live && (kp < 2 || (kp == 2 && s + 1 < len[n]))) ? slot[nthr] : 0.f;
-      const float gi = __shfl_sync(0xffffffffu, v1, quad + 0);
-      const float gf = __shfl_sync(0xffffffffu, v1, quad + 1);
-      const float gg = __shfl_sync(0xffffffffu, v1, quad + 2);
-      const float go = __shfl_sync(0xffffffffu, v1, quad + 3);
-      const float ct = __shfl_sync(0xffffffffu, v2, quad + 0);
-      const float dy = __shfl_sync(0xffffffffu, v2, quad + 1);
-      const float cp = __shfl_sync(0xffffffffu, v2, quad + 2);
+      const bool on = live && s < len[n];
+      const float* rs = ring_t + (slot * NB + n) * 4 * nthr;
+      const float g0 = on ? rs[0] : 0.f, g1 = on ? rs[nthr] : 0.f;          // lane 0: i, f   lane 1: g, o
+      const float x2 = on ? rs[2 * nthr] : 0.f;                             // lane 0: c_t    lane 1: d out
+      const float x3 = (on && kp == 0 && s + 1 < len[n]) ? rs[3 * nthr] : 0.f;   // lane 0: c_prev
+      const float o0 = __shfl_xor_sync(0xffffffffu, g0, 1), o1 = __shfl_xor_sync(0xffffffffu, g1, 1);
+      const float y2 = __shfl_xor_sync(0xffffffffu, x2, 1), y3 = __shfl_xor_sync(0xffffffffu, x3, 1);
+      const float gi = kp ? o0 : g0, gf = kp ? o1 : g1, gg = kp ? g0 : o0, go = kp ? g1 : o1;
+      const float ct = kp ? y2 : x2, dy = kp ? x2 : y2, cprev = kp ? y3 : x3;
       const float dh = dy + dh_rec[n];
-      const float tc = tanhf(ct);
+      const float tc = tanh_fast(ct);
       const float dct = fmaf(dh * go, 1.f - tc * tc, dc[n]);
-      float da;
-      if (kp == 0) da = dct * gg * gi * (1.f - gi);
-      else if (kp == 1) da = dct * cp * gf * (1.f - gf);
-      else if (kp == 2) da = dct * gi * (1.f - gg * gg);
-      else da = dh * tc * go * (1.f - go);
-      if (active && live) {
+      // lane 0: (d a_i, d a_f)   lane 1: (d a_g, d a_o)
+      const float d0 = kp ? dct * gi * (1.f - gg * gg) : dct * gg * gi * (1.f - gi);
+      const float d1 = kp ? dh * tc * go * (1.f - go) : dct * cprev * gf * (1.f - gf);
+      if (on) {
         dc[n] = dct * gf;
-        dcur[(n * 4 + kp) * HP + j] = da;
-        const size_t bt = (size_t)seq[n] * L + time_of(n, s);
-        a.gates[(bt * ndir + dir) * 4 * H + kp * H + j] = da;
+        dcur[(n * 4 + 2 * kp) * HP + j] = d0;
+        dcur[(n * 4 + 2 * kp + 1) * HP + j] = d1;
+        gp[n][0] = d0;
+        gp[n][H] = d1;
       } else if (live) {
-        dcur[(n * 4 + kp) * HP + j] = 0.f;
+        dcur[(n * 4 + 2 * kp) * HP + j] = 0.f;
+        dcur[(n * 4 + 2 * kp + 1) * HP + j] = 0.f;
       }
+      gp[n] += g_stride;
     }
     __syncthreads();
-    // dh_rec[j] = sum_r W_hh[r][j] da[r]: this lane covers the rows of gate kp
-    float part[NB];
+    // dh_rec[j] = sum_r W_hh[r][j] da[r]: this lane covers the rows of gates 2kp, 2kp+1
+    float part[NB][2];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) part[n] = 0.f;
+    for (int n = 0; n < NB; ++n) part[n][0] = part[n][1] = 0.f;
 #pragma unroll
     for (int r4 = 0; r4 < HP / 4; ++r4) {
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const float4 dv = *reinterpret_cast<const float4*>(dcur + (n * 4 + kp) * HP + r4 * 4);
-        part[n] = fmaf(wt[r4 * 4 + 0], dv.x, part[n]);
-        part[n] = fmaf(wt[r4 * 4 + 1], dv.y, part[n]);
-        part[n] = fmaf(wt[r4 * 4 + 2], dv.z, part[n]);
-        part[n] = fmaf(wt[r4 * 4 + 3], dv.w, part[n]);
-      }
+      for (int n = 0; n < NB; ++n)
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const float4 dv = *reinterpret_cast<const float4*>(dcur + (n * 4 + 2 * kp + gg) * HP + r4 * 4);
+          part[n][gg] = fmaf(wt[gg][r4 * 4 + 0], dv.x, part[n][gg]);
+          part[n][gg] = fmaf(wt[gg][r4 * 4 + 1], dv.y, part[n][gg]);
+          part[n][gg] = fmaf(wt[gg][r4 * 4 + 2], dv.z, part[n][gg]);
+          part[n][gg] = fmaf(wt[gg][r4 * 4 + 3], dv.w, part[n][gg]);
+        }
     }
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
-      part[n] += __shfl_xor_sync(0xffffffffu, part[n], 1);
-      part[n] += __shfl_xor_sync(0xffffffffu, part[n], 2);
-      dh_rec[n] = part[n];
+      const float p = part[n][0] + part[n][1];
+      dh_rec[n] = p + __shfl_xor_sync(0xffffffffu, p, 1);
+    }
+    slot = (slot + 1) & (RING - 1);
+    {
+      float* t = dcur;
+      dcur = dnxt;
+      dnxt = t;
     }
   }
   cp_async_wait<0>();
@@ -320,16 +373,16 @@ __global__ void __launch_bounds__(4 * 4 * KS <= 128 ? 128 : 4 * 4 * KS) bilstm_b
 
 template <int KS, int NB>
 int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
-  constexpr int HP = 4 * KS;
-  const int nthr = ((4 * a.H + 31) / 32) * 32;
+  constexpr int HP = 2 * KS;
+  const int nthr = max(((2 * a.H + 31) / 32) * 32, 64);
   dim3 grid((a.B + NB - 1) / NB, a.ndir), block(nthr);
   if (!backward) {
-    const size_t smem = sizeof(float) * (2 * NB * HP + (size_t)RING * NB * nthr);
+    const size_t smem = sizeof(float) * (2 * NB * HP + (size_t)RING * NB * 2 * nthr);
     MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bilstm_fwd_kernel<KS, NB><<<grid, block, smem, stream>>>(a);
     return check_launch("bilstm_fwd_kernel");
   }
-  const size_t smem = sizeof(float) * (2 * NB * 4 * HP + (size_t)RING * NB * 2 * nthr);
+  const size_t smem = sizeof(float) * (2 * NB * 4 * HP + (size_t)RING * NB * 4 * nthr);
   MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bilstm_bwd_kernel<KS, NB><<<grid, block, smem, stream>>>(a);
   return check_launch("bilstm_bwd_kernel");
@@ -337,19 +390,17 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
 
 int pick_nb(int B, int ndir) {
   // Fewest sequences per CTA that still fits one wave of 148 SMs (latency-bound recurrence).
-  return ((B + 0) * ndir <= 148) ? 1 : 2;
+  return (B * ndir <= 148) ? 1 : 2;
 }
 
 int dispatch(const LstmArgs& a, bool backward, cudaStream_t stream) {
   const int nb = pick_nb(a.B, a.ndir);
-#define MMB_LSTM_CASE(KS)                                                       \
-  return nb == 1 ? launch<KS, 1>(a, backward, stream) : launch<KS, 2>(a, backward, stream)
-  if (a.H <= 16) { MMB_LSTM_CASE(4); }
-  if (a.H <= 64) { MMB_LSTM_CASE(16); }
-  if (a.H <= 112) { MMB_LSTM_CASE(28); }
-  if (a.H <= 128) { MMB_LSTM_CASE(32); }
+#define MMB_LSTM_CASE(KS) return nb == 1 ? launch<KS, 1>(a, backward, stream) : launch<KS, 2>(a, backward, stream)
+  if (a.H <= 16) { MMB_LSTM_CASE(8); }
+  if (a.H <= 64) { MMB_LSTM_CASE(32); }
+  if (a.H <= 104) { MMB_LSTM_CASE(52); }
 #undef MMB_LSTM_CASE
-  set_error("bilstm: hidden size %d > 128 unsupported", a.H);
+  set_error("bilstm: hidden size %d > 104 unsupported", a.H);
   return MMB_ERR_UNSUPPORTED;
 }
 

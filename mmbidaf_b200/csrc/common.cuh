@@ -48,5 +48,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Branch-free gate non-linearities for the serial LSTM chain: act_k(x) = 1 - k / (1 + e^{kx}) is tanh for
+// k = 2 and the logistic sigmoid for k = 1.  __expf / __fdividef keep the absolute error near 1e-7
+// (measured against the fp64 oracle in tests/test_lstm_gpu.py), which is what the gates need.
+__device__ __forceinline__ float gate_act(float x, float k) { return 1.0f - __fdividef(k, 1.0f + __expf(k * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return gate_act(x, 2.0f); }
 
 }  // namespace mmb

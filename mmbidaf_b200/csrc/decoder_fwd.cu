@@ -34,7 +34,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 struct AttnArgs {
   mmb_decoder_weights w;
   const float *proj_a, *proj_i, *enc_a, *enc_i, *h, *cov;
-  float *ctx, *att_cov, *cov_out, *alpha, *beta;
+  float *ctx, *att_cov, *cov_out, *alpha, *beta, *ctx12;
   int B, Lt, H;
 };
 
@@ -181,7 +181,13 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   const float mb = fmaxf(eb1, eb2);
   const float x1 = expf(eb1 - mb), x2 = expf(eb2 - mb);
   const float beta1 = x1 / (x1 + x2), beta2 = x2 / (x1 + x2);
-  for (int d = tid; d < D; d += ATT_THREADS) a.ctx[(size_t)b * D + d] = ctx1[d] * beta1 + ctx2[d] * beta2;
+  for (int d = tid; d < D; d += ATT_THREADS) {
+    a.ctx[(size_t)b * D + d] = ctx1[d] * beta1 + ctx2[d] * beta2;
+    if (a.ctx12) {
+      a.ctx12[((size_t)b * 2 + 0) * D + d] = ctx1[d];
+      a.ctx12[((size_t)b * 2 + 1) * D + d] = ctx2[d];
+    }
+  }
   for (int t = tid; t < Lt; t += ATT_THREADS) {
     const float att = e1[t] * beta1 + e2[t] * beta2;                 // bmm([a1 a2], beta), attention.py:167
     a.att_cov[(size_t)b * Lt + t] = att;
@@ -325,8 +331,8 @@ extern "C" int mmb_decoder_step_fwd(const mmb_decoder_weights* w, const float* p
                                     const float* enc_a, const float* enc_i, const float* sent_embed, const float* h,
                                     const float* cell, const float* coverage, const uint8_t* mask, float* probs,
                                     float* h_out, float* cell_out, float* att_cov, float* cov_out, long long* argmax,
-                                    float* ctx, float* alpha, float* beta, float* gates, int B, int Lt, int H, int E,
-                                    int M, mmb_stream_t stream) {
+                                    float* ctx, float* alpha, float* beta, float* gates, float* ctx12, int B, int Lt,
+                                    int H, int E, int M, mmb_stream_t stream) {
   using namespace mmb;
   MMB_REQUIRE(w && proj_a && proj_i && enc_a && enc_i && sent_embed && h && cell && coverage && mask && probs && h_out &&
                   cell_out && att_cov && cov_out && ctx,
@@ -336,7 +342,7 @@ extern "C" int mmb_decoder_step_fwd(const mmb_decoder_weights* w, const float* p
   MMB_REQUIRE(D <= ATT_THREADS, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fwd: hidden size %d > %d", H, ATT_THREADS / 2);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
-    AttnArgs a{*w, proj_a, proj_i, enc_a, enc_i, h, coverage, ctx, att_cov, cov_out, alpha, beta, B, Lt, H};
+    AttnArgs a{*w, proj_a, proj_i, enc_a, enc_i, h, coverage, ctx, att_cov, cov_out, alpha, beta, ctx12, B, Lt, H};
     const int groups = (D % 4 == 0) ? ATT_THREADS / (D / 4) : ATT_THREADS / D;
     const size_t smem = sizeof(float) * ((size_t)H + 10 * D + 32 + 2 * (size_t)Lt + (size_t)groups * 2 * D);
     MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fwd: Lt=%d needs %zu B of shared memory", Lt, smem);

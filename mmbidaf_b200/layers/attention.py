@@ -11,12 +11,37 @@ import weakref
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
+import torch.nn.functional as F  # noqa: F401
 
 from .. import functional as Fn
 from .. import ops
 
 __all__ = ["BiDAFAttention", "masked_softmax", "MultimodalAttentionDecoder"]
+
+
+def _lib_fields():
+    from .._lib import DECODER_WEIGHT_FIELDS
+    return DECODER_WEIGHT_FIELDS
+
+
+def _lin(attr, part):
+    return lambda m: getattr(getattr(m, attr), part)
+
+
+# C-ABI field (struct mmb_decoder_weights) -> module parameter
+_FIELD_TO_PARAM = {}
+for _f, _attr in (("W2", "W2"), ("Wc1", "Wc1"), ("v1", "v1"), ("W4", "W4"), ("Wc2", "Wc2"), ("v2", "v2")):
+    _FIELD_TO_PARAM[_f] = _lin(_attr, "weight")
+    _FIELD_TO_PARAM[("b" + _f[1:]) if _f[0] == "W" else _f + "b"] = _lin(_attr, "bias")
+for _k in "1234":
+    _FIELD_TO_PARAM["Wb" + _k] = _lin("W_beta_" + _k, "weight")
+    _FIELD_TO_PARAM["bb" + _k] = _lin("W_beta_" + _k, "bias")
+for _k in "12":
+    _FIELD_TO_PARAM["vb" + _k] = _lin("v_beta_" + _k, "weight")
+    _FIELD_TO_PARAM["vb" + _k + "b"] = _lin("v_beta_" + _k, "bias")
+_FIELD_TO_PARAM.update({"lstm_w_ih": _lin("lstm", "weight_ih_l0"), "lstm_w_hh": _lin("lstm", "weight_hh_l0"),
+                        "lstm_b_ih": _lin("lstm", "bias_ih_l0"), "lstm_b_hh": _lin("lstm", "bias_hh_l0"),
+                        "out_w": _lin("out", "weight"), "out_b": _lin("out", "bias")})
 
 
 def _keep_mask(x, drop_prob):
@@ -110,31 +135,39 @@ class MultimodalAttentionDecoder(nn.Module):
         self.softmax = nn.Softmax()
         self._cache = None
 
-    # ---- step-invariant projections --------------------------------------------------------------------
-    def _projections(self, enc_a, enc_i):
+    # ---- per-sequence state: step-invariant projections (+ the autograd tape when training) ----------------
+    def _sequence(self, enc_a, enc_i):
+        grad = torch.is_grad_enabled()
         c = self._cache
-        if c is not None and c[0]() is enc_a and c[1]() is enc_i and c[2] == (enc_a._version, enc_i._version,
-                                                                             torch.is_grad_enabled()):
-            return c[3], c[4]
-        proj_a, proj_i = self.W1(enc_a), self.W3(enc_i)
-        self._cache = (weakref.ref(enc_a), weakref.ref(enc_i), (enc_a._version, enc_i._version, torch.is_grad_enabled()),
-                       proj_a, proj_i)
-        return proj_a, proj_i
+        if c is not None and c["a"]() is enc_a and c["i"]() is enc_i and c["key"] == (enc_a._version, enc_i._version, grad):
+            return c
+        proj_a, proj_i = self.W1(enc_a), self.W3(enc_i)              # hoisted: the reference recomputes them per step
+        c = {"a": weakref.ref(enc_a), "i": weakref.ref(enc_i), "key": (enc_a._version, enc_i._version, grad),
+             "proj_a": proj_a, "proj_i": proj_i, "tape": None, "token": None}
+        needs_grad = grad and (proj_a.requires_grad or enc_a.requires_grad or enc_i.requires_grad)
+        if needs_grad:
+            w, held = self._weight_struct()
+            tape = Fn.DecoderTape(w, held, enc_a, enc_i, proj_a, proj_i, self.output_size)
+            params = [self._param_of(name) for name in _lib_fields()]
+            c["tape"], c["token"] = tape, Fn.decoder_open(tape, proj_a, proj_i, enc_a, enc_i, params)
+        self._cache = c
+        return c
+
+    def _param_of(self, field):
+        return _FIELD_TO_PARAM[field](self)
 
     def _weight_struct(self):
-        g = lambda lin: (lin.weight.detach().contiguous(), lin.bias.detach().contiguous())
-        t = {}
-        for name, lin in (("W2", self.W2), ("Wc1", self.Wc1), ("v1", self.v1), ("W4", self.W4), ("Wc2", self.Wc2),
-                          ("v2", self.v2)):
-            t[name], t[("b" + name[1:]) if name[0] == "W" else name + "b"] = g(lin)
-        for k, lin in (("1", self.W_beta_1), ("2", self.W_beta_2), ("3", self.W_beta_3), ("4", self.W_beta_4)):
-            t["Wb" + k], t["bb" + k] = g(lin)
-        t["vb1"], t["vb1b"] = g(self.v_beta_1)
-        t["vb2"], t["vb2b"] = g(self.v_beta_2)
-        t["lstm_w_ih"], t["lstm_w_hh"] = self.lstm.weight_ih_l0.detach().contiguous(), self.lstm.weight_hh_l0.detach().contiguous()
-        t["lstm_b_ih"], t["lstm_b_hh"] = self.lstm.bias_ih_l0.detach().contiguous(), self.lstm.bias_hh_l0.detach().contiguous()
-        t["out_w"], t["out_b"] = g(self.out)
-        return ops.decoder_weights(t), t
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        hit = getattr(self, "_wstruct", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        w, held = self._build_weight_struct()
+        object.__setattr__(self, "_wstruct", (key, w, held))
+        return w, held
+
+    def _build_weight_struct(self):
+        held = {f: self._param_of(f).detach().contiguous() for f in _lib_fields()}
+        return ops.decoder_weights(held), held
 
     def forward(self, sent_embed, decoder_hidden, decoder_cell_state, text_audio_enc_out, text_img_enc_out,
                 coverage_vec, mask):
@@ -142,44 +175,18 @@ class MultimodalAttentionDecoder(nn.Module):
             raise RuntimeError("mmbidaf_b200.layers.MultimodalAttentionDecoder runs on a B200 only (no CPU fallback)")
         if self.num_layers != 1:
             raise RuntimeError("MultimodalAttentionDecoder: only num_layers=1 is supported (the reference model uses 1)")
-        proj_a, proj_i = self._projections(text_audio_enc_out, text_img_enc_out)
-        needs_grad = torch.is_grad_enabled() and (
-            proj_a.requires_grad or decoder_hidden.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad:
-            return self._step_autograd(sent_embed, decoder_hidden, decoder_cell_state, text_audio_enc_out,
-                                       text_img_enc_out, proj_a, proj_i, coverage_vec, mask)
+        seq = self._sequence(text_audio_enc_out, text_img_enc_out)
         B, Lt, _ = text_audio_enc_out.shape
-        w, keep_alive = self._weight_struct()
-        probs, h, cell, att, cov, _, _ = ops.decoder_step_fwd(
-            w, proj_a.contiguous(), proj_i.contiguous(), text_audio_enc_out.contiguous(), text_img_enc_out.contiguous(),
-            sent_embed.reshape(B, -1).contiguous(), decoder_hidden.reshape(B, -1).contiguous(),
-            decoder_cell_state.reshape(B, -1).contiguous(), coverage_vec.reshape(B, Lt).contiguous(),
-            ops._u8(mask), self.output_size)
-        del keep_alive
+        sent = sent_embed.reshape(B, -1).contiguous()
+        h = decoder_hidden.reshape(B, -1).contiguous()
+        cell = decoder_cell_state.reshape(B, -1).contiguous()
+        cov = coverage_vec.reshape(B, Lt).contiguous()
+        if seq["tape"] is not None:
+            probs, h, cell, att, cov = Fn.decoder_step(seq["tape"], seq["token"], sent, h, cell, cov, ops._u8(mask))
+        else:
+            w, keep_alive = self._weight_struct()
+            probs, h, cell, att, cov, _, _ = ops.decoder_step_fwd(
+                w, seq["proj_a"].contiguous(), seq["proj_i"].contiguous(), text_audio_enc_out.contiguous(),
+                text_img_enc_out.contiguous(), sent, h, cell, cov, ops._u8(mask), self.output_size)
+            del keep_alive
         return probs, h.unsqueeze(1), cell.unsqueeze(0), att.unsqueeze(2), cov.unsqueeze(2)
-
-    def _step_autograd(self, sent_embed, h, cell, enc_a, enc_i, proj_a, proj_i, coverage, mask):
-        """Training step (INTERIM, round 1): same arithmetic as the fused kernels, expressed with cuBLAS /
-        ATen ops on the GPU so that autograd supplies the backward pass; the step-invariant projections are
-        still hoisted.  A fused backward kernel replaces this next ("decoder backward")."""
-        e1 = self.v1(torch.tanh(proj_a + self.W2(h) + self.Wc1(coverage)))
-        a1 = F.softmax(e1, dim=1)
-        c1 = (a1 * enc_a).sum(dim=1)
-        e2 = self.v2(torch.tanh(proj_i + self.W4(h) + self.Wc2(coverage)))
-        a2 = F.softmax(e2, dim=1)
-        c2 = (a2 * enc_i).sum(dim=1)
-        eb1 = self.v_beta_1(torch.tanh(self.W_beta_1(c1.unsqueeze(1)) + self.W_beta_2(h)))
-        eb2 = self.v_beta_2(torch.tanh(self.W_beta_3(c2.unsqueeze(1)) + self.W_beta_4(h)))
-        beta = F.softmax(torch.cat((eb1, eb2), dim=1), dim=1)
-        c3 = (torch.stack((c1, c2), dim=1) * beta).sum(dim=1)
-        att = torch.bmm(torch.cat((a1, a2), dim=2), beta)
-        coverage = coverage + att
-        x = torch.cat((c3, sent_embed.squeeze(1)), dim=1)
-        gates = F.linear(x, self.lstm.weight_ih_l0, self.lstm.bias_ih_l0) + \
-            F.linear(h.squeeze(1), self.lstm.weight_hh_l0, self.lstm.bias_hh_l0)
-        gi, gf, gg, go = gates.chunk(4, dim=1)
-        c_new = torch.sigmoid(gf) * cell.squeeze(0) + torch.sigmoid(gi) * torch.tanh(gg)
-        h_new = torch.sigmoid(go) * torch.tanh(c_new)
-        logits = self.out(h_new)
-        probs = F.softmax(torch.where(mask.bool(), logits, logits.new_full((), -1e30)), dim=-1)
-        return probs, h_new.unsqueeze(1), c_new.unsqueeze(0), att, coverage

@@ -40,6 +40,29 @@ class MMBiDAF(nn.Module):
         self.multimodal_att_decoder = MultimodalAttentionDecoder(text_embedding_size, hidden_size,
                                                                  max_transcript_length, num_layers=1)
 
+    # Independent branches (three encoders; two BiDAF + modality-encoder chains) run on side streams so
+    # that their latency-bound recurrences overlap on the 148 SMs.  autograd replays each backward op on
+    # the stream of its forward op, so the overlap carries over to the backward pass.
+    use_streams = True
+
+    def _fork_join(self, jobs):
+        if not (self.use_streams and torch.cuda.is_available()):
+            return [job() for job in jobs]
+        main = torch.cuda.current_stream()
+        if getattr(self, "_streams", None) is None or self._streams[0].device != main.device:
+            object.__setattr__(self, "_streams", [torch.cuda.Stream(device=main.device) for _ in range(3)])
+        results = []
+        for stream, job in zip(self._streams, jobs):
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                results.append(job())
+        for stream, res in zip(self._streams, results):
+            main.wait_stream(stream)
+            for t in res:
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)
+        return results
+
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts reference checkpoints saved from ``nn.DataParallel`` (keys prefixed ``module.``)."""
         if state_dict and all(k.startswith("module.") for k in state_dict):
@@ -54,12 +77,21 @@ class MMBiDAF(nn.Module):
     def forward(self, embedded_text, original_text_lengths, embedded_audio, original_audio_lengths, transformed_images,
                 original_image_lengths, batch_target_indices, original_target_len, max_dec_len):
         B, Lt = embedded_text.size(0), embedded_text.size(1)
-        text_emb = self.emb(embedded_text)
-        text_encoded, _ = self.text_enc(text_emb, original_text_lengths)
-        audio_encoded, _ = self.audio_enc(self.a_emb(embedded_audio), original_audio_lengths)
-        img = transformed_images.reshape(-1, *transformed_images.shape[2:])
-        image_emb = self.image_keyframes_emb(img).reshape(B, transformed_images.size(1), -1)
-        image_encoded, _ = self.image_enc(self.i_emb(image_emb), original_image_lengths)
+
+        def text_branch():
+            emb = self.emb(embedded_text)
+            return emb, self.text_enc(emb, original_text_lengths)[0]
+
+        def audio_branch():
+            return (self.audio_enc(self.a_emb(embedded_audio), original_audio_lengths)[0],)
+
+        def image_branch():
+            img = transformed_images.reshape(-1, *transformed_images.shape[2:])
+            feats = self.image_keyframes_emb(img).reshape(B, transformed_images.size(1), -1)
+            return feats, self.image_enc(self.i_emb(feats), original_image_lengths)[0]
+
+        (text_emb, text_encoded), (audio_encoded,), (image_emb, image_encoded) = \
+            self._fork_join([text_branch, audio_branch, image_branch])
 
         text_mask = self.get_mask(embedded_text, original_text_lengths)
         audio_mask = self.get_mask(embedded_audio, original_audio_lengths)
@@ -67,10 +99,16 @@ class MMBiDAF(nn.Module):
         decoder_mask = torch.zeros(B, self.max_transcript_length, dtype=torch.bool, device=text_mask.device)
         decoder_mask[:, :Lt] = text_mask                                   # models.py:121-123
 
-        text_audio_att = self.bidaf_att_audio(text_encoded, audio_encoded, text_mask, audio_mask)
-        text_image_att = self.bidaf_att_image(text_encoded, image_encoded, text_mask, image_mask)
-        mod_text_audio, text_audio_hidden = self.mod_t_a(text_audio_att, original_text_lengths)
-        mod_text_image, text_img_hidden = self.mod_t_i(text_image_att, original_text_lengths)
+        def audio_aware():
+            att = self.bidaf_att_audio(text_encoded, audio_encoded, text_mask, audio_mask)
+            return self.mod_t_a(att, original_text_lengths)
+
+        def image_aware():
+            att = self.bidaf_att_image(text_encoded, image_encoded, text_mask, image_mask)
+            return self.mod_t_i(att, original_text_lengths)
+
+        (mod_text_audio, text_audio_hidden), (mod_text_image, text_img_hidden) = \
+            self._fork_join([audio_aware, image_aware])
 
         # models.py:143-149 (the hidden-state rows are in descending-length order: reference quirk Q3)
         decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)

@@ -120,13 +120,39 @@ def decoder_step_fwd(w, proj_a, proj_i, enc_a, enc_i, sent_embed, h, cell, cover
     alpha = torch.empty(B, 2, Lt, **f32) if save else None
     beta = torch.empty(B, 2, **f32) if save else None
     gates = torch.empty(B, 4 * H, **f32) if save else None
+    ctx12 = torch.empty(B, 2, D, **f32) if save else None
     p = _lib.ptr
     _lib.check(lib.mmb_decoder_step_fwd(ctypes.addressof(w), p(proj_a), p(proj_i), p(enc_a), p(enc_i), p(sent_embed),
                                         p(h), p(cell), p(coverage), p(mask_u8), p(probs), p(h_out), p(cell_out),
                                         p(att_cov), p(cov_out), p(argmax), p(ctx), p(alpha), p(beta), p(gates),
-                                        B, Lt, H, E, M, _lib.stream()), "mmb_decoder_step_fwd")
+                                        p(ctx12), B, Lt, H, E, M, _lib.stream()), "mmb_decoder_step_fwd")
     _count(3)
-    return probs, h_out, cell_out, att_cov, cov_out, argmax, (ctx, alpha, beta, gates)
+    return probs, h_out, cell_out, att_cov, cov_out, argmax, (ctx, alpha, beta, gates, ctx12)
+
+
+def decoder_step_bwd(w, proj_a, proj_i, enc_a, enc_i, h, cell, coverage, probs, h_out, cell_out, gates, alpha, beta,
+                     ctx12, d_probs, d_h_out, d_cell_out, d_att_cov, d_cov_out, d_proj_a, d_proj_i, vec_acc, scal_acc,
+                     E: int, M: int):
+    """Backward of one decoder step.  ``d_proj_*`` (B,Lt,2H), ``vec_acc`` (B,6,2H) and ``scal_acc`` (B,4) are
+    accumulated in place.  Returns (d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_pre)."""
+    import ctypes
+    lib = _lib.lib()
+    B, Lt, D = enc_a.shape
+    H = D // 2
+    f32 = dict(device=enc_a.device, dtype=torch.float32)
+    d_h, d_cell, d_cov = torch.empty(B, H, **f32), torch.empty(B, H, **f32), torch.empty(B, Lt, **f32)
+    d_logits, d_gates = torch.empty(B, M, **f32), torch.empty(B, 4 * H, **f32)
+    d_ctx12, d_pre, d_ctx = torch.empty(B, 2, D, **f32), torch.empty(B, 4, D, **f32), torch.empty(B, D, **f32)
+    p = _lib.ptr
+    c = lambda t: None if t is None else t.contiguous()
+    _lib.check(lib.mmb_decoder_step_bwd(ctypes.addressof(w), p(proj_a), p(proj_i), p(enc_a), p(enc_i), p(h), p(cell),
+                                        p(coverage), p(probs), p(h_out), p(cell_out), p(gates), p(alpha), p(beta),
+                                        p(ctx12), p(c(d_probs)), p(c(d_h_out)), p(c(d_cell_out)), p(c(d_att_cov)),
+                                        p(c(d_cov_out)), p(d_h), p(d_cell), p(d_cov), p(d_proj_a), p(d_proj_i),
+                                        p(d_logits), p(d_gates), p(d_ctx12), p(d_pre), p(vec_acc), p(scal_acc),
+                                        p(d_ctx), B, Lt, H, E, M, _lib.stream()), "mmb_decoder_step_bwd")
+    _count(2)
+    return d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_pre
 
 
 def masked_softmax_fwd(x2d: torch.Tensor, mask2d_u8: torch.Tensor, log_mode: bool) -> torch.Tensor:

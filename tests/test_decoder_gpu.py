@@ -81,3 +81,33 @@ def test_decoder_step_matches_oracle(cfg):
     assert rel_err(att, want[3].squeeze(2)) < TOL and rel_err(cov1, want[4].squeeze(2)) < TOL
     assert torch.equal(amax.cpu(), want[0].argmax(dim=1))
     assert abs(float(probs.sum(dim=1).min()) - 1) < 1e-5
+
+
+def test_decoder_module_gradients_match_reference_golden():
+    """Two chained steps through the drop-in module (fused forward + fused backward kernels + tape GEMMs)
+    against the gradients the reference's autograd produced."""
+    from conftest import grad_err
+    from mmbidaf_b200.layers import MultimodalAttentionDecoder
+    g = load_golden("decoder_small.pt")
+    e, hid, m = g["sent"][0].shape[2], g["h0"].shape[2], g["mask"].shape[1]
+    mod = MultimodalAttentionDecoder(e, hid, m, num_layers=1)
+    mod.load_state_dict(g["state"])
+    mod = mod.cuda().train()
+    enc_a = g["enc_a"].cuda().requires_grad_(True)
+    enc_i = g["enc_i"].cuda().requires_grad_(True)
+    h = g["h0"].cuda().requires_grad_(True)
+    state = (h, g["cell0"].cuda(), g["cov0"].cuda())
+    mask = g["mask"].cuda()
+    loss = 0
+    for k, want in enumerate(g["steps"]):
+        probs, h1, c1, att, cov = mod(g["sent"][k].cuda(), state[0], state[1], enc_a, enc_i, state[2], mask)
+        assert rel_err(probs, want["probs"]) < TOL and rel_err(cov, want["coverage"]) < TOL
+        assert h1.shape == want["h"].shape and c1.shape == want["cell"].shape and att.shape == want["att_cov"].shape
+        loss = loss - torch.log(probs[:, k] + 1e-12).sum() + torch.min(att, cov).sum()
+        state = (h1, c1, cov)
+    assert rel_err(loss, g["loss"]) < TOL
+    loss.backward()
+    assert grad_err(enc_a.grad, g["grad_enc_a"]) < 5e-5 and grad_err(enc_i.grad, g["grad_enc_i"]) < 5e-5
+    assert grad_err(h.grad, g["grad_h0"]) < 5e-5
+    for name, p in mod.named_parameters():
+        assert grad_err(p.grad, g["grad_params"][name], name) < 5e-5, name

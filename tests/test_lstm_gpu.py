@@ -53,7 +53,7 @@ def test_encoder_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("cfg", [(1, 1, 3, 4), (7, 33, 20, 16), (5, 50, 100, 100), (40, 19, 100, 100),
-                                 (90, 12, 64, 100), (3, 300, 800, 100), (4, 9, 128, 128), (2, 6, 10, 60)])
+                                 (90, 12, 64, 100), (3, 300, 800, 100), (4, 9, 104, 104), (2, 6, 10, 60)])
 def test_encoder_matches_oracle(cfg):
     bsz, max_len, fan_in, hid = cfg
     gen = torch.Generator().manual_seed(31 * bsz + max_len)

@@ -92,3 +92,34 @@ def test_masked_softmax_function_matches_reference_golden():
     (masked_softmax(x, cu(g["flat_mask"])) * w.cuda()).sum().backward()
     (O.masked_softmax(xr, g["flat_mask"]) * w).sum().backward()
     assert grad_err(x.grad, xr.grad) < TOL
+
+
+def test_streams_do_not_change_results():
+    g = load_golden("model_small.pt")
+    batch = Batch(**g["batch"])
+    outs = []
+    for use in (True, False):
+        model = _model(g["dims"], g["params"])
+        model.use_streams = use
+        out, loss = _call(model, batch, True)
+        loss.backward()
+        torch.cuda.synchronize()
+        outs.append((out.detach().clone(), loss.detach().clone(), model.emb.proj.weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_tf32_library_gemms_stay_inside_the_reduced_precision_tier():
+    """north_star: rel <= 2e-2 on the TF32/bf16 path.  Only the plain library GEMMs change here."""
+    g = load_golden("model_readme.pt")
+    hidden, e_t, e_a, e_i, m = g["dims"]
+    params = O.make_params(hidden, e_t, e_a, e_i, m, seed=g["param_seed"])
+    model = _model(g["dims"], params)
+    batch = make_batch(*g["batch_shape"], e_t, e_a, e_i, seed=g["batch_seed"])
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out, loss = _call(model, batch, True)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert rel_err(out, g["train_out"]) < 2e-2 and rel_err(loss, g["train_loss"]) < 2e-2

@@ -65,13 +65,18 @@ MMB_API int mmb_device_supported(void);
  * Outputs
  *   out (B,Lc,4d) = [c, a, c*a, c*b]                                    (attention.py:52)
  *   q2c (B,Lq,d) = s2^T c, lse_row (B,Lc), lse_col (B,Lq): log-sum-exp of the row / column
- *   soft-max -- saved for mmb_bidaf_bwd.  d % 4 == 0, d <= 256.
+ *   soft-max -- saved for the backward pass.  MMB_PREC_FP32: d % 4 == 0, d <= 256 (workspace may be NULL).
+ *   MMB_PREC_BF16 (tcgen05 + TMEM + TMA): d % 8 == 0, d <= 200, workspace of mmb_bidaf_workspace_bytes().
  */
 MMB_API int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_t* text_mask, const uint8_t* modality_mask,
                   const float* w_text, const float* w_modality, const float* w_cross, const float* bias,
                   const uint8_t* keep_text, const uint8_t* keep_modality, float keep_scale,
-                  float* out, float* q2c, float* lse_row, float* lse_col,
+                  float* out, float* q2c, float* lse_row, float* lse_col, void* workspace,
                   int B, int Lc, int Lq, int d, int precision, mmb_stream_t stream);
+
+/* Bytes of scratch `workspace` mmb_bidaf_fwd needs (0 for MMB_PREC_FP32).  The bf16 tier keeps bf16 copies of
+ * its operands there in tensor-core order; dropout != 0 when keep_modality will be non-NULL. */
+MMB_API size_t mmb_bidaf_workspace_bytes(int B, int Lc, int Lq, int d, int precision, int dropout);
 
 /* --------------------------------------------------------------------------------------
  * Length-aware LSTM recurrence of one layer, 1 or 2 directions.  Replaces the nn.LSTM call of

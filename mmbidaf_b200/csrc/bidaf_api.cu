@@ -5,13 +5,24 @@ namespace mmb {
 int bidaf_fwd_f32(const float*, const float*, const uint8_t*, const uint8_t*, const float*, const float*, const float*,
                   const float*, const uint8_t*, const uint8_t*, float, float*, float*, float*, float*, int, int, int, int,
                   cudaStream_t);
+int bidaf_fwd_tc(const float*, const float*, const uint8_t*, const uint8_t*, const float*, const float*, const float*,
+                 const float*, const uint8_t*, const uint8_t*, float, float*, float*, float*, float*, void*, int, int, int,
+                 int, cudaStream_t);
+size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout);
+}
+
+extern "C" size_t mmb_bidaf_workspace_bytes(int B, int Lc, int Lq, int d, int precision, int dropout) {
+  (void)d;
+  if (precision != MMB_PREC_BF16 || B <= 0 || Lc <= 0 || Lq <= 0) return 0;
+  return mmb::bidaf_tc_workspace_bytes(B, Lc, Lq, dropout);
 }
 
 extern "C" int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_t* text_mask,
                              const uint8_t* modality_mask, const float* w_text, const float* w_modality,
                              const float* w_cross, const float* bias, const uint8_t* keep_text,
                              const uint8_t* keep_modality, float keep_scale, float* out, float* q2c, float* lse_row,
-                             float* lse_col, int B, int Lc, int Lq, int d, int precision, mmb_stream_t stream) {
+                             float* lse_col, void* workspace, int B, int Lc, int Lq, int d, int precision,
+                             mmb_stream_t stream) {
   MMB_REQUIRE(text && modality && text_mask && modality_mask && w_text && w_modality && w_cross && bias && out && q2c &&
                   lse_row && lse_col,
               MMB_ERR_INVALID, "mmb_bidaf_fwd: null pointer");
@@ -22,6 +33,9 @@ extern "C" int mmb_bidaf_fwd(const float* text, const float* modality, const uin
   if (precision == MMB_PREC_FP32)
     return mmb::bidaf_fwd_f32(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias, keep_text,
                               keep_modality, keep_scale, out, q2c, lse_row, lse_col, B, Lc, Lq, d, st);
+  if (precision == MMB_PREC_BF16)
+    return mmb::bidaf_fwd_tc(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias, keep_text,
+                             keep_modality, keep_scale, out, q2c, lse_row, lse_col, workspace, B, Lc, Lq, d, st);
   mmb::set_error("mmb_bidaf_fwd: precision %d not available", precision);
   return MMB_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,543 @@
+// Fused BiDAF attention forward, tensor-core tier (sm_100a: tcgen05.mma + TMEM + TMA bulk copies).
+// bf16 operands, fp32 accumulation / soft-max; rel <= 2e-2 tier of north_star.
+//
+// Same three streaming-soft-max contractions as the fp32 tier (bidaf_fwd_f32.cu), reorganised for the
+// 5th-generation tensor cores:
+//
+//  1. bidaf_pack_kernel   converts c, q (optionally dropped) to bf16 ONCE, in the UMMA "core matrix" order
+//       pack[b][row/8][chunk 0..25][row%8][8 x bf16]      (8 rows x 16 bytes = one 128-byte core matrix)
+//     so that ANY tile of consecutive rows is one contiguous run of memory: a tile is fetched with a single
+//     cp.async.bulk (TMA) that completes on an mbarrier and lands ready for tcgen05.mma -- no swizzle, no
+//     register staging.  The same bytes serve as a K-major operand (S = X Y^T: LBO 128, SBO 3328) and as an
+//     MN-major operand (O = P V: LBO 3328, SBO 128).  Chunk 25 is K padding (200 -> 208); it carries the
+//     additive terms of the trilinear form split into bf16 hi/lo halves: text rows hold
+//     [t_hi, t_lo, 1, 1, 0..] and modality rows [1, 1, m_hi, m_lo, 0..], so the GEMM itself adds
+//     c~.w_c + q~.w_q to every logit.  w_cq is folded into the text-side S operand.
+//  2. bidaf_tc_kernel<Q2C>  X = 128 modality rows, streams 64-row text tiles:   T = softmax_i(S)^T c
+//  3. bidaf_tc_kernel<C2Q>  X = 128 text rows, streams 64-row modality tiles:   a = softmax_j(S) q,
+//                                                                              b = softmax_j(S) T
+//     Per tile: thread 0 issues 13 MMAs (128 x 64 x 208) into TMEM, commits to an mbarrier; each of the 128
+//     threads owns one row of S (tcgen05.ld 32x32b.x64), does the masked streaming soft-max in registers
+//     (no shuffles: a thread holds its whole row), writes P as bf16 in core-matrix order, and thread 0 issues
+//     the P V MMAs (N = 208, K = 64) into the TMEM accumulators.  Accumulators are rescaled lazily (only
+//     when a row's running max moves by more than TAU), as in FlashAttention-4.
+//     The epilogue drains TMEM through shared memory so that the 4-way concat is written with coalesced
+//     128-bit stores; Q2C also emits T in packed bf16 form for pass 3.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace mmb {
+namespace {
+
+constexpr int DPAD = 208;                 // K / N padding of d (d <= 200 so that chunk 25 is free for the terms)
+constexpr int CHUNKS = DPAD / 8;          // 26 sixteen-byte chunks per row
+constexpr int GROUP_BYTES = CHUNKS * 128; // 8 rows
+constexpr int TX = 128, TY = 64;
+constexpr int X_BYTES = TX / 8 * GROUP_BYTES;   // 53248
+constexpr int Y_BYTES = TY / 8 * GROUP_BYTES;   // 26624
+constexpr int P_BYTES = TX * TY * 2;            // 16384
+constexpr int STAGES = 2;
+constexpr float TAU = 8.0f;               // lazy-rescale threshold (natural-log units)
+constexpr int TMEM_COLS = 512;
+constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 64 + DPAD;
+constexpr int STG_STRIDE = 204;           // fp32 staging row stride (conflict-free 128-bit stores)
+
+enum Kind { Q2C = 0, C2Q = 1 };
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends for a hardware time slice; the bound turns a protocol bug into a trap instead of a hang.
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, no swizzle ("interleave"), Blackwell version field = 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+// Instruction descriptor: D = F32, A = B = BF16, M = 128.
+constexpr uint32_t idesc_bf16(int n, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1. pack: fp32 (B, L, d) -> bf16 core-matrix order (+ folded weights, additive terms, mask words)
+// ---------------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* src;          // (B, L, d)
+  const uint8_t* keep;       // (B, L, d) or null
+  const uint8_t* mask;       // (B, L)
+  const float* w_term;       // (d): c-side text_weight / q-side modality_weight
+  const float* w_fold;       // (d) text_modality_weight for the text side, null for the modality side
+  __nv_bfloat16* s_pack;     // S operand (dropped, folded, with term chunk)
+  __nv_bfloat16* v_pack;     // plain values (value operand); may equal s_pack when identical (modality side, eval)
+  unsigned long long* mask_words;   // (B, LP/64, 2): [valid bits, unmasked bits]
+  float keep_scale;
+  int L, LP, d, text_side;
+};
+
+__global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackArgs a) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + warp;                 // 8-row group
+  if (g * 8 >= a.LP) return;
+  const int d = a.d, nchunk = d >> 3;
+  const float* src = a.src + (size_t)b * a.L * d;
+  const uint8_t* keep = a.keep ? a.keep + (size_t)b * a.L * d : nullptr;
+  float wt[8], wf[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = lane * 8 + e;
+    wt[e] = (lane < nchunk) ? a.w_term[k] : 0.f;
+    wf[e] = (lane < nchunk && a.w_fold) ? a.w_fold[k] : 1.f;
+  }
+  uint4 s_out[8], v_out[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = g * 8 + r;
+    float v[8], vd[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (row < a.L && lane < nchunk) {
+      const float4 lo = *reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8);
+      const float4 hi = *reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8 + 4);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    }
+    float dot = 0.f;
+    if (keep && row < a.L && lane < nchunk) {
+      const uint2 kk = *reinterpret_cast<const uint2*>(keep + (size_t)row * d + lane * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t word = e < 4 ? kk.x : kk.y;
+        vd[e] = ((word >> (8 * (e & 3))) & 0xffu) ? v[e] * a.keep_scale : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vd[e] = v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dot = fmaf(vd[e], wt[e], dot);
+    dot = warp_sum(dot);
+    __nv_bfloat162 sp[4], vp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sp[e] = __floats2bfloat162_rn(vd[2 * e] * wf[2 * e], vd[2 * e + 1] * wf[2 * e + 1]);
+      vp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    }
+    s_out[r] = *reinterpret_cast<uint4*>(sp);
+    v_out[r] = *reinterpret_cast<uint4*>(vp);
+    if (lane == CHUNKS - 1) {                           // the K-padding chunk carries the additive term
+      const bool in = row < a.L;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(dot);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(dot - __bfloat162float(hi));
+      const __nv_bfloat16 one = __float2bfloat16_rn(in ? 1.f : 0.f), zero = __float2bfloat16_rn(0.f);
+      __nv_bfloat16 t[8] = {zero, zero, zero, zero, zero, zero, zero, zero};
+      if (a.text_side) { t[0] = in ? hi : zero; t[1] = in ? lo : zero; t[2] = one; t[3] = one; }
+      else             { t[0] = one; t[1] = one; t[2] = in ? hi : zero; t[3] = in ? lo : zero; }
+      s_out[r] = *reinterpret_cast<uint4*>(t);
+      v_out[r] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (lane < CHUNKS) {
+    const size_t base = ((size_t)b * (a.LP / 8) + g) * GROUP_BYTES + (size_t)lane * 128;
+    uint4* sdst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.s_pack) + base);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sdst[r] = s_out[r];
+    if (a.v_pack != a.s_pack) {
+      uint4* vdst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.v_pack) + base);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) vdst[r] = v_out[r];
+    }
+  }
+  // mask words: one thread per 64-row tile of this block
+  if (threadIdx.x == 0) {
+    const int tile = blockIdx.x;                        // 8 groups x 8 rows = 64 rows per block
+    unsigned long long valid = 0ull, open = 0ull;
+    for (int i = 0; i < 64; ++i) {
+      const int row = tile * 64 + i;
+      if (row < a.L) {
+        valid |= 1ull << i;
+        if (a.mask[(size_t)b * a.L + row]) open |= 1ull << i;
+      }
+    }
+    a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 0] = valid;
+    a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 1] = open;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2./3. tensor-core passes
+// ---------------------------------------------------------------------------------------------------------
+struct TcArgs {
+  const __nv_bfloat16* x_pack;       // (B, LXP/8, 26, 8, 8) S operand of the X side
+  const __nv_bfloat16* y_pack;       // S operand of the Y side
+  const __nv_bfloat16* v0_pack;      // value operand 0 (plain Y rows); may equal y_pack
+  const __nv_bfloat16* v1_pack;      // value operand 1 (C2Q: packed T); null for Q2C
+  const unsigned long long* y_words; // (B, LYP/64, 2)
+  const float* bias;
+  const float* x_raw;                // C2Q: un-dropped text (B, LX, d) for the concat; null for Q2C
+  float* out;                        // Q2C: T fp32 (B, LX, d);   C2Q: out (B, LX, 4d)
+  __nv_bfloat16* t_pack;             // Q2C: packed T for pass 3
+  float* lse;                        // (B, LX)
+  int LX, LXP, LY, LYP, d;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
+  constexpr int NACC = KIND == C2Q ? 2 : 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const bool sep_v0 = a.v0_pack != a.y_pack;
+  const int nparts = 1 + (sep_v0 ? 1 : 0) + (KIND == C2Q ? 1 : 0);
+  const int stage_bytes = nparts * Y_BYTES;
+  unsigned char* Xs = smem;
+  unsigned char* Ps = Xs + X_BYTES;
+  unsigned char* St = Ps + P_BYTES;                               // STAGES x stage_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(St + STAGES * stage_bytes);   // [0] x, [1..2] full, [3] mma
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, x0 = blockIdx.x * TX;
+  const uint32_t bar_x = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_mma = smem_u32(bars + 3);
+
+  if (tid == 0) {
+    mbar_init(bar_x, 1);
+    mbar_init(bar_full0, 1);
+    mbar_init(bar_full0 + 8, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int nty = (a.LY + TY - 1) / TY;
+  const char* xg = reinterpret_cast<const char*>(a.x_pack) + ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
+  const size_t y_batch = (size_t)b * (a.LYP / 8) * GROUP_BYTES;
+  auto issue_stage = [&](int t) {
+    const int s = t % STAGES;
+    const uint32_t bar = bar_full0 + 8 * s;
+    const uint32_t dst = smem_u32(St + s * stage_bytes);
+    const size_t off = y_batch + (size_t)t * Y_BYTES;
+    mbar_expect_tx(bar, stage_bytes);
+    tma_bulk_g2s(dst, reinterpret_cast<const char*>(a.y_pack) + off, Y_BYTES, bar);
+    int part = 1;
+    if (sep_v0) tma_bulk_g2s(dst + (part++) * Y_BYTES, reinterpret_cast<const char*>(a.v0_pack) + off, Y_BYTES, bar);
+    if (KIND == C2Q) tma_bulk_g2s(dst + part * Y_BYTES, reinterpret_cast<const char*>(a.v1_pack) + off, Y_BYTES, bar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(bar_x, X_BYTES);
+    tma_bulk_g2s(smem_u32(Xs), xg, X_BYTES, bar_x);
+    for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
+  }
+
+  const float bias = a.bias[0];
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+  float m_ref = -INFINITY, l_run = 0.f;
+  uint32_t mma_phase = 0;
+  constexpr uint32_t IDESC_S = idesc_bf16(TY, 0), IDESC_PV = idesc_bf16(DPAD, 1);
+  const uint32_t xs_addr = smem_u32(Xs), ps_addr = smem_u32(Ps);
+
+  mbar_wait(bar_x, 0);
+  for (int t = 0; t < nty; ++t) {
+    const int s = t % STAGES;
+    const uint32_t st_addr = smem_u32(St + s * stage_bytes);
+    mbar_wait(bar_full0 + 8 * s, (t / STAGES) & 1);
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < DPAD / 16; ++k)                       // S = X Y^T, both K-major
+        umma_bf16(tmem + COL_S, smem_desc(xs_addr + k * 256, 128, GROUP_BYTES),
+                  smem_desc(st_addr + k * 256, 128, GROUP_BYTES), IDESC_S, k > 0);
+      umma_commit(bar_mma);
+    }
+    const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + t) * 2);
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // every MMA issued before this commit has retired: the previous tile's P V is done, its stage is free
+    if (tid == 0 && t >= 1 && t - 1 + STAGES < nty) issue_stage(t - 1 + STAGES);
+
+    // ---- this thread's row of S: masked streaming soft-max -------------------------------------------------
+    float sv[TY];
+#pragma unroll
+    for (int q = 0; q < TY / 16; ++q) tmem_ld16(lane_base + COL_S + q * 16, sv + q * 16);
+    float tile_max = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < TY; ++c) {
+      const bool open = (words.y >> c) & 1ull, valid = (words.x >> c) & 1ull;
+      const float v = open ? sv[c] + bias : kNegFill;           // attention.py:94
+      sv[c] = v;
+      if (valid) tile_max = fmaxf(tile_max, v);
+    }
+    float alpha = 1.f;
+    const bool bump = tile_max > m_ref + TAU;                   // first tile: m_ref = -inf -> always
+    if (bump) {
+      alpha = __expf(m_ref - tile_max);                         // 0 on the first tile
+      m_ref = tile_max;
+    }
+    const int any_bump = __syncthreads_or(bump && t > 0);
+    float psum = 0.f;
+    uint32_t packed[TY / 2];
+#pragma unroll
+    for (int c = 0; c < TY; c += 2) {
+      const float p0 = ((words.x >> c) & 1ull) ? __expf(sv[c] - m_ref) : 0.f;
+      const float p1 = ((words.x >> (c + 1)) & 1ull) ? __expf(sv[c + 1] - m_ref) : 0.f;
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+      // the row sum uses the bf16-rounded probabilities so that numerator and denominator match
+      psum += __low2float(pk) + __high2float(pk);
+      packed[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    l_run = l_run * alpha + psum;
+    // P in core-matrix order: chunk c8 (8 columns) at c8*2048 + row*16  (LBO 2048, SBO 128)
+    {
+      unsigned char* prow = Ps + (warp * 32 + lane) * 16;
+#pragma unroll
+      for (int c8 = 0; c8 < TY / 8; ++c8)
+        *reinterpret_cast<uint4*>(prow + c8 * 2048) =
+            make_uint4(packed[c8 * 4], packed[c8 * 4 + 1], packed[c8 * 4 + 2], packed[c8 * 4 + 3]);
+    }
+    if (any_bump) {                                             // lazy rescale of this thread's accumulator rows
+#pragma unroll 1
+      for (int acc = 0; acc < NACC; ++acc)
+#pragma unroll 1
+        for (int q = 0; q < DPAD / 16; ++q) {
+          float o[16];
+          const uint32_t addr = lane_base + (acc == 0 ? COL_O0 : COL_O1) + q * 16;
+          tmem_ld16(addr, o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] *= alpha;
+          tmem_st16(addr, o);
+        }
+      tmem_wait_st();
+    }
+    fence_proxy_async();                                        // st.shared P -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t v0_addr = sep_v0 ? st_addr + Y_BYTES : st_addr;
+#pragma unroll
+      for (int k = 0; k < TY / 16; ++k)                         // O0 += P V0 (V MN-major: LBO = group stride)
+        umma_bf16(tmem + COL_O0, smem_desc(ps_addr + k * 4096, 2048, 128),
+                  smem_desc(v0_addr + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
+      if (KIND == C2Q) {
+        const uint32_t v1_addr = st_addr + (nparts - 1) * Y_BYTES;
+#pragma unroll
+        for (int k = 0; k < TY / 16; ++k)
+          umma_bf16(tmem + COL_O1, smem_desc(ps_addr + k * 4096, 2048, 128),
+                    smem_desc(v1_addr + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
+      }
+      if (t == nty - 1) umma_commit(bar_mma);
+    }
+  }
+  mbar_wait(bar_mma, mma_phase);
+  tc_fence_after();
+
+  // ---- epilogue: TMEM -> registers -> fp32 staging in smem -> coalesced global stores -----------------------------
+  const int row = warp * 32 + lane, gx = x0 + row;
+  const float inv_l = 1.f / l_run;
+  if (gx < a.LX && a.lse) a.lse[(size_t)b * a.LX + gx] = m_ref + __logf(l_run);
+  float* stg = reinterpret_cast<float*>(St);                    // 128 x 204 fp32 = 104448 B <= 2 stages
+  const int d = a.d, dv4 = d >> 2;
+#pragma unroll 1
+  for (int acc = 0; acc < NACC; ++acc) {
+    if (acc > 0) __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < DPAD / 16; ++q) {
+      float o[16];
+      tmem_ld16(lane_base + (acc == 0 ? COL_O0 : COL_O1) + q * 16, o);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4)
+        if (q * 16 + i < STG_STRIDE)
+          *reinterpret_cast<float4*>(stg + row * STG_STRIDE + q * 16 + i) =
+              make_float4(o[i] * inv_l, o[i + 1] * inv_l, o[i + 2] * inv_l, o[i + 3] * inv_l);
+    }
+    __syncthreads();
+    if (KIND == Q2C) {
+      for (int r = warp; r < TX; r += 4) {                      // fp32 T rows, coalesced
+        const int g = x0 + r;
+        if (g >= a.LX) break;
+        for (int c4 = lane; c4 < dv4; c4 += 32)
+          *reinterpret_cast<float4*>(a.out + ((size_t)b * a.LX + g) * d + c4 * 4) =
+              *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
+      }
+      // packed bf16 T (value operand of pass 3): one 16-byte chunk per (row, chunk)
+      char* tp = reinterpret_cast<char*>(a.t_pack) + ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
+      for (int i = tid; i < TX * CHUNKS; i += 128) {
+        const int g8 = i / (CHUNKS * 8), rem = i - g8 * CHUNKS * 8, ch = rem >> 3, r8 = rem & 7;
+        const int r = g8 * 8 + r8;
+        __nv_bfloat162 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = ch * 8 + 2 * e;
+          const bool ok = (x0 + r < a.LX) && col < d;
+          v[e] = __floats2bfloat162_rn(ok ? stg[r * STG_STRIDE + col] : 0.f, ok ? stg[r * STG_STRIDE + col + 1] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(tp + (size_t)g8 * GROUP_BYTES + ch * 128 + r8 * 16) = *reinterpret_cast<uint4*>(v);
+      }
+    } else {
+      for (int r = warp; r < TX; r += 4) {
+        const int g = x0 + r;
+        if (g >= a.LX) break;
+        const float* crow = a.x_raw + ((size_t)b * a.LX + g) * d;
+        float* orow = a.out + ((size_t)b * a.LX + g) * 4 * d;
+        for (int c4 = lane; c4 < dv4; c4 += 32) {
+          const float4 c = *reinterpret_cast<const float4*>(crow + c4 * 4);
+          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
+          const float4 cv = make_float4(c.x * v.x, c.y * v.y, c.z * v.z, c.w * v.w);
+          if (acc == 0) {
+            *reinterpret_cast<float4*>(orow + c4 * 4) = c;                    // attention.py:52
+            *reinterpret_cast<float4*>(orow + d + c4 * 4) = v;
+            *reinterpret_cast<float4*>(orow + 2 * d + c4 * 4) = cv;
+          } else {
+            *reinterpret_cast<float4*>(orow + 3 * d + c4 * 4) = cv;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+size_t tc_smem_bytes(int nparts) { return (size_t)X_BYTES + P_BYTES + (size_t)STAGES * nparts * Y_BYTES + 64 + 16; }
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+// Workspace (bytes): packed operands, mask words.  Layout is private to this file.
+size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout) {
+  const size_t LcP = round_up(Lc, TX), LqP = round_up(Lq, TX);
+  const size_t c_pack = (size_t)B * (LcP / 8) * GROUP_BYTES, q_pack = (size_t)B * (LqP / 8) * GROUP_BYTES;
+  return 2 * c_pack + (2 + (dropout ? 1 : 0)) * q_pack + 16 * (size_t)B * (LcP / 64 + LqP / 64) + 1024;
+}
+
+int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_mask, const uint8_t* modality_mask,
+                 const float* w_text, const float* w_modality, const float* w_cross, const float* bias,
+                 const uint8_t* keep_text, const uint8_t* keep_modality, float keep_scale, float* out, float* q2c,
+                 float* lse_row, float* lse_col, void* workspace, int B, int Lc, int Lq, int d, cudaStream_t stream) {
+  MMB_REQUIRE(d % 8 == 0 && d <= 200, MMB_ERR_UNSUPPORTED, "mmb_bidaf_fwd (bf16 tier): d=%d (need d %% 8 == 0, d <= 200)", d);
+  MMB_REQUIRE(workspace, MMB_ERR_INVALID, "mmb_bidaf_fwd (bf16 tier): workspace is null");
+  const int LcP = round_up(Lc, TX), LqP = round_up(Lq, TX);
+  const size_t c_pack = (size_t)B * (LcP / 8) * GROUP_BYTES, q_pack = (size_t)B * (LqP / 8) * GROUP_BYTES;
+  char* ws = static_cast<char*>(workspace);
+  auto* cw = reinterpret_cast<__nv_bfloat16*>(ws);
+  auto* cp = reinterpret_cast<__nv_bfloat16*>(ws + c_pack);
+  auto* qs = reinterpret_cast<__nv_bfloat16*>(ws + 2 * c_pack);
+  auto* tp = reinterpret_cast<__nv_bfloat16*>(ws + 2 * c_pack + q_pack);
+  char* next = ws + 2 * c_pack + 2 * q_pack;
+  __nv_bfloat16* qp = qs;
+  if (keep_modality) {
+    qp = reinterpret_cast<__nv_bfloat16*>(next);
+    next += q_pack;
+  }
+  auto* c_words = reinterpret_cast<unsigned long long*>(next);
+  auto* q_words = c_words + (size_t)B * (LcP / 64) * 2;
+
+  PackArgs pc{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, keep_scale, Lc, LcP, d, 1};
+  bidaf_pack_kernel<<<dim3(LcP / 64, B), 256, 0, stream>>>(pc);
+  if (int rc = check_launch("bidaf_pack_kernel(text)")) return rc;
+  PackArgs pq{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, keep_scale, Lq, LqP, d, 0};
+  bidaf_pack_kernel<<<dim3(LqP / 64, B), 256, 0, stream>>>(pq);
+  if (int rc = check_launch("bidaf_pack_kernel(modality)")) return rc;
+
+  {   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
+    TcArgs a{qs, cw, cp, nullptr, c_words, bias, nullptr, q2c, tp, lse_col, Lq, LqP, Lc, LcP, d};
+    const size_t smem = tc_smem_bytes(2);
+    MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<Q2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), 128, smem, stream>>>(a);
+    if (int rc = check_launch("bidaf_tc_kernel<Q2C>")) return rc;
+  }
+  {   // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)
+    TcArgs a{cw, qs, qp, tp, q_words, bias, text, out, nullptr, lse_row, Lc, LcP, Lq, LqP, d};
+    const int nparts = 2 + (qp != qs ? 1 : 0);
+    const size_t smem = tc_smem_bytes(nparts);
+    MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "bidaf bf16 tier: %zu B of shared memory", smem);
+    MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<C2Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bidaf_tc_kernel<C2Q><<<dim3(LcP / TX, B), 128, smem, stream>>>(a);
+    if (int rc = check_launch("bidaf_tc_kernel<C2Q>")) return rc;
+  }
+  return MMB_OK;
+}
+
+}  // namespace mmb

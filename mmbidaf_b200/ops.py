@@ -49,10 +49,12 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
     lse_row = torch.empty(B, Lc, device=text.device, dtype=torch.float32)
     lse_col = torch.empty(B, Lq, device=text.device, dtype=torch.float32)
     p = _lib.ptr
+    ws_bytes = L.mmb_bidaf_workspace_bytes(B, Lc, Lq, d, int(precision), int(km is not None))
+    ws = torch.empty(ws_bytes, device=text.device, dtype=torch.uint8) if ws_bytes else None
     _lib.check(L.mmb_bidaf_fwd(p(text), p(modality), p(tm), p(mm), p(wt), p(wm), p(wc), p(bias.detach().contiguous()),
-                               p(kt), p(km), float(keep_scale), p(out), p(q2c), p(lse_row), p(lse_col),
+                               p(kt), p(km), float(keep_scale), p(out), p(q2c), p(lse_row), p(lse_col), p(ws),
                                B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
-    _count(2)
+    _count(2 if precision == PREC_FP32 else 4)
     return out, q2c, lse_row, lse_col
 
 

@@ -96,3 +96,68 @@ def test_unsupported_shape_raises():
     w = torch.randn(6, device="cuda")
     with pytest.raises(RuntimeError, match="d=6"):
         ops.bidaf_fwd(t, t, m, m, w, w, w, torch.zeros(1, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Tensor-core tier (tcgen05 + TMEM + TMA, bf16 operands): north_star tolerance rel <= 2e-2
+# ------------------------------------------------------------------------------------------------------------
+BF16_TOL = 2e-2
+
+
+@pytest.mark.parametrize("name", ["bidaf_small.pt", "bidaf_d200.pt"])
+def test_bf16_tier_matches_reference_golden(name):
+    g = load_golden(name)
+    out, q2c, lse_r, lse_c = _run(g["state"], g["text"], g["modality"], g["text_mask"], g["modality_mask"], precision=1)
+    assert rel_err(out, g["out"]) < BF16_TOL
+    d = g["text"].shape[2]
+    assert torch.equal(out[:, :, :d], g["text"])               # block 0 stays the exact fp32 text
+    s = g["similarity"]
+    neg = torch.full_like(s, -1e30)
+    lse_row = torch.logsumexp(torch.where(g["modality_mask"].unsqueeze(1), s, neg), dim=2)
+    assert rel_err(lse_r, lse_row) < BF16_TOL
+
+
+@pytest.mark.parametrize("name", ["bidaf_small.pt", "bidaf_d200.pt"])
+def test_bf16_tier_training_dropout_matches_reference_golden(name):
+    import torch.nn.functional as F
+    g = load_golden(name)
+    pr = g["train_drop_prob"]
+    torch.manual_seed(g["train_seed"])
+    keep_c = F.dropout(torch.ones_like(g["text"]), pr, True) != 0
+    keep_q = F.dropout(torch.ones_like(g["modality"]), pr, True) != 0
+    out, *_ = _run(g["state"], g["text"], g["modality"], g["text_mask"], g["modality_mask"], keep_c, keep_q, pr, precision=1)
+    assert rel_err(out, g["train_out"]) < BF16_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 8), (2, 5, 3, 8), (3, 64, 128, 200), (2, 65, 129, 200), (2, 130, 257, 200),
+                                   (4, 100, 70, 64), (2, 300, 520, 200), (3, 409, 1024, 200)])
+def test_bf16_tier_matches_oracle_ragged(shape):
+    bsz, lc, lq, d = shape
+    gen = torch.Generator().manual_seed(2000 + lc * 7 + lq)
+    p = {"text_weight": torch.randn(d, 1, generator=gen) * 0.1, "modality_weight": torch.randn(d, 1, generator=gen) * 0.1,
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen) * 0.1, "bias": torch.tensor([0.3])}
+    text = torch.randn(bsz, lc, d, generator=gen)
+    modality = torch.randn(bsz, lq, d, generator=gen)
+    c_len = torch.randint(1, lc + 1, (bsz,), generator=gen).tolist()
+    q_len = torch.randint(1, lq + 1, (bsz,), generator=gen).tolist()
+    c_len[0], q_len[0] = lc, lq
+    tmask, mmask = O.length_mask(lc, c_len), O.length_mask(lq, q_len)
+    want = O.bidaf_attention({k: v.double() for k, v in p.items()}, text.double(), modality.double(), tmask, mmask)
+    out, q2c, lse_r, lse_c = _run(p, text, modality, tmask, mmask, precision=1)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, want) < BF16_TOL
+    fp32_out, fp32_q2c, *_ = _run(p, text, modality, tmask, mmask, precision=0)
+    assert rel_err(q2c, fp32_q2c) < BF16_TOL
+
+
+def test_bf16_tier_fully_masked_is_uniform_and_large_logits_are_stable():
+    gen = torch.Generator().manual_seed(6)
+    d, lc, lq = 8, 70, 130
+    p = {"text_weight": torch.randn(d, 1, generator=gen), "modality_weight": torch.randn(d, 1, generator=gen),
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen) * 3, "bias": torch.tensor([0.0])}
+    text, modality = torch.randn(2, lc, d, generator=gen) * 3, torch.randn(2, lq, d, generator=gen) * 3   # logits ~ +-100
+    tmask = O.length_mask(lc, [lc, 0])
+    mmask = O.length_mask(lq, [0, lq])
+    want = O.bidaf_attention({k: v.double() for k, v in p.items()}, text.double(), modality.double(), tmask, mmask)
+    out, *_ = _run(p, text, modality, tmask, mmask, precision=1)
+    assert torch.isfinite(out).all() and rel_err(out, want) < 5e-2      # bf16 logits of magnitude 100: looser

@@ -156,7 +156,7 @@ def workload_config(n_gpus: int):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
-def bidaf_microbench(device, iters: int, warmup: int):
+def bidaf_microbench(device, iters: int, warmup: int, precision: int):
     """Fused BiDAF forward on BASELINE config 2; returns (avg seconds per forward, algorithmic bytes)."""
     from mmbidaf_b200 import ops
     B, Lc, Lq, d = CFG2["batch"], CFG2["lc"], CFG2["lq"], CFG2["d"]
@@ -172,7 +172,7 @@ def bidaf_microbench(device, iters: int, warmup: int):
         sets.append((c, q, cm, qm))
     w = [torch.randn(d, generator=gen).to(device) * 0.1 for _ in range(3)]
     bias = torch.zeros(1, device=device)
-    run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias)
+    run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision)
     for i in range(warmup):
         run(sets[i % 4])
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,8 +200,8 @@ def run_gpu_arm(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
+    import mmbidaf_b200
+    mmbidaf_b200.set_precision(args.precision)
 
     torch.manual_seed(224)                                   # args.py:43-46
     model = MMBiDAF(HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, device, drop_prob=DROP, max_transcript_length=M).to(device)
@@ -250,17 +250,21 @@ def run_gpu_arm(args):
     line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
-        t_bidaf, algo = bidaf_microbench(device, iters=20, warmup=5) if "bidaf" in sections else (float("nan"), 1)
+        fast = args.precision == "fast"
+        t_bidaf, algo = bidaf_microbench(device, 20, 5, ops.PREC_BF16 if fast else ops.PREC_FP32) \
+            if "bidaf" in sections else (float("nan"), 1)
         achieved = algo / t_bidaf / 1e9
         line = {"metric": METRIC, "value": round(videos / seconds, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world), "clocks": clocks.summary(),
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 tcgen05 BiDAF + tf32 library GEMMs, fp32 accumulate / soft-max / LSTM" if fast else "f32",
+                "data": "synthetic", "config": workload_config(world), "clocks": clocks.summary(),
                 "e2e": {"value": round(videos / e2e_seconds, 2), "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(),
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_seconds / args.steps * 1e3, 3)},
                 "gpu_launches": launches,
-                "roofline": {"kernel": "fused BiDAF forward (bidaf_pass_f32 x2 launches), BASELINE config 2 "
-                                       "(B=64, Lc=512, Lq=256, d=200), fp32 tier",
+                "roofline": {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel x2 + bidaf_tc_kernel<Q2C> + "
+                                        "bidaf_tc_kernel<C2Q>)" if fast else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
+                                       + ", BASELINE config 2 (B=64, Lc=512, Lq=256, d=200)",
                              "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1)}}
@@ -280,6 +284,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fast", choices=["fast", "fp32"],
+                    help="fast: bf16 tensor-core BiDAF + TF32 GEMMs (rel<=2e-2); fp32: rel<=1e-5 tier")
     ap.add_argument("--sections", default="step,e2e,bidaf", help="profiling aid: which GPU sections to run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -168,20 +168,31 @@ __global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackArgs a) {
     wf[e] = (lane < nchunk && a.w_fold) ? a.w_fold[k] : 1.f;
   }
   uint4 s_out[8], v_out[8];
+  // phase 1: every global load of the 8-row group is issued before any is used
+  float4 raw[8][2];
+  uint2 kraw[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = g * 8 + r;
+    raw[r][0] = raw[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    kraw[r] = make_uint2(0u, 0u);
+    if (row < a.L && lane < nchunk) {
+      raw[r][0] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8));
+      raw[r][1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8 + 4));
+      if (keep) kraw[r] = __ldg(reinterpret_cast<const uint2*>(keep + (size_t)row * d + lane * 8));
+    }
+  }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int row = g * 8 + r;
     float v[8], vd[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (row < a.L && lane < nchunk) {
-      const float4 lo = *reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8);
-      const float4 hi = *reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8 + 4);
+    {
+      const float4 lo = raw[r][0], hi = raw[r][1];
       v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
     }
     float dot = 0.f;
     if (keep && row < a.L && lane < nchunk) {
-      const uint2 kk = *reinterpret_cast<const uint2*>(keep + (size_t)row * d + lane * 8);
+      const uint2 kk = kraw[r];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const uint32_t word = e < 4 ? kk.x : kk.y;
@@ -454,21 +465,34 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
         *reinterpret_cast<uint4*>(tp + (size_t)g8 * GROUP_BYTES + ch * 128 + r8 * 16) = *reinterpret_cast<uint4*>(v);
       }
     } else {
-      for (int r = warp; r < TX; r += 4) {
-        const int g = x0 + r;
-        if (g >= a.LX) break;
-        const float* crow = a.x_raw + ((size_t)b * a.LX + g) * d;
-        float* orow = a.out + ((size_t)b * a.LX + g) * 4 * d;
-        for (int c4 = lane; c4 < dv4; c4 += 32) {
-          const float4 c = *reinterpret_cast<const float4*>(crow + c4 * 4);
-          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
-          const float4 cv = make_float4(c.x * v.x, c.y * v.y, c.z * v.z, c.w * v.w);
+      // 4-way concat rows (attention.py:52).  Items are (row, float4 column); each thread walks them 8 at a
+      // time with all global loads of the un-dropped text issued before the first use (memory-level parallelism).
+      const int items = TX * dv4;
+      constexpr int U = 8;
+      for (int base = tid; base < items; base += 128 * U) {
+        float4 c[U];
+        int rr[U], cc[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * 128;
+          rr[u] = i / dv4;
+          cc[u] = i - rr[u] * dv4;
+          ok[u] = i < items && x0 + rr[u] < a.LX;
+          if (ok[u]) c[u] = __ldg(reinterpret_cast<const float4*>(a.x_raw + ((size_t)b * a.LX + x0 + rr[u]) * d + cc[u] * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+          const float4 v = *reinterpret_cast<const float4*>(stg + rr[u] * STG_STRIDE + cc[u] * 4);
+          const float4 cv = make_float4(c[u].x * v.x, c[u].y * v.y, c[u].z * v.z, c[u].w * v.w);
+          float* orow = a.out + ((size_t)b * a.LX + x0 + rr[u]) * 4 * d + cc[u] * 4;
           if (acc == 0) {
-            *reinterpret_cast<float4*>(orow + c4 * 4) = c;                    // attention.py:52
-            *reinterpret_cast<float4*>(orow + d + c4 * 4) = v;
-            *reinterpret_cast<float4*>(orow + 2 * d + c4 * 4) = cv;
+            __stcs(reinterpret_cast<float4*>(orow), c[u]);
+            __stcs(reinterpret_cast<float4*>(orow + d), v);
+            __stcs(reinterpret_cast<float4*>(orow + 2 * d), cv);
           } else {
-            *reinterpret_cast<float4*>(orow + 3 * d + c4 * 4) = cv;
+            __stcs(reinterpret_cast<float4*>(orow + 3 * d), cv);
           }
         }
       }

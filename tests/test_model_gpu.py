@@ -123,3 +123,27 @@ def test_tf32_library_gemms_stay_inside_the_reduced_precision_tier():
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
     assert rel_err(out, g["train_out"]) < 2e-2 and rel_err(loss, g["train_loss"]) < 2e-2
+
+
+def test_fast_tier_whole_model_within_reduced_precision_tolerance():
+    """set_precision('fast'): tcgen05 bf16 BiDAF + TF32 library GEMMs; north_star rel <= 2e-2."""
+    import mmbidaf_b200
+    g = load_golden("model_readme.pt")
+    hidden, e_t, e_a, e_i, m = g["dims"]
+    params = O.make_params(hidden, e_t, e_a, e_i, m, seed=g["param_seed"])
+    model = _model(g["dims"], params)
+    batch = make_batch(*g["batch_shape"], e_t, e_a, e_i, seed=g["batch_seed"])
+    mmbidaf_b200.set_precision("fast")
+    try:
+        out, loss = _call(model, batch, True)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = dict(model.named_parameters())
+        assert rel_err(out, g["train_out"]) < 2e-2 and rel_err(loss, g["train_loss"]) < 2e-2
+        for name, want in g["train_grads_sample"].items():
+            assert grad_err(grads[name].grad, want, name) < 5e-2, name
+        with torch.no_grad():
+            out_e, _ = _call(model, batch, False)
+        assert rel_err(out_e, g["eval_out"]) < 2e-2
+    finally:
+        mmbidaf_b200.set_precision("fp32")

@@ -17,9 +17,10 @@ from mmbidaf_b200.trainer import Trainer  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=bench.CFG3["batch"])
 ap.add_argument("--top", type=int, default=40)
-ap.add_argument("--tf32", action="store_true")
+ap.add_argument("--precision", default="fast")
 args = ap.parse_args()
-torch.backends.cuda.matmul.allow_tf32 = args.tf32
+import mmbidaf_b200  # noqa: E402
+mmbidaf_b200.set_precision(args.precision)
 dev = torch.device("cuda:0")
 torch.manual_seed(224)
 model = MMBiDAF(bench.HIDDEN, bench.E_TEXT, bench.E_AUDIO, bench.E_IMAGE, dev, drop_prob=bench.DROP,

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) decoder_tail_bwd_kernel(const Ta
   // ---- d h' = upstream + W_out^T dlogit ---------------------------------------------------------------
   for (int k = tid; k < H; k += TAIL_THREADS) {
     float acc = a.d_h_out ? a.d_h_out[(size_t)b * H + k] : 0.f;
+#pragma unroll 16
     for (int m = 0; m < M; ++m) acc = fmaf(dlog[m], a.out_w[(size_t)m * H + k], acc);
     dh[k] = acc;
   }
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) decoder_tail_bwd_kernel(const Ta
   for (int k = tid; k < H; k += TAIL_THREADS) {
     const float* g = a.gates + (size_t)b * 4 * H;
     const float gi = g[k], gf = g[H + k], gg = g[2 * H + k], go = g[3 * H + k];
-    const float tc = tanhf(a.cell_out[(size_t)b * H + k]);
+    const float tc = tanh_fast(a.cell_out[(size_t)b * H + k]);
     const float dc = fmaf(dh[k] * go, 1.f - tc * tc, a.d_cell_out ? a.d_cell_out[(size_t)b * H + k] : 0.f);
     const float ai = dc * gg * gi * (1.f - gi);
     const float af = dc * a.cell_in[(size_t)b * H + k] * gf * (1.f - gf);
@@ -83,10 +84,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) decoder_tail_bwd_kernel(const Ta
   for (int d = tid; d < D + H; d += TAIL_THREADS) {
     float acc = 0.f;
     if (d < D) {
+#pragma unroll 16
       for (int r = 0; r < 4 * H; ++r) acc = fmaf(da[r], a.w_ih[(size_t)r * (D + E) + d], acc);
       a.d_ctx[(size_t)b * D + d] = acc;
     } else {
       const int k = d - D;
+#pragma unroll 16
       for (int r = 0; r < 4 * H; ++r) acc = fmaf(da[r], a.w_hh[(size_t)r * H + k], acc);
       a.d_h[(size_t)b * H + k] = acc;
     }
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
   }
   __syncthreads();
   // ---- recompute the h-side projections (as forward) ---------------------------------------------------------
+#pragma unroll 4
   for (int r = warp; r < 4 * D; r += NW) {
     const int m = r / D, d = r - m * D;
     const float* W = m == 0 ? a.w.W2 : m == 1 ? a.w.W4 : m == 2 ? a.w.Wb2 : a.w.Wb4;
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
   const float mix = beta1 * db1 + beta2 * db2;
   const float deb1 = beta1 * (db1 - mix), deb2 = beta2 * (db2 - mix);
   // ---- W_beta paths: pre_k = W_beta_{1,3} c_k + bias + (W_beta_{2,4} h + bias) -------------------------------------
+#pragma unroll 4
   for (int r = warp; r < 2 * D; r += NW) {
     const int m = r / D, d = r - m * D;
     const float* W = m == 0 ? a.w.Wb1 : a.w.Wb3;
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
     for (int k = lane; k < D; k += 32) acc = fmaf(W[(size_t)d * D + k], cx[k], acc);
     acc = warp_sum(acc);
     if (lane == 0) {
-      const float tb = tanhf((acc + (m == 0 ? a.w.bb1[d] : a.w.bb3[d])) + hw[(2 + m) * D + d]);
+      const float tb = tanh_fast((acc + (m == 0 ? a.w.bb1[d] : a.w.bb3[d])) + hw[(2 + m) * D + d]);
       const float de = m == 0 ? deb1 : deb2;
       const float vb = m == 0 ? a.w.vb1[d] : a.w.vb2[d];
       dpre[(2 + m) * D + d] = de * vb * (1.f - tb * tb);
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
     const float* W = m == 0 ? a.w.Wb1 : a.w.Wb3;
     const float* dp = dpre + (2 + m) * D;
     float acc = (m == 0 ? beta1 : beta2) * a.d_ctx[(size_t)b * D + d];
+#pragma unroll 16
     for (int r = 0; r < D; ++r) acc = fmaf(W[(size_t)r * D + d], dp[r], acc);
     dctx[i] = acc;
     a.d_ctx12[((size_t)b * 2 + m) * D + d] = acc;
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
   __syncthreads();
   // ---- sweep 1 over enc: d alpha_k[t] = beta_k datt[t] + d c_k . enc_k[t]; soft-max backward over t ------------------
   float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
   for (int t = warp; t < Lt; t += NW) {
     const float* ea = a.enc_a + ((size_t)b * Lt + t) * D;
     const float* ei = a.enc_i + ((size_t)b * Lt + t) * D;
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
     float c_dz[MAXJ], c_cov[MAXJ], c_v[MAXJ];
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) c_dz[j] = c_cov[j] = c_v[j] = 0.f;
+#pragma unroll 2
     for (int t = warp; t < Lt; t += NW) {
       const float cv = a.cov[(size_t)b * Lt + t];
       const float det = de[t];
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
       for (int j = 0; j < MAXJ; ++j) {
         const int d = lane + 32 * j;
         if (d < D) {
-          const float tz = tanhf((proj[(size_t)t * D + d] + hwm[d]) + cv * wc[d]);
+          const float tz = tanh_fast((proj[(size_t)t * D + d] + hwm[d]) + cv * wc[d]);
           const float dz = det * vv[d] * (1.f - tz * tz);
           dproj[(size_t)t * D + d] += dz;
           c_dz[j] += dz;
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) decoder_attn_bwd_kernel(const At
   // ---- attention part of d h: W2^T d0 + W4^T d1 + W_beta_2^T d2 + W_beta_4^T d3 ---------------------------------------
   for (int k = tid; k < H; k += ATTB_THREADS) {
     float acc = 0.f;
+#pragma unroll 8
     for (int d = 0; d < D; ++d) {
       acc = fmaf(a.w.W2[(size_t)d * H + k], dpre[d], acc);
       acc = fmaf(a.w.W4[(size_t)d * H + k], dpre[D + d], acc);

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   }
   __syncthreads();
   // ---- the four h-side projections ------------------------------------------------------------------
+#pragma unroll 4
   for (int r = warp; r < 4 * D; r += NW) {
     const int m = r / D, d = r - m * D;
     const float* W = m == 0 ? a.w.W2 : m == 1 ? a.w.W4 : m == 2 ? a.w.Wb2 : a.w.Wb4;
@@ -78,14 +79,15 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   __syncthreads();
   // ---- energies e_k[t] = v_k . tanh(proj_k[t] + W h + cov[t] wc_k) + v_k bias --------------------------
   const float v1b = a.w.v1b[0], v2b = a.w.v2b[0];
+#pragma unroll 4
   for (int t = warp; t < Lt; t += NW) {
     const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
     const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
     const float c = a.cov[(size_t)b * Lt + t];
     float s1 = 0.f, s2 = 0.f;
     for (int d = lane; d < D; d += 32) {
-      s1 = fmaf(vec[d], tanhf((pa[d] + hw[d]) + c * vec[D + d]), s1);
-      s2 = fmaf(vec[2 * D + d], tanhf((pi[d] + hw[D + d]) + c * vec[3 * D + d]), s2);
+      s1 = fmaf(vec[d], tanh_fast((pa[d] + hw[d]) + c * vec[D + d]), s1);
+      s2 = fmaf(vec[2 * D + d], tanh_fast((pi[d] + hw[D + d]) + c * vec[3 * D + d]), s2);
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
     const int g = tid / dv4, c4 = tid - g * dv4;
     if (g < groups) {
       float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 4
+#pragma unroll 8
       for (int t = g; t < Lt; t += groups) {
         const float w1 = e1[t], w2 = e2[t];
         const float4 x1 = *reinterpret_cast<const float4*>(ea + (size_t)t * D + c4 * 4);
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
   __syncthreads();
   // ---- modality attention beta (attention.py:161-164) ---------------------------------------------------
   float eb1 = 0.f, eb2 = 0.f;
+#pragma unroll 4
   for (int r = warp; r < 2 * D; r += NW) {
     const int m = r / D, d = r - m * D;
     const float* W = m == 0 ? a.w.Wb1 : a.w.Wb3;
@@ -172,8 +175,8 @@ __global__ void __launch_bounds__(ATT_THREADS) decoder_attn_kernel(const AttnArg
     for (int k = lane; k < D; k += 32) acc = fmaf(W[(size_t)d * D + k], cx[k], acc);
     acc = warp_sum(acc);
     if (lane == 0) {
-      if (m == 0) eb1 = fmaf(a.w.vb1[d], tanhf((acc + a.w.bb1[d]) + hw[2 * D + d]), eb1);
-      else eb2 = fmaf(a.w.vb2[d], tanhf((acc + a.w.bb3[d]) + hw[3 * D + d]), eb2);
+      if (m == 0) eb1 = fmaf(a.w.vb1[d], tanh_fast((acc + a.w.bb1[d]) + hw[2 * D + d]), eb1);
+      else eb2 = fmaf(a.w.vb2[d], tanh_fast((acc + a.w.bb3[d]) + hw[3 * D + d]), eb2);
     }
   }
   eb1 = block_reduce(eb1, red, false) + a.w.vb1b[0];
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(CELL_THREADS) decoder_cell_kernel(const CellAr
     float acc[UPC * 4];
 #pragma unroll
     for (int r = 0; r < UPC * 4; ++r) acc[r] = 0.f;
+#pragma unroll 4
     for (int k = lane; k < K; k += 32) {
       const float x = k < D ? a.ctx[(size_t)b * D + k] : k < D + E ? a.sent[(size_t)b * E + (k - D)]
                                                                  : a.h[(size_t)b * H + (k - D - E)];
@@ -251,10 +255,10 @@ __global__ void __launch_bounds__(CELL_THREADS) decoder_cell_kernel(const CellAr
 #pragma unroll
           for (int g = 0; g < 4; ++g) pre[g] = acc[u * 4 + g] + bs[u * 4 + g];
         }
-      const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]), gg = tanhf(pre[2]), go = sigmoidf_acc(pre[3]);
+      const float gi = gate_act(pre[0], 1.f), gf = gate_act(pre[1], 1.f), gg = tanh_fast(pre[2]), go = gate_act(pre[3], 1.f);
       const float c = fmaf(gf, a.cell[(size_t)b * H + j], gi * gg);
       a.cell_out[(size_t)b * H + j] = c;
-      a.h_out[(size_t)b * H + j] = go * tanhf(c);
+      a.h_out[(size_t)b * H + j] = go * tanh_fast(c);
       if (a.gates) {
         float* gs = a.gates + (size_t)b * 4 * H;
         gs[j] = gi; gs[H + j] = gf; gs[2 * H + j] = gg; gs[3 * H + j] = go;
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(OUT_THREADS) decoder_out_kernel(const OutArgs 
   for (int i = tid; i < H; i += OUT_THREADS) h_s[i] = a.h[(size_t)b * H + i];
   __syncthreads();
   const uint8_t* mk = a.mask + (size_t)b * M;
+#pragma unroll 8
   for (int m = warp; m < M; m += NW) {
     float acc = 0.f;
     for (int k = lane; k < H; k += 32) acc = fmaf(a.w[(size_t)m * H + k], h_s[k], acc);

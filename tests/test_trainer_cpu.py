@@ -92,3 +92,21 @@ def test_two_rank_step_equals_single_process_global_batch():
             assert torch.allclose(got, w, rtol=1e-5, atol=1e-7)
     for a, b in zip(results[0], results[1]):
         assert torch.equal(a, b)                         # replicas bit-identical after the update
+
+
+def test_flat_adadelta_matches_torch_optimizer():
+    from mmbidaf_b200.trainer import FlatAdadelta, FlatState
+    a, b = TinyModel(), TinyModel()
+    batch = make_batch(3, 6, 7, 2, 2, seed=4)
+    state = FlatState(a.parameters())
+    mine = FlatAdadelta(state, lr=0.5, weight_decay=0.01)
+    ref = torch.optim.Adadelta(b.parameters(), lr=0.5, weight_decay=0.01)
+    for _ in range(3):
+        state.zero()
+        ref.zero_grad()
+        for m in (a, b):
+            m(batch.text, batch.text_len, batch.audio, batch.audio_len, None, None, None, None, None)[1].backward()
+        mine.step()
+        ref.step()
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)

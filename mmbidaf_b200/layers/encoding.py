@@ -70,6 +70,11 @@ class _LengthCache:
 _lengths = _LengthCache()
 
 
+def device_lengths(lengths, device):
+    """int32 device tensor of a host list of lengths (cached per distinct list)."""
+    return _lengths.get(lengths, device)[0]
+
+
 class RNNEncoder(nn.Module):
     """Length-aware bidirectional LSTM encoder (reference encoding.py:62-108).
 

@@ -56,8 +56,11 @@ class MMBiDAF(nn.Module):
             stream.wait_stream(main)
             with torch.cuda.stream(stream):
                 results.append(job())
+        capturing = torch.cuda.is_current_stream_capturing()
         for stream, res in zip(self._streams, results):
             main.wait_stream(stream)
+            if capturing:
+                continue                      # graph-private pool: lifetimes are fixed by the captured order
             for t in res:
                 if isinstance(t, torch.Tensor):
                     t.record_stream(main)
@@ -71,7 +74,8 @@ class MMBiDAF(nn.Module):
 
     def get_mask(self, X, X_len):
         """bool (B, L): position < length, on X's device (reference models.py:86-92 builds it on the CPU)."""
-        lens = torch.as_tensor(list(X_len), dtype=torch.long).to(X.device, non_blocking=True)
+        from .layers.encoding import device_lengths
+        lens = device_lengths(X_len, X.device)        # cached: no host->device copy after the first call
         return torch.arange(X.size(1), device=X.device).unsqueeze(0) < lens.unsqueeze(1)
 
     def forward(self, embedded_text, original_text_lengths, embedded_audio, original_audio_lengths, transformed_images,
@@ -128,7 +132,7 @@ class MMBiDAF(nn.Module):
                 self.multimodal_att_decoder(decoder_input, decoder_hidden, decoder_cell_state, mod_text_audio,
                                             mod_text_image, coverage_vec, decoder_mask)
             tgt = targets[:, idx]
-            loss = loss - torch.log(out_distribution[rows, tgt] + eps).sum()                # models.py:168-170
+            loss = loss - torch.log(out_distribution.gather(1, tgt.unsqueeze(1)) + eps).sum()   # models.py:168-170
             nxt = tgt if self.training else out_distribution.max(dim=1)[1]                  # models.py:173 / :184,:193
             decoder_input = embedded_text[rows, nxt].unsqueeze(1)
             out_distributions.append(out_distribution)

@@ -42,21 +42,33 @@ class FlatState:
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        pad = lambda n: (n + 3) // 4 * 4                 # every parameter stays 16-byte aligned (kernels use float4)
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += pad(p.numel())
         first = self.params[0]
-        self.flat_param = torch.empty(total, dtype=first.dtype, device=first.device)
+        self.flat_param = torch.zeros(total, dtype=first.dtype, device=first.device)
         self.flat = torch.zeros(total, dtype=first.dtype, device=first.device)        # gradients
-        offset = 0
         with torch.no_grad():
-            for p in self.params:
+            for p, offset in zip(self.params, self.offsets):
                 n = p.numel()
                 self.flat_param[offset:offset + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_param[offset:offset + n].view_as(p)
                 p.grad = self.flat[offset:offset + n].view_as(p)
-                offset += n
 
     def zero(self) -> None:
         self.flat.zero_()
+
+    def pack(self, grads) -> None:
+        """Copy a tuple of per-parameter gradients (None = zero) into the flat buffer with one kernel."""
+        pieces = []
+        for g, p in zip(grads, self.params):
+            n = p.numel()
+            pieces.append(g.reshape(-1) if g is not None else p.new_zeros(n))
+            if n % 4:
+                pieces.append(p.new_zeros(4 - n % 4))
+        torch.cat(pieces, out=self.flat)
 
     def all_reduce_sum(self, group=None) -> None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -106,13 +118,53 @@ class Trainer:
         self.optimizer = FlatAdadelta(self.grads, lr=lr, weight_decay=l2_wd)                  # train.py:110
         self.last_grad_norm: Optional[torch.Tensor] = None
 
+    # ---- CUDA-graph replay of the whole step (launch-bound at ~1200 kernels per step) ----------------------
+    def capture(self, batch: Batch, warmup: int = 3, error_mode: str = "global") -> None:
+        """Capture forward + backward + all-reduce + clip + Adadelta for ``batch`` (resident on the device) into
+        one CUDA graph.  Later ``step_graphed(other)`` copies a batch of the SAME padded shapes and lengths into
+        the captured input tensors and replays.  Dropout draws fresh masks on every replay (torch's generator
+        is graph-aware)."""
+        import gc
+        self._static = batch
+        # drop per-sequence caches that still own tensors (and stream-usage records) from eager steps, so that
+        # nothing created on another stream is released while the capture is in flight
+        for m in self.model.modules():
+            if hasattr(m, "_cache"):
+                m._cache = None
+        gc.collect()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(batch)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, capture_error_mode=error_mode):
+            self._static_loss = self.step(batch)
+
+    def step_graphed(self, batch: Optional[Batch] = None) -> torch.Tensor:
+        if batch is not None and batch is not self._static:
+            s = self._static
+            if (batch.text_len, batch.audio_len, batch.image_len, batch.target_len) != \
+                    (s.text_len, s.audio_len, s.image_len, s.target_len):
+                raise ValueError("step_graphed: lengths differ from the captured batch; call capture() again")
+            s.text.copy_(batch.text, non_blocking=True)
+            s.audio.copy_(batch.audio, non_blocking=True)
+            s.images.copy_(batch.images, non_blocking=True)
+            s.targets.copy_(batch.targets, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
     def step(self, batch: Batch) -> torch.Tensor:
         """forward + backward + all-reduce + clip + Adadelta on this rank's shard; returns the local loss."""
         self.model.train()
-        self.grads.zero()
         _, loss = self.model(batch.text, batch.text_len, batch.audio, batch.audio_len, batch.images, batch.image_len,
                              batch.targets, batch.target_len, batch.max_dec_len)
-        loss.backward()
+        # functional backward: gradients are produced fresh and packed into the flat buffer with one copy
+        # kernel (no per-parameter accumulation nodes, which also keeps the step CUDA-graph capturable)
+        grads = torch.autograd.grad(loss, self.grads.params, allow_unused=True)
+        self.grads.pack(grads)
         self.grads.all_reduce_sum(self.group)
         self.last_grad_norm = self.grads.clip_(self.max_grad_norm)
         self.optimizer.step()

@@ -139,9 +139,14 @@ class Trainer:
             for _ in range(warmup):
                 self.step(batch)
         torch.cuda.current_stream().wait_stream(side)
+        # The NCCL all-reduce stays outside the graphs (one eager call on the static flat buffer between two
+        # replays): graph A = forward + backward + pack, graph B = clip + Adadelta.
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, capture_error_mode=error_mode):
-            self._static_loss = self.step(batch)
+            self._static_loss = self._forward_backward(batch)
+        self._graph_update = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_update, capture_error_mode=error_mode):
+            self._update()
 
     def step_graphed(self, batch: Optional[Batch] = None) -> torch.Tensor:
         if batch is not None and batch is not self._static:
@@ -154,10 +159,11 @@ class Trainer:
             s.images.copy_(batch.images, non_blocking=True)
             s.targets.copy_(batch.targets, non_blocking=True)
         self._graph.replay()
+        self.grads.all_reduce_sum(self.group)
+        self._graph_update.replay()
         return self._static_loss
 
-    def step(self, batch: Batch) -> torch.Tensor:
-        """forward + backward + all-reduce + clip + Adadelta on this rank's shard; returns the local loss."""
+    def _forward_backward(self, batch: Batch) -> torch.Tensor:
         self.model.train()
         _, loss = self.model(batch.text, batch.text_len, batch.audio, batch.audio_len, batch.images, batch.image_len,
                              batch.targets, batch.target_len, batch.max_dec_len)
@@ -165,7 +171,15 @@ class Trainer:
         # kernel (no per-parameter accumulation nodes, which also keeps the step CUDA-graph capturable)
         grads = torch.autograd.grad(loss, self.grads.params, allow_unused=True)
         self.grads.pack(grads)
-        self.grads.all_reduce_sum(self.group)
+        return loss.detach()
+
+    def _update(self) -> None:
         self.last_grad_norm = self.grads.clip_(self.max_grad_norm)
         self.optimizer.step()
-        return loss.detach()
+
+    def step(self, batch: Batch) -> torch.Tensor:
+        """forward + backward + all-reduce + clip + Adadelta on this rank's shard; returns the local loss."""
+        loss = self._forward_backward(batch)
+        self.grads.all_reduce_sum(self.group)
+        self._update()
+        return loss

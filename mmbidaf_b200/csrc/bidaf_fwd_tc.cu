@@ -37,7 +37,6 @@ constexpr int X_BYTES = TX / 8 * GROUP_BYTES;   // 53248
 constexpr int Y_BYTES = TY / 8 * GROUP_BYTES;   // 26624
 constexpr int P_BYTES = TX * TY * 2;            // 16384
 constexpr int STAGES = 2;
-constexpr float TAU = 8.0f;               // lazy-rescale threshold (natural-log units)
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 64 + DPAD;
 constexpr int STG_STRIDE = 204;           // fp32 staging row stride (conflict-free 128-bit stores)
@@ -149,14 +148,17 @@ struct PackArgs {
   __nv_bfloat16* s_pack;     // S operand (dropped, folded, with term chunk)
   __nv_bfloat16* v_pack;     // plain values (value operand); may equal s_pack when identical (modality side, eval)
   unsigned long long* mask_words;   // (B, LP/64, 2): [valid bits, unmasked bits]
+  float* out_copy;           // text side: block 0 of the output (B, L, 4d) <- the text itself (attention.py:52)
   float keep_scale;
   int L, LP, d, text_side;
 };
 
+constexpr int PACK_CHUNK_STRIDE = 144;   // 128-byte core matrix + 16 bytes: spreads the staging stores over banks
+
 __global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackArgs a) {
+  __shared__ __align__(16) unsigned char stage[8][CHUNKS * PACK_CHUNK_STRIDE];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * 8 + warp;                 // 8-row group
-  if (g * 8 >= a.LP) return;
+  const int g = blockIdx.x * 8 + warp;                 // 8-row group (LP is a multiple of 64: always in range)
   const int d = a.d, nchunk = d >> 3;
   const float* src = a.src + (size_t)b * a.L * d;
   const uint8_t* keep = a.keep ? a.keep + (size_t)b * a.L * d : nullptr;
@@ -189,6 +191,11 @@ __global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackArgs a) {
     {
       const float4 lo = raw[r][0], hi = raw[r][1];
       v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    }
+    if (a.out_copy && row < a.L && lane < nchunk) {     // out[:, :, 0:d] = text, exact fp32
+      float* o = a.out_copy + ((size_t)b * a.L + row) * 4 * d + lane * 8;
+      __stcs(reinterpret_cast<float4*>(o), raw[r][0]);
+      __stcs(reinterpret_cast<float4*>(o + 4), raw[r][1]);
     }
     float dot = 0.f;
     if (keep && row < a.L && lane < nchunk) {
@@ -225,30 +232,34 @@ __global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackArgs a) {
       v_out[r] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  if (lane < CHUNKS) {
-    const size_t base = ((size_t)b * (a.LP / 8) + g) * GROUP_BYTES + (size_t)lane * 128;
-    uint4* sdst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.s_pack) + base);
+  // phase 3: transpose through shared memory so the 3328-byte group leaves as contiguous 512-byte bursts
+  unsigned char* buf = stage[warp];
+  const size_t base = ((size_t)b * (a.LP / 8) + g) * GROUP_BYTES;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    if (which == 1 && a.v_pack == a.s_pack) break;
+    if (lane < CHUNKS) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sdst[r] = s_out[r];
-    if (a.v_pack != a.s_pack) {
-      uint4* vdst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.v_pack) + base);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) vdst[r] = v_out[r];
+      for (int r = 0; r < 8; ++r)
+        *reinterpret_cast<uint4*>(buf + lane * PACK_CHUNK_STRIDE + r * 16) = which == 0 ? s_out[r] : v_out[r];
     }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(which == 0 ? a.s_pack : a.v_pack) + base);
+    for (int i = lane; i < CHUNKS * 8; i += 32)
+      dst[i] = *reinterpret_cast<const uint4*>(buf + (i >> 3) * PACK_CHUNK_STRIDE + (i & 7) * 16);
+    __syncwarp();
   }
-  // mask words: one thread per 64-row tile of this block
-  if (threadIdx.x == 0) {
-    const int tile = blockIdx.x;                        // 8 groups x 8 rows = 64 rows per block
-    unsigned long long valid = 0ull, open = 0ull;
-    for (int i = 0; i < 64; ++i) {
-      const int row = tile * 64 + i;
-      if (row < a.L) {
-        valid |= 1ull << i;
-        if (a.mask[(size_t)b * a.L + row]) open |= 1ull << i;
-      }
+  // mask words of this block's 64-row tile
+  if (warp == 0) {
+    const int tile = blockIdx.x;
+    const int r0 = tile * 64 + lane, r1 = r0 + 32;
+    const unsigned v0 = __ballot_sync(0xffffffffu, r0 < a.L), v1 = __ballot_sync(0xffffffffu, r1 < a.L);
+    const unsigned o0 = __ballot_sync(0xffffffffu, r0 < a.L && a.mask[(size_t)b * a.L + min(r0, a.L - 1)] != 0);
+    const unsigned o1 = __ballot_sync(0xffffffffu, r1 < a.L && a.mask[(size_t)b * a.L + min(r1, a.L - 1)] != 0);
+    if (lane == 0) {
+      a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 0] = ((unsigned long long)v1 << 32) | v0;
+      a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 1] = ((unsigned long long)o1 << 32) | o0;
     }
-    a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 0] = valid;
-    a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 1] = open;
   }
 }
 
@@ -260,18 +271,23 @@ struct TcArgs {
   const __nv_bfloat16* y_pack;       // S operand of the Y side
   const __nv_bfloat16* v0_pack;      // value operand 0 (plain Y rows); may equal y_pack
   const __nv_bfloat16* v1_pack;      // value operand 1 (C2Q: packed T); null for Q2C
+  const __nv_bfloat16* x_plain;      // C2Q: plain (un-dropped, un-folded) text pack for the c*a / c*b products
   const unsigned long long* y_words; // (B, LYP/64, 2)
   const float* bias;
-  const float* x_raw;                // C2Q: un-dropped text (B, LX, d) for the concat; null for Q2C
   float* out;                        // Q2C: T fp32 (B, LX, d);   C2Q: out (B, LX, 4d)
   __nv_bfloat16* t_pack;             // Q2C: packed T for pass 3
   float* lse;                        // (B, LX)
   int LX, LXP, LY, LYP, d;
 };
 
+constexpr int NTHREADS = 256;            // two threads per X row: warps 0-3 take S columns 0-31, warps 4-7 columns 32-63
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+constexpr float TAU2 = 11.0f;            // lazy-rescale threshold in log2 units (factor 2048)
+
 template <int KIND>
-__global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   constexpr int NACC = KIND == C2Q ? 2 : 1;
+  constexpr int HALF = TY / 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const bool sep_v0 = a.v0_pack != a.y_pack;
   const int nparts = 1 + (sep_v0 ? 1 : 0) + (KIND == C2Q ? 1 : 0);
@@ -281,8 +297,11 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
   unsigned char* St = Ps + P_BYTES;                               // STAGES x stage_bytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(St + STAGES * stage_bytes);   // [0] x, [1..2] full, [3] mma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xbuf = reinterpret_cast<float*>(bars + 10);              // [2][TX] cross-half exchange (max, then sum)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2, wq = warp & 3;
+  const int row = wq * 32 + lane;
   const int b = blockIdx.y, x0 = blockIdx.x * TX;
   const uint32_t bar_x = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_mma = smem_u32(bars + 3);
 
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
   const uint32_t tmem = *tmem_slot;
 
   const int nty = (a.LY + TY - 1) / TY;
-  const char* xg = reinterpret_cast<const char*>(a.x_pack) + ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
+  const size_t x_off = ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
   const size_t y_batch = (size_t)b * (a.LYP / 8) * GROUP_BYTES;
   auto issue_stage = [&](int t) {
     const int s = t % STAGES;
@@ -315,13 +334,13 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
   };
   if (tid == 0) {
     mbar_expect_tx(bar_x, X_BYTES);
-    tma_bulk_g2s(smem_u32(Xs), xg, X_BYTES, bar_x);
+    tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_pack) + x_off, X_BYTES, bar_x);
     for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
   }
 
-  const float bias = a.bias[0];
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
-  float m_ref = -INFINITY, l_run = 0.f;
+  const float bias2 = a.bias[0] * LOG2E;
+  const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);     // this warp's 32 TMEM lanes
+  float m_ref = -INFINITY, l_part = 0.f;                             // log2 domain; l over this thread's columns
   uint32_t mma_phase = 0;
   constexpr uint32_t IDESC_S = idesc_bf16(TY, 0), IDESC_PV = idesc_bf16(DPAD, 1);
   const uint32_t xs_addr = smem_u32(Xs), ps_addr = smem_u32(Ps);
@@ -340,56 +359,84 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
       umma_commit(bar_mma);
     }
     const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + t) * 2);
+    const uint32_t wvalid = (uint32_t)(words.x >> (HALF * half)), wopen = (uint32_t)(words.y >> (HALF * half));
+    const bool all_open = (words.x & words.y) == ~0ull;         // CTA-uniform: interior tile, nothing masked
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
     // every MMA issued before this commit has retired: the previous tile's P V is done, its stage is free
     if (tid == 0 && t >= 1 && t - 1 + STAGES < nty) issue_stage(t - 1 + STAGES);
-
-    // ---- this thread's row of S: masked streaming soft-max -------------------------------------------------
-    float sv[TY];
-#pragma unroll
-    for (int q = 0; q < TY / 16; ++q) tmem_ld16(lane_base + COL_S + q * 16, sv + q * 16);
-    float tile_max = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < TY; ++c) {
-      const bool open = (words.y >> c) & 1ull, valid = (words.x >> c) & 1ull;
-      const float v = open ? sv[c] + bias : kNegFill;           // attention.py:94
-      sv[c] = v;
-      if (valid) tile_max = fmaxf(tile_max, v);
+    if (KIND == C2Q && tid == 0 && t == nty - 1) {              // X operand no longer needed: fetch the plain text
+      mbar_expect_tx(bar_x, X_BYTES);
+      tma_bulk_g2s(xs_addr, reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x);
     }
+
+    // ---- this thread's half row of S: masked streaming soft-max (base-2) -------------------------------------
+    float sv[HALF];
+    tmem_ld16(lane_base + COL_S + half * HALF, sv);
+    tmem_ld16(lane_base + COL_S + half * HALF + 16, sv + 16);
+    float tile_max = -INFINITY;
+    if (all_open) {
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        sv[c] = fmaf(sv[c], LOG2E, bias2);
+        tile_max = fmaxf(tile_max, sv[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < HALF; ++c) {
+        const float v = ((wopen >> c) & 1u) ? fmaf(sv[c], LOG2E, bias2) : kNegFill * LOG2E;   // attention.py:94
+        sv[c] = v;
+        if ((wvalid >> c) & 1u) tile_max = fmaxf(tile_max, v);
+      }
+    }
+    xbuf[half * TX + row] = tile_max;
+    __syncthreads();
+    tile_max = fmaxf(tile_max, xbuf[(half ^ 1) * TX + row]);    // both threads of the row now agree
     float alpha = 1.f;
-    const bool bump = tile_max > m_ref + TAU;                   // first tile: m_ref = -inf -> always
+    const bool bump = tile_max > m_ref + TAU2;                  // first tile: m_ref = -inf -> always
     if (bump) {
-      alpha = __expf(m_ref - tile_max);                         // 0 on the first tile
+      alpha = exp2f(m_ref - tile_max);                          // 0 on the first tile
       m_ref = tile_max;
     }
-    const int any_bump = __syncthreads_or(bump && t > 0);
     float psum = 0.f;
-    uint32_t packed[TY / 2];
+    uint32_t packed[HALF / 2];
+    if (all_open) {
 #pragma unroll
-    for (int c = 0; c < TY; c += 2) {
-      const float p0 = ((words.x >> c) & 1ull) ? __expf(sv[c] - m_ref) : 0.f;
-      const float p1 = ((words.x >> (c + 1)) & 1ull) ? __expf(sv[c + 1] - m_ref) : 0.f;
-      const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-      // the row sum uses the bf16-rounded probabilities so that numerator and denominator match
-      psum += __low2float(pk) + __high2float(pk);
-      packed[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
+      for (int c = 0; c < HALF; c += 2) {
+        const float p0 = exp2f(sv[c] - m_ref), p1 = exp2f(sv[c + 1] - m_ref);
+        psum += p0 + p1;
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+        packed[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < HALF; c += 2) {
+        const float p0 = ((wvalid >> c) & 1u) ? exp2f(sv[c] - m_ref) : 0.f;
+        const float p1 = ((wvalid >> (c + 1)) & 1u) ? exp2f(sv[c + 1] - m_ref) : 0.f;
+        psum += p0 + p1;
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+        packed[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
     }
-    l_run = l_run * alpha + psum;
+    l_part = l_part * alpha + psum;
     // P in core-matrix order: chunk c8 (8 columns) at c8*2048 + row*16  (LBO 2048, SBO 128)
     {
-      unsigned char* prow = Ps + (warp * 32 + lane) * 16;
+      unsigned char* prow = Ps + row * 16 + (half * (HALF / 8)) * 2048;
 #pragma unroll
-      for (int c8 = 0; c8 < TY / 8; ++c8)
+      for (int c8 = 0; c8 < HALF / 8; ++c8)
         *reinterpret_cast<uint4*>(prow + c8 * 2048) =
             make_uint4(packed[c8 * 4], packed[c8 * 4 + 1], packed[c8 * 4 + 2], packed[c8 * 4 + 3]);
     }
-    if (any_bump) {                                             // lazy rescale of this thread's accumulator rows
+    fence_proxy_async();                                        // st.shared P -> visible to the tensor core
+    tc_fence_before();
+    const int any_bump = __syncthreads_or(bump && t > 0);
+    if (any_bump) {                                             // lazy rescale: the two threads of a row split the columns
+      tc_fence_after();
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc)
 #pragma unroll 1
-        for (int q = 0; q < DPAD / 16; ++q) {
+        for (int q = half; q < DPAD / 16; q += 2) {
           float o[16];
           const uint32_t addr = lane_base + (acc == 0 ? COL_O0 : COL_O1) + q * 16;
           tmem_ld16(addr, o);
@@ -398,10 +445,9 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
           tmem_st16(addr, o);
         }
       tmem_wait_st();
+      tc_fence_before();
+      __syncthreads();
     }
-    fence_proxy_async();                                        // st.shared P -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       const uint32_t v0_addr = sep_v0 ? st_addr + Y_BYTES : st_addr;
@@ -419,20 +465,23 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
       if (t == nty - 1) umma_commit(bar_mma);
     }
   }
+  // ---- epilogue: TMEM -> registers -> fp32 staging in smem -> coalesced global stores -----------------------------
+  xbuf[half * TX + row] = l_part;                               // combine the two half-row sums
   mbar_wait(bar_mma, mma_phase);
   tc_fence_after();
-
-  // ---- epilogue: TMEM -> registers -> fp32 staging in smem -> coalesced global stores -----------------------------
-  const int row = warp * 32 + lane, gx = x0 + row;
+  __syncthreads();
+  const float l_run = xbuf[row] + xbuf[TX + row];
+  const int gx = x0 + row;
   const float inv_l = 1.f / l_run;
-  if (gx < a.LX && a.lse) a.lse[(size_t)b * a.LX + gx] = m_ref + __logf(l_run);
+  if (half == 0 && gx < a.LX && a.lse) a.lse[(size_t)b * a.LX + gx] = (m_ref + log2f(l_run)) * LN2;
   float* stg = reinterpret_cast<float*>(St);                    // 128 x 204 fp32 = 104448 B <= 2 stages
   const int d = a.d, dv4 = d >> 2;
+  if (KIND == C2Q) mbar_wait(bar_x, 1);                         // plain text tile (bf16, core-matrix order) in Xs
 #pragma unroll 1
   for (int acc = 0; acc < NACC; ++acc) {
     if (acc > 0) __syncthreads();
 #pragma unroll 1
-    for (int q = 0; q < DPAD / 16; ++q) {
+    for (int q = half; q < DPAD / 16; q += 2) {
       float o[16];
       tmem_ld16(lane_base + (acc == 0 ? COL_O0 : COL_O1) + q * 16, o);
 #pragma unroll
@@ -443,16 +492,15 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
     }
     __syncthreads();
     if (KIND == Q2C) {
-      for (int r = warp; r < TX; r += 4) {                      // fp32 T rows, coalesced
-        const int g = x0 + r;
-        if (g >= a.LX) break;
-        for (int c4 = lane; c4 < dv4; c4 += 32)
-          *reinterpret_cast<float4*>(a.out + ((size_t)b * a.LX + g) * d + c4 * 4) =
+      for (int i = tid; i < TX * dv4; i += NTHREADS) {          // fp32 T rows, coalesced
+        const int r = i / dv4, c4 = i - r * dv4;
+        if (x0 + r < a.LX)
+          *reinterpret_cast<float4*>(a.out + ((size_t)b * a.LX + x0 + r) * d + c4 * 4) =
               *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
       }
-      // packed bf16 T (value operand of pass 3): one 16-byte chunk per (row, chunk)
-      char* tp = reinterpret_cast<char*>(a.t_pack) + ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
-      for (int i = tid; i < TX * CHUNKS; i += 128) {
+      // packed bf16 T (value operand of pass 3): one 16-byte chunk per (row, chunk), contiguous per 8-row group
+      char* tp = reinterpret_cast<char*>(a.t_pack) + x_off;
+      for (int i = tid; i < TX * CHUNKS; i += NTHREADS) {
         const int g8 = i / (CHUNKS * 8), rem = i - g8 * CHUNKS * 8, ch = rem >> 3, r8 = rem & 7;
         const int r = g8 * 8 + r8;
         __nv_bfloat162 v[4];
@@ -462,38 +510,26 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
           const bool ok = (x0 + r < a.LX) && col < d;
           v[e] = __floats2bfloat162_rn(ok ? stg[r * STG_STRIDE + col] : 0.f, ok ? stg[r * STG_STRIDE + col + 1] : 0.f);
         }
-        *reinterpret_cast<uint4*>(tp + (size_t)g8 * GROUP_BYTES + ch * 128 + r8 * 16) = *reinterpret_cast<uint4*>(v);
+        *reinterpret_cast<uint4*>(tp + (size_t)i * 16) = *reinterpret_cast<uint4*>(v);
       }
     } else {
-      // 4-way concat rows (attention.py:52).  Items are (row, float4 column); each thread walks them 8 at a
-      // time with all global loads of the un-dropped text issued before the first use (memory-level parallelism).
-      const int items = TX * dv4;
-      constexpr int U = 8;
-      for (int base = tid; base < items; base += 128 * U) {
-        float4 c[U];
-        int rr[U], cc[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = base + u * 128;
-          rr[u] = i / dv4;
-          cc[u] = i - rr[u] * dv4;
-          ok[u] = i < items && x0 + rr[u] < a.LX;
-          if (ok[u]) c[u] = __ldg(reinterpret_cast<const float4*>(a.x_raw + ((size_t)b * a.LX + x0 + rr[u]) * d + cc[u] * 4));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (!ok[u]) continue;
-          const float4 v = *reinterpret_cast<const float4*>(stg + rr[u] * STG_STRIDE + cc[u] * 4);
-          const float4 cv = make_float4(c[u].x * v.x, c[u].y * v.y, c[u].z * v.z, c[u].w * v.w);
-          float* orow = a.out + ((size_t)b * a.LX + x0 + rr[u]) * 4 * d + cc[u] * 4;
-          if (acc == 0) {
-            __stcs(reinterpret_cast<float4*>(orow), c[u]);
-            __stcs(reinterpret_cast<float4*>(orow + d), v);
-            __stcs(reinterpret_cast<float4*>(orow + 2 * d), cv);
-          } else {
-            __stcs(reinterpret_cast<float4*>(orow + 3 * d), cv);
-          }
+      // blocks 1..3 of the concat (attention.py:52); block 0 was written by the pack kernel.  The products use
+      // the bf16 text tile already in shared memory: no global loads in the epilogue.
+      for (int i = tid; i < TX * dv4; i += NTHREADS) {
+        const int r = i / dv4, c4 = i - r * dv4;
+        if (x0 + r >= a.LX) continue;
+        const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
+        const int col = c4 * 4;
+        const uint2 cb = *reinterpret_cast<const uint2*>(Xs + (r >> 3) * GROUP_BYTES + (col >> 3) * 128 + (r & 7) * 16 + (col & 7) * 2);
+        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cb.x));
+        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cb.y));
+        const float4 cv = make_float4(c01.x * v.x, c01.y * v.y, c23.x * v.z, c23.y * v.w);
+        float* orow = a.out + ((size_t)b * a.LX + x0 + r) * 4 * d + col;
+        if (acc == 0) {
+          __stcs(reinterpret_cast<float4*>(orow + d), v);
+          __stcs(reinterpret_cast<float4*>(orow + 2 * d), cv);
+        } else {
+          __stcs(reinterpret_cast<float4*>(orow + 3 * d), cv);
         }
       }
     }
@@ -503,7 +539,7 @@ __global__ void __launch_bounds__(128, 1) bidaf_tc_kernel(const TcArgs a) {
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-size_t tc_smem_bytes(int nparts) { return (size_t)X_BYTES + P_BYTES + (size_t)STAGES * nparts * Y_BYTES + 64 + 16; }
+size_t tc_smem_bytes(int nparts) { return (size_t)X_BYTES + P_BYTES + (size_t)STAGES * nparts * Y_BYTES + 80 + 2 * TX * 4; }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -538,27 +574,27 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   auto* c_words = reinterpret_cast<unsigned long long*>(next);
   auto* q_words = c_words + (size_t)B * (LcP / 64) * 2;
 
-  PackArgs pc{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, keep_scale, Lc, LcP, d, 1};
+  PackArgs pc{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
   bidaf_pack_kernel<<<dim3(LcP / 64, B), 256, 0, stream>>>(pc);
   if (int rc = check_launch("bidaf_pack_kernel(text)")) return rc;
-  PackArgs pq{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, keep_scale, Lq, LqP, d, 0};
+  PackArgs pq{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, nullptr, keep_scale, Lq, LqP, d, 0};
   bidaf_pack_kernel<<<dim3(LqP / 64, B), 256, 0, stream>>>(pq);
   if (int rc = check_launch("bidaf_pack_kernel(modality)")) return rc;
 
   {   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
-    TcArgs a{qs, cw, cp, nullptr, c_words, bias, nullptr, q2c, tp, lse_col, Lq, LqP, Lc, LcP, d};
+    TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, Lq, LqP, Lc, LcP, d};
     const size_t smem = tc_smem_bytes(2);
     MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<Q2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), 128, smem, stream>>>(a);
+    bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), NTHREADS, smem, stream>>>(a);
     if (int rc = check_launch("bidaf_tc_kernel<Q2C>")) return rc;
   }
   {   // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)
-    TcArgs a{cw, qs, qp, tp, q_words, bias, text, out, nullptr, lse_row, Lc, LcP, Lq, LqP, d};
+    TcArgs a{cw, qs, qp, tp, cp, q_words, bias, out, nullptr, lse_row, Lc, LcP, Lq, LqP, d};
     const int nparts = 2 + (qp != qs ? 1 : 0);
     const size_t smem = tc_smem_bytes(nparts);
     MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "bidaf bf16 tier: %zu B of shared memory", smem);
     MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<C2Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_tc_kernel<C2Q><<<dim3(LcP / TX, B), 128, smem, stream>>>(a);
+    bidaf_tc_kernel<C2Q><<<dim3(LcP / TX, B), NTHREADS, smem, stream>>>(a);
     if (int rc = check_launch("bidaf_tc_kernel<C2Q>")) return rc;
   }
   return MMB_OK;

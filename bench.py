@@ -278,7 +278,7 @@ def run_gpu_arm(args):
                 "e2e": {"value": round(videos / e2e_seconds, 2), "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(),
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_seconds / args.steps * 1e3, 3)},
                 "gpu_launches": launches,
-                "roofline": {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel x2 + bidaf_tc_kernel<Q2C> + "
+                "roofline": {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel + bidaf_tc_kernel<Q2C> + "
                                         "bidaf_tc_kernel<C2Q>)" if fast else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
                                        + ", BASELINE config 2 (B=64, Lc=512, Lq=256, d=200)",
                              "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

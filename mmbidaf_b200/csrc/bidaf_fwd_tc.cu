@@ -155,7 +155,11 @@ struct PackArgs {
 
 constexpr int PACK_CHUNK_STRIDE = 144;   // 128-byte core matrix + 16 bytes: spreads the staging stores over banks
 
-__global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackArgs a) {
+struct PackPair { PackArgs side[2]; };
+
+__global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackPair pp) {
+  const PackArgs& a = pp.side[blockIdx.z];
+  if ((int)blockIdx.x * 64 >= a.LP) return;
   __shared__ __align__(16) unsigned char stage[8][CHUNKS * PACK_CHUNK_STRIDE];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * 8 + warp;                 // 8-row group (LP is a multiple of 64: always in range)
@@ -514,13 +518,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
       }
     } else {
       // blocks 1..3 of the concat (attention.py:52); block 0 was written by the pack kernel.  The products use
-      // the bf16 text tile already in shared memory: no global loads in the epilogue.
-      for (int i = tid; i < TX * dv4; i += NTHREADS) {
-        const int r = i / dv4, c4 = i - r * dv4;
-        if (x0 + r >= a.LX) continue;
-        const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
-        const int col = c4 * 4;
-        const uint2 cb = *reinterpret_cast<const uint2*>(Xs + (r >> 3) * GROUP_BYTES + (col >> 3) * 128 + (r & 7) * 16 + (col & 7) * 2);
+      // the bf16 text tile already in shared memory: no global loads in the epilogue.  A warp step covers one
+      // 8-row group x 16 columns (lane = row-in-group + 8 * float4-in-block), which reads the core-matrix text
+      // tile as one contiguous 256-byte run (no bank conflicts) and stores 64-byte runs per output row.
+      const int nblk = (d + 15) >> 4;
+      for (int it = warp; it < (TX / 8) * nblk; it += NTHREADS / 32) {
+        const int g8 = it / nblk, blk = it - g8 * nblk;
+        const int r = g8 * 8 + (lane & 7), col = blk * 16 + (lane >> 3) * 4;
+        if (x0 + r >= a.LX || col >= d) continue;
+        const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + col);
+        const uint2 cb = *reinterpret_cast<const uint2*>(Xs + g8 * GROUP_BYTES + (col >> 3) * 128 + (r & 7) * 16 + (col & 7) * 2);
         const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cb.x));
         const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cb.y));
         const float4 cv = make_float4(c01.x * v.x, c01.y * v.y, c23.x * v.z, c23.y * v.w);
@@ -574,12 +581,12 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   auto* c_words = reinterpret_cast<unsigned long long*>(next);
   auto* q_words = c_words + (size_t)B * (LcP / 64) * 2;
 
-  PackArgs pc{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
-  bidaf_pack_kernel<<<dim3(LcP / 64, B), 256, 0, stream>>>(pc);
-  if (int rc = check_launch("bidaf_pack_kernel(text)")) return rc;
-  PackArgs pq{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, nullptr, keep_scale, Lq, LqP, d, 0};
-  bidaf_pack_kernel<<<dim3(LqP / 64, B), 256, 0, stream>>>(pq);
-  if (int rc = check_launch("bidaf_pack_kernel(modality)")) return rc;
+  PackPair pp;
+  pp.side[0] = PackArgs{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
+  pp.side[1] = PackArgs{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, nullptr, keep_scale,
+                        Lq, LqP, d, 0};
+  bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 64, B, 2), 256, 0, stream>>>(pp);
+  if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
   {   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
     TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, Lq, LqP, Lc, LcP, d};

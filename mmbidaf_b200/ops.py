@@ -54,7 +54,7 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
     _lib.check(L.mmb_bidaf_fwd(p(text), p(modality), p(tm), p(mm), p(wt), p(wm), p(wc), p(bias.detach().contiguous()),
                                p(kt), p(km), float(keep_scale), p(out), p(q2c), p(lse_row), p(lse_col), p(ws),
                                B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
-    _count(2 if precision == PREC_FP32 else 4)
+    _count(2 if precision == PREC_FP32 else 3)
     return out, q2c, lse_row, lse_col
 
 

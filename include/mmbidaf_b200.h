@@ -101,53 +101,71 @@ MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, c
                            int H, int ndir, mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
- * Multimodal attention decoder, one step.  Replaces attention.py:145-186.
- * Device pointers to the module's parameters, named as in attention.py:119-142 (weights are
- * nn.Linear layout (out,in); *b are the biases).
+ * Multimodal attention decoder, one step (replaces attention.py:145-186).
+ *
+ * The step is a chain of chunk-parallel kernels around small batched GEMMs that the caller issues with its
+ * BLAS (they are plain (B x K) x (K x N) products over the whole batch):
+ *   hw    (B,4*2H) = h [W2;W4;W_beta_2;W_beta_4]^T + [b2+bc1; b4+bc2; bb2; bb4]
+ *   mmb_decoder_attn_fwd      energies + un-masked soft-max over the text axis + contexts c1,c2 (attention.py:147-156)
+ *   pb    (2,B,2H) = c_k W_beta_{1,3}^T + bias
+ *   mmb_decoder_attn_finish   2-way modality soft-max, attended context, att_cov, coverage (attention.py:161-177);
+ *                             also assembles xcat (B, 2H+E+H) = [ctx | sent_embed | h]
+ *   gates (B,4H)   = xcat [W_ih | W_hh]^T + b_ih + b_hh
+ *   mmb_decoder_cell_fwd      LSTM cell point-wise part (attention.py:181); gates become the activated gates
+ *   logits (B,M)   = h' out.weight^T + out.bias
+ *   mmb_decoder_out_softmax   masked soft-max (attention.py:184) in place + first-max arg-max
+ * proj_a = W1(enc_a) + b1 and proj_i = W3(enc_i) + b3 are step invariant and computed once by the caller.
+ * Vectors v1, wc1 (= Wc1.weight), v2, wc2, vb1 (= v_beta_1.weight), vb2 have 2H entries; *b are 1-element biases.
+ * nch = mmb_decoder_chunks(B, Lt) is the number of text chunks (scratch sizes depend on it):
+ *   p (B,2,Lt)  stats (B,nch,4)  ctxp (B,nch,2,2H)  ctx12 (2,B,2H)  scale (B,2,nch)
  */
-typedef struct mmb_decoder_weights {
-  const float *W2, *b2, *Wc1, *bc1, *v1, *v1b;           /* text-audio additive attention (W1 is pre-applied) */
-  const float *W4, *b4, *Wc2, *bc2, *v2, *v2b;           /* text-image additive attention (W3 is pre-applied) */
-  const float *Wb1, *bb1, *Wb2, *bb2, *Wb3, *bb3, *Wb4, *bb4, *vb1, *vb1b, *vb2, *vb2b;   /* W_beta_1..4, v_beta_1..2 */
-  const float *lstm_w_ih, *lstm_w_hh, *lstm_b_ih, *lstm_b_hh;   /* lstm.weight_ih_l0 (4H, 2H+E) ... */
-  const float *out_w, *out_b;                            /* out: Linear(H -> M) */
-} mmb_decoder_weights;
+MMB_API int mmb_decoder_chunks(int B, int Lt);
+MMB_API int mmb_decoder_attn_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
+                                 const float* hw, const float* coverage, const float* v1, const float* wc1,
+                                 const float* v2, const float* wc2, const float* v1b, const float* v2b, float* p,
+                                 float* stats, float* ctxp, float* ctx12, float* scale, int B, int Lt, int D, int nch,
+                                 mmb_stream_t stream);
+/* p_alpha: in = p from mmb_decoder_attn_fwd, out = the attention weights alpha (B,2,Lt). */
+MMB_API int mmb_decoder_attn_finish(const float* pb, const float* hw, const float* ctx12, const float* scale,
+                                    const float* coverage, const float* sent, const float* h, const float* vb1,
+                                    const float* vb2, const float* vb1b, const float* vb2b, float* p_alpha, float* xcat,
+                                    float* att_cov, float* cov_out, float* beta, int B, int Lt, int D, int E, int H,
+                                    int nch, mmb_stream_t stream);
+MMB_API int mmb_decoder_cell_fwd(float* gates, const float* cell, float* h_out, float* cell_out, int B, int H,
+                                 mmb_stream_t stream);
+MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long long* argmax, int B, int M,
+                                    mmb_stream_t stream);
 
-/*   proj_a = W1(enc_a) + b1, proj_i = W3(enc_i) + b3 (B,Lt,2H): step-invariant GEMMs done once by the caller
- *   enc_a, enc_i (B,Lt,2H)   sent_embed (B,E)   h, cell (B,H)   coverage (B,Lt)   mask (B,M)
- * Outputs: probs (B,M) = masked_softmax(out(h')) (attention.py:184); h_out, cell_out (B,H);
- *   att_cov, cov_out (B,Lt) (attention.py:167,177); argmax (B) int64 first-max index of probs (nullable);
- *   ctx (B,2H) the attended context (also a workspace); alpha (B,2,Lt), beta (B,2), gates (B,4H): nullable,
- *   saved for a backward pass.  `w` is a HOST pointer to the struct.
+/* Backward of the step, same structure in reverse (GEMMs by the caller between the kernels):
+ *   mmb_decoder_out_softmax_bwd   d_logits = p (d_probs - sum p d_probs)            [d_probs may be NULL = 0]
+ *   d_h'   = d_h_out + d_logits out.weight
+ *   mmb_decoder_cell_bwd          activated gates -> d pre-activations d_gates (B,4H), d_cell
+ *   d_xcat = d_gates [W_ih | W_hh]                 (its first 2H columns are d ctx, row stride ldx)
+ *   mmb_decoder_attn_finish_bwd   datt (B,Lt) = d_att_cov + d_cov_out, d_pre_b (2,B,2H) = d(W_beta tanh argument),
+ *                                 d_ctx12 (2,B,2H) = beta_k d ctx   (the caller adds d_pre_b W_beta_{1,3})
+ *   mmb_decoder_attn_bwd          sweeps over the text chunks: d_alpha, soft-max / tanh backward, d_cov,
+ *                                 d_proj_a / d_proj_i ACCUMULATED in place (+=), d_hw4 (B,4*2H) = d(hw)
+ *   d_h    = d_xcat[:, 2H+E:] + d_hw4 [W2;W4;W_beta_2;W_beta_4]
+ * vec_acc (B,6,2H) += [dWc1, dWc2, dv1, dv2, dv_beta_1, dv_beta_2]; scal_acc (B,4) += their scalar biases.
+ * Scratch: d_alpha (B,2,Lt)  spart (B,nch,2)  colp (B,nch,2,3,2H)  separt (B,nch,2).
  */
-MMB_API int mmb_decoder_step_fwd(const mmb_decoder_weights* w, const float* proj_a, const float* proj_i,
-                                 const float* enc_a, const float* enc_i, const float* sent_embed, const float* h,
-                                 const float* cell, const float* coverage, const uint8_t* mask, float* probs,
-                                 float* h_out, float* cell_out, float* att_cov, float* cov_out, long long* argmax,
-                                 float* ctx, float* alpha, float* beta, float* gates, float* ctx12, int B, int Lt,
-                                 int H, int E, int M, mmb_stream_t stream);
-
-/* Backward of one decoder step (two launches: output layer + LSTM cell, then the attentions).
- * Inputs: the step's saved forward tensors (probs, h_out, cell_out, gates, alpha, beta, ctx12, and the
- * step inputs h, cell, coverage, proj_*, enc_*) and the incoming gradients d_probs (B,M), d_h_out,
- * d_cell_out (B,H), d_att_cov, d_cov_out (B,Lt).
- * Outputs
- *   d_h, d_cell (B,H), d_cov (B,Lt): gradients of the step inputs
- *   d_proj_a, d_proj_i (B,Lt,2H): ACCUMULATED in place (+=) across the steps of one sequence
- *   per-step rows for the deferred weight-gradient GEMMs:
- *     d_logits (B,M), d_gates (B,4H), d_ctx12 (B,2,2H) = d(loss)/d(c1), d(c2),
- *     d_pre (B,4,2H) = d tanh-argument sums [W2-side, W4-side, W_beta_1/2-side, W_beta_3/4-side]
- *   vec_acc (B,6,2H) += [dWc1, dWc2, dv1, dv2, dv_beta_1, dv_beta_2];  scal_acc (B,4) += their biases.
- */
-MMB_API int mmb_decoder_step_bwd(const mmb_decoder_weights* w, const float* proj_a, const float* proj_i,
-                                 const float* enc_a, const float* enc_i, const float* h, const float* cell,
-                                 const float* coverage, const float* probs, const float* h_out, const float* cell_out,
-                                 const float* gates, const float* alpha, const float* beta, const float* ctx12,
-                                 const float* d_probs, const float* d_h_out, const float* d_cell_out,
-                                 const float* d_att_cov, const float* d_cov_out, float* d_h, float* d_cell, float* d_cov,
-                                 float* d_proj_a, float* d_proj_i, float* d_logits, float* d_gates, float* d_ctx12,
-                                 float* d_pre, float* vec_acc, float* scal_acc, float* d_ctx, int B, int Lt, int H,
-                                 int E, int M, mmb_stream_t stream);
+MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, float* d_logits, int B, int M,
+                                        mmb_stream_t stream);
+MMB_API int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const float* cell_out, const float* d_h,
+                                 const float* d_cell_out, float* d_gates, float* d_cell, int B, int H,
+                                 mmb_stream_t stream);
+MMB_API int mmb_decoder_attn_finish_bwd(const float* d_xcat, int ldx, const float* d_att_cov, const float* d_cov_out,
+                                        const float* alpha, const float* beta, const float* ctx12, const float* pb,
+                                        const float* hw, const float* vb1, const float* vb2, float* datt, float* d_pre_b,
+                                        float* d_ctx12, float* vec_acc, float* scal_acc, int B, int Lt, int D,
+                                        mmb_stream_t stream);
+MMB_API int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
+                                 const float* hw, const float* coverage, const float* alpha, const float* beta,
+                                 const float* datt, const float* d_ctx12, const float* d_cov_out, const float* d_pre_b,
+                                 const float* v1, const float* wc1, const float* v2, const float* wc2, float* d_alpha,
+                                 float* spart, float* d_proj_a, float* d_proj_i, float* d_cov, float* colp, float* separt,
+                                 float* d_hw4, float* vec_acc, float* scal_acc, int B, int Lt, int D, int nch,
+                                 mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
  * masked_softmax over the last axis (attention.py:78-98): y = softmax(mask ? x : -1e30), or

@@ -29,8 +29,15 @@ SIGNATURES = {
     "mmb_bidaf_workspace_bytes": [c_int] * 6,
     "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
-    "mmb_decoder_step_fwd": [c_void_p] * 21 + [c_int] * 5 + [c_void_p],
-    "mmb_decoder_step_bwd": [c_void_p] * 32 + [c_int] * 5 + [c_void_p],
+    "mmb_decoder_chunks": [c_int, c_int],
+    "mmb_decoder_attn_fwd": [c_void_p] * 17 + [c_int] * 4 + [c_void_p],
+    "mmb_decoder_attn_finish": [c_void_p] * 16 + [c_int] * 6 + [c_void_p],
+    "mmb_decoder_cell_fwd": [c_void_p] * 4 + [c_int] * 2 + [c_void_p],
+    "mmb_decoder_out_softmax": [c_void_p] * 3 + [c_int] * 2 + [c_void_p],
+    "mmb_decoder_out_softmax_bwd": [c_void_p] * 3 + [c_int] * 2 + [c_void_p],
+    "mmb_decoder_cell_bwd": [c_void_p] * 7 + [c_int] * 2 + [c_void_p],
+    "mmb_decoder_attn_finish_bwd": [c_void_p, c_int] + [c_void_p] * 14 + [c_int] * 3 + [c_void_p],
+    "mmb_decoder_attn_bwd": [c_void_p] * 26 + [c_int] * 4 + [c_void_p],
     "mmb_masked_softmax_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p],
     "mmb_masked_softmax_bwd": [c_void_p] * 4 + [ctypes.c_longlong, c_int, c_int, c_void_p],
 }
@@ -40,11 +47,6 @@ _RESTYPES = {"mmb_last_error": ctypes.c_char_p, "mmb_bidaf_workspace_bytes": c_s
 DECODER_WEIGHT_FIELDS = ("W2", "b2", "Wc1", "bc1", "v1", "v1b", "W4", "b4", "Wc2", "bc2", "v2", "v2b",
                          "Wb1", "bb1", "Wb2", "bb2", "Wb3", "bb3", "Wb4", "bb4", "vb1", "vb1b", "vb2", "vb2b",
                          "lstm_w_ih", "lstm_w_hh", "lstm_b_ih", "lstm_b_hh", "out_w", "out_b")
-
-
-class DecoderWeights(ctypes.Structure):
-    """struct mmb_decoder_weights: device pointers to the decoder's parameters."""
-    _fields_ = [(name, c_void_p) for name in DECODER_WEIGHT_FIELDS]
 
 
 def load() -> ctypes.CDLL:

@@ -154,26 +154,23 @@ def masked_softmax(logits: torch.Tensor, mask: torch.Tensor, dim: int = -1, log_
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Decoder: fused step kernels under autograd.  Weight gradients are not formed per step: every step's
-# backward appends the rows they are built from to a tape, and one set of GEMMs per sequence finishes them.
+# Decoder: step kernels under autograd.  Weight gradients are not formed per step: every step's backward
+# appends the rows they are built from to a tape, and one set of GEMMs per sequence finishes them.
 # ---------------------------------------------------------------------------------------------------------
 class DecoderTape:
     """State shared by the steps of one decode sequence (same encoder outputs)."""
 
-    def __init__(self, w_struct, held, enc_a, enc_i, proj_a, proj_i, out_size):
-        self.w, self.held = w_struct, held
-        self.enc_a, self.enc_i = enc_a.detach().contiguous(), enc_i.detach().contiguous()
-        self.proj_a, self.proj_i = proj_a.detach().contiguous(), proj_i.detach().contiguous()
-        self.M = out_size
-        self.rows = {k: [] for k in ("h_prev", "xcat", "h_out", "alpha", "dlog", "da", "dctx12", "dpre", "ctx12")}
+    def __init__(self, seq):
+        self.seq = seq
+        self.rows = {k: [] for k in ("h_prev", "xcat", "h_out", "alpha", "dlog", "da", "dctx12", "dhw4", "dpre", "ctx12")}
         self.d_proj_a = self.d_proj_i = self.vec_acc = self.scal_acc = None
 
     def open_accumulators(self):
         if self.d_proj_a is None:
-            B, Lt, D = self.enc_a.shape
-            self.d_proj_a, self.d_proj_i = torch.zeros_like(self.proj_a), torch.zeros_like(self.proj_i)
-            self.vec_acc = self.enc_a.new_zeros(B, 6, D)
-            self.scal_acc = self.enc_a.new_zeros(B, 4)
+            s = self.seq
+            self.d_proj_a, self.d_proj_i = torch.zeros_like(s.proj_a), torch.zeros_like(s.proj_i)
+            self.vec_acc = s.enc_a.new_zeros(s.B, 6, s.D)
+            self.scal_acc = s.enc_a.new_zeros(s.B, 4)
 
 
 class _DecoderOpen(torch.autograd.Function):
@@ -191,28 +188,35 @@ class _DecoderOpen(torch.autograd.Function):
         tape, r = ctx.tape, ctx.tape.rows
         if not r["dlog"]:
             return (None,) * (5 + len(ctx.shapes))
-        B, Lt, D = tape.enc_a.shape
+        s = tape.seq
+        B, D, H, E = s.B, s.D, s.H, s.E
         cat = lambda k: torch.cat(r[k], dim=0)
-        h_prev, xcat, h_out, dlog, da = cat("h_prev"), cat("xcat"), cat("h_out"), cat("dlog"), cat("da")
-        dpre, ctx12 = cat("dpre"), cat("ctx12")                              # (S*B, 4, D), (S*B, 2, D)
+        h_prev, xcat, h_out, dlog, da, dhw4 = cat("h_prev"), cat("xcat"), cat("h_out"), cat("dlog"), cat("da"), cat("dhw4")
+        S = len(r["dlog"])
+        kmajor = lambda k: torch.stack(r[k], dim=0).permute(1, 0, 2, 3).reshape(2, S * B, D)   # (S,2,B,D) -> (2,S*B,D)
+        dpre, ctx12 = kmajor("dpre"), kmajor("ctx12")
         vec, scal = tape.vec_acc.sum(dim=0), tape.scal_acc.sum(dim=0)        # (6, D), (4)
-        pre_sum = dpre.sum(dim=0)                                            # (4, D)
+        d_wh4 = dhw4.t() @ h_prev                                            # (4D, H): W2 | W4 | W_beta_2 | W_beta_4
+        hw_sum = dhw4.sum(dim=0)
+        d_wb13 = torch.bmm(dpre.transpose(1, 2), ctx12)                      # (2, D, D): W_beta_1 | W_beta_3
+        pre_sum = dpre.sum(dim=1)
+        d_wcat = da.t() @ xcat                                               # (4H, D+E+H): W_ih | W_hh
         gate_sum = da.sum(dim=0)
         g = {
-            "W2": dpre[:, 0].t() @ h_prev, "b2": pre_sum[0], "Wc1": vec[0].reshape(D, 1), "bc1": pre_sum[0],
+            "W2": d_wh4[:D], "b2": hw_sum[:D], "Wc1": vec[0].reshape(D, 1), "bc1": hw_sum[:D],
             "v1": vec[2].reshape(1, D), "v1b": scal[0:1],
-            "W4": dpre[:, 1].t() @ h_prev, "b4": pre_sum[1], "Wc2": vec[1].reshape(D, 1), "bc2": pre_sum[1],
+            "W4": d_wh4[D:2 * D], "b4": hw_sum[D:2 * D], "Wc2": vec[1].reshape(D, 1), "bc2": hw_sum[D:2 * D],
             "v2": vec[3].reshape(1, D), "v2b": scal[1:2],
-            "Wb1": dpre[:, 2].t() @ ctx12[:, 0], "bb1": pre_sum[2], "Wb2": dpre[:, 2].t() @ h_prev, "bb2": pre_sum[2],
-            "Wb3": dpre[:, 3].t() @ ctx12[:, 1], "bb3": pre_sum[3], "Wb4": dpre[:, 3].t() @ h_prev, "bb4": pre_sum[3],
+            "Wb1": d_wb13[0], "bb1": pre_sum[0], "Wb2": d_wh4[2 * D:3 * D], "bb2": hw_sum[2 * D:3 * D],
+            "Wb3": d_wb13[1], "bb3": pre_sum[1], "Wb4": d_wh4[3 * D:], "bb4": hw_sum[3 * D:],
             "vb1": vec[4].reshape(1, D), "vb1b": scal[2:3], "vb2": vec[5].reshape(1, D), "vb2b": scal[3:4],
-            "lstm_w_ih": da.t() @ xcat, "lstm_w_hh": da.t() @ h_prev, "lstm_b_ih": gate_sum, "lstm_b_hh": gate_sum,
+            "lstm_w_ih": d_wcat[:, :D + E], "lstm_w_hh": d_wcat[:, D + E:], "lstm_b_ih": gate_sum, "lstm_b_hh": gate_sum,
             "out_w": dlog.t() @ h_out, "out_b": dlog.sum(dim=0),
         }
         alpha = torch.stack(r["alpha"], dim=0)                               # (S, B, 2, Lt)
-        dctx12 = torch.stack(r["dctx12"], dim=0)                             # (S, B, 2, D)
-        d_enc_a = torch.bmm(alpha[:, :, 0].permute(1, 2, 0), dctx12[:, :, 0].permute(1, 0, 2))
-        d_enc_i = torch.bmm(alpha[:, :, 1].permute(1, 2, 0), dctx12[:, :, 1].permute(1, 0, 2))
+        dctx12 = torch.stack(r["dctx12"], dim=0)                             # (S, 2, B, D)
+        d_enc_a = torch.bmm(alpha[:, :, 0].permute(1, 2, 0), dctx12[:, 0].permute(1, 0, 2))
+        d_enc_i = torch.bmm(alpha[:, :, 1].permute(1, 2, 0), dctx12[:, 1].permute(1, 0, 2))
         from ._lib import DECODER_WEIGHT_FIELDS
         grads = [g[name].reshape(shape) for name, shape in zip(DECODER_WEIGHT_FIELDS, ctx.shapes)]
         for v in r.values():
@@ -223,27 +227,25 @@ class _DecoderOpen(torch.autograd.Function):
 class _DecoderStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tape, token, sent, h, cell, cov, mask_u8):
-        probs, h_out, cell_out, att, cov_out, _, saved = ops.decoder_step_fwd(
-            tape.w, tape.proj_a, tape.proj_i, tape.enc_a, tape.enc_i, sent, h, cell, cov, mask_u8, tape.M, save=True)
+        probs, h_out, cell_out, att, cov_out, _, saved = ops.decoder_step_fwd(tape.seq, sent, h, cell, cov, mask_u8)
         ctx.tape = tape
-        ctx.E = sent.shape[1]
-        ctx.save_for_backward(sent, h, cell, cov, probs, h_out, cell_out, *saved)
+        ctx.save_for_backward(h, cell, cov, probs, h_out, cell_out, *saved)
         ctx.set_materialize_grads(False)
         return probs, h_out, cell_out, att, cov_out
 
     @staticmethod
     def backward(ctx, d_probs, d_h_out, d_cell_out, d_att, d_cov_out):
         tape = ctx.tape
-        sent, h, cell, cov, probs, h_out, cell_out, cvec, alpha, beta, gates, ctx12 = ctx.saved_tensors
+        h, cell, cov, probs, h_out, cell_out, *saved = ctx.saved_tensors
         tape.open_accumulators()
-        d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_pre = ops.decoder_step_bwd(
-            tape.w, tape.proj_a, tape.proj_i, tape.enc_a, tape.enc_i, h, cell, cov, probs, h_out, cell_out, gates, alpha,
-            beta, ctx12, d_probs, d_h_out, d_cell_out, d_att, d_cov_out, tape.d_proj_a, tape.d_proj_i, tape.vec_acc,
-            tape.scal_acc, ctx.E, tape.M)
+        d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b = ops.decoder_step_bwd(
+            tape.seq, h, cell, cov, probs, cell_out, saved, d_probs, d_h_out, d_cell_out, d_att, d_cov_out,
+            tape.d_proj_a, tape.d_proj_i, tape.vec_acc, tape.scal_acc)
+        hw, alpha, beta, ctx12, pb, xcat, gates = saved
         r = tape.rows
-        r["h_prev"].append(h); r["xcat"].append(torch.cat([cvec, sent], dim=1)); r["h_out"].append(h_out)
-        r["alpha"].append(alpha); r["dlog"].append(d_logits); r["da"].append(d_gates)
-        r["dctx12"].append(d_ctx12); r["dpre"].append(d_pre); r["ctx12"].append(ctx12)
+        r["h_prev"].append(h); r["xcat"].append(xcat); r["h_out"].append(h_out); r["alpha"].append(alpha)
+        r["dlog"].append(d_logits); r["da"].append(d_gates); r["dctx12"].append(d_ctx12); r["dhw4"].append(d_hw4)
+        r["dpre"].append(d_pre_b); r["ctx12"].append(ctx12)
         return None, torch.zeros_like(d_h[:1, 0]), None, d_h, d_cell, d_cov, None
 
 

@@ -143,31 +143,18 @@ class MultimodalAttentionDecoder(nn.Module):
             return c
         proj_a, proj_i = self.W1(enc_a), self.W3(enc_i)              # hoisted: the reference recomputes them per step
         c = {"a": weakref.ref(enc_a), "i": weakref.ref(enc_i), "key": (enc_a._version, enc_i._version, grad),
-             "proj_a": proj_a, "proj_i": proj_i, "tape": None, "token": None}
+             "proj_a": proj_a, "proj_i": proj_i, "seq": None, "tape": None, "token": None}
+        params = {name: self._param_of(name) for name in _lib_fields()}
+        c["seq"] = ops.DecoderSeq(params, enc_a, enc_i, proj_a, proj_i, self.output_size)
         needs_grad = grad and (proj_a.requires_grad or enc_a.requires_grad or enc_i.requires_grad)
         if needs_grad:
-            w, held = self._weight_struct()
-            tape = Fn.DecoderTape(w, held, enc_a, enc_i, proj_a, proj_i, self.output_size)
-            params = [self._param_of(name) for name in _lib_fields()]
-            c["tape"], c["token"] = tape, Fn.decoder_open(tape, proj_a, proj_i, enc_a, enc_i, params)
+            tape = Fn.DecoderTape(c["seq"])
+            c["tape"], c["token"] = tape, Fn.decoder_open(tape, proj_a, proj_i, enc_a, enc_i, list(params.values()))
         self._cache = c
         return c
 
     def _param_of(self, field):
         return _FIELD_TO_PARAM[field](self)
-
-    def _weight_struct(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        hit = getattr(self, "_wstruct", None)
-        if hit is not None and hit[0] == key:
-            return hit[1], hit[2]
-        w, held = self._build_weight_struct()
-        object.__setattr__(self, "_wstruct", (key, w, held))
-        return w, held
-
-    def _build_weight_struct(self):
-        held = {f: self._param_of(f).detach().contiguous() for f in _lib_fields()}
-        return ops.decoder_weights(held), held
 
     def forward(self, sent_embed, decoder_hidden, decoder_cell_state, text_audio_enc_out, text_img_enc_out,
                 coverage_vec, mask):
@@ -184,9 +171,5 @@ class MultimodalAttentionDecoder(nn.Module):
         if seq["tape"] is not None:
             probs, h, cell, att, cov = Fn.decoder_step(seq["tape"], seq["token"], sent, h, cell, cov, ops._u8(mask))
         else:
-            w, keep_alive = self._weight_struct()
-            probs, h, cell, att, cov, _, _ = ops.decoder_step_fwd(
-                w, seq["proj_a"].contiguous(), seq["proj_i"].contiguous(), text_audio_enc_out.contiguous(),
-                text_img_enc_out.contiguous(), sent, h, cell, cov, ops._u8(mask), self.output_size)
-            del keep_alive
+            probs, h, cell, att, cov, _, _ = ops.decoder_step_fwd(seq["seq"], sent, h, cell, cov, ops._u8(mask))
         return probs, h.unsqueeze(1), cell.unsqueeze(0), att.unsqueeze(2), cov.unsqueeze(2)

@@ -93,68 +93,100 @@ def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, 
     return gates
 
 
-def decoder_weights(params: dict) -> "_lib.DecoderWeights":
-    """Pack device pointers of the decoder parameters (keys = _lib.DECODER_WEIGHT_FIELDS)."""
-    w = _lib.DecoderWeights()
-    for name in _lib.DECODER_WEIGHT_FIELDS:
-        t = params[name]
-        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, name
-        setattr(w, name, t.data_ptr())
-    return w
+class DecoderSeq:
+    """Everything that is constant over the steps of one decode sequence (attention.py:145-186): the batched
+    weight matrices of the small GEMMs, the vectors the kernels read, the hoisted projections and the chunking.
+
+    ``params`` maps the names of ``_lib.DECODER_WEIGHT_FIELDS`` to (detached) parameter tensors."""
+
+    def __init__(self, params: dict, enc_a, enc_i, proj_a, proj_i, out_size: int):
+        P = {k: v.detach() for k, v in params.items()}
+        self.enc_a, self.enc_i = enc_a.detach().contiguous(), enc_i.detach().contiguous()
+        self.proj_a, self.proj_i = proj_a.detach().contiguous(), proj_i.detach().contiguous()
+        self.B, self.Lt, self.D = self.enc_a.shape
+        self.H, self.M = self.D // 2, out_size
+        self.E = P["lstm_w_ih"].shape[1] - self.D
+        self.Wh4 = torch.cat([P["W2"], P["W4"], P["Wb2"], P["Wb4"]], dim=0).contiguous()           # (4D, H)
+        self.bh4 = torch.cat([P["b2"] + P["bc1"], P["b4"] + P["bc2"], P["bb2"], P["bb4"]]).contiguous()
+        self.Wb13 = torch.stack([P["Wb1"], P["Wb3"]]).contiguous()                                 # (2, D, D)
+        self.bb13 = torch.stack([P["bb1"], P["bb3"]]).unsqueeze(1).contiguous()                    # (2, 1, D)
+        self.Wcat = torch.cat([P["lstm_w_ih"], P["lstm_w_hh"]], dim=1).contiguous()                # (4H, D+E+H)
+        self.bcat = (P["lstm_b_ih"] + P["lstm_b_hh"]).contiguous()
+        self.out_w, self.out_b = P["out_w"].contiguous(), P["out_b"].contiguous()
+        flat = lambda k: P[k].reshape(-1).contiguous()
+        self.v1, self.wc1, self.v2, self.wc2 = flat("v1"), flat("Wc1"), flat("v2"), flat("Wc2")
+        self.vb1, self.vb2 = flat("vb1"), flat("vb2")
+        self.v1b, self.v2b, self.vb1b, self.vb2b = flat("v1b"), flat("v2b"), flat("vb1b"), flat("vb2b")
+        self.nch = _lib.lib().mmb_decoder_chunks(self.B, self.Lt)
 
 
-def decoder_step_fwd(w, proj_a, proj_i, enc_a, enc_i, sent_embed, h, cell, coverage, mask_u8, M: int,
-                     want_argmax: bool = False, save: bool = False):
-    """One fused decoder step (attention.py:145-186).  All tensors 2-D/3-D contiguous fp32 CUDA:
-    proj_*/enc_* (B,Lt,2H), sent_embed (B,E), h/cell (B,H), coverage (B,Lt), mask_u8 (B,M) uint8.
-    Returns (probs, h', cell', att_cov, coverage', argmax|None, saved) with saved = (ctx, alpha, beta, gates)."""
-    import ctypes
+def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_argmax: bool = False):
+    """One decoder step.  sent (B,E), h/cell (B,H), coverage (B,Lt), mask_u8 (B,M) uint8 -- contiguous fp32 CUDA.
+    Returns (probs, h', cell', att_cov, coverage', argmax|None, saved) where ``saved`` is what
+    :func:`decoder_step_bwd` needs: (hw, alpha, beta, ctx12, pb, xcat, gates)."""
     lib = _lib.lib()
-    B, Lt, D = enc_a.shape
-    H, E = D // 2, sent_embed.shape[1]
-    dev = enc_a.device
-    f32 = dict(device=dev, dtype=torch.float32)
-    probs = torch.empty(B, M, **f32)
+    B, Lt, D, H, E, M, nch = seq.B, seq.Lt, seq.D, seq.H, seq.E, seq.M, seq.nch
+    f32 = dict(device=h.device, dtype=torch.float32)
+    p = _lib.ptr
+    st = _lib.stream()
+    hw = torch.addmm(seq.bh4, h, seq.Wh4.t())                                  # (B, 4D)  library GEMM
+    alpha = torch.empty(B, 2, Lt, **f32)
+    stats, ctxp = torch.empty(B, nch, 4, **f32), torch.empty(B, nch, 2, D, **f32)
+    ctx12, scale = torch.empty(2, B, D, **f32), torch.empty(B, 2, nch, **f32)
+    _lib.check(lib.mmb_decoder_attn_fwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
+                                        p(seq.v1), p(seq.wc1), p(seq.v2), p(seq.wc2), p(seq.v1b), p(seq.v2b), p(alpha),
+                                        p(stats), p(ctxp), p(ctx12), p(scale), B, Lt, D, nch, st), "mmb_decoder_attn_fwd")
+    pb = torch.baddbmm(seq.bb13, ctx12, seq.Wb13.transpose(1, 2))              # (2, B, D)  library GEMM
+    xcat = torch.empty(B, D + E + H, **f32)
+    att_cov, cov_out, beta = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32), torch.empty(B, 2, **f32)
+    _lib.check(lib.mmb_decoder_attn_finish(p(pb), p(hw), p(ctx12), p(scale), p(coverage), p(sent), p(h), p(seq.vb1),
+                                           p(seq.vb2), p(seq.vb1b), p(seq.vb2b), p(alpha), p(xcat), p(att_cov),
+                                           p(cov_out), p(beta), B, Lt, D, E, H, nch, st), "mmb_decoder_attn_finish")
+    gates = torch.addmm(seq.bcat, xcat, seq.Wcat.t())                          # (B, 4H)  library GEMM
     h_out, cell_out = torch.empty(B, H, **f32), torch.empty(B, H, **f32)
-    att_cov, cov_out = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32)
-    ctx = torch.empty(B, D, **f32)
-    argmax = torch.empty(B, device=dev, dtype=torch.int64) if want_argmax else None
-    alpha = torch.empty(B, 2, Lt, **f32) if save else None
-    beta = torch.empty(B, 2, **f32) if save else None
-    gates = torch.empty(B, 4 * H, **f32) if save else None
-    ctx12 = torch.empty(B, 2, D, **f32) if save else None
-    p = _lib.ptr
-    _lib.check(lib.mmb_decoder_step_fwd(ctypes.addressof(w), p(proj_a), p(proj_i), p(enc_a), p(enc_i), p(sent_embed),
-                                        p(h), p(cell), p(coverage), p(mask_u8), p(probs), p(h_out), p(cell_out),
-                                        p(att_cov), p(cov_out), p(argmax), p(ctx), p(alpha), p(beta), p(gates),
-                                        p(ctx12), B, Lt, H, E, M, _lib.stream()), "mmb_decoder_step_fwd")
-    _count(3)
-    return probs, h_out, cell_out, att_cov, cov_out, argmax, (ctx, alpha, beta, gates, ctx12)
+    _lib.check(lib.mmb_decoder_cell_fwd(p(gates), p(cell), p(h_out), p(cell_out), B, H, st), "mmb_decoder_cell_fwd")
+    probs = torch.addmm(seq.out_b, h_out, seq.out_w.t())                       # (B, M) logits, library GEMM
+    argmax = torch.empty(B, device=h.device, dtype=torch.int64) if want_argmax else None
+    _lib.check(lib.mmb_decoder_out_softmax(p(probs), p(mask_u8), p(argmax), B, M, st), "mmb_decoder_out_softmax")
+    _count(6)
+    return probs, h_out, cell_out, att_cov, cov_out, argmax, (hw, alpha, beta, ctx12, pb, xcat, gates)
 
 
-def decoder_step_bwd(w, proj_a, proj_i, enc_a, enc_i, h, cell, coverage, probs, h_out, cell_out, gates, alpha, beta,
-                     ctx12, d_probs, d_h_out, d_cell_out, d_att_cov, d_cov_out, d_proj_a, d_proj_i, vec_acc, scal_acc,
-                     E: int, M: int):
-    """Backward of one decoder step.  ``d_proj_*`` (B,Lt,2H), ``vec_acc`` (B,6,2H) and ``scal_acc`` (B,4) are
-    accumulated in place.  Returns (d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_pre)."""
-    import ctypes
+def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved, d_probs, d_h_out, d_cell_out,
+                     d_att_cov, d_cov_out, d_proj_a, d_proj_i, vec_acc, scal_acc):
+    """Backward of one decoder step.  ``d_proj_*`` (B,Lt,2H), ``vec_acc`` (B,6,2H), ``scal_acc`` (B,4) are accumulated
+    in place.  Returns (d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b)."""
     lib = _lib.lib()
-    B, Lt, D = enc_a.shape
-    H = D // 2
-    f32 = dict(device=enc_a.device, dtype=torch.float32)
-    d_h, d_cell, d_cov = torch.empty(B, H, **f32), torch.empty(B, H, **f32), torch.empty(B, Lt, **f32)
-    d_logits, d_gates = torch.empty(B, M, **f32), torch.empty(B, 4 * H, **f32)
-    d_ctx12, d_pre, d_ctx = torch.empty(B, 2, D, **f32), torch.empty(B, 4, D, **f32), torch.empty(B, D, **f32)
+    B, Lt, D, H, E, M, nch = seq.B, seq.Lt, seq.D, seq.H, seq.E, seq.M, seq.nch
+    hw, alpha, beta, ctx12, pb, xcat, gates = saved
+    f32 = dict(device=h.device, dtype=torch.float32)
     p = _lib.ptr
+    st = _lib.stream()
     c = lambda t: None if t is None else t.contiguous()
-    _lib.check(lib.mmb_decoder_step_bwd(ctypes.addressof(w), p(proj_a), p(proj_i), p(enc_a), p(enc_i), p(h), p(cell),
-                                        p(coverage), p(probs), p(h_out), p(cell_out), p(gates), p(alpha), p(beta),
-                                        p(ctx12), p(c(d_probs)), p(c(d_h_out)), p(c(d_cell_out)), p(c(d_att_cov)),
-                                        p(c(d_cov_out)), p(d_h), p(d_cell), p(d_cov), p(d_proj_a), p(d_proj_i),
-                                        p(d_logits), p(d_gates), p(d_ctx12), p(d_pre), p(vec_acc), p(scal_acc),
-                                        p(d_ctx), B, Lt, H, E, M, _lib.stream()), "mmb_decoder_step_bwd")
-    _count(2)
-    return d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_pre
+    d_logits = torch.empty(B, M, **f32)
+    _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(d_logits), B, M, st), "mmb_decoder_out_softmax_bwd")
+    dh_tot = d_logits @ seq.out_w if d_h_out is None else torch.addmm(d_h_out, d_logits, seq.out_w)
+    d_gates, d_cell = torch.empty(B, 4 * H, **f32), torch.empty(B, H, **f32)
+    _lib.check(lib.mmb_decoder_cell_bwd(p(gates), p(cell), p(cell_out), p(dh_tot), p(c(d_cell_out)), p(d_gates), p(d_cell),
+                                        B, H, st), "mmb_decoder_cell_bwd")
+    d_xcat = d_gates @ seq.Wcat                                                # (B, D+E+H)  library GEMM
+    datt, d_pre_b, d_ctx12 = torch.empty(B, Lt, **f32), torch.empty(2, B, D, **f32), torch.empty(2, B, D, **f32)
+    _lib.check(lib.mmb_decoder_attn_finish_bwd(p(d_xcat), D + E + H, p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
+                                               p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(datt), p(d_pre_b),
+                                               p(d_ctx12), p(vec_acc), p(scal_acc), B, Lt, D, st),
+               "mmb_decoder_attn_finish_bwd")
+    d_ctx12.baddbmm_(d_pre_b, seq.Wb13)                                        # += d_pre W_beta   library GEMM
+    d_alpha, spart = torch.empty(B, 2, Lt, **f32), torch.empty(B, nch, 2, **f32)
+    d_cov, colp = torch.empty(B, Lt, **f32), torch.empty(B, nch, 2, 3, D, **f32)
+    separt, d_hw4 = torch.empty(B, nch, 2, **f32), torch.empty(B, 4 * D, **f32)
+    _lib.check(lib.mmb_decoder_attn_bwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
+                                        p(alpha), p(beta), p(datt), p(d_ctx12), p(c(d_cov_out)), p(d_pre_b), p(seq.v1),
+                                        p(seq.wc1), p(seq.v2), p(seq.wc2), p(d_alpha), p(spart), p(d_proj_a), p(d_proj_i),
+                                        p(d_cov), p(colp), p(separt), p(d_hw4), p(vec_acc), p(scal_acc), B, Lt, D, nch, st),
+               "mmb_decoder_attn_bwd")
+    d_h = torch.addmm(d_xcat[:, D + E:], d_hw4, seq.Wh4)                       # (B, H)  library GEMM
+    _count(6)
+    return d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b
 
 
 def masked_softmax_fwd(x2d: torch.Tensor, mask2d_u8: torch.Tensor, log_mode: bool) -> torch.Tensor:

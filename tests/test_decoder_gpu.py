@@ -22,7 +22,6 @@ def _step_fn(state):
     from mmbidaf_b200 import ops
     dev = "cuda"
     held = {f: state[p].to(dev).contiguous() for f, p in FIELD_TO_PARAM.items()}
-    w = ops.decoder_weights(held)
     W1, b1 = state["W1.weight"].to(dev), state["W1.bias"].to(dev)
     W3, b3 = state["W3.weight"].to(dev), state["W3.bias"].to(dev)
 
@@ -31,12 +30,11 @@ def _step_fn(state):
         B, Lt, D = enc_a.shape
         proj_a = torch.addmm(b1, enc_a.view(B * Lt, D), W1.t()).view(B, Lt, D)
         proj_i = torch.addmm(b3, enc_i.view(B * Lt, D), W3.t()).view(B, Lt, D)
-        out = ops.decoder_step_fwd(w, proj_a, proj_i, enc_a, enc_i, sent.to(dev).reshape(B, -1).contiguous(),
-                                   h.to(dev).reshape(B, -1).contiguous(), cell.to(dev).reshape(B, -1).contiguous(),
-                                   cov.to(dev).reshape(B, Lt).contiguous(), mask.to(dev).to(torch.uint8).contiguous(),
-                                   M, want_argmax=True, save=True)
+        seq = ops.DecoderSeq(held, enc_a, enc_i, proj_a, proj_i, M)
+        out = ops.decoder_step_fwd(seq, sent.to(dev).reshape(B, -1).contiguous(), h.to(dev).reshape(B, -1).contiguous(),
+                                   cell.to(dev).reshape(B, -1).contiguous(), cov.to(dev).reshape(B, Lt).contiguous(),
+                                   mask.to(dev).to(torch.uint8).contiguous(), want_argmax=True)
         torch.cuda.synchronize()
-        _ = held                                     # keep parameters alive while kernels run
         return out
     return run
 

@@ -282,7 +282,9 @@ def run_gpu_arm(args):
                                         "bidaf_tc_kernel<C2Q>)" if fast else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
                                        + ", BASELINE config 2 (B=64, Lc=512, Lq=256, d=200)",
                              "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "frac": round(achieved / peak, 4),
+                             "traffic": 154355456 if fast else None,      # dram read+write per forward, ncu (profiles/r01_bidaf_tc_ncu.md)
+                             "peak_source": peak_src,
                              "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1)}}
         if world == 1 and not args.no_cpu_baseline:
             vps, _, cores, sample = cpu_training_throughput(4, 3, 1)

@@ -113,7 +113,9 @@ MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, c
  *   gates (B,4H)   = xcat [W_ih | W_hh]^T + b_ih + b_hh
  *   mmb_decoder_cell_fwd      LSTM cell point-wise part (attention.py:181); gates become the activated gates
  *   logits (B,M)   = h' out.weight^T + out.bias
- *   mmb_decoder_out_softmax   masked soft-max (attention.py:184) in place + first-max arg-max
+ *   mmb_decoder_out_softmax   masked soft-max (attention.py:184) in place + first-max arg-max; with `target` (B) it
+ *                             also emits the per-video loss term nll = -log(p[target] + 1e-12)  (models.py:168-170)
+ * mmb_decoder_attn_finish likewise emits cov_loss (B) = sum_t min(att_cov, coverage') (models.py:177) when non-NULL.
  * proj_a = W1(enc_a) + b1 and proj_i = W3(enc_i) + b3 are step invariant and computed once by the caller.
  * Vectors v1, wc1 (= Wc1.weight), v2, wc2, vb1 (= v_beta_1.weight), vb2 have 2H entries; *b are 1-element biases.
  * nch = mmb_decoder_chunks(B, Lt) is the number of text chunks (scratch sizes depend on it):
@@ -129,35 +131,38 @@ MMB_API int mmb_decoder_attn_fwd(const float* proj_a, const float* proj_i, const
 MMB_API int mmb_decoder_attn_finish(const float* pb, const float* hw, const float* ctx12, const float* scale,
                                     const float* coverage, const float* sent, const float* h, const float* vb1,
                                     const float* vb2, const float* vb1b, const float* vb2b, float* p_alpha, float* xcat,
-                                    float* att_cov, float* cov_out, float* beta, int B, int Lt, int D, int E, int H,
-                                    int nch, mmb_stream_t stream);
+                                    float* att_cov, float* cov_out, float* beta, float* cov_loss, int B, int Lt, int D,
+                                    int E, int H, int nch, mmb_stream_t stream);
 MMB_API int mmb_decoder_cell_fwd(float* gates, const float* cell, float* h_out, float* cell_out, int B, int H,
                                  mmb_stream_t stream);
-MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long long* argmax, int B, int M,
-                                    mmb_stream_t stream);
+MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long long* argmax, const long long* target,
+                                    float* nll, int B, int M, mmb_stream_t stream);
 
 /* Backward of the step, same structure in reverse (GEMMs by the caller between the kernels):
  *   mmb_decoder_out_softmax_bwd   d_logits = p (d_probs - sum p d_probs)            [d_probs may be NULL = 0]
  *   d_h'   = d_h_out + d_logits out.weight
  *   mmb_decoder_cell_bwd          activated gates -> d pre-activations d_gates (B,4H), d_cell
  *   d_xcat = d_gates [W_ih | W_hh]                 (its first 2H columns are d ctx, row stride ldx)
- *   mmb_decoder_attn_finish_bwd   datt (B,Lt) = d_att_cov + d_cov_out, d_pre_b (2,B,2H) = d(W_beta tanh argument),
+ *   mmb_decoder_attn_finish_bwd   dcov_tot (B,Lt) = d_cov_out + d cov_loss, datt (B,Lt) = d_att_cov + d cov_loss + dcov_tot
+ *                                 (g_cov (B) = gradient of the fused coverage-loss term; ties of min() split evenly),
+ *                                 d_pre_b (2,B,2H) = d(W_beta tanh argument),
  *                                 d_ctx12 (2,B,2H) = beta_k d ctx   (the caller adds d_pre_b W_beta_{1,3})
- *   mmb_decoder_attn_bwd          sweeps over the text chunks: d_alpha, soft-max / tanh backward, d_cov,
+ *   mmb_decoder_attn_bwd          (d_cov_out = dcov_tot) sweeps over the text chunks: d_alpha, soft-max / tanh backward, d_cov,
  *                                 d_proj_a / d_proj_i ACCUMULATED in place (+=), d_hw4 (B,4*2H) = d(hw)
  *   d_h    = d_xcat[:, 2H+E:] + d_hw4 [W2;W4;W_beta_2;W_beta_4]
  * vec_acc (B,6,2H) += [dWc1, dWc2, dv1, dv2, dv_beta_1, dv_beta_2]; scal_acc (B,4) += their scalar biases.
  * Scratch: d_alpha (B,2,Lt)  spart (B,nch,2)  colp (B,nch,2,3,2H)  separt (B,nch,2).
  */
-MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, float* d_logits, int B, int M,
-                                        mmb_stream_t stream);
+MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
+                                        const float* g_nll, float* d_logits, int B, int M, mmb_stream_t stream);
 MMB_API int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const float* cell_out, const float* d_h,
                                  const float* d_cell_out, float* d_gates, float* d_cell, int B, int H,
                                  mmb_stream_t stream);
 MMB_API int mmb_decoder_attn_finish_bwd(const float* d_xcat, int ldx, const float* d_att_cov, const float* d_cov_out,
                                         const float* alpha, const float* beta, const float* ctx12, const float* pb,
                                         const float* hw, const float* vb1, const float* vb2, float* datt, float* d_pre_b,
-                                        float* d_ctx12, float* vec_acc, float* scal_acc, int B, int Lt, int D,
+                                        float* d_ctx12, float* vec_acc, float* scal_acc, const float* att_cov,
+                                        const float* cov_out, const float* g_cov, float* dcov_tot, int B, int Lt, int D,
                                         mmb_stream_t stream);
 MMB_API int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
                                  const float* hw, const float* coverage, const float* alpha, const float* beta,

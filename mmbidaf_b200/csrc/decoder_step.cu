@@ -198,6 +198,7 @@ struct FinishArgs {
   const float *vb1, *vb2, *vb1b, *vb2b;
   float *p_alpha;                                             // in: p (B,2,Lt)  out: alpha
   float *xcat, *att_cov, *cov_out, *beta;                     // xcat (B, D+E+H) = [ctx | sent | h]
+  float* cov_loss;                                            // (B) sum_t min(att_cov, coverage') (models.py:177) or null
   int B, Lt, D, E, H, chunk, nch;
 };
 
@@ -222,14 +223,21 @@ __global__ void __launch_bounds__(NT) dec_attn_finish_kernel(const FinishArgs a)
   float* p1 = a.p_alpha + ((size_t)b * 2 + 0) * Lt;
   float* p2 = a.p_alpha + ((size_t)b * 2 + 1) * Lt;
   const float* sc = a.scale + (size_t)b * 2 * a.nch;
+  float closs = 0.f;
   for (int t = tid; t < Lt; t += NT) {
     const int c = t / a.chunk;
     const float a1 = p1[t] * sc[c], a2 = p2[t] * sc[a.nch + c];
     p1[t] = a1;
     p2[t] = a2;
     const float att = a1 * beta1 + a2 * beta2;                 // bmm([a1 a2], beta), attention.py:167
+    const float cnew = a.cov[(size_t)b * Lt + t] + att;
     a.att_cov[(size_t)b * Lt + t] = att;
-    a.cov_out[(size_t)b * Lt + t] = a.cov[(size_t)b * Lt + t] + att;
+    a.cov_out[(size_t)b * Lt + t] = cnew;
+    closs += fminf(att, cnew);
+  }
+  if (a.cov_loss) {
+    closs = block_sum(closs, red);
+    if (tid == 0) a.cov_loss[b] = closs;
   }
   if (tid == 0) {
     a.beta[b * 2 + 0] = beta1;
@@ -254,7 +262,8 @@ __global__ void __launch_bounds__(NT) dec_cell_pointwise_kernel(float* __restric
 
 // forward 5: masked soft-max over the M outputs (attention.py:184) + first-max arg-max; logits -> probs in place
 __global__ void __launch_bounds__(NT) dec_out_softmax_kernel(float* __restrict__ logits, const uint8_t* __restrict__ mask,
-                                                             long long* __restrict__ argmax, int M) {
+                                                             long long* __restrict__ argmax, const long long* __restrict__ tgt,
+                                                             float* __restrict__ nll, int M) {
   __shared__ float red[32];
   __shared__ int redi[NW];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,6 +282,7 @@ __global__ void __launch_bounds__(NT) dec_out_softmax_kernel(float* __restrict__
     const float p = expf((mk[m] ? lg[m] : kNegFill) - mx) * inv;
     lg[m] = p;
     if (p > best) { best = p; best_i = m; }
+    if (tgt && m == (int)tgt[b]) nll[b] = -logf(p + 1e-12f);     // models.py:168-170
   }
   if (argmax) {                                                 // first maximal index, as torch.max(dim) documents
     const float gbest = block_max(best, red);
@@ -295,15 +305,22 @@ __global__ void __launch_bounds__(NT) dec_out_softmax_kernel(float* __restrict__
 // ----------------------------------------------------------------------------------------------------------
 // 1: masked soft-max backward: dlogit = p (dp - sum p dp); masked entries have p = 0
 __global__ void __launch_bounds__(NT) dec_out_softmax_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ d_probs,
+                                                                 const long long* __restrict__ tgt, const float* __restrict__ g_nll,
                                                                  float* __restrict__ d_logits, int M) {
   __shared__ float red[32];
   const int b = blockIdx.x, tid = threadIdx.x;
+  // optional sparse part: d(-log(p_tgt + eps)) = -g / (p_tgt + eps) at the target column only
+  const int tg = tgt ? (int)tgt[b] : -1;
+  const float dp_t = tgt ? -g_nll[b] / (probs[(size_t)b * M + tg] + 1e-12f) : 0.f;
   float dot = 0.f;
   if (d_probs)
     for (int m = tid; m < M; m += NT) dot = fmaf(probs[(size_t)b * M + m], d_probs[(size_t)b * M + m], dot);
   dot = block_sum(dot, red);
-  for (int m = tid; m < M; m += NT)
-    d_logits[(size_t)b * M + m] = d_probs ? probs[(size_t)b * M + m] * (d_probs[(size_t)b * M + m] - dot) : 0.f;
+  if (tgt) dot = fmaf(probs[(size_t)b * M + tg], dp_t, dot);
+  for (int m = tid; m < M; m += NT) {
+    const float dp = (d_probs ? d_probs[(size_t)b * M + m] : 0.f) + (m == tg ? dp_t : 0.f);
+    d_logits[(size_t)b * M + m] = probs[(size_t)b * M + m] * (dp - dot);
+  }
 }
 
 // 2: LSTM cell backward (point-wise): activated gates -> d pre-activations (in place), d cell
@@ -331,6 +348,8 @@ __global__ void __launch_bounds__(NT) dec_cell_bwd_kernel(float* __restrict__ ga
 struct FinishBwdArgs {
   const float *d_xcat, *d_att_cov, *d_cov_out, *alpha, *beta, *ctx12, *pb, *hw, *vb1, *vb2;
   float *datt, *d_pre_b, *d_ctx12, *vec_acc, *scal_acc;       // datt (B,Lt); d_pre_b, d_ctx12 (2,B,D)
+  const float *att, *cov_out, *g_cov;                         // fused coverage loss (g_cov (B) or null)
+  float* dcov_tot;                                            // (B,Lt) d coverage' incl. the loss term
   int B, Lt, D, ldx;
 };
 
@@ -345,8 +364,18 @@ __global__ void __launch_bounds__(NT) dec_attn_finish_bwd_kernel(const FinishBwd
     db1 = fmaf(a.ctx12[(size_t)b * D + d], g, db1);
     db2 = fmaf(a.ctx12[((size_t)a.B + b) * D + d], g, db2);
   }
+  const float gc = a.g_cov ? a.g_cov[b] : 0.f;
   for (int t = tid; t < Lt; t += NT) {
-    const float g = (a.d_att_cov ? a.d_att_cov[(size_t)b * Lt + t] : 0.f) + (a.d_cov_out ? a.d_cov_out[(size_t)b * Lt + t] : 0.f);
+    float dcv = a.d_cov_out ? a.d_cov_out[(size_t)b * Lt + t] : 0.f;
+    float g = a.d_att_cov ? a.d_att_cov[(size_t)b * Lt + t] : 0.f;
+    if (a.g_cov) {                                              // d sum min(att, cov'): ties split evenly (torch.minimum)
+      const float av = a.att[(size_t)b * Lt + t], cv = a.cov_out[(size_t)b * Lt + t];
+      const float tie = av == cv ? 0.5f * gc : 0.f;
+      g += av < cv ? gc : tie;
+      dcv += cv < av ? gc : tie;
+    }
+    a.dcov_tot[(size_t)b * Lt + t] = dcv;
+    g += dcv;                                                   // coverage' = coverage + att
     a.datt[(size_t)b * Lt + t] = g;
     db1 = fmaf(a.alpha[((size_t)b * 2 + 0) * Lt + t], g, db1);
     db2 = fmaf(a.alpha[((size_t)b * 2 + 1) * Lt + t], g, db2);
@@ -581,14 +610,14 @@ extern "C" int mmb_decoder_attn_fwd(const float* proj_a, const float* proj_i, co
 extern "C" int mmb_decoder_attn_finish(const float* pb, const float* hw, const float* ctx12, const float* scale,
                                        const float* coverage, const float* sent, const float* h, const float* vb1,
                                        const float* vb2, const float* vb1b, const float* vb2b, float* p_alpha, float* xcat,
-                                       float* att_cov, float* cov_out, float* beta, int B, int Lt, int D, int E, int H,
-                                       int nch, mmb_stream_t stream) {
+                                       float* att_cov, float* cov_out, float* beta, float* cov_loss, int B, int Lt, int D,
+                                       int E, int H, int nch, mmb_stream_t stream) {
   MMB_REQUIRE(pb && hw && ctx12 && scale && coverage && sent && h && vb1 && vb2 && vb1b && vb2b && p_alpha && xcat &&
                   att_cov && cov_out && beta,
               MMB_ERR_INVALID, "mmb_decoder_attn_finish: null pointer");
   const int chunk = (Lt + nch - 1) / nch;
   FinishArgs a{pb, hw, ctx12, scale, coverage, sent, h, vb1, vb2, vb1b, vb2b, p_alpha, xcat, att_cov, cov_out, beta,
-               B, Lt, D, E, H, chunk, nch};
+               cov_loss, B, Lt, D, E, H, chunk, nch};
   dec_attn_finish_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("dec_attn_finish_kernel");
 }
@@ -600,17 +629,18 @@ extern "C" int mmb_decoder_cell_fwd(float* gates, const float* cell, float* h_ou
   return check_launch("dec_cell_pointwise_kernel");
 }
 
-extern "C" int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long long* argmax, int B, int M,
-                                       mmb_stream_t stream) {
-  MMB_REQUIRE(logits && mask && B > 0 && M > 0, MMB_ERR_INVALID, "mmb_decoder_out_softmax: bad arguments");
-  dec_out_softmax_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(logits, mask, argmax, M);
+extern "C" int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long long* argmax, const long long* target,
+                                       float* nll, int B, int M, mmb_stream_t stream) {
+  MMB_REQUIRE(logits && mask && B > 0 && M > 0 && (!target || nll), MMB_ERR_INVALID, "mmb_decoder_out_softmax: bad arguments");
+  dec_out_softmax_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(logits, mask, argmax, target, nll, M);
   return check_launch("dec_out_softmax_kernel");
 }
 
-extern "C" int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, float* d_logits, int B, int M,
-                                           mmb_stream_t stream) {
-  MMB_REQUIRE(probs && d_logits && B > 0 && M > 0, MMB_ERR_INVALID, "mmb_decoder_out_softmax_bwd: bad arguments");
-  dec_out_softmax_bwd_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(probs, d_probs, d_logits, M);
+extern "C" int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
+                                           const float* g_nll, float* d_logits, int B, int M, mmb_stream_t stream) {
+  MMB_REQUIRE(probs && d_logits && B > 0 && M > 0 && (!target || g_nll), MMB_ERR_INVALID,
+              "mmb_decoder_out_softmax_bwd: bad arguments");
+  dec_out_softmax_bwd_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(probs, d_probs, target, g_nll, d_logits, M);
   return check_launch("dec_out_softmax_bwd_kernel");
 }
 
@@ -627,12 +657,14 @@ extern "C" int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const fl
 extern "C" int mmb_decoder_attn_finish_bwd(const float* d_xcat, int ldx, const float* d_att_cov, const float* d_cov_out,
                                            const float* alpha, const float* beta, const float* ctx12, const float* pb,
                                            const float* hw, const float* vb1, const float* vb2, float* datt, float* d_pre_b,
-                                           float* d_ctx12, float* vec_acc, float* scal_acc, int B, int Lt, int D,
+                                           float* d_ctx12, float* vec_acc, float* scal_acc, const float* att_cov,
+                                           const float* cov_out, const float* g_cov, float* dcov_tot, int B, int Lt, int D,
                                            mmb_stream_t stream) {
-  MMB_REQUIRE(d_xcat && alpha && beta && ctx12 && pb && hw && vb1 && vb2 && datt && d_pre_b && d_ctx12 && vec_acc && scal_acc,
+  MMB_REQUIRE(d_xcat && alpha && beta && ctx12 && pb && hw && vb1 && vb2 && datt && d_pre_b && d_ctx12 && vec_acc &&
+                  scal_acc && dcov_tot && (!g_cov || (att_cov && cov_out)),
               MMB_ERR_INVALID, "mmb_decoder_attn_finish_bwd: null pointer");
   FinishBwdArgs a{d_xcat, d_att_cov, d_cov_out, alpha, beta, ctx12, pb, hw, vb1, vb2, datt, d_pre_b, d_ctx12, vec_acc,
-                  scal_acc, B, Lt, D, ldx};
+                  scal_acc, att_cov, cov_out, g_cov, dcov_tot, B, Lt, D, ldx};
   dec_attn_finish_bwd_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("dec_attn_finish_bwd_kernel");
 }

@@ -225,33 +225,44 @@ class _DecoderOpen(torch.autograd.Function):
 
 
 class _DecoderStep(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, tape, token, sent, h, cell, cov, mask_u8):
-        probs, h_out, cell_out, att, cov_out, _, saved = ops.decoder_step_fwd(tape.seq, sent, h, cell, cov, mask_u8)
-        ctx.tape = tape
-        ctx.save_for_backward(h, cell, cov, probs, h_out, cell_out, *saved)
-        ctx.set_materialize_grads(False)
-        return probs, h_out, cell_out, att, cov_out
+    """One decoder step.  With ``target`` (B) int64 the kernels also emit the step's loss terms (2,B) and the
+    backward pass folds their gradient in (no separate gather / log / min kernels)."""
 
     @staticmethod
-    def backward(ctx, d_probs, d_h_out, d_cell_out, d_att, d_cov_out):
+    def forward(ctx, tape, token, sent, h, cell, cov, mask_u8, target):
+        probs, h_out, cell_out, att, cov_out, _, saved, lossvec = ops.decoder_step_fwd(
+            tape.seq, sent, h, cell, cov, mask_u8, target=target)
+        ctx.tape = tape
+        ctx.fused = target is not None
+        extra = (target, att, cov_out) if ctx.fused else ()
+        ctx.save_for_backward(h, cell, cov, probs, h_out, cell_out, *saved, *extra)
+        ctx.set_materialize_grads(False)
+        if lossvec is None:
+            lossvec = probs.new_zeros(0)
+        return probs, h_out, cell_out, att, cov_out, lossvec
+
+    @staticmethod
+    def backward(ctx, d_probs, d_h_out, d_cell_out, d_att, d_cov_out, d_lossvec):
         tape = ctx.tape
-        h, cell, cov, probs, h_out, cell_out, *saved = ctx.saved_tensors
+        h, cell, cov, probs, h_out, cell_out, *rest = ctx.saved_tensors
+        saved, extra = rest[:7], rest[7:]
+        target, att, cov_new = extra if ctx.fused else (None, None, None)
         tape.open_accumulators()
         d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b = ops.decoder_step_bwd(
             tape.seq, h, cell, cov, probs, cell_out, saved, d_probs, d_h_out, d_cell_out, d_att, d_cov_out,
-            tape.d_proj_a, tape.d_proj_i, tape.vec_acc, tape.scal_acc)
+            tape.d_proj_a, tape.d_proj_i, tape.vec_acc, tape.scal_acc,
+            target=target if d_lossvec is not None else None, d_lossvec=d_lossvec, att_cov=att, cov_out=cov_new)
         hw, alpha, beta, ctx12, pb, xcat, gates = saved
         r = tape.rows
         r["h_prev"].append(h); r["xcat"].append(xcat); r["h_out"].append(h_out); r["alpha"].append(alpha)
         r["dlog"].append(d_logits); r["da"].append(d_gates); r["dctx12"].append(d_ctx12); r["dhw4"].append(d_hw4)
         r["dpre"].append(d_pre_b); r["ctx12"].append(ctx12)
-        return None, torch.zeros_like(d_h[:1, 0]), None, d_h, d_cell, d_cov, None
+        return None, torch.zeros_like(d_h[:1, 0]), None, d_h, d_cell, d_cov, None, None
 
 
 def decoder_open(tape, proj_a, proj_i, enc_a, enc_i, params):
     return _DecoderOpen.apply(tape, proj_a, proj_i, enc_a, enc_i, *params)
 
 
-def decoder_step(tape, token, sent, h, cell, cov, mask_u8):
-    return _DecoderStep.apply(tape, token, sent, h, cell, cov, mask_u8)
+def decoder_step(tape, token, sent, h, cell, cov, mask_u8, target=None):
+    return _DecoderStep.apply(tape, token, sent, h, cell, cov, mask_u8, target)

@@ -158,6 +158,13 @@ class MultimodalAttentionDecoder(nn.Module):
 
     def forward(self, sent_embed, decoder_hidden, decoder_cell_state, text_audio_enc_out, text_img_enc_out,
                 coverage_vec, mask):
+        return self.step(sent_embed, decoder_hidden, decoder_cell_state, text_audio_enc_out, text_img_enc_out,
+                         coverage_vec, mask)[:5]
+
+    def step(self, sent_embed, decoder_hidden, decoder_cell_state, text_audio_enc_out, text_img_enc_out, coverage_vec,
+             mask, target=None):
+        """``forward`` plus, when ``target`` (B) int64 is given, the step's fused loss terms as a sixth result:
+        (2, B) = [-log(final_out[b, target[b]] + 1e-12), sum_t min(att_cov_dist, coverage_vec)] (models.py:168-178)."""
         if not text_audio_enc_out.is_cuda:
             raise RuntimeError("mmbidaf_b200.layers.MultimodalAttentionDecoder runs on a B200 only (no CPU fallback)")
         if self.num_layers != 1:
@@ -168,8 +175,11 @@ class MultimodalAttentionDecoder(nn.Module):
         h = decoder_hidden.reshape(B, -1).contiguous()
         cell = decoder_cell_state.reshape(B, -1).contiguous()
         cov = coverage_vec.reshape(B, Lt).contiguous()
+        tgt = None if target is None else target.reshape(B).to(torch.int64).contiguous()
         if seq["tape"] is not None:
-            probs, h, cell, att, cov = Fn.decoder_step(seq["tape"], seq["token"], sent, h, cell, cov, ops._u8(mask))
+            probs, h, cell, att, cov, lossvec = Fn.decoder_step(seq["tape"], seq["token"], sent, h, cell, cov,
+                                                                ops._u8(mask), tgt)
         else:
-            probs, h, cell, att, cov, _, _ = ops.decoder_step_fwd(seq["seq"], sent, h, cell, cov, ops._u8(mask))
-        return probs, h.unsqueeze(1), cell.unsqueeze(0), att.unsqueeze(2), cov.unsqueeze(2)
+            probs, h, cell, att, cov, _, _, lossvec = ops.decoder_step_fwd(seq["seq"], sent, h, cell, cov, ops._u8(mask),
+                                                                           target=tgt)
+        return probs, h.unsqueeze(1), cell.unsqueeze(0), att.unsqueeze(2), cov.unsqueeze(2), (lossvec if tgt is not None else None)

@@ -120,25 +120,24 @@ class MMBiDAF(nn.Module):
         decoder_input = embedded_text.new_zeros(B, 1, embedded_text.size(-1))
         coverage_vec = text_emb.new_zeros(B, Lt, 1)
 
-        eps = 1e-12
         rows = torch.arange(B, device=embedded_text.device)
         targets = batch_target_indices.reshape(B, -1).to(embedded_text.device).long()      # int(tensor), models.py:168
-        loss = text_emb.new_zeros(())
-        out_distributions = []
+        out_distributions, step_losses = [], []
         steps = batch_target_indices.size(1) if self.training else max_dec_len
-        att_cov_dist = None
         for idx in range(steps):
-            out_distribution, decoder_hidden, decoder_cell_state, att_cov_dist, coverage_vec = \
-                self.multimodal_att_decoder(decoder_input, decoder_hidden, decoder_cell_state, mod_text_audio,
-                                            mod_text_image, coverage_vec, decoder_mask)
             tgt = targets[:, idx]
-            loss = loss - torch.log(out_distribution.gather(1, tgt.unsqueeze(1)) + eps).sum()   # models.py:168-170
+            # the decoder kernels also emit this step's loss terms: -log(p[target] + 1e-12) (models.py:168-170)
+            # and sum(min(att_cov_dist, coverage_vec)) (models.py:177), one value per video
+            out_distribution, decoder_hidden, decoder_cell_state, att_cov_dist, coverage_vec, step_loss = \
+                self.multimodal_att_decoder.step(decoder_input, decoder_hidden, decoder_cell_state, mod_text_audio,
+                                                 mod_text_image, coverage_vec, decoder_mask, target=tgt)
             nxt = tgt if self.training else out_distribution.max(dim=1)[1]                  # models.py:173 / :184,:193
             decoder_input = embedded_text[rows, nxt].unsqueeze(1)
             out_distributions.append(out_distribution)
-            if self.training:                                                               # models.py:177-178
-                loss = loss + torch.min(att_cov_dist, coverage_vec).sum()
-        if not self.training:                                                               # models.py:197-198
-            loss = loss + torch.min(att_cov_dist, coverage_vec).sum()
-        loss = loss / steps
+            step_losses.append(step_loss)
+        terms = torch.stack(step_losses)                                                    # (steps, 2, B)
+        cov_loss_wt = 1.0
+        # training adds the coverage loss at every step (models.py:177-178), evaluation once after the loop (:197-198)
+        coverage_loss = terms[:, 1].sum() if self.training else terms[-1, 1].sum()
+        loss = (terms[:, 0].sum() + cov_loss_wt * coverage_loss) / steps                    # models.py:179 / :199
         return torch.stack(out_distributions).transpose(0, 1), loss

@@ -120,9 +120,11 @@ class DecoderSeq:
         self.nch = _lib.lib().mmb_decoder_chunks(self.B, self.Lt)
 
 
-def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_argmax: bool = False):
+def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_argmax: bool = False, target=None):
     """One decoder step.  sent (B,E), h/cell (B,H), coverage (B,Lt), mask_u8 (B,M) uint8 -- contiguous fp32 CUDA.
-    Returns (probs, h', cell', att_cov, coverage', argmax|None, saved) where ``saved`` is what
+    With ``target`` (B) int64 the kernels also emit the step's loss terms ``lossvec`` (B,2) =
+    [-log(p[target]+1e-12), sum_t min(att_cov, coverage')] (models.py:168-178).
+    Returns (probs, h', cell', att_cov, coverage', argmax|None, saved, lossvec|None) where ``saved`` is what
     :func:`decoder_step_bwd` needs: (hw, alpha, beta, ctx12, pb, xcat, gates)."""
     lib = _lib.lib()
     B, Lt, D, H, E, M, nch = seq.B, seq.Lt, seq.D, seq.H, seq.E, seq.M, seq.nch
@@ -139,21 +141,25 @@ def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_arg
     pb = torch.baddbmm(seq.bb13, ctx12, seq.Wb13.transpose(1, 2))              # (2, B, D)  library GEMM
     xcat = torch.empty(B, D + E + H, **f32)
     att_cov, cov_out, beta = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32), torch.empty(B, 2, **f32)
+    lossvec = torch.empty(2, B, **f32) if target is not None else None       # [nll | coverage term]
     _lib.check(lib.mmb_decoder_attn_finish(p(pb), p(hw), p(ctx12), p(scale), p(coverage), p(sent), p(h), p(seq.vb1),
                                            p(seq.vb2), p(seq.vb1b), p(seq.vb2b), p(alpha), p(xcat), p(att_cov),
-                                           p(cov_out), p(beta), B, Lt, D, E, H, nch, st), "mmb_decoder_attn_finish")
+                                           p(cov_out), p(beta), p(None if lossvec is None else lossvec[1]),
+                                           B, Lt, D, E, H, nch, st), "mmb_decoder_attn_finish")
     gates = torch.addmm(seq.bcat, xcat, seq.Wcat.t())                          # (B, 4H)  library GEMM
     h_out, cell_out = torch.empty(B, H, **f32), torch.empty(B, H, **f32)
     _lib.check(lib.mmb_decoder_cell_fwd(p(gates), p(cell), p(h_out), p(cell_out), B, H, st), "mmb_decoder_cell_fwd")
     probs = torch.addmm(seq.out_b, h_out, seq.out_w.t())                       # (B, M) logits, library GEMM
     argmax = torch.empty(B, device=h.device, dtype=torch.int64) if want_argmax else None
-    _lib.check(lib.mmb_decoder_out_softmax(p(probs), p(mask_u8), p(argmax), B, M, st), "mmb_decoder_out_softmax")
+    _lib.check(lib.mmb_decoder_out_softmax(p(probs), p(mask_u8), p(argmax), p(target),
+                                           p(None if lossvec is None else lossvec[0]), B, M, st), "mmb_decoder_out_softmax")
     _count(6)
-    return probs, h_out, cell_out, att_cov, cov_out, argmax, (hw, alpha, beta, ctx12, pb, xcat, gates)
+    return probs, h_out, cell_out, att_cov, cov_out, argmax, (hw, alpha, beta, ctx12, pb, xcat, gates), lossvec
 
 
 def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved, d_probs, d_h_out, d_cell_out,
-                     d_att_cov, d_cov_out, d_proj_a, d_proj_i, vec_acc, scal_acc):
+                     d_att_cov, d_cov_out, d_proj_a, d_proj_i, vec_acc, scal_acc, target=None, d_lossvec=None,
+                     att_cov=None, cov_out=None):
     """Backward of one decoder step.  ``d_proj_*`` (B,Lt,2H), ``vec_acc`` (B,6,2H), ``scal_acc`` (B,4) are accumulated
     in place.  Returns (d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b)."""
     lib = _lib.lib()
@@ -164,23 +170,29 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     st = _lib.stream()
     c = lambda t: None if t is None else t.contiguous()
     d_logits = torch.empty(B, M, **f32)
-    _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(d_logits), B, M, st), "mmb_decoder_out_softmax_bwd")
+    fused = target is not None and d_lossvec is not None
+    g = c(d_lossvec) if fused else None                                        # (2, B): [d nll | d coverage term]
+    _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(target if fused else None),
+                                               p(g[0] if fused else None), p(d_logits), B, M, st),
+               "mmb_decoder_out_softmax_bwd")
     dh_tot = d_logits @ seq.out_w if d_h_out is None else torch.addmm(d_h_out, d_logits, seq.out_w)
     d_gates, d_cell = torch.empty(B, 4 * H, **f32), torch.empty(B, H, **f32)
     _lib.check(lib.mmb_decoder_cell_bwd(p(gates), p(cell), p(cell_out), p(dh_tot), p(c(d_cell_out)), p(d_gates), p(d_cell),
                                         B, H, st), "mmb_decoder_cell_bwd")
     d_xcat = d_gates @ seq.Wcat                                                # (B, D+E+H)  library GEMM
     datt, d_pre_b, d_ctx12 = torch.empty(B, Lt, **f32), torch.empty(2, B, D, **f32), torch.empty(2, B, D, **f32)
+    dcov_tot = torch.empty(B, Lt, **f32)
     _lib.check(lib.mmb_decoder_attn_finish_bwd(p(d_xcat), D + E + H, p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
                                                p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(datt), p(d_pre_b),
-                                               p(d_ctx12), p(vec_acc), p(scal_acc), B, Lt, D, st),
-               "mmb_decoder_attn_finish_bwd")
+                                               p(d_ctx12), p(vec_acc), p(scal_acc), p(att_cov if fused else None),
+                                               p(cov_out if fused else None), p(g[1] if fused else None), p(dcov_tot),
+                                               B, Lt, D, st), "mmb_decoder_attn_finish_bwd")
     d_ctx12.baddbmm_(d_pre_b, seq.Wb13)                                        # += d_pre W_beta   library GEMM
     d_alpha, spart = torch.empty(B, 2, Lt, **f32), torch.empty(B, nch, 2, **f32)
     d_cov, colp = torch.empty(B, Lt, **f32), torch.empty(B, nch, 2, 3, D, **f32)
     separt, d_hw4 = torch.empty(B, nch, 2, **f32), torch.empty(B, 4 * D, **f32)
     _lib.check(lib.mmb_decoder_attn_bwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
-                                        p(alpha), p(beta), p(datt), p(d_ctx12), p(c(d_cov_out)), p(d_pre_b), p(seq.v1),
+                                        p(alpha), p(beta), p(datt), p(d_ctx12), p(dcov_tot), p(d_pre_b), p(seq.v1),
                                         p(seq.wc1), p(seq.v2), p(seq.wc2), p(d_alpha), p(spart), p(d_proj_a), p(d_proj_i),
                                         p(d_cov), p(colp), p(separt), p(d_hw4), p(vec_acc), p(scal_acc), B, Lt, D, nch, st),
                "mmb_decoder_attn_bwd")

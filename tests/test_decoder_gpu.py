@@ -45,7 +45,7 @@ def test_decoder_steps_match_reference_golden():
     h, cell, cov = g["h0"], g["cell0"], g["cov0"]
     M = g["mask"].shape[1]
     for k, want in enumerate(g["steps"]):
-        probs, h, cell, att, cov, amax, _ = run(g["sent"][k], h, cell, g["enc_a"], g["enc_i"], cov, g["mask"], M)
+        probs, h, cell, att, cov, amax, _, _ = run(g["sent"][k], h, cell, g["enc_a"], g["enc_i"], cov, g["mask"], M)
         assert rel_err(probs, want["probs"]) < TOL
         assert rel_err(h, want["h"].squeeze(1)) < TOL and rel_err(cell, want["cell"].squeeze(0)) < TOL
         assert rel_err(att, want["att_cov"].squeeze(2)) < TOL and rel_err(cov, want["coverage"].squeeze(2)) < TOL
@@ -73,7 +73,7 @@ def test_decoder_step_matches_oracle(cfg):
     d64 = lambda t: t.double()
     want = O.decoder_step({k: d64(v) for k, v in state.items()}, d64(sent), d64(h), d64(cell), d64(enc_a), d64(enc_i),
                           d64(cov), mask)
-    probs, h1, c1, att, cov1, amax, saved = _step_fn(state)(sent, h, cell, enc_a, enc_i, cov, mask, m)
+    probs, h1, c1, att, cov1, amax, saved, _ = _step_fn(state)(sent, h, cell, enc_a, enc_i, cov, mask, m)
     assert rel_err(probs, want[0]) < TOL
     assert rel_err(h1, want[1].squeeze(1)) < TOL and rel_err(c1, want[2].squeeze(0)) < TOL
     assert rel_err(att, want[3].squeeze(2)) < TOL and rel_err(cov1, want[4].squeeze(2)) < TOL
@@ -109,3 +109,40 @@ def test_decoder_module_gradients_match_reference_golden():
     assert grad_err(h.grad, g["grad_h0"]) < 5e-5
     for name, p in mod.named_parameters():
         assert grad_err(p.grad, g["grad_params"][name], name) < 5e-5, name
+
+
+def test_fused_step_loss_terms_and_gradients_match_torch_composition():
+    """module.step(..., target=) emits [-log(p[target]+1e-12), sum min(att, coverage)] per video from inside the
+    kernels; values and gradients must equal the same terms composed with torch ops on the plain outputs."""
+    from conftest import grad_err
+    from mmbidaf_b200.layers import MultimodalAttentionDecoder
+    g = load_golden("decoder_small.pt")
+    e, hid, m = g["sent"][0].shape[2], g["h0"].shape[2], g["mask"].shape[1]
+    results = []
+    for fused in (True, False):
+        mod = MultimodalAttentionDecoder(e, hid, m, num_layers=1)
+        mod.load_state_dict(g["state"])
+        mod = mod.cuda().train()
+        enc_a = g["enc_a"].cuda().requires_grad_(True)
+        enc_i = g["enc_i"].cuda().requires_grad_(True)
+        h = g["h0"].cuda().requires_grad_(True)
+        state = (h, g["cell0"].cuda(), g["cov0"].cuda())
+        mask = g["mask"].cuda()
+        loss = 0
+        for k in range(2):
+            tgt = torch.full((3,), k, dtype=torch.long, device="cuda")
+            if fused:
+                probs, h1, c1, att, cov, terms = mod.step(g["sent"][k].cuda(), state[0], state[1], enc_a, enc_i, state[2],
+                                                          mask, target=tgt)
+                loss = loss + terms.sum()
+            else:
+                probs, h1, c1, att, cov = mod(g["sent"][k].cuda(), state[0], state[1], enc_a, enc_i, state[2], mask)
+                loss = loss - torch.log(probs[:, k] + 1e-12).sum() + torch.min(att, cov).sum()
+            state = (h1, c1, cov)
+        loss.backward()
+        results.append((loss.detach(), enc_a.grad, enc_i.grad, h.grad, [p.grad for p in mod.parameters()]))
+    (lf, af, if_, hf, pf), (lp, ap, ip, hp, pp) = results
+    assert rel_err(lf, g["loss"]) < TOL and rel_err(lf, lp) < 1e-6
+    assert grad_err(af, ap) < 1e-5 and grad_err(if_, ip) < 1e-5 and grad_err(hf, hp) < 1e-5
+    for a, b in zip(pf, pp):
+        assert grad_err(a, b) < 1e-5

@@ -182,6 +182,15 @@ MMB_API int mmb_masked_softmax_fwd(const float* x, const uint8_t* mask, float* y
 MMB_API int mmb_masked_softmax_bwd(const float* y, const float* dy, const uint8_t* mask, float* dx, long long rows,
                                    int n, int log_mode, mmb_stream_t stream);
 
+/* --------------------------------------------------------------------------------------
+ * Highway layer (encoding.py:52-59), point-wise part.  pre (n,2H) = x [gates.k.weight; transforms.k.weight]^T + bias
+ * is one GEMM by the caller; y = sigmoid(pre_g) * relu(pre_t) + (1 - sigmoid(pre_g)) * x.  Backward returns
+ * d_pre (n,2H) (for dW = d_pre^T x, dx += d_pre W) and the direct path dx_direct = dy (1 - g).
+ */
+MMB_API int mmb_highway_fwd(const float* pre, const float* x, float* y, long long n, int H, mmb_stream_t stream);
+MMB_API int mmb_highway_bwd(const float* pre, const float* x, const float* dy, float* d_pre, float* dx_direct,
+                            long long n, int H, mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

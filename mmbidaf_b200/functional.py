@@ -266,3 +266,32 @@ def decoder_open(tape, proj_a, proj_i, enc_a, enc_i, params):
 
 def decoder_step(tape, token, sent, h, cell, cov, mask_u8, target=None):
     return _DecoderStep.apply(tape, token, sent, h, cell, cov, mask_u8, target)
+
+
+class _HighwayLayer(torch.autograd.Function):
+    """One highway layer: ONE GEMM for gate and transform together + one fused point-wise kernel
+    (reference encoding.py:52-59: two GEMMs and seven element-wise kernels per layer)."""
+
+    @staticmethod
+    def forward(ctx, x2d, w_gate, b_gate, w_trans, b_trans):
+        w = torch.cat([w_gate, w_trans], dim=0)                 # (2H, H)
+        pre = torch.addmm(torch.cat([b_gate, b_trans]), x2d, w.t())
+        y = ops.highway_fwd(pre, x2d)
+        ctx.save_for_backward(x2d, pre, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, pre, w = ctx.saved_tensors
+        H = x2d.shape[1]
+        d_pre, dx = ops.highway_bwd(pre, x2d, dy)
+        dx = torch.addmm(dx, d_pre, w)                          # direct path + through both linears
+        dw = d_pre.t() @ x2d                                    # (2H, H)
+        db = d_pre.sum(dim=0)
+        return dx, dw[:H], db[:H], dw[H:], db[H:]
+
+
+def highway_layer(x: torch.Tensor, gate: torch.nn.Linear, transform: torch.nn.Linear) -> torch.Tensor:
+    shape = x.shape
+    y = _HighwayLayer.apply(x.reshape(-1, shape[-1]).contiguous(), gate.weight, gate.bias, transform.weight, transform.bias)
+    return y.view(shape)

@@ -18,7 +18,8 @@ __all__ = ["Embedding", "HighwayEncoder", "RNNEncoder", "ImageEmbedding"]
 
 class HighwayEncoder(nn.Module):
     """``num_layers`` highway layers x <- g*relu(T x) + (1-g)*x  (reference encoding.py:45-59).
-    Adjacent to the hot path: plain cuBLAS GEMMs + ATen element-wise for now."""
+    Each layer is one GEMM (gate and transform stacked) plus one fused point-wise kernel, forward and backward
+    (csrc/highway.cu); the reference runs two GEMMs and seven element-wise kernels per layer."""
 
     def __init__(self, num_layers, hidden_size):
         super().__init__()
@@ -26,9 +27,10 @@ class HighwayEncoder(nn.Module):
         self.gates = nn.ModuleList(nn.Linear(hidden_size, hidden_size) for _ in range(num_layers))
 
     def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("mmbidaf_b200.layers.HighwayEncoder runs on a B200 only (no CPU fallback)")
         for gate, transform in zip(self.gates, self.transforms):
-            g = torch.sigmoid(gate(x))
-            x = g * F.relu(transform(x)) + (1 - g) * x
+            x = Fn.highway_layer(x, gate, transform)
         return x
 
 

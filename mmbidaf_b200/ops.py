@@ -219,3 +219,23 @@ def masked_softmax_bwd(y2d: torch.Tensor, dy2d: torch.Tensor, mask2d_u8: torch.T
                                           rows, n, int(log_mode), _lib.stream()), "mmb_masked_softmax_bwd")
     _count(1)
     return dx
+
+
+def highway_fwd(pre: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """y = sigmoid(pre[:, :H]) * relu(pre[:, H:]) + (1 - sigmoid(pre[:, :H])) * x  (encoding.py:55-57)."""
+    lib = _lib.lib()
+    n, H = x.shape
+    y = torch.empty_like(x)
+    _lib.check(lib.mmb_highway_fwd(_lib.ptr(pre), _lib.ptr(x), _lib.ptr(y), n, H, _lib.stream()), "mmb_highway_fwd")
+    _count(1)
+    return y
+
+
+def highway_bwd(pre: torch.Tensor, x: torch.Tensor, dy: torch.Tensor):
+    lib = _lib.lib()
+    n, H = x.shape
+    d_pre, dx = torch.empty_like(pre), torch.empty_like(x)
+    _lib.check(lib.mmb_highway_bwd(_lib.ptr(pre), _lib.ptr(x), _lib.ptr(dy.contiguous()), _lib.ptr(d_pre), _lib.ptr(dx),
+                                   n, H, _lib.stream()), "mmb_highway_bwd")
+    _count(1)
+    return d_pre, dx

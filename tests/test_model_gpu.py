@@ -147,3 +147,23 @@ def test_fast_tier_whole_model_within_reduced_precision_tolerance():
         assert rel_err(out_e, g["eval_out"]) < 2e-2
     finally:
         mmbidaf_b200.set_precision("fp32")
+
+
+def test_embedding_highway_matches_reference_golden():
+    from mmbidaf_b200.layers import Embedding
+    g = load_golden("embedding.pt")
+    mod = Embedding(embedding_size=10, hidden_size=6, drop_prob=0.0)
+    mod.load_state_dict(g["state"])
+    mod = mod.cuda().eval()
+    x = g["x"].cuda().requires_grad_(True)
+    out = mod(x)
+    assert rel_err(out, g["out"]) < TOL
+    # gradients against the oracle's autograd
+    w = torch.randn(2, 5, 6)
+    (out * w.cuda()).sum().backward()
+    p = {k: v.clone().requires_grad_(True) for k, v in g["state"].items()}
+    xr = g["x"].clone().requires_grad_(True)
+    (O.embedding(p, xr) * w).sum().backward()
+    assert grad_err(x.grad, xr.grad) < 1e-5
+    for name, param in mod.named_parameters():
+        assert grad_err(param.grad, p[name].grad, name) < 1e-5, name

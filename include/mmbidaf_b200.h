@@ -65,18 +65,35 @@ MMB_API int mmb_device_supported(void);
  * Outputs
  *   out (B,Lc,4d) = [c, a, c*a, c*b]                                    (attention.py:52)
  *   q2c (B,Lq,d) = s2^T c, lse_row (B,Lc), lse_col (B,Lq): log-sum-exp of the row / column
- *   soft-max -- saved for the backward pass.  MMB_PREC_FP32: d % 4 == 0, d <= 256 (workspace may be NULL).
+ *   soft-max -- saved for the backward pass; bm (B,Lc,d) = s1 q2c (the b of attention.py:50 before the
+ *   product with c), optional (NULL in inference), also for the backward pass.  MMB_PREC_FP32: d % 4 == 0, d <= 256 (workspace may be NULL).
  *   MMB_PREC_BF16 (tcgen05 + TMEM + TMA): d % 8 == 0, d <= 200, workspace of mmb_bidaf_workspace_bytes().
  */
 MMB_API int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_t* text_mask, const uint8_t* modality_mask,
                   const float* w_text, const float* w_modality, const float* w_cross, const float* bias,
                   const uint8_t* keep_text, const uint8_t* keep_modality, float keep_scale,
-                  float* out, float* q2c, float* lse_row, float* lse_col, void* workspace,
+                  float* out, float* q2c, float* bm, float* lse_row, float* lse_col, void* workspace,
                   int B, int Lc, int Lq, int d, int precision, mmb_stream_t stream);
 
 /* Bytes of scratch `workspace` mmb_bidaf_fwd needs (0 for MMB_PREC_FP32).  The bf16 tier keeps bf16 copies of
  * its operands there in tensor-core order; dropout != 0 when keep_modality will be non-NULL. */
 MMB_API size_t mmb_bidaf_workspace_bytes(int B, int Lc, int Lq, int d, int precision, int dropout);
+
+/* BiDAF attention, backward: the gradient of attention.py:37-75 that the reference obtains from autograd
+ * (loss.backward(), train.py:148).  S, both soft-maxes and dS are recomputed on chip from lse_row / lse_col;
+ * nothing of size Lc x Lq is read or written.
+ *   grad_out (B,Lc,4d); text, modality, weights, keep masks, keep_scale: as given to mmb_bidaf_fwd;
+ *   out, bm, q2c, lse_row, lse_col: as produced by mmb_bidaf_fwd; fwd_workspace: the workspace of that call,
+ *   untouched since (MMB_PREC_BF16: it holds the bf16 operands); workspace: mmb_bidaf_bwd_workspace_bytes().
+ * Outputs (all overwritten): d_text (B,Lc,d), d_modality (B,Lq,d), d_w_text (d), d_w_modality (d), d_w_cross (d), d_bias (1).
+ */
+MMB_API int mmb_bidaf_bwd(const float* grad_out, const float* text, const float* modality, const float* w_text,
+                  const float* w_modality, const float* w_cross, const float* bias, const uint8_t* keep_text,
+                  const uint8_t* keep_modality, float keep_scale, const float* out, const float* bm, const float* q2c,
+                  const float* lse_row, const float* lse_col, const void* fwd_workspace, void* workspace,
+                  float* d_text, float* d_modality, float* d_w_text, float* d_w_modality, float* d_w_cross, float* d_bias,
+                  int B, int Lc, int Lq, int d, int precision, mmb_stream_t stream);
+MMB_API size_t mmb_bidaf_bwd_workspace_bytes(int B, int Lc, int Lq, int d, int precision);
 
 /* --------------------------------------------------------------------------------------
  * Length-aware LSTM recurrence of one layer, 1 or 2 directions.  Replaces the nn.LSTM call of

@@ -25,8 +25,10 @@ SIGNATURES = {
     "mmb_version": [],
     "mmb_last_error": [],
     "mmb_device_supported": [],
-    "mmb_bidaf_fwd": [c_void_p] * 10 + [c_float] + [c_void_p] * 5 + [c_int] * 5 + [c_void_p],
+    "mmb_bidaf_fwd": [c_void_p] * 10 + [c_float] + [c_void_p] * 6 + [c_int] * 5 + [c_void_p],
     "mmb_bidaf_workspace_bytes": [c_int] * 6,
+    "mmb_bidaf_bwd": [c_void_p] * 9 + [c_float] + [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
+    "mmb_bidaf_bwd_workspace_bytes": [c_int] * 5,
     "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_chunks": [c_int, c_int],
@@ -43,7 +45,8 @@ SIGNATURES = {
     "mmb_masked_softmax_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p],
     "mmb_masked_softmax_bwd": [c_void_p] * 4 + [ctypes.c_longlong, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"mmb_last_error": ctypes.c_char_p, "mmb_bidaf_workspace_bytes": c_size_t}
+_RESTYPES = {"mmb_last_error": ctypes.c_char_p, "mmb_bidaf_workspace_bytes": c_size_t,
+             "mmb_bidaf_bwd_workspace_bytes": c_size_t}
 
 
 DECODER_WEIGHT_FIELDS = ("W2", "b2", "Wc1", "bc1", "v1", "v1b", "W4", "b4", "Wc2", "bc2", "v2", "v2b",

@@ -42,6 +42,7 @@ struct PassArgs {
   float keep_scale;
   float* out;               // kQ2C: T (B,LX,D);  kC2Q/kC2QB: out (B,LX,4D)
   float* lse;               // kQ2C: lse_col (B,LX); kC2Q: lse_row (B,LX); kC2QB: unused
+  float* bm;                // kC2QB: optional (B,LX,D) copy of b = s1 T for the backward pass
   int LX, LY, D;
 };
 
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(NT) bidaf_pass_f32(const PassPair pp) {
           *reinterpret_cast<float4*>(o + 2 * D) = cv;
         } else {
           *reinterpret_cast<float4*>(o + 3 * D) = cv;
+          if (a.bm) *reinterpret_cast<float4*>(a.bm + ((size_t)b * a.LX + gx) * D + c4 * 4) = v;
         }
       }
     }
@@ -319,20 +321,21 @@ int launch_pass(const PassPair& pp, int npass, int B, cudaStream_t stream) {
 int bidaf_fwd_f32(const float* text, const float* modality, const uint8_t* text_mask, const uint8_t* modality_mask,
                   const float* w_text, const float* w_modality, const float* w_cross, const float* bias,
                   const uint8_t* keep_text, const uint8_t* keep_modality, float keep_scale, float* out, float* q2c,
-                  float* lse_row, float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream) {
+                  float* bm, float* lse_row, float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream) {
   PassPair q{};
   q.kind[0] = kQ2C;
   q.p[0] = PassArgs{modality, text, nullptr, keep_modality, keep_text, text_mask, w_modality, w_text, w_cross, bias,
-                    keep_scale, q2c, lse_col, Lq, Lc, d};
+                    keep_scale, q2c, lse_col, nullptr, Lq, Lc, d};
   int rc = launch_pass(q, 1, B, stream);
   if (rc) return rc;
   PassPair c{};
   c.kind[0] = kC2Q;
   c.p[0] = PassArgs{text, modality, nullptr, keep_text, keep_modality, modality_mask, w_text, w_modality, w_cross, bias,
-                    keep_scale, out, lse_row, Lc, Lq, d};
+                    keep_scale, out, lse_row, nullptr, Lc, Lq, d};
   c.kind[1] = kC2QB;
   c.p[1] = c.p[0];
   c.p[1].v_feat = q2c;
+  c.p[1].bm = bm;
   return launch_pass(c, 2, B, stream);
 }
 

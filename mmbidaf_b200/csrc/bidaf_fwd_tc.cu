@@ -23,118 +23,22 @@
 //     when a row's running max moves by more than TAU), as in FlashAttention-4.
 //     The epilogue drains TMEM through shared memory so that the 4-way concat is written with coalesced
 //     128-bit stores; Q2C also emits T in packed bf16 form for pass 3.
-#include <cuda_bf16.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mmb {
+using namespace tc;
 namespace {
 
-constexpr int DPAD = 208;                 // K / N padding of d (d <= 200 so that chunk 25 is free for the terms)
-constexpr int CHUNKS = DPAD / 8;          // 26 sixteen-byte chunks per row
-constexpr int GROUP_BYTES = CHUNKS * 128; // 8 rows
 constexpr int TX = 128, TY = 64;
 constexpr int X_BYTES = TX / 8 * GROUP_BYTES;   // 53248
 constexpr int Y_BYTES = TY / 8 * GROUP_BYTES;   // 26624
 constexpr int P_BYTES = TX * TY * 2;            // 16384
-constexpr int STAGES = 2;
-constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 3;
+constexpr int PRODUCER = 32;              // thread that issues the Y-stage TMA loads (tid 0 issues the MMAs)
 constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 64 + DPAD;
 constexpr int STG_STRIDE = 204;           // fp32 staging row stride (conflict-free 128-bit stores)
 
 enum Kind { Q2C = 0, C2Q = 1 };
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait suspends for a hardware time slice; the bound turns a protocol bug into a trap instead of a hang.
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  tmem_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-      : "memory");
-}
-
-// Shared-memory matrix descriptor, no swizzle ("interleave"), Blackwell version field = 1.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46);
-}
-// Instruction descriptor: D = F32, A = B = BF16, M = 128.
-constexpr uint32_t idesc_bf16(int n, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // 1. pack: fp32 (B, L, d) -> bf16 core-matrix order (+ folded weights, additive terms, mask words)
@@ -281,11 +185,11 @@ struct TcArgs {
   float* out;                        // Q2C: T fp32 (B, LX, d);   C2Q: out (B, LX, 4d)
   __nv_bfloat16* t_pack;             // Q2C: packed T for pass 3
   float* lse;                        // (B, LX)
+  float* bm;                         // C2Q: optional (B, LX, d) copy of b = s1 T for the backward pass
   int LX, LXP, LY, LYP, d;
 };
 
 constexpr int NTHREADS = 256;            // two threads per X row: warps 0-3 take S columns 0-31, warps 4-7 columns 32-63
-constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float TAU2 = 11.0f;            // lazy-rescale threshold in log2 units (factor 2048)
 
 template <int KIND>
@@ -296,10 +200,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   const bool sep_v0 = a.v0_pack != a.y_pack;
   const int nparts = 1 + (sep_v0 ? 1 : 0) + (KIND == C2Q ? 1 : 0);
   const int stage_bytes = nparts * Y_BYTES;
+  const int STAGES = nparts == 2 ? 3 : 2;                        // what fits in 227 KB next to X and P
   unsigned char* Xs = smem;
   unsigned char* Ps = Xs + X_BYTES;
   unsigned char* St = Ps + P_BYTES;                               // STAGES x stage_bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(St + STAGES * stage_bytes);   // [0] x, [1..2] full, [3] mma
+  uint64_t* bars = reinterpret_cast<uint64_t*>(St + STAGES * stage_bytes);   // [0] x, [1] mma, [2..4] full, [5..7] free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* xbuf = reinterpret_cast<float*>(bars + 10);              // [2][TX] cross-half exchange (max, then sum)
 
@@ -307,12 +212,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   const int half = warp >> 2, wq = warp & 3;
   const int row = wq * 32 + lane;
   const int b = blockIdx.y, x0 = blockIdx.x * TX;
-  const uint32_t bar_x = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_mma = smem_u32(bars + 3);
+  const uint32_t bar_x = smem_u32(bars), bar_mma = smem_u32(bars + 1), bar_full0 = smem_u32(bars + 2);
+  const uint32_t bar_free0 = smem_u32(bars + 2 + MAX_STAGES);
 
   if (tid == 0) {
     mbar_init(bar_x, 1);
-    mbar_init(bar_full0, 1);
-    mbar_init(bar_full0 + 8, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full0 + 8 * s, 1);
+      mbar_init(bar_free0 + 8 * s, 1);
+    }
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
@@ -339,8 +247,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   if (tid == 0) {
     mbar_expect_tx(bar_x, X_BYTES);
     tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_pack) + x_off, X_BYTES, bar_x);
-    for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
   }
+  if (tid == PRODUCER)
+    for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
 
   const float bias2 = a.bias[0] * LOG2E;
   const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);     // this warp's 32 TMEM lanes
@@ -349,12 +258,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   constexpr uint32_t IDESC_S = idesc_bf16(TY, 0), IDESC_PV = idesc_bf16(DPAD, 1);
   const uint32_t xs_addr = smem_u32(Xs), ps_addr = smem_u32(Ps);
 
-  mbar_wait(bar_x, 0);
+  if (tid == 0) mbar_wait(bar_x, 0);
   for (int t = 0; t < nty; ++t) {
     const int s = t % STAGES;
     const uint32_t st_addr = smem_u32(St + s * stage_bytes);
-    mbar_wait(bar_full0 + 8 * s, (t / STAGES) & 1);
     if (tid == 0) {
+      mbar_wait(bar_full0 + 8 * s, (t / STAGES) & 1);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < DPAD / 16; ++k)                       // S = X Y^T, both K-major
@@ -365,11 +274,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
     const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + t) * 2);
     const uint32_t wvalid = (uint32_t)(words.x >> (HALF * half)), wopen = (uint32_t)(words.y >> (HALF * half));
     const bool all_open = (words.x & words.y) == ~0ull;         // CTA-uniform: interior tile, nothing masked
+    // the previous tile's P V MMAs commit to the "free" barrier of their stage: refill it while this tile's S MMAs
+    // run, so the load has a whole tile of tensor-core + soft-max time to land
+    if (tid == PRODUCER && t >= 1 && t - 1 + STAGES < nty) {
+      mbar_wait(bar_free0 + 8 * ((t - 1) % STAGES), ((t - 1) / STAGES) & 1);
+      issue_stage(t - 1 + STAGES);
+    }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    // every MMA issued before this commit has retired: the previous tile's P V is done, its stage is free
-    if (tid == 0 && t >= 1 && t - 1 + STAGES < nty) issue_stage(t - 1 + STAGES);
     if (KIND == C2Q && tid == 0 && t == nty - 1) {              // X operand no longer needed: fetch the plain text
       mbar_expect_tx(bar_x, X_BYTES);
       tma_bulk_g2s(xs_addr, reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x);
@@ -466,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
           umma_bf16(tmem + COL_O1, smem_desc(ps_addr + k * 4096, 2048, 128),
                     smem_desc(v1_addr + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
       }
-      if (t == nty - 1) umma_commit(bar_mma);
+      umma_commit(t == nty - 1 ? bar_mma : bar_free0 + 8 * s);
     }
   }
   // ---- epilogue: TMEM -> registers -> fp32 staging in smem -> coalesced global stores -----------------------------
@@ -537,6 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
           __stcs(reinterpret_cast<float4*>(orow + 2 * d), cv);
         } else {
           __stcs(reinterpret_cast<float4*>(orow + 3 * d), cv);
+          if (a.bm) __stcs(reinterpret_cast<float4*>(a.bm + ((size_t)b * a.LX + x0 + r) * d + col), v);
         }
       }
     }
@@ -546,40 +460,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-size_t tc_smem_bytes(int nparts) { return (size_t)X_BYTES + P_BYTES + (size_t)STAGES * nparts * Y_BYTES + 80 + 2 * TX * 4; }
-
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+size_t tc_smem_bytes(int nparts) {
+  return (size_t)X_BYTES + P_BYTES + (size_t)(nparts == 2 ? 3 : 2) * nparts * Y_BYTES + 80 + 2 * TX * 4;
+}
 
 }  // namespace
 
-// Workspace (bytes): packed operands, mask words.  Layout is private to this file.
-size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout) {
-  const size_t LcP = round_up(Lc, TX), LqP = round_up(Lq, TX);
-  const size_t c_pack = (size_t)B * (LcP / 8) * GROUP_BYTES, q_pack = (size_t)B * (LqP / 8) * GROUP_BYTES;
-  return 2 * c_pack + (2 + (dropout ? 1 : 0)) * q_pack + 16 * (size_t)B * (LcP / 64 + LqP / 64) + 1024;
-}
+// Workspace (bytes): packed operands, mask words (layout: tc_common.cuh::bidaf_packs).
+size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout) { return bidaf_packs(nullptr, B, Lc, Lq, dropout != 0).bytes; }
 
 int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_mask, const uint8_t* modality_mask,
                  const float* w_text, const float* w_modality, const float* w_cross, const float* bias,
                  const uint8_t* keep_text, const uint8_t* keep_modality, float keep_scale, float* out, float* q2c,
-                 float* lse_row, float* lse_col, void* workspace, int B, int Lc, int Lq, int d, cudaStream_t stream) {
+                 float* bm, float* lse_row, float* lse_col, void* workspace, int B, int Lc, int Lq, int d, cudaStream_t stream) {
   MMB_REQUIRE(d % 8 == 0 && d <= 200, MMB_ERR_UNSUPPORTED, "mmb_bidaf_fwd (bf16 tier): d=%d (need d %% 8 == 0, d <= 200)", d);
   MMB_REQUIRE(workspace, MMB_ERR_INVALID, "mmb_bidaf_fwd (bf16 tier): workspace is null");
-  const int LcP = round_up(Lc, TX), LqP = round_up(Lq, TX);
-  const size_t c_pack = (size_t)B * (LcP / 8) * GROUP_BYTES, q_pack = (size_t)B * (LqP / 8) * GROUP_BYTES;
-  char* ws = static_cast<char*>(workspace);
-  auto* cw = reinterpret_cast<__nv_bfloat16*>(ws);
-  auto* cp = reinterpret_cast<__nv_bfloat16*>(ws + c_pack);
-  auto* qs = reinterpret_cast<__nv_bfloat16*>(ws + 2 * c_pack);
-  auto* tp = reinterpret_cast<__nv_bfloat16*>(ws + 2 * c_pack + q_pack);
-  char* next = ws + 2 * c_pack + 2 * q_pack;
-  __nv_bfloat16* qp = qs;
-  if (keep_modality) {
-    qp = reinterpret_cast<__nv_bfloat16*>(next);
-    next += q_pack;
-  }
-  auto* c_words = reinterpret_cast<unsigned long long*>(next);
-  auto* q_words = c_words + (size_t)B * (LcP / 64) * 2;
+  static_assert(PACK_ROWS == TX, "pack padding must match the X tile");
+  const BidafPacks pk = bidaf_packs(workspace, B, Lc, Lq, keep_modality != nullptr);
+  const int LcP = pk.LcP, LqP = pk.LqP;
+  __nv_bfloat16 *cw = pk.cw, *cp = pk.cp, *qs = pk.qs, *qp = pk.qp, *tp = pk.tp;
+  unsigned long long *c_words = pk.c_words, *q_words = pk.q_words;
 
   PackPair pp;
   pp.side[0] = PackArgs{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
@@ -589,14 +489,14 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
   {   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
-    TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, Lq, LqP, Lc, LcP, d};
+    TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, Lq, LqP, Lc, LcP, d};
     const size_t smem = tc_smem_bytes(2);
     MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<Q2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), NTHREADS, smem, stream>>>(a);
     if (int rc = check_launch("bidaf_tc_kernel<Q2C>")) return rc;
   }
   {   // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)
-    TcArgs a{cw, qs, qp, tp, cp, q_words, bias, out, nullptr, lse_row, Lc, LcP, Lq, LqP, d};
+    TcArgs a{cw, qs, qp, tp, cp, q_words, bias, out, nullptr, lse_row, bm, Lc, LcP, Lq, LqP, d};
     const int nparts = 2 + (qp != qs ? 1 : 0);
     const size_t smem = tc_smem_bytes(nparts);
     MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "bidaf bf16 tier: %zu B of shared memory", smem);

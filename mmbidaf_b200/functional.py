@@ -69,25 +69,34 @@ def lstm_layer(x: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Ten
 
 class _BidafAttention(torch.autograd.Function):
     """Fused BiDAF attention (attention.py:37-75).  Forward = the fused kernels (S never materialised).
-    Backward (INTERIM, round 1): the closed-form gradient evaluated with cuBLAS batched GEMMs and ATen
-    element-wise ops on the GPU from the saved soft-max statistics; a fused recompute-S kernel replaces it
-    next (DESIGN.md, "BiDAF backward")."""
+    Backward: bf16 tier = the fused tcgen05 kernels of csrc/bidaf_bwd_tc.cu (S, the soft-maxes and dS are
+    recomputed on chip); fp32 tier = the closed-form gradient evaluated with fp32 library GEMMs from the
+    saved soft-max statistics."""
 
     @staticmethod
     def forward(ctx, text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
                 keep_text, keep_modality, keep_scale, precision):
-        out, q2c, lse_row, lse_col = ops.bidaf_fwd(text, modality, text_mask, modality_mask, w_text, w_modality,
-                                                   w_cross, bias, keep_text, keep_modality, keep_scale, precision)
-        ctx.save_for_backward(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
-                              keep_text, keep_modality, out, q2c, lse_row, lse_col)
-        ctx.keep_scale = keep_scale
-        return out
+        save = any(ctx.needs_input_grad)
+        res = ops.bidaf_fwd(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
+                            keep_text, keep_modality, keep_scale, precision, save=save)
+        if save:
+            out, q2c, lse_row, lse_col, bm, ws = res
+            ctx.save_for_backward(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
+                                  keep_text, keep_modality, out, q2c, lse_row, lse_col, bm, ws)
+            ctx.keep_scale = keep_scale
+            ctx.precision = precision
+        return res[0]
 
     @staticmethod
     def backward(ctx, grad):
-        (c, q, c_mask, q_mask, w_c, w_q, w_cq, bias, keep_c, keep_q, out, q2c, lse_row, lse_col) = ctx.saved_tensors
+        (c, q, c_mask, q_mask, w_c, w_q, w_cq, bias, keep_c, keep_q, out, q2c, lse_row, lse_col, bm, ws) = ctx.saved_tensors
         B, Lc, d = c.shape
         scale = ctx.keep_scale
+        if ctx.precision == ops.PREC_BF16:
+            dc, dq, dw_c, dw_q, dw_cq, dbias = ops.bidaf_bwd(grad, c, q, w_c, w_q, w_cq, bias, keep_c, keep_q, scale,
+                                                             out, bm, q2c, lse_row, lse_col, ws, ctx.precision)
+            return (dc, dq, None, None, dw_c.reshape(w_c.shape), dw_q.reshape(w_q.shape), dw_cq.reshape(w_cq.shape),
+                    dbias.reshape(bias.shape), None, None, None, None)
         cd = c if keep_c is None else c * keep_c.to(c.dtype) * scale
         qd = q if keep_q is None else q * keep_q.to(q.dtype) * scale
         wc, wq, wx = w_c.reshape(d), w_q.reshape(d), w_cq.reshape(d)

@@ -32,10 +32,9 @@ def _u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tensor, modality_mask: torch.Tensor,
               w_text: torch.Tensor, w_modality: torch.Tensor, w_cross: torch.Tensor, bias: torch.Tensor,
               keep_text: Optional[torch.Tensor] = None, keep_modality: Optional[torch.Tensor] = None,
-              keep_scale: float = 1.0, precision: int = PREC_FP32
-              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Fused BiDAF forward (attention.py:37-75).  Returns (out (B,Lc,4d), q2c (B,Lq,d),
-    lse_row (B,Lc), lse_col (B,Lq)); the last three are what the backward pass needs."""
+              keep_scale: float = 1.0, precision: int = PREC_FP32, save: bool = False):
+    """Fused BiDAF forward (attention.py:37-75).  Returns (out (B,Lc,4d), q2c (B,Lq,d), lse_row (B,Lc),
+    lse_col (B,Lq)); with ``save`` also (bm (B,Lc,d), workspace) -- everything the backward pass needs."""
     L = _lib.lib()
     assert text.dtype == torch.float32 and modality.dtype == torch.float32
     B, Lc, d = text.shape
@@ -46,16 +45,47 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
     wt, wm, wc = (w.detach().reshape(-1).contiguous() for w in (w_text, w_modality, w_cross))
     out = torch.empty(B, Lc, 4 * d, device=text.device, dtype=torch.float32)
     q2c = torch.empty(B, Lq, d, device=text.device, dtype=torch.float32)
+    bm = torch.empty(B, Lc, d, device=text.device, dtype=torch.float32) if save else None
     lse_row = torch.empty(B, Lc, device=text.device, dtype=torch.float32)
     lse_col = torch.empty(B, Lq, device=text.device, dtype=torch.float32)
     p = _lib.ptr
     ws_bytes = L.mmb_bidaf_workspace_bytes(B, Lc, Lq, d, int(precision), int(km is not None))
     ws = torch.empty(ws_bytes, device=text.device, dtype=torch.uint8) if ws_bytes else None
     _lib.check(L.mmb_bidaf_fwd(p(text), p(modality), p(tm), p(mm), p(wt), p(wm), p(wc), p(bias.detach().contiguous()),
-                               p(kt), p(km), float(keep_scale), p(out), p(q2c), p(lse_row), p(lse_col), p(ws),
+                               p(kt), p(km), float(keep_scale), p(out), p(q2c), p(bm), p(lse_row), p(lse_col), p(ws),
                                B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
     _count(2 if precision == PREC_FP32 else 3)
+    if save:
+        return out, q2c, lse_row, lse_col, bm, ws
     return out, q2c, lse_row, lse_col
+
+
+def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor, w_text: torch.Tensor,
+              w_modality: torch.Tensor, w_cross: torch.Tensor, bias: torch.Tensor, keep_text: Optional[torch.Tensor],
+              keep_modality: Optional[torch.Tensor], keep_scale: float, out: torch.Tensor, bm: torch.Tensor,
+              q2c: torch.Tensor, lse_row: torch.Tensor, lse_col: torch.Tensor, fwd_ws: Optional[torch.Tensor],
+              precision: int):
+    """Fused BiDAF backward (the autograd gradient of attention.py:37-75) from what :func:`bidaf_fwd` saved.
+    Returns (d_text, d_modality, d_w_text (d), d_w_modality (d), d_w_cross (d), d_bias (1))."""
+    L = _lib.lib()
+    B, Lc, d = text.shape
+    Lq = modality.shape[1]
+    dev = text.device
+    kt, km = _u8(keep_text), _u8(keep_modality)
+    wt, wm, wc = (w.detach().reshape(-1).contiguous() for w in (w_text, w_modality, w_cross))
+    d_text = torch.empty_like(text)
+    d_modality = torch.empty_like(modality)
+    d_w = torch.empty(3, d, device=dev, dtype=torch.float32)
+    d_bias = torch.empty(1, device=dev, dtype=torch.float32)
+    ws_bytes = L.mmb_bidaf_bwd_workspace_bytes(B, Lc, Lq, d, int(precision))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if ws_bytes else None
+    p = _lib.ptr
+    _lib.check(L.mmb_bidaf_bwd(p(grad_out.contiguous()), p(text), p(modality), p(wt), p(wm), p(wc),
+                               p(bias.detach().contiguous()), p(kt), p(km), float(keep_scale), p(out), p(bm), p(q2c),
+                               p(lse_row), p(lse_col), p(fwd_ws), p(ws), p(d_text), p(d_modality), p(d_w[0]), p(d_w[1]),
+                               p(d_w[2]), p(d_bias), B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_bwd")
+    _count(5)
+    return d_text, d_modality, d_w[0], d_w[1], d_w[2], d_bias
 
 
 def lstm_layer_fwd(gates: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Tensor],

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import grad_err, load_golden, rel_err
 from oracle import mmbidaf_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -161,3 +161,98 @@ def test_bf16_tier_fully_masked_is_uniform_and_large_logits_are_stable():
     want = O.bidaf_attention({k: v.double() for k, v in p.items()}, text.double(), modality.double(), tmask, mmask)
     out, *_ = _run(p, text, modality, tmask, mmask, precision=1)
     assert torch.isfinite(out).all() and rel_err(out, want) < 5e-2      # bf16 logits of magnitude 100: looser
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Backward: the reference gets it from autograd (loss.backward(), train.py:148); here it is a fused kernel chain
+# (csrc/bidaf_bwd_tc.cu) on the bf16 tier and the closed form on fp32 library GEMMs on the fp32 tier.
+# ------------------------------------------------------------------------------------------------------------
+BWD_TOL = {0: 2e-4, 1: 5e-2}      # max|d| / max|ref| per gradient tensor
+
+
+def _grads(state, text, modality, tmask, mmask, grad_out, keep_c=None, keep_q=None, p=0.0, precision=0):
+    from mmbidaf_b200 import functional as F
+    cu = lambda t: None if t is None else t.cuda()
+    c, q = text.cuda().requires_grad_(True), modality.cuda().requires_grad_(True)
+    w = {k: v.cuda().requires_grad_(True) for k, v in state.items()}
+    out = F.bidaf_attention(c, q, cu(tmask), cu(mmask), w["text_weight"], w["modality_weight"], w["text_modality_weight"],
+                            w["bias"], cu(keep_c), cu(keep_q), 1.0 / (1.0 - p), precision)
+    out.backward(grad_out.cuda())
+    torch.cuda.synchronize()
+    return c.grad.cpu(), q.grad.cpu(), {k: v.grad.cpu() for k, v in w.items()}
+
+
+def _ds_abs_sum(state, text, modality, tmask, mmask, grad_out, keep_c=None, keep_q=None, p=0.0):
+    """sum |dS| of the fp64 oracle: the scale of the (identically zero) bias gradient's rounding noise."""
+    pd = {k: v.double() for k, v in state.items()}
+    c, q = text.double(), modality.double()
+    s = O.bidaf_similarity(pd, c, q, keep_c, keep_q, p).requires_grad_(True)
+    s1 = O.masked_softmax(s, mmask.unsqueeze(1), dim=2)
+    s2 = O.masked_softmax(s, tmask.unsqueeze(2), dim=1)
+    a = torch.bmm(s1, q)
+    b = torch.bmm(torch.bmm(s1, s2.transpose(1, 2)), c)
+    torch.cat([c, a, c * a, c * b], dim=2).backward(grad_out.double())
+    return float(s.grad.abs().sum())
+
+
+def _check_grads(got, want_c, want_q, want_w, tol, ds_scale=None, w_floor=1e-3):
+    dc, dq, dw = got
+    errs = {"d_text": grad_err(dc, want_c), "d_modality": grad_err(dq, want_q)}
+    for k, v in want_w.items():
+        if k == "bias" and ds_scale is not None:
+            # d loss / d bias = sum(dS) = 0 identically (both soft-maxes are shift invariant); what any implementation
+            # returns is rounding noise, which for bf16 operands scales with sum |dS|
+            errs[k] = float(dw[k].abs().max()) / max(ds_scale, 1e-30) * (tol / 2e-3)
+        else:
+            errs[k] = grad_err(dw[k], v, k, floor=w_floor)
+    assert all(e < tol for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("name", ["bidaf_small.pt", "bidaf_d200.pt"])
+def test_backward_matches_reference_golden(name, precision):
+    import torch.nn.functional as F
+    g = load_golden(name)
+    tol = BWD_TOL[precision]
+    args = (g["state"], g["text"], g["modality"], g["text_mask"], g["modality_mask"], g["grad_out"])
+    got = _grads(*args, precision=precision)
+    _check_grads(got, g["grad_text"], g["grad_modality"], g["grad_params"], tol, _ds_abs_sum(*args) if precision else None)
+    pr = g["train_drop_prob"]
+    torch.manual_seed(g["train_seed"])
+    keep_c = F.dropout(torch.ones_like(g["text"]), pr, True) != 0
+    keep_q = F.dropout(torch.ones_like(g["modality"]), pr, True) != 0
+    got = _grads(*args, keep_c, keep_q, pr, precision)
+    _check_grads(got, g["train_grad_text"], g["train_grad_modality"], g["train_grad_params"], tol,
+                 _ds_abs_sum(*args, keep_c, keep_q, pr) if precision else None)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 8), (2, 1, 9, 8), (2, 5, 3, 8), (3, 64, 128, 200), (2, 65, 129, 200),
+                                   (2, 130, 257, 200), (4, 100, 70, 64), (2, 300, 520, 200), (3, 409, 1024, 200)])
+@pytest.mark.parametrize("dropout", [False, True])
+def test_bf16_backward_matches_oracle_ragged(shape, dropout):
+    bsz, lc, lq, d = shape
+    gen = torch.Generator().manual_seed(3000 + lc * 7 + lq)
+    p = {"text_weight": torch.randn(d, 1, generator=gen) * 0.1, "modality_weight": torch.randn(d, 1, generator=gen) * 0.1,
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen) * 0.1, "bias": torch.tensor([0.3])}
+    text = torch.randn(bsz, lc, d, generator=gen)
+    modality = torch.randn(bsz, lq, d, generator=gen)
+    c_len = torch.randint(1, lc + 1, (bsz,), generator=gen).tolist()
+    q_len = torch.randint(1, lq + 1, (bsz,), generator=gen).tolist()
+    c_len[0], q_len[0] = lc, lq
+    tmask, mmask = O.length_mask(lc, c_len), O.length_mask(lq, q_len)
+    grad_out = torch.randn(bsz, lc, 4 * d, generator=gen)
+    pr = 0.2 if dropout else 0.0
+    keep_c = (torch.rand(bsz, lc, d, generator=gen) >= pr) if dropout else None
+    keep_q = (torch.rand(bsz, lq, d, generator=gen) >= pr) if dropout else None
+    # fp64 oracle + autograd
+    pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    cd, qd = text.double().requires_grad_(True), modality.double().requires_grad_(True)
+    want = O.bidaf_attention(pd, cd, qd, tmask, mmask, keep_c, keep_q, pr)
+    want.backward(grad_out.double())
+    got = _grads(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr, precision=1)
+    assert torch.isfinite(got[0]).all() and torch.isfinite(got[1]).all()
+    # a soft-max over a single element has an identically zero gradient: with lc == 1 or lq == 1 some weight gradients
+    # are pure cancellation noise (bf16: ~1e-3 of the terms that cancel), so their floor is set from the upstream scale
+    w_floor = 1e-2 * float(grad_out.abs().sum()) if min(lc, lq) == 1 else 1e-3
+    ds_scale = max(_ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr), w_floor)
+    _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pd.items()}, BWD_TOL[1], ds_scale, w_floor)

@@ -35,7 +35,6 @@ namespace {
 constexpr int TY = 32;                              // Y rows per streamed tile
 constexpr int Y_PART = TY / 8 * GROUP_BYTES;        // 13312 bytes per operand per tile
 constexpr int MAX_STAGES = 3;
-constexpr int PRODUCER = 32;                        // thread that issues the Y-stage TMA loads (tid 0 issues the MMAs)
 constexpr int COL_S = 0, COL_GA = 32, COL_GB = 64, COL_ACC0 = 96, COL_ACC1 = 96 + DPAD;   // 96 + 2 * 208 = 512
 constexpr int STG_STRIDE = 204;
 constexpr int NTHREADS = 256;
@@ -145,6 +144,7 @@ struct BwdArgs {
   __nv_bfloat16* dt_pack;              // PT: packed dT
   float* d_col;                        // PT: Dcol (B, LX)
   float* part;                         // DC/DQ: (B, nxb, PART_STRIDE) weight-gradient partials
+  long long* trace;                    // debugging aid: clock64() stamps of CTA (0,0), or null
   float keep_scale;
   int LX, LXP, LY, LYP, d;
 };
@@ -172,6 +172,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   const int half = warp >> 2, wq = warp & 3;
   const int row = wq * 32 + lane;
   const bool active = wq * 32 < ROWS;                    // warp-uniform: owns real TMEM lanes
+  // issuing warps (one elected lane each, see tc_common.cuh): DC/DQ use two warps that own no rows
+  constexpr int MMA_WARP = IS_PT ? 0 : 2, TMA_WARP = IS_PT ? 1 : 3;
+  const int warp_u = uniform_warp_idx();
+  const uint32_t leader = elect_one();                   // one lane per warp: the issuer in the MMA / TMA warps
   const int b = blockIdx.y, x0 = blockIdx.x * ROWS;
   if (x0 >= a.LX) return;
   const uint32_t bar_x = smem_u32(bars), bar_mma = smem_u32(bars + 1), bar_full0 = smem_u32(bars + 2);
@@ -216,26 +220,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   auto issue_stage = [&](int t) {
     const int s = t % STAGES;
     const uint32_t bar = bar_full0 + 8 * s;
     const uint32_t dst = smem_u32(St + s * STAGE_BYTES);
     const size_t off = y_batch + (size_t)t * Y_PART;
-    mbar_expect_tx(bar, STAGE_BYTES);
+    mbar_expect_tx(bar, STAGE_BYTES, leader);
 #pragma unroll
     for (int p = 0; p < NY; ++p)
-      tma_bulk_g2s(dst + p * Y_PART, reinterpret_cast<const char*>(a.y_ops[p]) + off, Y_PART, bar);
+      tma_bulk_g2s(dst + p * Y_PART, reinterpret_cast<const char*>(a.y_ops[p]) + off, Y_PART, bar, leader);
   };
-  if (tid == 0) {
-    mbar_expect_tx(bar_x, NX * X_BYTES);
+  if (warp_u == TMA_WARP) {
+    mbar_expect_tx(bar_x, NX * X_BYTES, leader);
 #pragma unroll
     for (int p = 0; p < NX; ++p)
-      tma_bulk_g2s(smem_u32(Xs + p * X_BYTES), reinterpret_cast<const char*>(a.x_ops[p]) + x_off, X_BYTES, bar_x);
-  }
-  if (tid == PRODUCER)
+      tma_bulk_g2s(smem_u32(Xs + p * X_BYTES), reinterpret_cast<const char*>(a.x_ops[p]) + x_off, X_BYTES, bar_x, leader);
     for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
+  }
 
   // ---- per-thread constants of this X row ------------------------------------------------------------------------
   const float bias2 = a.bias[0] * LOG2E;
@@ -255,15 +258,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   uint32_t mma_phase = 0;
   float rsum = 0.f;                                      // DC/DQ: fp32 sum over y of this thread's dS columns
   constexpr uint32_t IDESC_S = idesc_bf16(TY, 0), IDESC_PV = idesc_bf16(DPAD, 1);
-  const uint32_t xs_addr = smem_u32(Xs), ts_addr = smem_u32(Ts);
+  const uint32_t xs_lo = desc_lo(smem_u32(Xs), 128), ts_lo = desc_lo(smem_u32(Ts), TILE_LBO);
 
-  if (tid == 0) mbar_wait(bar_x, 0);
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == MMA_WARP * 32;
+  int ntrace = 0;
+  auto stamp = [&]() {
+    if (tracing && ntrace < 250) a.trace[ntrace++] = clock64();
+  };
+  stamp();
+  if (warp_u == MMA_WARP) mbar_wait(bar_x, 0);
+  stamp();
   for (int t = 0; t < nty; ++t) {
     const int s = t % STAGES;
     const uint32_t st_addr = smem_u32(St + s * STAGE_BYTES);
-    if (tid == 0) {
+    if (warp_u == MMA_WARP) {
       mbar_wait(bar_full0 + 8 * s, (t / STAGES) & 1);
+      stamp();
       tc_fence_after();
+      const uint32_t st_lo = desc_lo(st_addr, 128);
       // product p: X operand p times Y operand p, K-major both, into S / GA / GB
       constexpr int NPROD = IS_PT ? 1 : 4;
 #pragma unroll
@@ -273,10 +285,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
         const bool fresh = p == 0 || p == 1 || (p == 2 && MODE == DQ) || (p == 3 && MODE == DC);
 #pragma unroll
         for (int k = 0; k < DPAD / 16; ++k)
-          umma_bf16(tmem + col, smem_desc(xs_addr + p * X_BYTES + k * 256, 128, GROUP_BYTES),
-                    smem_desc(st_addr + p * Y_PART + k * 256, 128, GROUP_BYTES), IDESC_S, !(fresh && k == 0));
+          umma_bf16_lh(tmem + col, xs_lo + (p * X_BYTES + k * 256) / 16, desc_hi(GROUP_BYTES),
+                       st_lo + (p * Y_PART + k * 256) / 16, desc_hi(GROUP_BYTES), IDESC_S, !(fresh && k == 0), leader);
       }
-      umma_commit(bar_mma);
+      umma_commit(bar_mma, leader);
+      stamp();
     }
     const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + (t >> 1)) * 2);
     const int sh = (t & 1) * 32 + half * HALF;
@@ -284,13 +297,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
     if (t + 1 < nty) load_ycol(t + 1);
     // the previous tile's second MMAs commit to the "free" barrier of their stage: refill it while this tile's
     // first MMAs run, so the load has a whole tile of tensor-core time to land
-    if (tid == PRODUCER && t >= 1 && t - 1 + STAGES < nty) {
+    if (warp_u == TMA_WARP && t >= 1 && t - 1 + STAGES < nty) {
       mbar_wait(bar_free0 + 8 * ((t - 1) % STAGES), ((t - 1) / STAGES) & 1);
       issue_stage(t - 1 + STAGES);
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    stamp();
 
     if (active) {
       const float* yc = ycol + (t & 1) * 3 * TY + half * HALF;
@@ -348,28 +362,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    stamp();
+    if (warp_u == MMA_WARP) {
       tc_fence_after();
       // acc0 += tile0 * value0;  PT: value0 = dA (part 1), acc1 += tile0 * dBm (part 2);  DC: acc1 += R * dT (part 3)
-      const uint32_t v0 = st_addr + (IS_PT ? 1 : 0) * Y_PART;
+      const uint32_t v_lo = desc_lo(st_addr, GROUP_BYTES);
 #pragma unroll
       for (int k = 0; k < TY / 16; ++k)
-        umma_bf16(tmem + COL_ACC0, smem_desc(ts_addr + k * 2 * TILE_LBO, TILE_LBO, 128),
-                  smem_desc(v0 + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
+        umma_bf16_lh(tmem + COL_ACC0, ts_lo + k * 2 * TILE_LBO / 16, desc_hi(128),
+                     v_lo + ((IS_PT ? 1 : 0) * Y_PART + k * 2 * GROUP_BYTES) / 16, desc_hi(128), IDESC_PV, (t > 0) || (k > 0),
+                     leader);
       if (MODE != DQ) {
-        const uint32_t a1 = ts_addr + (IS_PT ? 0 : TILE_BYTES);
-        const uint32_t v1 = st_addr + (IS_PT ? 2 : 3) * Y_PART;
 #pragma unroll
         for (int k = 0; k < TY / 16; ++k)
-          umma_bf16(tmem + COL_ACC1, smem_desc(a1 + k * 2 * TILE_LBO, TILE_LBO, 128),
-                    smem_desc(v1 + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
+          umma_bf16_lh(tmem + COL_ACC1, ts_lo + ((IS_PT ? 0 : TILE_BYTES) + k * 2 * TILE_LBO) / 16, desc_hi(128),
+                       v_lo + ((IS_PT ? 2 : 3) * Y_PART + k * 2 * GROUP_BYTES) / 16, desc_hi(128), IDESC_PV,
+                       (t > 0) || (k > 0), leader);
       }
-      umma_commit(t == nty - 1 ? bar_mma : bar_free0 + 8 * s);
+      umma_commit(t == nty - 1 ? bar_mma : bar_free0 + 8 * s, leader);
     }
   }
   mbar_wait(bar_mma, mma_phase);
   tc_fence_after();
   __syncthreads();
+  stamp();
 
   // ---- epilogue: TMEM -> fp32 staging in shared memory (over the operands) -> coalesced global traffic ---------------
   float* stg = reinterpret_cast<float*>(smem);
@@ -412,17 +428,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
       }
       *reinterpret_cast<uint4*>(tp + (size_t)i * 16) = *reinterpret_cast<uint4*>(v);
     }
-    for (int r = warp; r < ROWS; r += NTHREADS / 32) {              // Dcol_j = dT_j . T_j
-      if (x0 + r >= a.LX) break;
-      const float* trow = a.t_feat + ((size_t)b * a.LX + x0 + r) * d;
-      float dot = 0.f;
-      for (int c4 = lane; c4 < dv4; c4 += 32) {
-        const float4 tv = __ldg(reinterpret_cast<const float4*>(trow + c4 * 4));
-        const float4 sv4 = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
-        dot += tv.x * sv4.x + tv.y * sv4.y + tv.z * sv4.z + tv.w * sv4.w;
+    // Dcol_j = dT_j . T_j: a warp per row, the T loads of four rows in flight at a time
+    constexpr int NW = NTHREADS / 32, RB = 4;
+#pragma unroll 1
+    for (int r0 = warp; r0 < ROWS; r0 += NW * RB) {
+      float4 tv[RB][2];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int r = r0 + u * NW;
+        const float* trow = a.t_feat + ((size_t)b * a.LX + min(x0 + r, a.LX - 1)) * d;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c4 = lane + 32 * h;
+          tv[u][h] = c4 < dv4 ? __ldg(reinterpret_cast<const float4*>(trow + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      dot = warp_sum(dot);
-      if (lane == 0) a.d_col[(size_t)b * a.LX + x0 + r] = dot;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int r = r0 + u * NW;
+        float dot = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c4 = lane + 32 * h;
+          if (c4 < dv4) {
+            const float4 sv4 = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
+            dot += tv[u][h].x * sv4.x + tv[u][h].y * sv4.y + tv[u][h].z * sv4.z + tv[u][h].w * sv4.w;
+          }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0 && x0 + r < a.LX) a.d_col[(size_t)b * a.LX + x0 + r] = dot;
+      }
     }
   } else {
     float* stg1 = stg + ROWS * STG_STRIDE;
@@ -506,6 +541,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   }
   tc_fence_before();
   __syncthreads();
+  stamp();
+  if (tracing) a.trace[255] = ntrace;
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -571,6 +608,7 @@ __global__ void __launch_bounds__(256) bidaf_bwd_reduce_kernel(const ReduceArgs 
 struct BwdWorkspace {
   __nv_bfloat16 *da_pack, *dbm_pack, *dt_pack;
   float *d_row, *d_col, *part_c, *part_q;
+  long long* trace;          // 3 x 256 clock stamps (MMB_BIDAF_BWD_TRACE=1)
   size_t bytes;
 };
 BwdWorkspace bwd_workspace(void* workspace, int B, int Lc, int Lq) {
@@ -590,6 +628,7 @@ BwdWorkspace bwd_workspace(void* workspace, int B, int Lc, int Lq) {
   w.d_col = reinterpret_cast<float*>(take((size_t)B * Lq * 4));
   w.part_c = reinterpret_cast<float*>(take((size_t)B * (pk.LcP / 64) * PART_STRIDE * 4));
   w.part_q = reinterpret_cast<float*>(take((size_t)B * (pk.LqP / 64) * PART_STRIDE * 4));
+  w.trace = reinterpret_cast<long long*>(take(3 * 256 * 8));
   w.bytes = off;
   return w;
 }
@@ -612,6 +651,7 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
   // debugging aid: MMB_BIDAF_BWD_STAGES = bit mask of the launches to run (1 prep, 2 PT, 4 DC, 8 DQ, 16 reduce)
   const char* env = getenv("MMB_BIDAF_BWD_STAGES");
   const int stages = env ? atoi(env) : 31;
+  const bool tracing = getenv("MMB_BIDAF_BWD_TRACE") != nullptr;   // stamps land at the end of `workspace`
 
   if (stages & 1) {
   PrepArgs pa{grad_out, text, out, bm, w.da_pack, w.dbm_pack, d_text, w.d_row, Lc, LcP, d};
@@ -626,6 +666,7 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.norm_y = lse_row;
     a.t_feat = q2c; a.dx = d_modality; a.dt_pack = w.dt_pack; a.d_col = w.d_col;
     a.LX = Lq; a.LXP = LqP; a.LY = Lc; a.LYP = LcP; a.d = d;
+    a.trace = tracing ? w.trace : nullptr;
     constexpr size_t smem = bwd_smem_bytes<PT>();
     MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bidaf_bwd_tc_kernel<PT><<<dim3(LqP / 128, B), NTHREADS, smem, stream>>>(a);
@@ -640,6 +681,7 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.x_feat = text; a.x_keep = keep_text; a.w_term = w_text; a.w_fold = w_cross;
     a.dx = d_text; a.part = w.part_c; a.keep_scale = keep_scale;
     a.LX = Lc; a.LXP = LcP; a.LY = Lq; a.LYP = LqP; a.d = d;
+    a.trace = tracing ? w.trace + 256 : nullptr;
     constexpr size_t smem = bwd_smem_bytes<DC>();
     static_assert(smem <= 227 * 1024, "DC shared memory");
     MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -655,6 +697,7 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.x_feat = modality; a.x_keep = keep_modality; a.w_term = w_modality; a.w_fold = nullptr;
     a.dx = d_modality; a.part = w.part_q; a.keep_scale = keep_scale;
     a.LX = Lq; a.LXP = LqP; a.LY = Lc; a.LYP = LcP; a.d = d;
+    a.trace = tracing ? w.trace + 512 : nullptr;
     constexpr size_t smem = bwd_smem_bytes<DQ>();
     MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bidaf_bwd_tc_kernel<DQ><<<dim3(LqP / 64, B), NTHREADS, smem, stream>>>(a);

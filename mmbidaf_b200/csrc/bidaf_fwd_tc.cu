@@ -34,7 +34,7 @@ constexpr int X_BYTES = TX / 8 * GROUP_BYTES;   // 53248
 constexpr int Y_BYTES = TY / 8 * GROUP_BYTES;   // 26624
 constexpr int P_BYTES = TX * TY * 2;            // 16384
 constexpr int MAX_STAGES = 3;
-constexpr int PRODUCER = 32;              // thread that issues the Y-stage TMA loads (tid 0 issues the MMAs)
+constexpr int MMA_WARP = 0, TMA_WARP = 1;  // issuing warps (one elected lane each, see tc_common.cuh)
 constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 64 + DPAD;
 constexpr int STG_STRIDE = 204;           // fp32 staging row stride (conflict-free 128-bit stores)
 
@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2, wq = warp & 3;
+  const int warp_u = uniform_warp_idx();
+  const uint32_t leader = elect_one();                   // one lane per warp: the issuer in the MMA / TMA warps
   const int row = wq * 32 + lane;
   const int b = blockIdx.y, x0 = blockIdx.x * TX;
   const uint32_t bar_x = smem_u32(bars), bar_mma = smem_u32(bars + 1), bar_full0 = smem_u32(bars + 2);
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int nty = (a.LY + TY - 1) / TY;
   const size_t x_off = ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
@@ -238,54 +240,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
     const uint32_t bar = bar_full0 + 8 * s;
     const uint32_t dst = smem_u32(St + s * stage_bytes);
     const size_t off = y_batch + (size_t)t * Y_BYTES;
-    mbar_expect_tx(bar, stage_bytes);
-    tma_bulk_g2s(dst, reinterpret_cast<const char*>(a.y_pack) + off, Y_BYTES, bar);
+    mbar_expect_tx(bar, stage_bytes, leader);
+    tma_bulk_g2s(dst, reinterpret_cast<const char*>(a.y_pack) + off, Y_BYTES, bar, leader);
     int part = 1;
-    if (sep_v0) tma_bulk_g2s(dst + (part++) * Y_BYTES, reinterpret_cast<const char*>(a.v0_pack) + off, Y_BYTES, bar);
-    if (KIND == C2Q) tma_bulk_g2s(dst + part * Y_BYTES, reinterpret_cast<const char*>(a.v1_pack) + off, Y_BYTES, bar);
+    if (sep_v0) tma_bulk_g2s(dst + (part++) * Y_BYTES, reinterpret_cast<const char*>(a.v0_pack) + off, Y_BYTES, bar, leader);
+    if (KIND == C2Q) tma_bulk_g2s(dst + part * Y_BYTES, reinterpret_cast<const char*>(a.v1_pack) + off, Y_BYTES, bar, leader);
   };
-  if (tid == 0) {
-    mbar_expect_tx(bar_x, X_BYTES);
-    tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_pack) + x_off, X_BYTES, bar_x);
-  }
-  if (tid == PRODUCER)
+  if (warp_u == TMA_WARP) {
+    mbar_expect_tx(bar_x, X_BYTES, leader);
+    tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_pack) + x_off, X_BYTES, bar_x, leader);
     for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
+  }
 
   const float bias2 = a.bias[0] * LOG2E;
   const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);     // this warp's 32 TMEM lanes
   float m_ref = -INFINITY, l_part = 0.f;                             // log2 domain; l over this thread's columns
   uint32_t mma_phase = 0;
   constexpr uint32_t IDESC_S = idesc_bf16(TY, 0), IDESC_PV = idesc_bf16(DPAD, 1);
-  const uint32_t xs_addr = smem_u32(Xs), ps_addr = smem_u32(Ps);
+  const uint32_t xs_addr = smem_u32(Xs);
+  const uint32_t xs_lo = desc_lo(xs_addr, 128), ps_lo = desc_lo(smem_u32(Ps), 2048);
 
-  if (tid == 0) mbar_wait(bar_x, 0);
+  if (warp_u == MMA_WARP) mbar_wait(bar_x, 0);
   for (int t = 0; t < nty; ++t) {
     const int s = t % STAGES;
     const uint32_t st_addr = smem_u32(St + s * stage_bytes);
-    if (tid == 0) {
+    if (warp_u == MMA_WARP) {
       mbar_wait(bar_full0 + 8 * s, (t / STAGES) & 1);
       tc_fence_after();
+      const uint32_t st_lo = desc_lo(st_addr, 128);
 #pragma unroll
       for (int k = 0; k < DPAD / 16; ++k)                       // S = X Y^T, both K-major
-        umma_bf16(tmem + COL_S, smem_desc(xs_addr + k * 256, 128, GROUP_BYTES),
-                  smem_desc(st_addr + k * 256, 128, GROUP_BYTES), IDESC_S, k > 0);
-      umma_commit(bar_mma);
+        umma_bf16_lh(tmem + COL_S, xs_lo + k * 16, desc_hi(GROUP_BYTES), st_lo + k * 16, desc_hi(GROUP_BYTES), IDESC_S, k > 0,
+                     leader);
+      umma_commit(bar_mma, leader);
     }
     const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + t) * 2);
     const uint32_t wvalid = (uint32_t)(words.x >> (HALF * half)), wopen = (uint32_t)(words.y >> (HALF * half));
     const bool all_open = (words.x & words.y) == ~0ull;         // CTA-uniform: interior tile, nothing masked
     // the previous tile's P V MMAs commit to the "free" barrier of their stage: refill it while this tile's S MMAs
     // run, so the load has a whole tile of tensor-core + soft-max time to land
-    if (tid == PRODUCER && t >= 1 && t - 1 + STAGES < nty) {
+    if (warp_u == TMA_WARP && t >= 1 && t - 1 + STAGES < nty) {
       mbar_wait(bar_free0 + 8 * ((t - 1) % STAGES), ((t - 1) / STAGES) & 1);
       issue_stage(t - 1 + STAGES);
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    if (KIND == C2Q && tid == 0 && t == nty - 1) {              // X operand no longer needed: fetch the plain text
-      mbar_expect_tx(bar_x, X_BYTES);
-      tma_bulk_g2s(xs_addr, reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x);
+    if (KIND == C2Q && warp_u == TMA_WARP && t == nty - 1) {    // X operand no longer needed: fetch the plain text
+      mbar_expect_tx(bar_x, X_BYTES, leader);
+      tma_bulk_g2s(xs_addr, reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x, leader);
     }
 
     // ---- this thread's half row of S: masked streaming soft-max (base-2) -------------------------------------
@@ -365,21 +368,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
       tc_fence_before();
       __syncthreads();
     }
-    if (tid == 0) {
+    if (warp_u == MMA_WARP) {
       tc_fence_after();
-      const uint32_t v0_addr = sep_v0 ? st_addr + Y_BYTES : st_addr;
+      const uint32_t v0_lo = desc_lo(sep_v0 ? st_addr + Y_BYTES : st_addr, GROUP_BYTES);
 #pragma unroll
       for (int k = 0; k < TY / 16; ++k)                         // O0 += P V0 (V MN-major: LBO = group stride)
-        umma_bf16(tmem + COL_O0, smem_desc(ps_addr + k * 4096, 2048, 128),
-                  smem_desc(v0_addr + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
+        umma_bf16_lh(tmem + COL_O0, ps_lo + k * 256, desc_hi(128), v0_lo + k * 2 * GROUP_BYTES / 16, desc_hi(128), IDESC_PV,
+                     (t > 0) || (k > 0), leader);
       if (KIND == C2Q) {
-        const uint32_t v1_addr = st_addr + (nparts - 1) * Y_BYTES;
+        const uint32_t v1_lo = desc_lo(st_addr + (nparts - 1) * Y_BYTES, GROUP_BYTES);
 #pragma unroll
         for (int k = 0; k < TY / 16; ++k)
-          umma_bf16(tmem + COL_O1, smem_desc(ps_addr + k * 4096, 2048, 128),
-                    smem_desc(v1_addr + k * 2 * GROUP_BYTES, GROUP_BYTES, 128), IDESC_PV, (t > 0) || (k > 0));
+          umma_bf16_lh(tmem + COL_O1, ps_lo + k * 256, desc_hi(128), v1_lo + k * 2 * GROUP_BYTES / 16, desc_hi(128), IDESC_PV,
+                       (t > 0) || (k > 0), leader);
       }
-      umma_commit(t == nty - 1 ? bar_mma : bar_free0 + 8 * s);
+      umma_commit(t == nty - 1 ? bar_mma : bar_free0 + 8 * s, leader);
     }
   }
   // ---- epilogue: TMEM -> registers -> fp32 staging in smem -> coalesced global stores -----------------------------

@@ -21,11 +21,36 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a converged warp (1 for the elected lane, 0 for the others).  The single-thread instructions below
+// (tcgen05.mma / commit, TMA issue) take it as `leader` and are executed by ALL lanes of the issuing warp with the
+// instruction itself predicated on it: their operands are then computed in warp-uniform control flow and ptxas keeps
+// them in uniform registers.  Issuing them under `if (tid == 0)` makes it emit a per-instruction ELECT /
+// R2UR.BROADCAST loop instead (measured: 63 cycles per tcgen05.mma).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+// Warp index as a value the compiler knows to be warp-uniform.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}" ::"r"(bar), "r"(bytes), "r"(leader)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // try_wait suspends for a hardware time slice; the bound turns a protocol bug into a trap instead of a hang.
@@ -44,10 +69,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+      "}" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "r"(leader)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -61,18 +90,44 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Executed by a converged warp, issued by its leader.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc,
+                                          uint32_t leader) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(leader)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// Same with the descriptors given as (low word, high word): the high word (SBO, version) is a constant and the low
+// word (address >> 4 | LBO) advances by a constant per K step, so the issue loop is one integer add per operand.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t acc, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar), "r"(leader)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

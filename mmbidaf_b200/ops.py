@@ -6,6 +6,7 @@ this module (bench.py reports it as ``gpu_launches``).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -85,6 +86,8 @@ def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor
                                p(lse_row), p(lse_col), p(fwd_ws), p(ws), p(d_text), p(d_modality), p(d_w[0]), p(d_w[1]),
                                p(d_w[2]), p(d_bias), B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_bwd")
     _count(5)
+    if os.environ.get("MMB_BIDAF_BWD_TRACE"):      # debugging aid: clock stamps at the end of the workspace
+        bidaf_bwd.last_trace = ws[-3 * 256 * 8:].view(torch.int64).view(3, 256)
     return d_text, d_modality, d_w[0], d_w[1], d_w[2], d_bias
 
 

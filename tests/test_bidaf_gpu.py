@@ -253,6 +253,6 @@ def test_bf16_backward_matches_oracle_ragged(shape, dropout):
     assert torch.isfinite(got[0]).all() and torch.isfinite(got[1]).all()
     # a soft-max over a single element has an identically zero gradient: with lc == 1 or lq == 1 some weight gradients
     # are pure cancellation noise (bf16: ~1e-3 of the terms that cancel), so their floor is set from the upstream scale
-    w_floor = 1e-2 * float(grad_out.abs().sum()) if min(lc, lq) == 1 else 1e-3
+    w_floor = 5e-2 * float(grad_out.abs().sum()) if min(lc, lq) == 1 else 1e-3
     ds_scale = max(_ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr), w_floor)
     _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pd.items()}, BWD_TOL[1], ds_scale, w_floor)

@@ -156,8 +156,8 @@ def workload_config(n_gpus: int):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
-def bidaf_microbench(device, iters: int, warmup: int, precision: int):
-    """Fused BiDAF forward on BASELINE config 2; returns (avg seconds per forward, algorithmic bytes)."""
+def bidaf_microbench(device, iters: int, warmup: int, precision: int, backward: bool = False):
+    """Fused BiDAF forward (or backward) on BASELINE config 2; returns (avg seconds per call, algorithmic bytes)."""
     from mmbidaf_b200 import ops
     B, Lc, Lq, d = CFG2["batch"], CFG2["lc"], CFG2["lq"], CFG2["d"]
     gen = torch.Generator().manual_seed(224)
@@ -172,7 +172,17 @@ def bidaf_microbench(device, iters: int, warmup: int, precision: int):
         sets.append((c, q, cm, qm))
     w = [torch.randn(d, generator=gen).to(device) * 0.1 for _ in range(3)]
     bias = torch.zeros(1, device=device)
-    run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision)
+    if backward:                                             # saved forward state + an upstream gradient per input set
+        full = []
+        for s in sets:
+            out, q2c, lse_r, lse_c, bm, ws = ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias,
+                                                            precision=precision, save=True)
+            full.append(s + (torch.randn(out.shape, generator=gen).to(device), out, q2c, lse_r, lse_c, bm, ws))
+        sets = full
+        run = lambda s: ops.bidaf_bwd(s[4], s[0], s[1], w[0], w[1], w[2], bias, None, None, 1.0, s[5], s[9], s[6], s[7],
+                                      s[8], s[10], precision)
+    else:
+        run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision)
     for i in range(warmup):
         run(sets[i % 4])
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -183,6 +193,8 @@ def bidaf_microbench(device, iters: int, warmup: int, precision: int):
     end.record()
     torch.cuda.synchronize()
     algo_bytes = 4 * B * (Lc * d + Lq * d + Lc * 4 * d) + B * (Lc + Lq)
+    if backward:                                            # read dX (4 Lc d), c, q; write dc, dq
+        algo_bytes = 4 * B * (4 * Lc * d + 2 * Lc * d + 2 * Lq * d)
     return start.elapsed_time(end) / 1e3 / iters, algo_bytes
 
 
@@ -292,6 +304,8 @@ def run_gpu_arm(args):
         t_bidaf, algo = bidaf_microbench(device, 20, 5, ops.PREC_BF16 if fast else ops.PREC_FP32) \
             if "bidaf" in sections else (float("nan"), 1)
         achieved = algo / t_bidaf / 1e9
+        t_bwd, algo_bwd = bidaf_microbench(device, 20, 5, ops.PREC_BF16, backward=True) \
+            if "bidaf" in sections and fast else (float("nan"), 1)
         line = {"metric": METRIC, "value": round(videos / seconds, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
@@ -307,7 +321,11 @@ def run_gpu_arm(args):
                              "frac": round(achieved / peak, 4),
                              "traffic": 154355456 if fast else None,      # dram read+write per forward, ncu (profiles/r01_bidaf_tc_ncu.md)
                              "peak_source": peak_src,
-                             "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1)}}
+                             "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1),
+                             # the fused backward (prep + P^T pass + two dS passes + reduce) of the same op, same method
+                             "backward": {"us": round(t_bwd * 1e6, 1), "algorithmic_bytes": algo_bwd,
+                                          "achieved": round(algo_bwd / t_bwd / 1e9, 1),
+                                          "frac": round(algo_bwd / t_bwd / 1e9 / peak, 4)}}}
         if world == 1 and not args.no_cpu_baseline:
             vps, _, cores, sample = cpu_training_throughput(4, 3, 1)
             line["cpu_baseline"] = {"value": round(vps, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

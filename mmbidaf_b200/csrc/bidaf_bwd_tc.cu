@@ -196,27 +196,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   const size_t x_off = ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
   const size_t y_batch = (size_t)b * (a.LYP / 8) * GROUP_BYTES;
   const float log2_lx = log2f((float)a.LX);
-  // per-column scalars of tile t -> ycol[t & 1]  (visible after the next __syncthreads)
-  auto load_ycol = [&](int t) {
-    if (tid < TY) {
-      const int y = t * TY + tid;
-      float n2 = 0.f, d2 = 0.f, fill = NEG2;
-      if (y < a.LY) {
-        const float lse = a.norm_y[(size_t)b * a.LY + y];
-        // a fully masked soft-max is uniform (attention.py:94 uses -1e30, not -inf): every logit of the column
-        // is the fill value, so logit - lse = -log(LX) -- which fp32 cannot hold next to 1e30; re-base both to 0.
-        const bool degenerate = lse < -5e29f;
-        n2 = degenerate ? log2_lx : lse * LOG2E;
-        fill = degenerate ? 0.f : NEG2;
-        if (!IS_PT) d2 = a.dlt_y[(size_t)b * a.LY + y];
-      }
-      float* yc = ycol + (t & 1) * 3 * TY;
-      yc[tid] = n2;
-      yc[TY + tid] = d2;
-      yc[2 * TY + tid] = fill;
+  // per-column scalars of tile t -> ycol[t & 1], by one warp (an idle one in DC/DQ), in two steps so that the global
+  // loads are issued a whole tile before their values are stored (visible after the next __syncthreads)
+  const int yl = tid - (IS_PT ? 0 : 6 * 32);
+  float yl_lse = 0.f, yl_d2 = 0.f;
+  auto fetch_ycol = [&](int t) {
+    const int y = t * TY + yl;
+    if ((unsigned)yl < (unsigned)TY && y < a.LY) {
+      yl_lse = a.norm_y[(size_t)b * a.LY + y];
+      if (!IS_PT) yl_d2 = a.dlt_y[(size_t)b * a.LY + y];
     }
   };
-  load_ycol(0);
+  auto store_ycol = [&](int t) {
+    if ((unsigned)yl < (unsigned)TY) {
+      float n2 = 0.f, d2 = 0.f, fill = NEG2;
+      if (t * TY + yl < a.LY) {
+        // a fully masked soft-max is uniform (attention.py:94 uses -1e30, not -inf): every logit of the column
+        // is the fill value, so logit - lse = -log(LX) -- which fp32 cannot hold next to 1e30; re-base both to 0.
+        const bool degenerate = yl_lse < -5e29f;
+        n2 = degenerate ? log2_lx : yl_lse * LOG2E;
+        fill = degenerate ? 0.f : NEG2;
+        d2 = yl_d2;
+      }
+      float* yc = ycol + (t & 1) * 3 * TY;
+      yc[yl] = n2;
+      yc[TY + yl] = d2;
+      yc[2 * TY + yl] = fill;
+    }
+  };
+  fetch_ycol(0);
+  store_ycol(0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
     const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + (t >> 1)) * 2);
     const int sh = (t & 1) * 32 + half * HALF;
     const uint32_t wvalid = (uint32_t)(words.x >> sh) & 0xffffu, wopen = (uint32_t)(words.y >> sh) & 0xffffu;
-    if (t + 1 < nty) load_ycol(t + 1);
+    if (t + 1 < nty) fetch_ycol(t + 1);
     // the previous tile's second MMAs commit to the "free" barrier of their stage: refill it while this tile's
     // first MMAs run, so the load has a whole tile of tensor-core time to land
     if (warp_u == TMA_WARP && t >= 1 && t - 1 + STAGES < nty) {
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
               make_uint4(pk1[c8 * 4], pk1[c8 * 4 + 1], pk1[c8 * 4 + 2], pk1[c8 * 4 + 3]);
       }
     }
+    if (t + 1 < nty) store_ycol(t + 1);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();

@@ -23,6 +23,7 @@
 //     when a row's running max moves by more than TAU), as in FlashAttention-4.
 //     The epilogue drains TMEM through shared memory so that the 4-way concat is written with coalesced
 //     128-bit stores; Q2C also emits T in packed bf16 form for pass 3.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace mmb {
@@ -186,6 +187,7 @@ struct TcArgs {
   __nv_bfloat16* t_pack;             // Q2C: packed T for pass 3
   float* lse;                        // (B, LX)
   float* bm;                         // C2Q: optional (B, LX, d) copy of b = s1 T for the backward pass
+  long long* trace;                  // debugging aid: clock64() stamps of CTA (0,0), or null
   int LX, LXP, LY, LYP, d;
 };
 
@@ -260,12 +262,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   const uint32_t xs_addr = smem_u32(Xs);
   const uint32_t xs_lo = desc_lo(xs_addr, 128), ps_lo = desc_lo(smem_u32(Ps), 2048);
 
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  int ntrace = 0;
+  auto stamp = [&]() {
+    if (tracing && ntrace < 250) a.trace[ntrace++] = clock64();
+  };
+  stamp();
   if (warp_u == MMA_WARP) mbar_wait(bar_x, 0);
+  stamp();
   for (int t = 0; t < nty; ++t) {
     const int s = t % STAGES;
     const uint32_t st_addr = smem_u32(St + s * stage_bytes);
     if (warp_u == MMA_WARP) {
       mbar_wait(bar_full0 + 8 * s, (t / STAGES) & 1);
+      stamp();
       tc_fence_after();
       const uint32_t st_lo = desc_lo(st_addr, 128);
 #pragma unroll
@@ -273,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
         umma_bf16_lh(tmem + COL_S, xs_lo + k * 16, desc_hi(GROUP_BYTES), st_lo + k * 16, desc_hi(GROUP_BYTES), IDESC_S, k > 0,
                      leader);
       umma_commit(bar_mma, leader);
+      stamp();
     }
     const ulonglong2 words = *reinterpret_cast<const ulonglong2*>(a.y_words + ((size_t)b * (a.LYP / 64) + t) * 2);
     const uint32_t wvalid = (uint32_t)(words.x >> (HALF * half)), wopen = (uint32_t)(words.y >> (HALF * half));
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    stamp();
     if (KIND == C2Q && warp_u == TMA_WARP && t == nty - 1) {    // X operand no longer needed: fetch the plain text
       mbar_expect_tx(bar_x, X_BYTES, leader);
       tma_bulk_g2s(xs_addr, reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x, leader);
@@ -312,6 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
     }
     xbuf[half * TX + row] = tile_max;
     __syncthreads();
+    stamp();
     tile_max = fmaxf(tile_max, xbuf[(half ^ 1) * TX + row]);    // both threads of the row now agree
     float alpha = 1.f;
     const bool bump = tile_max > m_ref + TAU2;                  // first tile: m_ref = -inf -> always
@@ -351,6 +364,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
     fence_proxy_async();                                        // st.shared P -> visible to the tensor core
     tc_fence_before();
     const int any_bump = __syncthreads_or(bump && t > 0);
+    stamp();
     if (any_bump) {                                             // lazy rescale: the two threads of a row split the columns
       tc_fence_after();
 #pragma unroll 1
@@ -368,6 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
       tc_fence_before();
       __syncthreads();
     }
+    stamp();
     if (warp_u == MMA_WARP) {
       tc_fence_after();
       const uint32_t v0_lo = desc_lo(sep_v0 ? st_addr + Y_BYTES : st_addr, GROUP_BYTES);
@@ -390,6 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   mbar_wait(bar_mma, mma_phase);
   tc_fence_after();
   __syncthreads();
+  stamp();
   const float l_run = xbuf[row] + xbuf[TX + row];
   const int gx = x0 + row;
   const float inv_l = 1.f / l_run;
@@ -460,6 +476,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  stamp();
+  if (tracing) a.trace[255] = ntrace;
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -483,6 +501,7 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   const int LcP = pk.LcP, LqP = pk.LqP;
   __nv_bfloat16 *cw = pk.cw, *cp = pk.cp, *qs = pk.qs, *qp = pk.qp, *tp = pk.tp;
   unsigned long long *c_words = pk.c_words, *q_words = pk.q_words;
+  long long* trace = getenv("MMB_BIDAF_FWD_TRACE") ? pk.trace : nullptr;   // debugging aid (tools/bidaf_trace.py)
 
   PackPair pp;
   pp.side[0] = PackArgs{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
@@ -492,14 +511,14 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
   {   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
-    TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, Lq, LqP, Lc, LcP, d};
+    TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, trace, Lq, LqP, Lc, LcP, d};
     const size_t smem = tc_smem_bytes(2);
     MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<Q2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), NTHREADS, smem, stream>>>(a);
     if (int rc = check_launch("bidaf_tc_kernel<Q2C>")) return rc;
   }
   {   // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)
-    TcArgs a{cw, qs, qp, tp, cp, q_words, bias, out, nullptr, lse_row, bm, Lc, LcP, Lq, LqP, d};
+    TcArgs a{cw, qs, qp, tp, cp, q_words, bias, out, nullptr, lse_row, bm, trace ? trace + 256 : nullptr, Lc, LcP, Lq, LqP, d};
     const int nparts = 2 + (qp != qs ? 1 : 0);
     const size_t smem = tc_smem_bytes(nparts);
     MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "bidaf bf16 tier: %zu B of shared memory", smem);

@@ -56,6 +56,8 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
                                p(kt), p(km), float(keep_scale), p(out), p(q2c), p(bm), p(lse_row), p(lse_col), p(ws),
                                B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
     _count(2 if precision == PREC_FP32 else 3)
+    if ws is not None and os.environ.get("MMB_BIDAF_FWD_TRACE"):      # debugging aid: clock stamps
+        bidaf_fwd.last_trace = ws[-4096:].view(torch.int64).view(2, 256)
     if save:
         return out, q2c, lse_row, lse_col, bm, ws
     return out, q2c, lse_row, lse_col

@@ -195,14 +195,14 @@ def _ds_abs_sum(state, text, modality, tmask, mmask, grad_out, keep_c=None, keep
     return float(s.grad.abs().sum())
 
 
-def _check_grads(got, want_c, want_q, want_w, tol, ds_scale=None, w_floor=1e-3):
+def _check_grads(got, want_c, want_q, want_w, tol, ds_scale=None, w_floor=1e-3, bias_slack=0.0):
     dc, dq, dw = got
     errs = {"d_text": grad_err(dc, want_c), "d_modality": grad_err(dq, want_q)}
     for k, v in want_w.items():
         if k == "bias" and ds_scale is not None:
             # d loss / d bias = sum(dS) = 0 identically (both soft-maxes are shift invariant); what any implementation
-            # returns is rounding noise, which for bf16 operands scales with sum |dS|
-            errs[k] = float(dw[k].abs().max()) / max(ds_scale, 1e-30) * (tol / 2e-3)
+            # returns is rounding noise, which for bf16 operands scales with sum |dS| (observed <= 3e-4 of it)
+            errs[k] = float(dw[k].abs().max()) / (2e-3 * ds_scale + bias_slack + 1e-30) * tol
         else:
             errs[k] = grad_err(dw[k], v, k, floor=w_floor)
     assert all(e < tol for e in errs.values()), errs
@@ -254,5 +254,6 @@ def test_bf16_backward_matches_oracle_ragged(shape, dropout):
     # a soft-max over a single element has an identically zero gradient: with lc == 1 or lq == 1 some weight gradients
     # are pure cancellation noise (bf16: ~1e-3 of the terms that cancel), so their floor is set from the upstream scale
     w_floor = 5e-2 * float(grad_out.abs().sum()) if min(lc, lq) == 1 else 1e-3
-    ds_scale = max(_ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr), w_floor)
-    _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pd.items()}, BWD_TOL[1], ds_scale, w_floor)
+    ds_scale = _ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr)
+    _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pd.items()}, BWD_TOL[1], ds_scale, w_floor,
+                 bias_slack=w_floor if min(lc, lq) == 1 else 0.0)

@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackPair pp) {
     }
     if (a.out_copy && row < a.L && lane < nchunk) {     // out[:, :, 0:d] = text, exact fp32
       float* o = a.out_copy + ((size_t)b * a.L + row) * 4 * d + lane * 8;
-      __stcs(reinterpret_cast<float4*>(o), raw[r][0]);
-      __stcs(reinterpret_cast<float4*>(o + 4), raw[r][1]);
+      *reinterpret_cast<float4*>(o) = raw[r][0];
+      *reinterpret_cast<float4*>(o + 4) = raw[r][1];
     }
     float dot = 0.f;
     if (keep && row < a.L && lane < nchunk) {
@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   float* stg = reinterpret_cast<float*>(St);                    // 128 x 204 fp32 = 104448 B <= 2 stages
   const int d = a.d, dv4 = d >> 2;
   if (KIND == C2Q) mbar_wait(bar_x, 1);                         // plain text tile (bf16, core-matrix order) in Xs
+  stamp();
 #pragma unroll 1
   for (int acc = 0; acc < NACC; ++acc) {
     if (acc > 0) __syncthreads();
+    stamp();
 #pragma unroll 1
     for (int q = half; q < DPAD / 16; q += 2) {
       float o[16];
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
               make_float4(o[i] * inv_l, o[i + 1] * inv_l, o[i + 2] * inv_l, o[i + 3] * inv_l);
     }
     __syncthreads();
+    stamp();
     if (KIND == Q2C) {
       for (int i = tid; i < TX * dv4; i += NTHREADS) {          // fp32 T rows, coalesced
         const int r = i / dv4, c4 = i - r * dv4;
@@ -465,11 +468,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
         const float4 cv = make_float4(c01.x * v.x, c01.y * v.y, c23.x * v.z, c23.y * v.w);
         float* orow = a.out + ((size_t)b * a.LX + x0 + r) * 4 * d + col;
         if (acc == 0) {
-          __stcs(reinterpret_cast<float4*>(orow + d), v);
-          __stcs(reinterpret_cast<float4*>(orow + 2 * d), cv);
+          *reinterpret_cast<float4*>(orow + d) = v;
+          *reinterpret_cast<float4*>(orow + 2 * d) = cv;
         } else {
-          __stcs(reinterpret_cast<float4*>(orow + 3 * d), cv);
-          if (a.bm) __stcs(reinterpret_cast<float4*>(a.bm + ((size_t)b * a.LX + x0 + r) * d + col), v);
+          *reinterpret_cast<float4*>(orow + 3 * d) = cv;
+          if (a.bm) *reinterpret_cast<float4*>(a.bm + ((size_t)b * a.LX + x0 + r) * d + col) = v;
         }
       }
     }

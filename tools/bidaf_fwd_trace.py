@@ -28,11 +28,14 @@ for k, name in enumerate(["Q2C", "C2Q"]):
     n = int(tr[k, 255])
     t = tr[k, :n] - tr[k, 0]
     print(f"{name}: {n} stamps, total {int(t[-1])} cycles;  prologue (X landed) {int(t[1])}")
-    body = t[2:n - 2].view(-1, 6)
+    nep = 4 if name == "Q2C" else 6          # stamps after the last P V wait: text tile landed, [start, drained] per accumulator, end
+    last = n - 1 - nep
+    ep = [int(v) for v in t[last:n]]
+    body = t[2:last].view(-1, 6)
     prev = int(t[1])
     for i, row in enumerate(body):
         v = [int(x) for x in row]
         print(f"  tile {i}: wait stage {v[0] - prev:5d}  issue S {v[1] - v[0]:5d}  wait S {v[2] - v[1]:5d}  ld+max+exchange {v[3] - v[2]:5d}"
               f"  exp+P store+sync {v[4] - v[3]:5d}  rescale {v[5] - v[4]:5d}")
         prev = v[5]
-    print(f"  last P V wait {int(t[n - 2]) - prev}  epilogue {int(t[n - 1] - t[n - 2])}")
+    print(f"  last P V wait {ep[0] - prev}  epilogue steps {[b - a for a, b in zip(ep[:-1], ep[1:])]}")

@@ -13,8 +13,8 @@
 //     additive terms of the trilinear form split into bf16 hi/lo halves: text rows hold
 //     [t_hi, t_lo, 1, 1, 0..] and modality rows [1, 1, m_hi, m_lo, 0..], so the GEMM itself adds
 //     c~.w_c + q~.w_q to every logit.  w_cq is folded into the text-side S operand.
-//  2. bidaf_tc_kernel<Q2C>  X = 128 modality rows, streams 64-row text tiles:   T = softmax_i(S)^T c
-//  3. bidaf_tc_kernel<C2Q>  X = 128 text rows, streams 64-row modality tiles:   a = softmax_j(S) q,
+//  2. Q2C blocks             X = 128 modality rows, streams 64-row text tiles:   T = softmax_i(S)^T c
+//  3. C2Q blocks             X = 128 text rows, streams 64-row modality tiles:   a = softmax_j(S) q,
 //                                                                              b = softmax_j(S) T
 //     Per tile: thread 0 issues 13 MMAs (128 x 64 x 208) into TMEM, commits to an mbarrier; each of the 128
 //     threads owns one row of S (tcgen05.ld 32x32b.x64), does the masked streaming soft-max in registers
@@ -180,7 +180,6 @@ struct TcArgs {
   const __nv_bfloat16* y_pack;       // S operand of the Y side
   const __nv_bfloat16* v0_pack;      // value operand 0 (plain Y rows); may equal y_pack
   const __nv_bfloat16* v1_pack;      // value operand 1 (C2Q: packed T); null for Q2C
-  const __nv_bfloat16* x_plain;      // C2Q: plain (un-dropped, un-folded) text pack for the c*a / c*b products
   const unsigned long long* y_words; // (B, LYP/64, 2)
   const float* bias;
   float* out;                        // Q2C: T fp32 (B, LX, d);   C2Q: out (B, LX, 4d)
@@ -194,8 +193,11 @@ struct TcArgs {
 constexpr int NTHREADS = 256;            // two threads per X row: warps 0-3 take S columns 0-31, warps 4-7 columns 32-63
 constexpr float TAU2 = 11.0f;            // lazy-rescale threshold in log2 units (factor 2048)
 
+// One X block of one pass.  `ready` (per batch row) orders the two passes inside ONE launch: a Q2C block bumps
+// ready[b] once its T rows are in memory, a C2Q block of the same batch row waits for all of them.
 template <int KIND>
-__global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
+__device__ __forceinline__ void bidaf_tc_block(const TcArgs& a, const int b, const int xblk, int* ready, const int ready_target,
+                                               long long* cta_times = nullptr) {
   constexpr int NACC = KIND == C2Q ? 2 : 1;
   constexpr int HALF = TY / 2;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   const int warp_u = uniform_warp_idx();
   const uint32_t leader = elect_one();                   // one lane per warp: the issuer in the MMA / TMA warps
   const int row = wq * 32 + lane;
-  const int b = blockIdx.y, x0 = blockIdx.x * TX;
+  const int x0 = xblk * TX;
   const uint32_t bar_x = smem_u32(bars), bar_mma = smem_u32(bars + 1), bar_full0 = smem_u32(bars + 2);
   const uint32_t bar_free0 = smem_u32(bars + 2 + MAX_STAGES);
 
@@ -234,7 +236,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  const int nty = (a.LY + TY - 1) / TY;
+  // Tiles past the last un-masked Y row contribute exp(-1e30 - m) = 0 to every soft-max: stop there.  (If nothing at
+  // all is un-masked the soft-max is uniform over the whole range, attention.py:94, and every tile is needed.)
+  int nty = (a.LY + TY - 1) / TY;
+  {
+    int last = 0;
+    for (int t = lane; t < nty; t += 32)
+      if (a.y_words[((size_t)b * (a.LYP / 64) + t) * 2 + 1] != 0ull) last = t + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (last > 0) nty = last;
+  }
   const size_t x_off = ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
   const size_t y_batch = (size_t)b * (a.LYP / 8) * GROUP_BYTES;
   auto issue_stage = [&](int t) {
@@ -251,6 +263,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   if (warp_u == TMA_WARP) {
     mbar_expect_tx(bar_x, X_BYTES, leader);
     tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_pack) + x_off, X_BYTES, bar_x, leader);
+    if (KIND == C2Q && ready) {                                   // the stages carry T: wait for this batch row's Q2C blocks
+      wait_counter(ready + b, ready_target);
+      fence_proxy_async_all();                                    // their generic-proxy stores -> our async-proxy (TMA) loads
+    }
     for (int t = 0; t < STAGES && t < nty; ++t) issue_stage(t);
   }
 
@@ -262,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   const uint32_t xs_addr = smem_u32(Xs);
   const uint32_t xs_lo = desc_lo(xs_addr, 128), ps_lo = desc_lo(smem_u32(Ps), 2048);
 
-  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  const bool tracing = a.trace != nullptr && b == 0 && xblk == 0 && tid == 0;
   int ntrace = 0;
   auto stamp = [&]() {
     if (tracing && ntrace < 250) a.trace[ntrace++] = clock64();
@@ -298,10 +314,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
     mma_phase ^= 1;
     tc_fence_after();
     stamp();
-    if (KIND == C2Q && warp_u == TMA_WARP && t == nty - 1) {    // X operand no longer needed: fetch the plain text
-      mbar_expect_tx(bar_x, X_BYTES, leader);
-      tma_bulk_g2s(xs_addr, reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x, leader);
-    }
 
     // ---- this thread's half row of S: masked streaming soft-max (base-2) -------------------------------------
     float sv[HALF];
@@ -406,13 +418,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   tc_fence_after();
   __syncthreads();
   stamp();
+  if (cta_times && tid == 0) cta_times[1] = globaltimer_ns();          // main loop done
   const float l_run = xbuf[row] + xbuf[TX + row];
   const int gx = x0 + row;
   const float inv_l = 1.f / l_run;
   if (half == 0 && gx < a.LX && a.lse) a.lse[(size_t)b * a.LX + gx] = (m_ref + log2f(l_run)) * LN2;
   float* stg = reinterpret_cast<float*>(St);                    // 128 x 204 fp32 = 104448 B <= 2 stages
   const int d = a.d, dv4 = d >> 2;
-  if (KIND == C2Q) mbar_wait(bar_x, 1);                         // plain text tile (bf16, core-matrix order) in Xs
   stamp();
 #pragma unroll 1
   for (int acc = 0; acc < NACC; ++acc) {
@@ -452,27 +464,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
         *reinterpret_cast<uint4*>(tp + (size_t)i * 16) = *reinterpret_cast<uint4*>(v);
       }
     } else {
-      // blocks 1..3 of the concat (attention.py:52); block 0 was written by the pack kernel.  The products use
-      // the bf16 text tile already in shared memory: no global loads in the epilogue.  A warp step covers one
-      // 8-row group x 16 columns (lane = row-in-group + 8 * float4-in-block), which reads the core-matrix text
-      // tile as one contiguous 256-byte run (no bank conflicts) and stores 64-byte runs per output row.
-      const int nblk = (d + 15) >> 4;
-      for (int it = warp; it < (TX / 8) * nblk; it += NTHREADS / 32) {
-        const int g8 = it / nblk, blk = it - g8 * nblk;
-        const int r = g8 * 8 + (lane & 7), col = blk * 16 + (lane >> 3) * 4;
-        if (x0 + r >= a.LX || col >= d) continue;
-        const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + col);
-        const uint2 cb = *reinterpret_cast<const uint2*>(Xs + g8 * GROUP_BYTES + (col >> 3) * 128 + (r & 7) * 16 + (col & 7) * 2);
-        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cb.x));
-        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cb.y));
-        const float4 cv = make_float4(c01.x * v.x, c01.y * v.y, c23.x * v.z, c23.y * v.w);
-        float* orow = a.out + ((size_t)b * a.LX + x0 + r) * 4 * d + col;
-        if (acc == 0) {
-          *reinterpret_cast<float4*>(orow + d) = v;
-          *reinterpret_cast<float4*>(orow + 2 * d) = cv;
-        } else {
-          *reinterpret_cast<float4*>(orow + 3 * d) = cv;
-          if (a.bm) *reinterpret_cast<float4*>(a.bm + ((size_t)b * a.LX + x0 + r) * d + col) = v;
+      // blocks 1..3 of the concat (attention.py:52); block 0 (the text itself, exact fp32) was written by the pack
+      // kernel and is read back here for the products.  A warp instruction stores 512 contiguous bytes of ONE row:
+      // measured 30 B/clk/SM against 15 for 64-byte runs over 8 rows (tools/micro/store_rate.cu).
+      constexpr int NW = NTHREADS / 32, RB = 4;
+#pragma unroll 1
+      for (int r0 = warp; r0 < TX; r0 += NW * RB) {
+        float4 cv[RB][2];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u * NW;
+          const float* crow = a.out + ((size_t)b * a.LX + min(x0 + r, a.LX - 1)) * 4 * d;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c4 = lane + 32 * h;
+            if (c4 < dv4) cv[u][h] = *reinterpret_cast<const float4*>(crow + c4 * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int r = r0 + u * NW;
+          if (x0 + r >= a.LX) continue;
+          float* orow = a.out + ((size_t)b * a.LX + x0 + r) * 4 * d;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c4 = lane + 32 * h;
+            if (c4 >= dv4) continue;
+            const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + c4 * 4);
+            const float4 c = cv[u][h];
+            const float4 p = make_float4(c.x * v.x, c.y * v.y, c.z * v.z, c.w * v.w);
+            if (acc == 0) {
+              *reinterpret_cast<float4*>(orow + d + c4 * 4) = v;
+              *reinterpret_cast<float4*>(orow + 2 * d + c4 * 4) = p;
+            } else {
+              *reinterpret_cast<float4*>(orow + 3 * d + c4 * 4) = p;
+              if (a.bm) *reinterpret_cast<float4*>(a.bm + ((size_t)b * a.LX + x0 + r) * d + c4 * 4) = v;
+            }
+          }
         }
       }
     }
@@ -482,6 +510,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
   stamp();
   if (tracing) a.trace[255] = ntrace;
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  if (KIND == Q2C && ready && tid == 0) signal_counter(ready + b);   // after the barrier: every thread's T stores are ordered before it
+}
+
+// Both passes in one launch: the Q2C blocks come first in block order (so they are resident or done before any C2Q
+// block that waits for them is scheduled), then the C2Q blocks.  A C2Q block starts as soon as ITS batch row's Q2C
+// blocks are done, on whichever SM frees up: no launch boundary between the passes, and the store-bound C2Q epilogues
+// (the chip writes ~3.5 TB/s) spread over time instead of hitting memory together.
+struct FusedArgs {
+  TcArgs q2c, c2q;
+  int* ready;            // (B) zeroed before the launch
+  int nq, nc;            // X blocks per batch row of each pass
+  int n_q2c;             // B * nq
+  long long* cta_times;  // debugging aid (MMB_BIDAF_FWD_CTA_TIMES: a device pointer, 4 x int64 per block) or null
+};
+
+// (separate launches: debugging aid, MMB_BIDAF_FWD_SPLIT=1)
+template <int KIND>
+__global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
+  bidaf_tc_block<KIND>(a, blockIdx.y, blockIdx.x, nullptr, 0);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_fused_kernel(const FusedArgs f) {
+  const int blk = blockIdx.x;
+  long long* times = f.cta_times ? f.cta_times + 4 * (size_t)blk : nullptr;   // debugging aid: [start, loop end, end, SM id]
+  if (times && threadIdx.x == 0) {
+    times[0] = globaltimer_ns();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    times[3] = smid;
+  }
+  if (blk < f.n_q2c) {
+    bidaf_tc_block<Q2C>(f.q2c, blk / f.nq, blk % f.nq, f.ready, 0, times);
+  } else {
+    const int i = blk - f.n_q2c;
+    bidaf_tc_block<C2Q>(f.c2q, i / f.nc, i % f.nc, f.ready, f.nq, times);
+  }
+  if (times && threadIdx.x == 0) times[2] = globaltimer_ns();
 }
 
 size_t tc_smem_bytes(int nparts) {
@@ -513,22 +578,27 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 64, B, 2), 256, 0, stream>>>(pp);
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
-  {   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
-    TcArgs a{qs, cw, cp, nullptr, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, trace, Lq, LqP, Lc, LcP, d};
-    const size_t smem = tc_smem_bytes(2);
-    MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<Q2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), NTHREADS, smem, stream>>>(a);
+  // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
+  const TcArgs aq{qs, cw, cp, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, trace, Lq, LqP, Lc, LcP, d};
+  // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)
+  const TcArgs ac{cw, qs, qp, tp, q_words, bias, out, nullptr, lse_row, bm, trace ? trace + 256 : nullptr, Lc, LcP, Lq, LqP, d};
+  const size_t smem_q = tc_smem_bytes(2), smem_c = tc_smem_bytes(2 + (qp != qs ? 1 : 0));
+  MMB_REQUIRE(smem_c <= 227 * 1024 && smem_q <= 227 * 1024, MMB_ERR_UNSUPPORTED, "bidaf bf16 tier: %zu B of shared memory", smem_c);
+  if (getenv("MMB_BIDAF_FWD_SPLIT")) {
+    MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<Q2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    bidaf_tc_kernel<Q2C><<<dim3(LqP / TX, B), NTHREADS, smem_q, stream>>>(aq);
     if (int rc = check_launch("bidaf_tc_kernel<Q2C>")) return rc;
+    MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<C2Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    bidaf_tc_kernel<C2Q><<<dim3(LcP / TX, B), NTHREADS, smem_c, stream>>>(ac);
+    return check_launch("bidaf_tc_kernel<C2Q>");
   }
-  {   // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)
-    TcArgs a{cw, qs, qp, tp, cp, q_words, bias, out, nullptr, lse_row, bm, trace ? trace + 256 : nullptr, Lc, LcP, Lq, LqP, d};
-    const int nparts = 2 + (qp != qs ? 1 : 0);
-    const size_t smem = tc_smem_bytes(nparts);
-    MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "bidaf bf16 tier: %zu B of shared memory", smem);
-    MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_kernel<C2Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_tc_kernel<C2Q><<<dim3(LcP / TX, B), NTHREADS, smem, stream>>>(a);
-    if (int rc = check_launch("bidaf_tc_kernel<C2Q>")) return rc;
-  }
+  const size_t smem = smem_q > smem_c ? smem_q : smem_c;
+  MMB_CUDA(cudaMemsetAsync(pk.ready, 0, sizeof(int) * (size_t)B, stream));
+  const char* ct = getenv("MMB_BIDAF_FWD_CTA_TIMES");
+  FusedArgs f{aq, ac, pk.ready, LqP / TX, LcP / TX, B * (LqP / TX), ct ? reinterpret_cast<long long*>(strtoull(ct, nullptr, 0)) : nullptr};
+  MMB_CUDA(cudaFuncSetAttribute(bidaf_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bidaf_tc_fused_kernel<<<B * (LqP / TX + LcP / TX), NTHREADS, smem, stream>>>(f);
+  if (int rc = check_launch("bidaf_tc_fused_kernel")) return rc;
   return MMB_OK;
 }
 

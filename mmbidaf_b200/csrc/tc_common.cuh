@@ -79,6 +79,27 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Inter-CTA ordering inside one launch (producer blocks have lower block indices than their consumers).
+__device__ __forceinline__ void signal_counter(int* counter) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void wait_counter(const int* counter, int target) {
+  // bounded: a scheduling surprise becomes a trap (an error to the caller), not a hang
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) return;
+    __nanosleep(64);
+  }
+  __trap();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,6 +195,7 @@ struct BidafPacks {
   __nv_bfloat16 *qs, *qp;            // modality: S operand (dropped, term chunk) / plain values (== qs without dropout)
   __nv_bfloat16* tp;                 // packed T = s2^T c
   unsigned long long *c_words, *q_words;   // (B, LP/64, 2): [in-range bits, un-masked bits] per 64 rows
+  int* ready;                        // (B) Q2C -> C2Q dependency counters of the fused launch
   long long* trace;                  // 2 x 256 clock stamps (debugging aid), the last 4096 bytes
   int LcP, LqP;
   size_t c_pack, q_pack, bytes;
@@ -198,8 +220,10 @@ inline BidafPacks bidaf_packs(void* workspace, int B, int Lc, int Lq, bool modal
   p.c_words = reinterpret_cast<unsigned long long*>(next);
   p.q_words = p.c_words + (size_t)B * (p.LcP / 64) * 2;
   const size_t used = ((size_t)(next - ws) + 16 * (size_t)B * (p.LcP / 64 + p.LqP / 64) + 255) / 256 * 256;
-  p.trace = reinterpret_cast<long long*>(ws + used);
-  p.bytes = used + 4096;
+  p.ready = reinterpret_cast<int*>(ws + used);
+  const size_t used2 = used + ((size_t)B * 4 + 255) / 256 * 256;
+  p.trace = reinterpret_cast<long long*>(ws + used2);
+  p.bytes = used2 + 4096;
   return p;
 }
 

@@ -1,0 +1,46 @@
+"""Per-CTA timeline of the fused forward launch (debugging aid): start / loop end / end of every block by SM.
+    python tools/bidaf_fwd_timeline.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmbidaf_b200 import ops  # noqa: E402
+
+B, Lc, Lq, d = 64, 512, 256, 200
+dev = "cuda"
+gen = torch.Generator().manual_seed(224)
+c = torch.randn(B, Lc, d, generator=gen).to(dev)
+q = torch.randn(B, Lq, d, generator=gen).to(dev)
+clen = torch.randint(Lc // 2, Lc + 1, (B, 1), generator=gen)
+qlen = torch.randint(Lq // 2, Lq + 1, (B, 1), generator=gen)
+cm = (torch.arange(Lc).unsqueeze(0) < clen).to(dev)
+qm = (torch.arange(Lq).unsqueeze(0) < qlen).to(dev)
+w = [torch.randn(d, generator=gen).to(dev) * 0.1 for _ in range(3)]
+bias = torch.zeros(1, device=dev)
+nblk = B * (Lq // 128 + Lc // 128)
+times = torch.zeros(nblk, 4, dtype=torch.int64, device=dev)
+for _ in range(3):
+    ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, None, None, 1.0, 1)
+os.environ["MMB_BIDAF_FWD_CTA_TIMES"] = str(times.data_ptr())
+ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, None, None, 1.0, 1)
+torch.cuda.synchronize()
+t = times.cpu()
+t0 = int(t[:, 0].min())
+nq = B * (Lq // 128)
+print(f"launch span {int(t[:, 2].max()) - t0} ns over {nblk} blocks on {len(set(t[:, 3].tolist()))} SMs")
+for name, sl in (("Q2C", slice(0, nq)), ("C2Q", slice(nq, nblk))):
+    x = t[sl]
+    dur, loop, epi = x[:, 2] - x[:, 0], x[:, 1] - x[:, 0], x[:, 2] - x[:, 1]
+    print(f"{name}: {x.shape[0]} blocks; start {int(x[:, 0].min()) - t0}..{int(x[:, 0].max()) - t0} ns; duration mean {dur.float().mean():.0f} "
+          f"(min {int(dur.min())}, max {int(dur.max())}); wait+loop mean {loop.float().mean():.0f}; epilogue mean {epi.float().mean():.0f} "
+          f"(min {int(epi.min())}, max {int(epi.max())})")
+# occupancy over time: how many blocks are in their epilogue at each microsecond
+span = int(t[:, 2].max()) - t0
+for us in range(0, span // 1000 + 1, 4):
+    now = t0 + us * 1000
+    run = ((t[:, 0] <= now) & (t[:, 2] > now))
+    in_epi = run & (t[:, 1] <= now)
+    print(f"  t={us:3d} us: {int(run.sum()):3d} blocks resident ({int((run[:nq]).sum())} Q2C), {int(in_epi.sum()):3d} in their epilogue")

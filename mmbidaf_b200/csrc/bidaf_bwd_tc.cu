@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const float logit = open_x ? fmaf(sv[c + e], LOG2E, bias2) : yc[2 * TY + c + e];
-            w[e] = (valid_x && ((wvalid >> (c + e)) & 1u)) ? exp2f(logit - yc[c + e]) : 0.f;
+            w[e] = (valid_x && ((wvalid >> (c + e)) & 1u)) ? fast_exp2(logit - yc[c + e]) : 0.f;
           }
           const __nv_bfloat162 v = __floats2bfloat162_rn(w[0], w[1]);
           pk0[c / 2] = *reinterpret_cast<const uint32_t*>(&v);
@@ -343,12 +343,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
           for (int e = 0; e < 2; ++e) {
             const float s2 = fmaf(sv[c + e], LOG2E, bias2);
             const bool vy = (wvalid >> (c + e)) & 1u, oy = (wopen >> (c + e)) & 1u;
-            const float w1 = exp2f(s2 - n1), w2 = exp2f(s2 - yc[c + e]);
+            const float w1 = fast_exp2(s2 - n1), w2 = fast_exp2(s2 - yc[c + e]);
             const float t1 = (valid_x && oy) ? w1 * (ga[c + e] - d1) : 0.f;
             const float t2 = (open_x && vy) ? w2 * (gb[c + e] - yc[TY + c + e]) : 0.f;
             ds[e] = t1 + t2;
             rsum += t2;            // sum_y of the W1 part is zero analytically (soft-max along y): leave its noise out
-            if (MODE == DC) rr[e] = (valid_x && vy) ? (open_x ? w2 : exp2f(yc[2 * TY + c + e] - yc[c + e])) : 0.f;
+            if (MODE == DC) rr[e] = (valid_x && vy) ? (open_x ? w2 : fast_exp2(yc[2 * TY + c + e] - yc[c + e])) : 0.f;
           }
           const __nv_bfloat162 v = __floats2bfloat162_rn(ds[0], ds[1]);
           pk0[c / 2] = *reinterpret_cast<const uint32_t*>(&v);

@@ -341,7 +341,7 @@ __device__ __forceinline__ void bidaf_tc_block(const TcArgs& a, const int b, con
     float alpha = 1.f;
     const bool bump = tile_max > m_ref + TAU2;                  // first tile: m_ref = -inf -> always
     if (bump) {
-      alpha = exp2f(m_ref - tile_max);                          // 0 on the first tile
+      alpha = fast_exp2(m_ref - tile_max);                          // 0 on the first tile
       m_ref = tile_max;
     }
     float psum = 0.f;
@@ -349,7 +349,7 @@ __device__ __forceinline__ void bidaf_tc_block(const TcArgs& a, const int b, con
     if (all_open) {
 #pragma unroll
       for (int c = 0; c < HALF; c += 2) {
-        const float p0 = exp2f(sv[c] - m_ref), p1 = exp2f(sv[c + 1] - m_ref);
+        const float p0 = fast_exp2(sv[c] - m_ref), p1 = fast_exp2(sv[c + 1] - m_ref);
         psum += p0 + p1;
         const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
         packed[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
@@ -357,8 +357,8 @@ __device__ __forceinline__ void bidaf_tc_block(const TcArgs& a, const int b, con
     } else {
 #pragma unroll
       for (int c = 0; c < HALF; c += 2) {
-        const float p0 = ((wvalid >> c) & 1u) ? exp2f(sv[c] - m_ref) : 0.f;
-        const float p1 = ((wvalid >> (c + 1)) & 1u) ? exp2f(sv[c + 1] - m_ref) : 0.f;
+        const float p0 = ((wvalid >> c) & 1u) ? fast_exp2(sv[c] - m_ref) : 0.f;
+        const float p1 = ((wvalid >> (c + 1)) & 1u) ? fast_exp2(sv[c + 1] - m_ref) : 0.f;
         psum += p0 + p1;
         const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
         packed[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
@@ -555,6 +555,9 @@ size_t tc_smem_bytes(int nparts) {
 
 }  // namespace
 
+int bidaf_fwd_tc2_launch(const BidafPacks& pk, const float* bias, float* out, float* q2c, float* bm, float* lse_row,
+                         float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
+
 // Workspace (bytes): packed operands, mask words (layout: tc_common.cuh::bidaf_packs).
 size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout) { return bidaf_packs(nullptr, B, Lc, Lq, dropout != 0).bytes; }
 
@@ -578,6 +581,13 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 64, B, 2), 256, 0, stream>>>(pp);
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
+  // Two cuts of the same algorithm.  Short sequences are store-heavy (few tiles per 128-row block): the two-blocks-
+  // per-SM launch of bidaf_fwd_tc2.cu hides one block's stores under the other's MMAs (cfg2: 96.6 vs 103 us).  Long
+  // sequences are tile-heavy: there the 64-column S tiles and the single S evaluation per c2q block of the
+  // one-block-per-SM cut below win (B=16, 4096 x 2048: 436 vs 477 us).  MMB_BIDAF_FWD_CUT=1|2 forces one.
+  const char* cut = getenv("MMB_BIDAF_FWD_CUT");
+  const bool two_per_sm = cut ? atoi(cut) == 2 : (Lc <= 512 && Lq <= 512);
+  if (two_per_sm) return bidaf_fwd_tc2_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
   const TcArgs aq{qs, cw, cp, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, trace, Lq, LqP, Lc, LcP, d};
   // C2Q: X = text rows, Y = modality rows (S operand qs, values qp and packed T)

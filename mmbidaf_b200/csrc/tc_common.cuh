@@ -185,6 +185,14 @@ constexpr uint32_t idesc_bf16(int n, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// 2^x as one MUFU.EX2: results below 2^-126 flush to zero (exp2f spends three more instructions on them), which for
+// soft-max weights that are rounded to bf16 or summed in fp32 next is exact enough.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Layout of the forward workspace (mmb_bidaf_workspace_bytes): the bf16 packs and mask words the forward pass

@@ -20,7 +20,7 @@ cm = (torch.arange(Lc).unsqueeze(0) < clen).to(dev)
 qm = (torch.arange(Lq).unsqueeze(0) < qlen).to(dev)
 w = [torch.randn(d, generator=gen).to(dev) * 0.1 for _ in range(3)]
 bias = torch.zeros(1, device=dev)
-nblk = B * (Lq // 128 + Lc // 128)
+nblk = B * (Lq // 128 + 2 * (Lc // 128))
 times = torch.zeros(nblk, 4, dtype=torch.int64, device=dev)
 for _ in range(3):
     ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, None, None, 1.0, 1)
@@ -30,8 +30,9 @@ torch.cuda.synchronize()
 t = times.cpu()
 t0 = int(t[:, 0].min())
 nq = B * (Lq // 128)
+nc = B * (Lc // 128)
 print(f"launch span {int(t[:, 2].max()) - t0} ns over {nblk} blocks on {len(set(t[:, 3].tolist()))} SMs")
-for name, sl in (("Q2C", slice(0, nq)), ("C2Q", slice(nq, nblk))):
+for name, sl in (("Q2C", slice(0, nq)), ("C2QA", slice(nq, nq + nc)), ("C2QB", slice(nq + nc, nblk))):
     x = t[sl]
     dur, loop, epi = x[:, 2] - x[:, 0], x[:, 1] - x[:, 0], x[:, 2] - x[:, 1]
     print(f"{name}: {x.shape[0]} blocks; start {int(x[:, 0].min()) - t0}..{int(x[:, 0].max()) - t0} ns; duration mean {dur.float().mean():.0f} "

@@ -22,9 +22,9 @@
 //                                acc0 = dS^T (c~ o w_cq), colsum(dS) in registers; epilogue: dq, partial dw_q
 //   5. bidaf_bwd_reduce_kernel   deterministic sum of the per-CTA weight-gradient partials
 //
-// A DC / DQ CTA needs four X-side and four Y-side operands (1664 bytes per row and side), so it owns 64 rows:
-// the MMAs are still issued with M = 128 -- the A descriptors run 64 rows past each operand into whatever lies
-// behind it in shared memory; MMA rows are independent, those TMEM lanes are never read.
+// A DC / DQ CTA needs four X-side and four Y-side operands (1664 bytes per row and side), so it owns 64 rows and
+// issues M = 64 MMAs (25 cycles for 64 x 32 x 16 against 40 for M = 128, tools/micro/umma_rate.cu); their accumulator
+// rows sit in lanes 0-15 of each 32-lane TMEM quarter, so all eight warps take part with their lower half-warps.
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -49,7 +49,7 @@ enum Mode { PT = 0, DC = 1, DQ = 2 };
 struct PrepArgs {
   const float* grad;         // (B, L, 4d)
   const float* text;         // (B, L, d)
-  const float* out;          // (B, L, 4d) forward output: blocks 1 (a) and 3 (c o b) are read
+  const float* out;          // (B, L, 4d) forward output: block 1 (a) is read
   const float* bm;           // (B, L, d)  b = s1 T
   __nv_bfloat16* da_pack;
   __nv_bfloat16* dbm_pack;
@@ -79,16 +79,16 @@ __global__ void __launch_bounds__(256) bidaf_bwd_prep_kernel(const PrepArgs a) {
     const bool on = row < a.L && lane < nchunk;
     if (on) {
       const size_t r4 = ((size_t)b * a.L + row) * 4 * d + lane * 8, r1 = ((size_t)b * a.L + row) * d + lane * 8;
-      float g0[8], g1[8], g2[8], g3[8], c[8], av[8], cb[8], bv[8];
+      float g0[8], g1[8], g2[8], g3[8], c[8], av[8], bv[8];
       ld8(a.grad + r4, g0); ld8(a.grad + r4 + d, g1); ld8(a.grad + r4 + 2 * d, g2); ld8(a.grad + r4 + 3 * d, g3);
-      ld8(a.text + r1, c); ld8(a.out + r4 + d, av); ld8(a.out + r4 + 3 * d, cb); ld8(a.bm + r1, bv);
+      ld8(a.text + r1, c); ld8(a.out + r4 + d, av); ld8(a.bm + r1, bv);
       float da[8], db[8], dc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         da[e] = fmaf(c[e], g2[e], g1[e]);
         db[e] = c[e] * g3[e];
         dc[e] = fmaf(bv[e], g3[e], fmaf(av[e], g2[e], g0[e]));
-        dot = fmaf(da[e], av[e], fmaf(g3[e], cb[e], dot));
+        dot = fmaf(da[e], av[e], fmaf(db[e], bv[e], dot));           // Drow = dA.A + dBm.Bm
       }
       *reinterpret_cast<float4*>(a.d_text + r1) = make_float4(dc[0], dc[1], dc[2], dc[3]);
       *reinterpret_cast<float4*>(a.d_text + r1 + 4) = make_float4(dc[4], dc[5], dc[6], dc[7]);
@@ -170,8 +170,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2, wq = warp & 3;
-  const int row = wq * 32 + lane;
-  const bool active = wq * 32 < ROWS;                    // warp-uniform: owns real TMEM lanes
+  // PT: M = 128 MMAs, accumulator row = TMEM lane (32 rows per warp quarter).  DC / DQ: M = 64 MMAs, whose sixteen rows per
+  // quarter sit in lanes 0-15: every warp works, its upper half-warp carries garbage and never stores.
+  constexpr int MMA_M = IS_PT ? 128 : 64;
+  const int row = IS_PT ? wq * 32 + lane : wq * 16 + (lane & 15);
+  const bool owner = IS_PT || lane < 16;
   // issuing warps (one elected lane each, see tc_common.cuh): DC/DQ use two warps that own no rows
   constexpr int MMA_WARP = IS_PT ? 0 : 2, TMA_WARP = IS_PT ? 1 : 3;
   const int warp_u = uniform_warp_idx();
@@ -192,7 +195,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
 
-  const int nty = (a.LY + TY - 1) / TY;
+  int nty = (a.LY + TY - 1) / TY;
+  if (MODE == DC) {
+    // Y rows (modality positions) past the last un-masked one: P = 0 there, hence dT = Dcol = 0 and every term of dS and
+    // of R dT vanishes -- stop at the last tile that has an un-masked row (all tiles if nothing is un-masked: then the
+    // row soft-max is uniform and dT is not zero).
+    int last = 0;
+    for (int w = lane; w < (a.LY + 63) / 64; w += 32) {
+      const unsigned long long open = a.y_words[((size_t)b * (a.LYP / 64) + w) * 2 + 1];
+      if (open != 0ull) last = 2 * w + ((open >> 32) != 0ull ? 2 : 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (last > 0) nty = min(nty, last);
+  }
   const size_t x_off = ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
   const size_t y_batch = (size_t)b * (a.LYP / 8) * GROUP_BYTES;
   const float log2_lx = log2f((float)a.LX);
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   const int gx = x0 + row;
   bool valid_x = false, open_x = false;
   float n1 = 0.f, d1 = 0.f;
-  if (active) {
+  if (owner) {
     const ulonglong2 xw = *reinterpret_cast<const ulonglong2*>(a.x_words + ((size_t)b * (a.LXP / 64) + gx / 64) * 2);
     valid_x = (xw.x >> (gx & 63)) & 1ull;
     open_x = (xw.y >> (gx & 63)) & 1ull;
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);
   uint32_t mma_phase = 0;
   float rsum = 0.f;                                      // DC/DQ: fp32 sum over y of this thread's dS columns
-  constexpr uint32_t IDESC_S = idesc_bf16(TY, 0), IDESC_PV = idesc_bf16(DPAD, 1);
+  constexpr uint32_t IDESC_S = idesc_bf16(TY, 0, MMA_M), IDESC_PV = idesc_bf16(DPAD, 1, MMA_M);
   const uint32_t xs_lo = desc_lo(smem_u32(Xs), 128), ts_lo = desc_lo(smem_u32(Ts), TILE_LBO);
 
   const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == MMA_WARP * 32;
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
     tc_fence_after();
     stamp();
 
-    if (active) {
+    {
       const float* yc = ycol + (t & 1) * 3 * TY + half * HALF;
       float sv[HALF];
       tmem_ld16(lane_base + COL_S + half * HALF, sv);
@@ -333,39 +349,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
           pk0[c / 2] = *reinterpret_cast<const uint32_t*>(&v);
         }
       } else {
-        float ga[HALF], gb[HALF];
+        float ga[HALF], gb[HALF], n2[HALF], d2[HALF];
         tmem_ld16(lane_base + COL_GA + half * HALF, ga);
         tmem_ld16(lane_base + COL_GB + half * HALF, gb);
 #pragma unroll
-        for (int c = 0; c < HALF; c += 2) {
-          float ds[2], rr[2];
+        for (int c = 0; c < HALF; c += 4) {
+          *reinterpret_cast<float4*>(n2 + c) = *reinterpret_cast<const float4*>(yc + c);
+          *reinterpret_cast<float4*>(d2 + c) = *reinterpret_cast<const float4*>(yc + TY + c);
+        }
+        // interior tile (every column in range and un-masked: uniform over the CTA) and no masked row in this warp:
+        // no bit tests, no re-based logits
+        const bool interior = (wvalid & wopen) == 0xffffu && __all_sync(0xffffffffu, open_x || !valid_x);
+        if (interior) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float s2 = fmaf(sv[c + e], LOG2E, bias2);
-            const bool vy = (wvalid >> (c + e)) & 1u, oy = (wopen >> (c + e)) & 1u;
-            const float w1 = fast_exp2(s2 - n1), w2 = fast_exp2(s2 - yc[c + e]);
-            const float t1 = (valid_x && oy) ? w1 * (ga[c + e] - d1) : 0.f;
-            const float t2 = (open_x && vy) ? w2 * (gb[c + e] - yc[TY + c + e]) : 0.f;
-            ds[e] = t1 + t2;
-            rsum += t2;            // sum_y of the W1 part is zero analytically (soft-max along y): leave its noise out
-            if (MODE == DC) rr[e] = (valid_x && vy) ? (open_x ? w2 : fast_exp2(yc[2 * TY + c + e] - yc[c + e])) : 0.f;
+          for (int c = 0; c < HALF; c += 2) {
+            float ds[2], rr[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float s2 = fmaf(sv[c + e], LOG2E, bias2);
+              const float w1 = valid_x ? fast_exp2(s2 - n1) : 0.f, w2 = valid_x ? fast_exp2(s2 - n2[c + e]) : 0.f;   // rows past LX: zero
+              const float t2 = w2 * (gb[c + e] - d2[c + e]);
+              ds[e] = fmaf(w1, ga[c + e] - d1, t2);
+              rsum += t2;
+              rr[e] = w2;
+            }
+            const __nv_bfloat162 v = __floats2bfloat162_rn(ds[0], ds[1]);
+            pk0[c / 2] = *reinterpret_cast<const uint32_t*>(&v);
+            if (MODE == DC) {
+              const __nv_bfloat162 r2 = __floats2bfloat162_rn(rr[0], rr[1]);
+              pk1[c / 2] = *reinterpret_cast<const uint32_t*>(&r2);
+            }
           }
-          const __nv_bfloat162 v = __floats2bfloat162_rn(ds[0], ds[1]);
-          pk0[c / 2] = *reinterpret_cast<const uint32_t*>(&v);
-          if (MODE == DC) {
-            const __nv_bfloat162 r2 = __floats2bfloat162_rn(rr[0], rr[1]);
-            pk1[c / 2] = *reinterpret_cast<const uint32_t*>(&r2);
+        } else {
+#pragma unroll
+          for (int c = 0; c < HALF; c += 2) {
+            float ds[2], rr[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float s2 = fmaf(sv[c + e], LOG2E, bias2);
+              const bool vy = (wvalid >> (c + e)) & 1u, oy = (wopen >> (c + e)) & 1u;
+              const float w1 = fast_exp2(s2 - n1), w2 = fast_exp2(s2 - n2[c + e]);
+              const float t1 = (valid_x && oy) ? w1 * (ga[c + e] - d1) : 0.f;
+              const float t2 = (open_x && vy) ? w2 * (gb[c + e] - d2[c + e]) : 0.f;
+              ds[e] = t1 + t2;
+              rsum += t2;            // sum_y of the W1 part is zero analytically (soft-max along y): leave its noise out
+              if (MODE == DC) rr[e] = (valid_x && vy) ? (open_x ? w2 : fast_exp2(yc[2 * TY + c + e] - n2[c + e])) : 0.f;
+            }
+            const __nv_bfloat162 v = __floats2bfloat162_rn(ds[0], ds[1]);
+            pk0[c / 2] = *reinterpret_cast<const uint32_t*>(&v);
+            if (MODE == DC) {
+              const __nv_bfloat162 r2 = __floats2bfloat162_rn(rr[0], rr[1]);
+              pk1[c / 2] = *reinterpret_cast<const uint32_t*>(&r2);
+            }
           }
         }
       }
       // tiles in core-matrix order: chunk c8 (8 columns) at c8 * TILE_LBO + row * 16
       unsigned char* trow = Ts + row * 16 + (half * (HALF / 8)) * TILE_LBO;
+      if (owner) {
 #pragma unroll
-      for (int c8 = 0; c8 < HALF / 8; ++c8) {
-        *reinterpret_cast<uint4*>(trow + c8 * TILE_LBO) = make_uint4(pk0[c8 * 4], pk0[c8 * 4 + 1], pk0[c8 * 4 + 2], pk0[c8 * 4 + 3]);
-        if (MODE == DC)
-          *reinterpret_cast<uint4*>(trow + TILE_BYTES + c8 * TILE_LBO) =
-              make_uint4(pk1[c8 * 4], pk1[c8 * 4 + 1], pk1[c8 * 4 + 2], pk1[c8 * 4 + 3]);
+        for (int c8 = 0; c8 < HALF / 8; ++c8) {
+          *reinterpret_cast<uint4*>(trow + c8 * TILE_LBO) = make_uint4(pk0[c8 * 4], pk0[c8 * 4 + 1], pk0[c8 * 4 + 2], pk0[c8 * 4 + 3]);
+          if (MODE == DC)
+            *reinterpret_cast<uint4*>(trow + TILE_BYTES + c8 * TILE_LBO) =
+                make_uint4(pk1[c8 * 4], pk1[c8 * 4 + 1], pk1[c8 * 4 + 2], pk1[c8 * 4 + 3]);
+        }
       }
     }
     if (t + 1 < nty) store_ycol(t + 1);
@@ -401,11 +449,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   float* stg = reinterpret_cast<float*>(smem);
   const int d = a.d, dv4 = d >> 2;
   auto drain = [&](int col0, float* dst) {
-    if (active) {
 #pragma unroll 1
-      for (int q = half; q < DPAD / 16; q += 2) {
-        float o[16];
-        tmem_ld16(lane_base + col0 + q * 16, o);
+    for (int q = half; q < DPAD / 16; q += 2) {
+      float o[16];
+      tmem_ld16(lane_base + col0 + q * 16, o);
+      if (owner) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
           if (q * 16 + i < STG_STRIDE)
@@ -438,8 +486,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
       }
       *reinterpret_cast<uint4*>(tp + (size_t)i * 16) = *reinterpret_cast<uint4*>(v);
     }
-    // Dcol_j = dT_j . T_j: a warp per row, the T loads of four rows in flight at a time
-    constexpr int NW = NTHREADS / 32, RB = 4;
+    // Dcol_j = dT_j . T_j: a warp per row, the T loads of eight rows in flight at a time
+    constexpr int NW = NTHREADS / 32, RB = 8;
 #pragma unroll 1
     for (int r0 = warp; r0 < ROWS; r0 += NW * RB) {
       float4 tv[RB][2];
@@ -475,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
     static_assert(IS_PT || 2 * ROWS <= 2 * 3 * TY, "xsum fits in ycol");
     drain(COL_ACC0, stg);
     if (MODE == DC) drain(COL_ACC1, stg1);
-    if (active) xsum[half * ROWS + row] = rsum;
+    if (owner) xsum[half * ROWS + row] = rsum;
     __syncthreads();
     // Thread = one float4 column x a strided set of rows, loads batched ahead of the stores (the loop would
     // otherwise serialise on DRAM latency: the dx store may alias the next row's loads).
@@ -490,7 +538,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
         wtv[e] = a.w_term[c4 * 4 + e];
         wfv[e] = a.w_fold ? a.w_fold[c4 * 4 + e] : 1.f;
       }
-      constexpr int BATCH = 4;
+      constexpr int BATCH = 7;                                         // 13 rows per thread at d = 200: two rounds of loads
 #pragma unroll 1
       for (int r0 = rg; r0 < nrow; r0 += BATCH * ngrp) {
         float4 xv[BATCH], dv[BATCH];

@@ -180,9 +180,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          (1ull << 46);
 }
-// Instruction descriptor: D = F32, A = B = BF16, M = 128.
-constexpr uint32_t idesc_bf16(int n, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+// Instruction descriptor: D = F32, A = B = BF16.  M = 128: accumulator row i is TMEM lane i.  M = 64: row i is lane
+// (i / 16) * 32 + i % 16 -- sixteen rows in the low half of each 32-lane quarter (tools/micro/umma_m64_layout.cu).
+constexpr uint32_t idesc_bf16(int n, int b_mn_major, int m = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // 2^x as one MUFU.EX2: results below 2^-126 flush to zero (exp2f spends three more instructions on them), which for

@@ -257,3 +257,35 @@ def test_bf16_backward_matches_oracle_ragged(shape, dropout):
     ds_scale = _ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr)
     _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pd.items()}, BWD_TOL[1], ds_scale, w_floor,
                  bias_slack=w_floor if min(lc, lq) == 1 else 0.0)
+
+
+@pytest.mark.parametrize("cut", ["1", "2"])
+@pytest.mark.parametrize("shape", [(2, 130, 257, 200), (2, 600, 70, 200), (3, 409, 1024, 200)])
+def test_bf16_tier_both_kernel_cuts(shape, cut, monkeypatch):
+    """The forward has two cuts of the tcgen05 kernels (one / two blocks per SM) chosen by shape; force each on every
+    shape, with and without dropout, forward and (through the saved state) backward."""
+    monkeypatch.setenv("MMB_BIDAF_FWD_CUT", cut)
+    bsz, lc, lq, d = shape
+    gen = torch.Generator().manual_seed(4000 + lc * 7 + lq)
+    p = {"text_weight": torch.randn(d, 1, generator=gen) * 0.1, "modality_weight": torch.randn(d, 1, generator=gen) * 0.1,
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen) * 0.1, "bias": torch.tensor([0.3])}
+    text = torch.randn(bsz, lc, d, generator=gen)
+    modality = torch.randn(bsz, lq, d, generator=gen)
+    c_len = torch.randint(1, lc + 1, (bsz,), generator=gen).tolist()
+    q_len = torch.randint(1, lq + 1, (bsz,), generator=gen).tolist()
+    c_len[0], q_len[0] = lc, lq
+    tmask, mmask = O.length_mask(lc, c_len), O.length_mask(lq, q_len)
+    keep_c = torch.rand(bsz, lc, d, generator=gen) >= 0.2
+    keep_q = torch.rand(bsz, lq, d, generator=gen) >= 0.2
+    pd = {k: v.double() for k, v in p.items()}
+    for kc, kq, pr in ((None, None, 0.0), (keep_c, keep_q, 0.2)):
+        want = O.bidaf_attention(pd, text.double(), modality.double(), tmask, mmask, kc, kq, pr)
+        out, *_ = _run(p, text, modality, tmask, mmask, kc, kq, pr, precision=1)
+        assert torch.isfinite(out).all() and rel_err(out, want) < BF16_TOL
+    grad_out = torch.randn(bsz, lc, 4 * d, generator=gen)
+    pg = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    cd, qd = text.double().requires_grad_(True), modality.double().requires_grad_(True)
+    O.bidaf_attention(pg, cd, qd, tmask, mmask, keep_c, keep_q, 0.2).backward(grad_out.double())
+    got = _grads(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, 0.2, precision=1)
+    _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pg.items()}, BWD_TOL[1],
+                 _ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, 0.2))

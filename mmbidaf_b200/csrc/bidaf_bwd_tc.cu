@@ -21,6 +21,8 @@
 //   4. bidaf_bwd_tc_kernel<DQ>   X = 64 modality rows, streams text tiles: S^T, dP^T, dR^T -> dS^T;
 //                                acc0 = dS^T (c~ o w_cq), colsum(dS) in registers; epilogue: dq, partial dw_q
 //   5. bidaf_bwd_reduce_kernel   deterministic sum of the per-CTA weight-gradient partials
+// 2.-4. are ONE launch (bidaf_bwd_fused_kernel): PT blocks first, then the DC and DQ blocks, which wait on a per-batch-row
+// counter for the PT blocks they depend on.
 //
 // A DC / DQ CTA needs four X-side and four Y-side operands (1664 bytes per row and side), so it owns 64 rows and
 // issues M = 64 MMAs (25 cycles for 64 x 32 x 16 against 40 for M = 128, tools/micro/umma_rate.cu); their accumulator
@@ -149,8 +151,11 @@ struct BwdArgs {
   int LX, LXP, LY, LYP, d;
 };
 
+// One X block of one pass.  `ready` (per batch row) orders the passes inside ONE launch: a PT block bumps ready[b]
+// once its dq rows, dT pack and Dcol are in memory; the DC and DQ blocks of that batch row wait for all of them.
 template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs a) {
+__device__ __forceinline__ void bwd_block(const BwdArgs& a, const int b, const int xblk, const int nxb, int* ready,
+                                          const int ready_target) {
   constexpr bool IS_PT = MODE == PT;
   constexpr int ROWS = IS_PT ? 128 : 64;                 // real X rows per CTA
   constexpr int NX = IS_PT ? 1 : 4, NY = IS_PT ? 3 : 4;
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   constexpr int MMA_WARP = IS_PT ? 0 : 2, TMA_WARP = IS_PT ? 1 : 3;
   const int warp_u = uniform_warp_idx();
   const uint32_t leader = elect_one();                   // one lane per warp: the issuer in the MMA / TMA warps
-  const int b = blockIdx.y, x0 = blockIdx.x * ROWS;
+  const int x0 = xblk * ROWS;
   if (x0 >= a.LX) return;
   const uint32_t bar_x = smem_u32(bars), bar_mma = smem_u32(bars + 1), bar_full0 = smem_u32(bars + 2);
   const uint32_t bar_free0 = smem_u32(bars + 2 + MAX_STAGES);
@@ -240,6 +245,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
       yc[2 * TY + yl] = fill;
     }
   };
+  if (!IS_PT && ready) {                                 // dT pack, Dcol and dq come from this batch row's PT blocks
+    if (tid == 0) wait_counter(ready + b, ready_target);
+    __syncthreads();
+    fence_proxy_async_all();                             // their generic-proxy stores -> our async-proxy (TMA) loads
+  }
   fetch_ycol(0);
   store_ycol(0);
   tc_fence_before();
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   constexpr uint32_t IDESC_S = idesc_bf16(TY, 0, MMA_M), IDESC_PV = idesc_bf16(DPAD, 1, MMA_M);
   const uint32_t xs_lo = desc_lo(smem_u32(Xs), 128), ts_lo = desc_lo(smem_u32(Ts), TILE_LBO);
 
-  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == MMA_WARP * 32;
+  const bool tracing = a.trace != nullptr && b == 0 && xblk == 0 && tid == MMA_WARP * 32;
   int ntrace = 0;
   auto stamp = [&]() {
     if (tracing && ntrace < 250) a.trace[ntrace++] = clock64();
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
         s_fold += red[(g * 2 + 1) * d + tid];
         if (tid == 0) s_sum += red[ngrp * 2 * d + g];
       }
-      float* part = a.part + ((size_t)b * gridDim.x + blockIdx.x) * PART_STRIDE;
+      float* part = a.part + ((size_t)b * nxb + xblk) * PART_STRIDE;
       part[tid] = s_term;
       part[DPAD + tid] = s_fold;
       if (tid == 0) part[2 * DPAD] = s_sum;
@@ -602,6 +612,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
   stamp();
   if (tracing) a.trace[255] = ntrace;
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  if (IS_PT && ready && tid == 0) signal_counter(ready + b);     // after the barrier: every thread's stores are ordered before it
+}
+
+// (separate launches: debugging aid, MMB_BIDAF_BWD_STAGES)
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs a) {
+  bwd_block<MODE>(a, blockIdx.y, blockIdx.x, gridDim.x, nullptr, 0);
+}
+
+// All three passes in one launch: PT blocks first in block order, then the DC and DQ blocks, each of which starts as
+// soon as the PT blocks of ITS batch row are done -- no launch boundaries, no partially filled waves in between.
+struct BwdFusedArgs {
+  BwdArgs k[3];
+  int* ready;                  // (B) zeroed before the launch
+  int n_pt, n_dc;              // blocks of PT and DC (B * blocks per batch row)
+  int nb[3];                   // X blocks per batch row of PT, DC, DQ
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_fused_kernel(const BwdFusedArgs f) {
+  const int blk = blockIdx.x;
+  if (blk < f.n_pt) {
+    bwd_block<PT>(f.k[PT], blk / f.nb[PT], blk % f.nb[PT], f.nb[PT], f.ready, 0);
+  } else if (blk < f.n_pt + f.n_dc) {
+    const int i = blk - f.n_pt;
+    bwd_block<DC>(f.k[DC], i / f.nb[DC], i % f.nb[DC], f.nb[DC], f.ready, f.nb[PT]);
+  } else {
+    const int i = blk - f.n_pt - f.n_dc;
+    bwd_block<DQ>(f.k[DQ], i / f.nb[DQ], i % f.nb[DQ], f.nb[DQ], f.ready, f.nb[PT]);
+  }
 }
 
 template <int MODE>
@@ -666,6 +705,7 @@ __global__ void __launch_bounds__(256) bidaf_bwd_reduce_kernel(const ReduceArgs 
 struct BwdWorkspace {
   __nv_bfloat16 *da_pack, *dbm_pack, *dt_pack;
   float *d_row, *d_col, *part_c, *part_q;
+  int* ready;                // (B) PT -> DC / DQ dependency counters of the fused launch
   long long* trace;          // 3 x 256 clock stamps (MMB_BIDAF_BWD_TRACE=1)
   size_t bytes;
 };
@@ -686,6 +726,7 @@ BwdWorkspace bwd_workspace(void* workspace, int B, int Lc, int Lq) {
   w.d_col = reinterpret_cast<float*>(take((size_t)B * Lq * 4));
   w.part_c = reinterpret_cast<float*>(take((size_t)B * (pk.LcP / 64) * PART_STRIDE * 4));
   w.part_q = reinterpret_cast<float*>(take((size_t)B * (pk.LqP / 64) * PART_STRIDE * 4));
+  w.ready = reinterpret_cast<int*>(take((size_t)B * 4));
   w.trace = reinterpret_cast<long long*>(take(3 * 256 * 8));
   w.bytes = off;
   return w;
@@ -716,8 +757,9 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
   bidaf_bwd_prep_kernel<<<dim3(LcP / 64, B), 256, 0, stream>>>(pa);
   if (int rc = check_launch("bidaf_bwd_prep_kernel")) return rc;
   }
-  if (stages & 2) {   // PT: X = modality rows, Y = text rows
-    BwdArgs a{};
+  BwdArgs pt{}, dc{}, dq{};
+  {   // PT: X = modality rows, Y = text rows
+    BwdArgs& a = pt;
     a.x_ops[0] = pk.qs;
     a.y_ops[0] = pk.cw; a.y_ops[1] = w.da_pack; a.y_ops[2] = w.dbm_pack;
     a.x_words = pk.q_words; a.y_words = pk.c_words; a.bias = bias;
@@ -725,13 +767,9 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.t_feat = q2c; a.dx = d_modality; a.dt_pack = w.dt_pack; a.d_col = w.d_col;
     a.LX = Lq; a.LXP = LqP; a.LY = Lc; a.LYP = LcP; a.d = d;
     a.trace = tracing ? w.trace : nullptr;
-    constexpr size_t smem = bwd_smem_bytes<PT>();
-    MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_bwd_tc_kernel<PT><<<dim3(LqP / 128, B), NTHREADS, smem, stream>>>(a);
-    if (int rc = check_launch("bidaf_bwd_tc_kernel<PT>")) return rc;
   }
-  if (stages & 4) {   // DC: X = text rows, Y = modality rows
-    BwdArgs a{};
+  {   // DC: X = text rows, Y = modality rows
+    BwdArgs& a = dc;
     a.x_ops[0] = pk.cw; a.x_ops[1] = w.da_pack; a.x_ops[2] = w.dbm_pack; a.x_ops[3] = pk.cp;
     a.y_ops[0] = pk.qs; a.y_ops[1] = pk.qp; a.y_ops[2] = pk.tp; a.y_ops[3] = w.dt_pack;
     a.x_words = pk.c_words; a.y_words = pk.q_words; a.bias = bias;
@@ -740,14 +778,9 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.dx = d_text; a.part = w.part_c; a.keep_scale = keep_scale;
     a.LX = Lc; a.LXP = LcP; a.LY = Lq; a.LYP = LqP; a.d = d;
     a.trace = tracing ? w.trace + 256 : nullptr;
-    constexpr size_t smem = bwd_smem_bytes<DC>();
-    static_assert(smem <= 227 * 1024, "DC shared memory");
-    MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_bwd_tc_kernel<DC><<<dim3(LcP / 64, B), NTHREADS, smem, stream>>>(a);
-    if (int rc = check_launch("bidaf_bwd_tc_kernel<DC>")) return rc;
   }
-  if (stages & 8) {   // DQ: X = modality rows, Y = text rows
-    BwdArgs a{};
+  {   // DQ: X = modality rows, Y = text rows
+    BwdArgs& a = dq;
     a.x_ops[0] = pk.qs; a.x_ops[1] = w.dt_pack; a.x_ops[2] = pk.qp; a.x_ops[3] = pk.tp;
     a.y_ops[0] = pk.cw; a.y_ops[1] = pk.cp; a.y_ops[2] = w.da_pack; a.y_ops[3] = w.dbm_pack;
     a.x_words = pk.q_words; a.y_words = pk.c_words; a.bias = bias;
@@ -756,10 +789,32 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.dx = d_modality; a.part = w.part_q; a.keep_scale = keep_scale;
     a.LX = Lq; a.LXP = LqP; a.LY = Lc; a.LYP = LcP; a.d = d;
     a.trace = tracing ? w.trace + 512 : nullptr;
-    constexpr size_t smem = bwd_smem_bytes<DQ>();
-    MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_bwd_tc_kernel<DQ><<<dim3(LqP / 64, B), NTHREADS, smem, stream>>>(a);
-    if (int rc = check_launch("bidaf_bwd_tc_kernel<DQ>")) return rc;
+  }
+  constexpr size_t smem_pt = bwd_smem_bytes<PT>(), smem_dc = bwd_smem_bytes<DC>(), smem_dq = bwd_smem_bytes<DQ>();
+  static_assert(smem_dc <= 227 * 1024 && smem_dq <= 227 * 1024 && smem_pt <= 227 * 1024, "shared memory");
+  if (!env) {   // the normal path: one launch for the three tensor-core passes
+    constexpr size_t smem = smem_dc > smem_pt ? (smem_dc > smem_dq ? smem_dc : smem_dq) : (smem_pt > smem_dq ? smem_pt : smem_dq);
+    BwdFusedArgs f{{pt, dc, dq}, w.ready, B * (LqP / 128), B * (LcP / 64), {LqP / 128, LcP / 64, LqP / 64}};
+    MMB_CUDA(cudaMemsetAsync(w.ready, 0, sizeof(int) * (size_t)B, stream));
+    MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bidaf_bwd_fused_kernel<<<f.n_pt + f.n_dc + B * (LqP / 64), NTHREADS, smem, stream>>>(f);
+    if (int rc = check_launch("bidaf_bwd_fused_kernel")) return rc;
+  } else {
+    if (stages & 2) {
+      MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pt));
+      bidaf_bwd_tc_kernel<PT><<<dim3(LqP / 128, B), NTHREADS, smem_pt, stream>>>(pt);
+      if (int rc = check_launch("bidaf_bwd_tc_kernel<PT>")) return rc;
+    }
+    if (stages & 4) {
+      MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dc));
+      bidaf_bwd_tc_kernel<DC><<<dim3(LcP / 64, B), NTHREADS, smem_dc, stream>>>(dc);
+      if (int rc = check_launch("bidaf_bwd_tc_kernel<DC>")) return rc;
+    }
+    if (stages & 8) {
+      MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_tc_kernel<DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+      bidaf_bwd_tc_kernel<DQ><<<dim3(LqP / 64, B), NTHREADS, smem_dq, stream>>>(dq);
+      if (int rc = check_launch("bidaf_bwd_tc_kernel<DQ>")) return rc;
+    }
   }
   if (!(stages & 16)) return MMB_OK;
   ReduceArgs ra{w.part_c, w.part_q, d_w_text, d_w_cross, d_w_modality, d_bias, B, LcP / 64, (Lc + 63) / 64, LqP / 64,

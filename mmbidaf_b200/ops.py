@@ -55,7 +55,7 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
     _lib.check(L.mmb_bidaf_fwd(p(text), p(modality), p(tm), p(mm), p(wt), p(wm), p(wc), p(bias.detach().contiguous()),
                                p(kt), p(km), float(keep_scale), p(out), p(q2c), p(bm), p(lse_row), p(lse_col), p(ws),
                                B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_fwd")
-    _count(2 if precision == PREC_FP32 else 3)
+    _count(2)          # fp32: two pass launches; bf16: pack + one fused tensor-core launch
     if ws is not None and os.environ.get("MMB_BIDAF_FWD_TRACE"):      # debugging aid: clock stamps
         bidaf_fwd.last_trace = ws[-4096:].view(torch.int64).view(2, 256)
     if save:
@@ -87,7 +87,7 @@ def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor
                                p(bias.detach().contiguous()), p(kt), p(km), float(keep_scale), p(out), p(bm), p(q2c),
                                p(lse_row), p(lse_col), p(fwd_ws), p(ws), p(d_text), p(d_modality), p(d_w[0]), p(d_w[1]),
                                p(d_w[2]), p(d_bias), B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_bwd")
-    _count(5)
+    _count(3)
     if os.environ.get("MMB_BIDAF_BWD_TRACE"):      # debugging aid: clock stamps at the end of the workspace
         bidaf_bwd.last_trace = ws[-3 * 256 * 8:].view(torch.int64).view(3, 256)
     return d_text, d_modality, d_w[0], d_w[1], d_w[2], d_bias

@@ -314,12 +314,12 @@ def run_gpu_arm(args):
                 "e2e": {"value": round(videos / e2e_seconds, 2), "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(),
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_seconds / args.steps * 1e3, 3)},
                 "gpu_launches": launches,
-                "roofline": {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel + bidaf_tc_kernel<Q2C> + "
-                                        "bidaf_tc_kernel<C2Q>)" if fast else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
+                "roofline": {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel + bidaf_tc2_kernel: Q2C, "
+                                        "C2QA and C2QB blocks in one launch, two per SM)" if fast else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
                                        + ", BASELINE config 2 (B=64, Lc=512, Lq=256, d=200)",
                              "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4),
-                             "traffic": 154355456 if fast else None,      # dram read+write per forward, ncu (profiles/r01_bidaf_tc_ncu.md)
+                             "traffic": 151061248 if fast else None,      # dram read+write per forward, ncu (profiles/r01_bidaf_tc_ncu.md)
                              "peak_source": peak_src,
                              "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1),
                              # the fused backward (prep + P^T pass + two dS passes + reduce) of the same op, same method

@@ -211,7 +211,17 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION in this image): keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     import mmbidaf_b200
     mmbidaf_b200.set_precision(args.precision)
 

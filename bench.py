@@ -179,7 +179,7 @@ def bidaf_microbench(device, iters: int, warmup: int, precision: int, backward: 
                                                             precision=precision, save=True)
             full.append(s + (torch.randn(out.shape, generator=gen).to(device), out, q2c, lse_r, lse_c, bm, ws))
         sets = full
-        run = lambda s: ops.bidaf_bwd(s[4], s[0], s[1], w[0], w[1], w[2], bias, None, None, 1.0, s[5], s[9], s[6], s[7],
+        run = lambda s: ops.bidaf_bwd(s[4], s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, None, None, 1.0, s[5], s[9], s[6], s[7],
                                       s[8], s[10], precision)
     else:
         run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision)

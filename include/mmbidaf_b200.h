@@ -82,12 +82,14 @@ MMB_API size_t mmb_bidaf_workspace_bytes(int B, int Lc, int Lq, int d, int preci
 /* BiDAF attention, backward: the gradient of attention.py:37-75 that the reference obtains from autograd
  * (loss.backward(), train.py:148).  S, both soft-maxes and dS are recomputed on chip from lse_row / lse_col;
  * nothing of size Lc x Lq is read or written.
- *   grad_out (B,Lc,4d); text, modality, weights, keep masks, keep_scale: as given to mmb_bidaf_fwd;
+ *   grad_out (B,Lc,4d); text, modality, masks, weights, keep masks, keep_scale: as given to mmb_bidaf_fwd;
  *   out, bm, q2c, lse_row, lse_col: as produced by mmb_bidaf_fwd; fwd_workspace: the workspace of that call,
- *   untouched since (MMB_PREC_BF16: it holds the bf16 operands); workspace: mmb_bidaf_bwd_workspace_bytes().
+ *   untouched since (MMB_PREC_BF16: it holds the bf16 operands; MMB_PREC_FP32: NULL);
+ *   workspace: mmb_bidaf_bwd_workspace_bytes().  MMB_PREC_FP32: d % 4 == 0, d <= 208; MMB_PREC_BF16: d % 8 == 0, d <= 200.
  * Outputs (all overwritten): d_text (B,Lc,d), d_modality (B,Lq,d), d_w_text (d), d_w_modality (d), d_w_cross (d), d_bias (1).
  */
-MMB_API int mmb_bidaf_bwd(const float* grad_out, const float* text, const float* modality, const float* w_text,
+MMB_API int mmb_bidaf_bwd(const float* grad_out, const float* text, const float* modality,
+                  const uint8_t* text_mask, const uint8_t* modality_mask, const float* w_text,
                   const float* w_modality, const float* w_cross, const float* bias, const uint8_t* keep_text,
                   const uint8_t* keep_modality, float keep_scale, const float* out, const float* bm, const float* q2c,
                   const float* lse_row, const float* lse_col, const void* fwd_workspace, void* workspace,

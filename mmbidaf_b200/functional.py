@@ -69,9 +69,8 @@ def lstm_layer(x: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Ten
 
 class _BidafAttention(torch.autograd.Function):
     """Fused BiDAF attention (attention.py:37-75).  Forward = the fused kernels (S never materialised).
-    Backward: bf16 tier = the fused tcgen05 kernels of csrc/bidaf_bwd_tc.cu (S, the soft-maxes and dS are
-    recomputed on chip); fp32 tier = the closed-form gradient evaluated with fp32 library GEMMs from the
-    saved soft-max statistics."""
+    Backward = fused kernels too (S, the soft-maxes and dS are recomputed on chip from the saved soft-max
+    statistics): csrc/bidaf_bwd_tc.cu (tcgen05) on the bf16 tier, csrc/bidaf_bwd_f32.cu (FFMA) on the fp32 tier."""
 
     @staticmethod
     def forward(ctx, text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
@@ -92,42 +91,10 @@ class _BidafAttention(torch.autograd.Function):
         (c, q, c_mask, q_mask, w_c, w_q, w_cq, bias, keep_c, keep_q, out, q2c, lse_row, lse_col, bm, ws) = ctx.saved_tensors
         B, Lc, d = c.shape
         scale = ctx.keep_scale
-        if ctx.precision == ops.PREC_BF16:
-            dc, dq, dw_c, dw_q, dw_cq, dbias = ops.bidaf_bwd(grad, c, q, w_c, w_q, w_cq, bias, keep_c, keep_q, scale,
-                                                             out, bm, q2c, lse_row, lse_col, ws, ctx.precision)
-            return (dc, dq, None, None, dw_c.reshape(w_c.shape), dw_q.reshape(w_q.shape), dw_cq.reshape(w_cq.shape),
-                    dbias.reshape(bias.shape), None, None, None, None)
-        cd = c if keep_c is None else c * keep_c.to(c.dtype) * scale
-        qd = q if keep_q is None else q * keep_q.to(q.dtype) * scale
-        wc, wq, wx = w_c.reshape(d), w_q.reshape(d), w_cq.reshape(d)
-        cm, qm = c_mask.reshape(B, Lc, 1), q_mask.reshape(B, 1, -1)
-        s = torch.baddbmm((cd @ wc).unsqueeze(2) + (qd @ wq).unsqueeze(1) + bias, cd * wx, qd.transpose(1, 2))
-        neg = s.new_full((), -1e30)
-        p = torch.exp(torch.where(qm, s, neg) - lse_row.unsqueeze(2))      # row soft-max s1
-        r = torch.exp(torch.where(cm, s, neg) - lse_col.unsqueeze(1))      # column soft-max s2
-        g0, g1, g2, g3 = grad.split(d, dim=2)
-        a = out[:, :, d:2 * d]
-        bm = torch.bmm(p, q2c)
-        d_a = g1 + c * g2
-        d_bm = c * g3
-        dc = g0 + a * g2 + bm * g3
-        d_p = torch.bmm(d_a, q.transpose(1, 2)) + torch.bmm(d_bm, q2c.transpose(1, 2))
-        dq = torch.bmm(p.transpose(1, 2), d_a)
-        d_t = torch.bmm(p.transpose(1, 2), d_bm)
-        d_r = torch.bmm(c, d_t.transpose(1, 2))
-        dc = dc + torch.bmm(r, d_t)
-        ds = (p * (d_p - (d_p * p).sum(dim=2, keepdim=True))) * qm + (r * (d_r - (d_r * r).sum(dim=1, keepdim=True))) * cm
-        rows, cols = ds.sum(dim=2), ds.sum(dim=1)
-        ds_q = torch.bmm(ds, qd)
-        dcd = rows.unsqueeze(2) * wc + ds_q * wx
-        dqd = cols.unsqueeze(2) * wq + torch.bmm(ds.transpose(1, 2), cd * wx)
-        dw_c = (cd * rows.unsqueeze(2)).sum(dim=(0, 1)).reshape(w_c.shape)
-        dw_q = (qd * cols.unsqueeze(2)).sum(dim=(0, 1)).reshape(w_q.shape)
-        dw_cq = (cd * ds_q).sum(dim=(0, 1)).reshape(w_cq.shape)
-        dbias = ds.sum().reshape(bias.shape)
-        dc = dc + (dcd if keep_c is None else dcd * keep_c.to(c.dtype) * scale)
-        dq = dq + (dqd if keep_q is None else dqd * keep_q.to(q.dtype) * scale)
-        return dc, dq, None, None, dw_c, dw_q, dw_cq, dbias, None, None, None, None
+        dc, dq, dw_c, dw_q, dw_cq, dbias = ops.bidaf_bwd(grad, c, q, c_mask, q_mask, w_c, w_q, w_cq, bias, keep_c, keep_q,
+                                                         scale, out, bm, q2c, lse_row, lse_col, ws, ctx.precision)
+        return (dc, dq, None, None, dw_c.reshape(w_c.shape), dw_q.reshape(w_q.shape), dw_cq.reshape(w_cq.shape),
+                dbias.reshape(bias.shape), None, None, None, None)
 
 
 def bidaf_attention(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,

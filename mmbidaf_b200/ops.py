@@ -63,7 +63,8 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
     return out, q2c, lse_row, lse_col
 
 
-def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor, w_text: torch.Tensor,
+def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tensor,
+              modality_mask: torch.Tensor, w_text: torch.Tensor,
               w_modality: torch.Tensor, w_cross: torch.Tensor, bias: torch.Tensor, keep_text: Optional[torch.Tensor],
               keep_modality: Optional[torch.Tensor], keep_scale: float, out: torch.Tensor, bm: torch.Tensor,
               q2c: torch.Tensor, lse_row: torch.Tensor, lse_col: torch.Tensor, fwd_ws: Optional[torch.Tensor],
@@ -75,6 +76,7 @@ def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor
     Lq = modality.shape[1]
     dev = text.device
     kt, km = _u8(keep_text), _u8(keep_modality)
+    tm, mm = _u8(text_mask.reshape(B, Lc)), _u8(modality_mask.reshape(B, Lq))
     wt, wm, wc = (w.detach().reshape(-1).contiguous() for w in (w_text, w_modality, w_cross))
     d_text = torch.empty_like(text)
     d_modality = torch.empty_like(modality)
@@ -83,12 +85,12 @@ def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor
     ws_bytes = L.mmb_bidaf_bwd_workspace_bytes(B, Lc, Lq, d, int(precision))
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if ws_bytes else None
     p = _lib.ptr
-    _lib.check(L.mmb_bidaf_bwd(p(grad_out.contiguous()), p(text), p(modality), p(wt), p(wm), p(wc),
+    _lib.check(L.mmb_bidaf_bwd(p(grad_out.contiguous()), p(text), p(modality), p(tm), p(mm), p(wt), p(wm), p(wc),
                                p(bias.detach().contiguous()), p(kt), p(km), float(keep_scale), p(out), p(bm), p(q2c),
                                p(lse_row), p(lse_col), p(fwd_ws), p(ws), p(d_text), p(d_modality), p(d_w[0]), p(d_w[1]),
                                p(d_w[2]), p(d_bias), B, Lc, Lq, d, int(precision), _lib.stream()), "mmb_bidaf_bwd")
-    _count(3)
-    if os.environ.get("MMB_BIDAF_BWD_TRACE"):      # debugging aid: clock stamps at the end of the workspace
+    _count(3 if precision == PREC_BF16 else 5)
+    if precision == PREC_BF16 and os.environ.get("MMB_BIDAF_BWD_TRACE"):      # debugging aid: clock stamps at the end of the workspace
         bidaf_bwd.last_trace = ws[-3 * 256 * 8:].view(torch.int64).view(3, 256)
     return d_text, d_modality, d_w[0], d_w[1], d_w[2], d_bias
 

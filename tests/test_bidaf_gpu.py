@@ -289,3 +289,50 @@ def test_bf16_tier_both_kernel_cuts(shape, cut, monkeypatch):
     got = _grads(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, 0.2, precision=1)
     _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pg.items()}, BWD_TOL[1],
                  _ds_abs_sum(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, 0.2))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 4), (2, 1, 9, 8), (2, 5, 3, 8), (3, 64, 32, 200), (2, 65, 33, 200), (2, 130, 257, 200),
+                                   (4, 100, 70, 64), (2, 31, 95, 12)])
+@pytest.mark.parametrize("dropout", [False, True])
+def test_fp32_backward_matches_oracle_ragged(shape, dropout):
+    """fp32 tier: the FFMA backward kernels (csrc/bidaf_bwd_f32.cu) against fp64 autograd of the oracle."""
+    bsz, lc, lq, d = shape
+    gen = torch.Generator().manual_seed(5000 + lc * 7 + lq)
+    p = {"text_weight": torch.randn(d, 1, generator=gen) * 0.2, "modality_weight": torch.randn(d, 1, generator=gen) * 0.2,
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen) * 0.2, "bias": torch.tensor([0.3])}
+    text = torch.randn(bsz, lc, d, generator=gen)
+    modality = torch.randn(bsz, lq, d, generator=gen)
+    c_len = torch.randint(1, lc + 1, (bsz,), generator=gen).tolist()
+    q_len = torch.randint(1, lq + 1, (bsz,), generator=gen).tolist()
+    c_len[0], q_len[0] = lc, lq
+    tmask, mmask = O.length_mask(lc, c_len), O.length_mask(lq, q_len)
+    grad_out = torch.randn(bsz, lc, 4 * d, generator=gen)
+    pr = 0.2 if dropout else 0.0
+    keep_c = (torch.rand(bsz, lc, d, generator=gen) >= pr) if dropout else None
+    keep_q = (torch.rand(bsz, lq, d, generator=gen) >= pr) if dropout else None
+    pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    cd, qd = text.double().requires_grad_(True), modality.double().requires_grad_(True)
+    O.bidaf_attention(pd, cd, qd, tmask, mmask, keep_c, keep_q, pr).backward(grad_out.double())
+    got = _grads(p, text, modality, tmask, mmask, grad_out, keep_c, keep_q, pr, precision=0)
+    assert torch.isfinite(got[0]).all() and torch.isfinite(got[1]).all()
+    # weight gradients that vanish analytically (soft-max over one element) are fp32 cancellation noise: floor them
+    _check_grads(got, cd.grad, qd.grad, {k: v.grad for k, v in pd.items()}, BWD_TOL[0], None, 1e-2 if min(lc, lq) == 1 else 1e-3)
+
+
+def test_backward_fully_masked_rows_match_oracle():
+    """A fully masked soft-max is uniform (attention.py:94): its weights still carry dq, dT and R dT in the backward."""
+    gen = torch.Generator().manual_seed(9)
+    d, lc, lq = 8, 6, 5
+    p = {"text_weight": torch.randn(d, 1, generator=gen), "modality_weight": torch.randn(d, 1, generator=gen),
+         "text_modality_weight": torch.randn(1, 1, d, generator=gen), "bias": torch.tensor([0.0])}
+    text, modality = torch.randn(2, lc, d, generator=gen), torch.randn(2, lq, d, generator=gen)
+    tmask, mmask = O.length_mask(lc, [6, 0]), O.length_mask(lq, [0, 5])
+    grad_out = torch.randn(2, lc, 4 * d, generator=gen)
+    pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    cd, qd = text.double().requires_grad_(True), modality.double().requires_grad_(True)
+    O.bidaf_attention(pd, cd, qd, tmask, mmask).backward(grad_out.double())
+    for precision in (0, 1):
+        dc, dq, dw = _grads(p, text, modality, tmask, mmask, grad_out, precision=precision)
+        tol = BWD_TOL[precision]
+        assert torch.isfinite(dc).all() and torch.isfinite(dq).all()
+        assert grad_err(dc, cd.grad) < tol and grad_err(dq, qd.grad) < tol, (precision, grad_err(dc, cd.grad), grad_err(dq, qd.grad))

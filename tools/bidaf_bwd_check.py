@@ -73,7 +73,7 @@ def err(got, want):
 print(f"fwd: out {err(out, torch.cat([c64, A, c64 * A, c64 * Bm], 2)):.2e}  bm {err(bm, Bm):.2e}  q2c {err(q2c, T):.2e}")
 for stages, label in [(1, "prep"), (3, "prep+PT"), (7, "+DC"), (11, "prep+PT+DQ"), (31, "all")]:
     os.environ["MMB_BIDAF_BWD_STAGES"] = str(stages)
-    d_text, d_mod, g_c, g_q, g_x, g_b = ops.bidaf_bwd(G, c, q, w_c, w_q, w_x, bias, kc, kq, scale, out, bm, q2c, lse_row,
+    d_text, d_mod, g_c, g_q, g_x, g_b = ops.bidaf_bwd(G, c, q, cm, qm, w_c, w_q, w_x, bias, kc, kq, scale, out, bm, q2c, lse_row,
                                                      lse_col, ws, 1)
     torch.cuda.synchronize()
     if stages == 1:

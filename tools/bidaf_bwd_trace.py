@@ -24,7 +24,7 @@ bias = torch.zeros(1, device=dev)
 out, q2c, lr, lc_, bm, ws = ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, None, None, 1.0, 1, save=True)
 G = torch.randn_like(out)
 for _ in range(3):
-    ops.bidaf_bwd(G, c, q, w[0], w[1], w[2], bias, None, None, 1.0, out, bm, q2c, lr, lc_, ws, 1)
+    ops.bidaf_bwd(G, c, q, cm, qm, w[0], w[1], w[2], bias, None, None, 1.0, out, bm, q2c, lr, lc_, ws, 1)
 torch.cuda.synchronize()
 tr = ops.bidaf_bwd.last_trace.cpu()
 for k, name in enumerate(["PT", "DC", "DQ"]):

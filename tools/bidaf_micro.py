@@ -40,7 +40,7 @@ if a.bwd:
                                                   a.precision, save=True)
         saved.append((torch.randn_like(out), out, q2c, lr, lc_, bm, ws))
     sets = [s + k + v for s, k, v in zip(sets, keeps, saved)]
-    run = lambda s: ops.bidaf_bwd(s[6], s[0], s[1], w[0], w[1], w[2], bias, s[4], s[5], 1 / (1 - pr), s[7], s[11], s[8],
+    run = lambda s: ops.bidaf_bwd(s[6], s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, s[4], s[5], 1 / (1 - pr), s[7], s[11], s[8],
                                   s[9], s[10], s[12], a.precision)
 else:
     sets = [s + k for s, k in zip(sets, keeps)]

@@ -336,3 +336,47 @@ def test_backward_fully_masked_rows_match_oracle():
         tol = BWD_TOL[precision]
         assert torch.isfinite(dc).all() and torch.isfinite(dq).all()
         assert grad_err(dc, cd.grad) < tol and grad_err(dq, qd.grad) < tol, (precision, grad_err(dc, cd.grad), grad_err(dq, qd.grad))
+
+
+def test_full_size_config2_tiers_agree_and_backward_is_linear():
+    """BASELINE config 2 at full size (B=64, Lc=512, Lq=256, d=200), where the CPU oracle is too slow: the tensor-core tier
+    against the fp32 tier (itself pinned to the oracle at small sizes), forward and backward, plus two size-independent
+    properties: the backward is linear in the upstream gradient, and padded modality rows get exactly zero gradient."""
+    from mmbidaf_b200 import functional as F
+    bsz, lc, lq, d = 64, 512, 256, 200
+    gen = torch.Generator().manual_seed(224)
+    c = torch.randn(bsz, lc, d, generator=gen).cuda()
+    q = torch.randn(bsz, lq, d, generator=gen).cuda()
+    c_len = torch.randint(lc // 2, lc + 1, (bsz,), generator=gen)
+    q_len = torch.randint(lq // 2, lq + 1, (bsz,), generator=gen)
+    c_len[0], q_len[0] = lc, lq
+    tmask = (torch.arange(lc).unsqueeze(0) < c_len.unsqueeze(1)).cuda()
+    mmask = (torch.arange(lq).unsqueeze(0) < q_len.unsqueeze(1)).cuda()
+    w = [(torch.randn(d, generator=gen) * 0.1).cuda() for _ in range(3)]
+    bias = torch.full((1,), 0.3).cuda()
+    g1 = torch.randn(bsz, lc, 4 * d, generator=gen).cuda()
+    g2 = torch.randn(bsz, lc, 4 * d, generator=gen).cuda()
+
+    def run(precision, grad):
+        leaves = [c.clone().requires_grad_(True), q.clone().requires_grad_(True)] + [t.clone().requires_grad_(True) for t in w]
+        out = F.bidaf_attention(leaves[0], leaves[1], tmask, mmask, leaves[2].view(d, 1), leaves[3].view(d, 1),
+                                leaves[4].view(1, 1, d), bias, None, None, 1.0, precision)
+        out.backward(grad)
+        return out.detach(), [t.grad for t in leaves]
+
+    out32, grads32 = run(0, g1)
+    out16, grads16 = run(1, g1)
+    assert rel_err(out16, out32) < BF16_TOL
+    for a, b in zip(grads16, grads32):
+        assert grad_err(a, b) < BWD_TOL[1]
+    # linearity of the backward pass in the upstream gradient (exact in exact arithmetic)
+    _, ga = run(1, g1)
+    _, gb = run(1, g2)
+    _, gab = run(1, 0.5 * g1 + g2)
+    for x, y, z in zip(ga, gb, gab):
+        assert grad_err(z, 0.5 * x + y) < 2e-2
+    # padded modality rows are masked out of s1 and never reach the output: their gradient is exactly zero
+    dq = grads16[1]
+    for b_, n in enumerate(q_len.tolist()):
+        if n < lq:
+            assert (dq[b_, n:] == 0).all()

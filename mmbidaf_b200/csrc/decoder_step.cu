@@ -473,11 +473,14 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep2_kernel(const SweepArgs a) 
     vec[4 * D + i] = a.wc2[i];
     vec[5 * D + i] = a.hw[(size_t)b * 4 * D + D + i];
   }
-  float s[2] = {0.f, 0.f};
-  if (tid < 2)
-    for (int cc = 0; cc < a.nch; ++cc) s[tid] += a.spart[((size_t)b * a.nch + cc) * 2 + tid];
   __shared__ float stot[2];
-  if (tid < 2) stot[tid] = s[tid];
+  if (tid < 64) {                        // warps 0, 1: the chunk partials of sum_t alpha d alpha, loaded in parallel, summed in order
+    float v0 = lane < a.nch ? a.spart[((size_t)b * a.nch + lane) * 2 + warp] : 0.f;
+    float v1 = lane + 32 < a.nch ? a.spart[((size_t)b * a.nch + lane + 32) * 2 + warp] : 0.f;
+    float s = 0.f;
+    for (int cc = 0; cc < a.nch; ++cc) s += __shfl_sync(0xffffffffu, cc < 32 ? v0 : v1, cc & 31);
+    if (lane == 0) stot[warp] = s;
+  }
   for (int i = tid; i < n; i += NT) rowacc[i] = a.d_cov_out ? a.d_cov_out[(size_t)b * Lt + t0 + i] : 0.f;
   __syncthreads();
   constexpr int MAXJ = 8;                // D <= 256
@@ -492,35 +495,45 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep2_kernel(const SweepArgs a) 
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) c_dz[j] = c_cov[j] = c_v[j] = 0.f;
     float se = 0.f;
-    for (int i = warp; i < n; i += NW) {
-      const int t = t0 + i;
-      const float cv = a.cov[(size_t)b * Lt + t];
-      const float det = a.alpha[((size_t)b * 2 + m) * Lt + t] * (a.d_alpha[((size_t)b * 2 + m) * Lt + t] - stm);
-      float pv[MAXJ], dpv[MAXJ];
+    // two sentences per warp iteration: every load of both rows is in flight before the first tanh
+    for (int i0 = warp * 2; i0 < n; i0 += NW * 2) {
+      float cvs[2], dets[2], pv[2][MAXJ], dpv[2][MAXJ];
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {                          // loads first (memory-level parallelism)
-        const int d = lane + 32 * j;
-        pv[j] = d < D ? proj[(size_t)i * D + d] : 0.f;
-        dpv[j] = d < D ? dproj[(size_t)i * D + d] : 0.f;
-      }
-      float row = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int i = min(i0 + u, n - 1), t = t0 + i;
+        cvs[u] = a.cov[(size_t)b * Lt + t];
+        dets[u] = a.alpha[((size_t)b * 2 + m) * Lt + t] * (a.d_alpha[((size_t)b * 2 + m) * Lt + t] - stm);
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {
-        const int d = lane + 32 * j;
-        if (d < D) {
-          const float tz = tanh_fast((pv[j] + hwm[d]) + cv * wc[d]);
-          const float dz = det * vv[d] * (1.f - tz * tz);
-          dproj[(size_t)i * D + d] = dpv[j] + dz;
-          c_dz[j] += dz;
-          c_cov[j] = fmaf(dz, cv, c_cov[j]);
-          c_v[j] = fmaf(det, tz, c_v[j]);
-          row = fmaf(dz, wc[d], row);
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          pv[u][j] = d < D ? proj[(size_t)i * D + d] : 0.f;
+          dpv[u][j] = d < D ? dproj[(size_t)i * D + d] : 0.f;
         }
       }
-      row = warp_sum(row);
-      if (lane == 0) {
-        rowacc[i] += row;
-        se += det;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u;
+        if (i >= n) break;
+        const float cv = cvs[u], det = dets[u];
+        float row = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) {
+            const float tz = tanh_fast((pv[u][j] + hwm[d]) + cv * wc[d]);
+            const float dz = det * vv[d] * (1.f - tz * tz);
+            dproj[(size_t)i * D + d] = dpv[u][j] + dz;
+            c_dz[j] += dz;
+            c_cov[j] = fmaf(dz, cv, c_cov[j]);
+            c_v[j] = fmaf(det, tz, c_v[j]);
+            row = fmaf(dz, wc[d], row);
+          }
+        }
+        row = warp_sum(row);
+        if (lane == 0) {
+          rowacc[i] += row;
+          se += det;
+        }
       }
     }
 #pragma unroll
@@ -553,21 +566,36 @@ __global__ void __launch_bounds__(NT) dec_attn_reduce_kernel(const float* __rest
   for (int i = tid; i < 2 * D; i += NT) {
     const int m = i / D, d = i - m * D;
     float x = 0.f, y = 0.f, z = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      const float* q = colp + ((((size_t)b * nch + c) * 2 + m) * 3) * D;
-      x += q[d];
-      y += q[D + d];
-      z += q[2 * D + d];
+    constexpr int CB = 8;                                                  // chunk partials in flight (the sum order is unchanged)
+    for (int c0 = 0; c0 < nch; c0 += CB) {
+      float xs[CB], ys[CB], zs[CB];
+#pragma unroll
+      for (int u = 0; u < CB; ++u) {
+        const float* q = colp + ((((size_t)b * nch + min(c0 + u, nch - 1)) * 2 + m) * 3) * D;
+        xs[u] = q[d];
+        ys[u] = q[D + d];
+        zs[u] = q[2 * D + d];
+      }
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+        if (c0 + u < nch) {
+          x += xs[u];
+          y += ys[u];
+          z += zs[u];
+        }
     }
     d_hw4[(size_t)b * 4 * D + m * D + d] = x;                             // d (W2 h) | d (W4 h)
     d_hw4[(size_t)b * 4 * D + (2 + m) * D + d] = d_pre_b[((size_t)m * B + b) * D + d];   // d (W_beta_2 h) | d (W_beta_4 h)
     vec_acc[((size_t)b * 6 + m) * D + d] += y;                            // d Wc weight
     vec_acc[((size_t)b * 6 + 2 + m) * D + d] += z;                        // d v weight
   }
-  if (tid < 2) {
+  if (tid < 64) {                                                          // warps 0, 1: lane pairs (chunk, k) loaded in parallel
+    const int warp = tid >> 5, lane = tid & 31;
+    float v0 = lane < nch ? separt[((size_t)b * nch + lane) * 2 + warp] : 0.f;
+    float v1 = lane + 32 < nch ? separt[((size_t)b * nch + lane + 32) * 2 + warp] : 0.f;
     float s = 0.f;
-    for (int c = 0; c < nch; ++c) s += separt[((size_t)b * nch + c) * 2 + tid];
-    scal_acc[b * 4 + tid] += s;                                           // d v bias (identically 0 up to rounding)
+    for (int c = 0; c < nch; ++c) s += __shfl_sync(0xffffffffu, c < 32 ? v0 : v1, c & 31);   // fixed order
+    if (lane == 0) scal_acc[b * 4 + warp] += s;                           // d v bias (identically 0 up to rounding)
   }
 }
 

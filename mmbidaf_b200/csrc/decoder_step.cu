@@ -75,18 +75,32 @@ __global__ void __launch_bounds__(NT) dec_attn_partial_kernel(const PartialArgs 
   __syncthreads();
   const float v1b = a.v1b[0], v2b = a.v2b[0];
   // two sentences per warp iteration: all loads of both rows are in flight before the first tanh
+  constexpr int MAXJ = 8;                // D <= 256
   for (int i = warp * 2; i < n; i += NW * 2) {
     float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float pav[2][MAXJ], piv[2][MAXJ], cvs[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {          // loads first (memory-level parallelism)
+      const int t = t0 + min(i + u, n - 1);
+      const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
+      const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
+      cvs[u] = a.cov[(size_t)b * Lt + t];
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int d = lane + 32 * j;
+        pav[u][j] = d < D ? pa[d] : 0.f;
+        piv[u][j] = d < D ? pi[d] : 0.f;
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int t = t0 + i + u;
-      if (i + u < n) {
-        const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
-        const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
-        const float cv = a.cov[(size_t)b * Lt + t];
-        for (int d = lane; d < D; d += 32) {
-          s[u][0] = fmaf(vec[d], tanh_fast((pa[d] + vec[2 * D + d]) + cv * vec[D + d]), s[u][0]);
-          s[u][1] = fmaf(vec[3 * D + d], tanh_fast((pi[d] + vec[5 * D + d]) + cv * vec[4 * D + d]), s[u][1]);
+      const float cv = cvs[u];
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D) {
+          s[u][0] = fmaf(vec[d], tanh_fast((pav[u][j] + vec[2 * D + d]) + cv * vec[D + d]), s[u][0]);
+          s[u][1] = fmaf(vec[3 * D + d], tanh_fast((piv[u][j] + vec[5 * D + d]) + cv * vec[4 * D + d]), s[u][1]);
         }
       }
     }
@@ -422,17 +436,29 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep1_kernel(const SweepArgs a) 
   float s1 = 0.f, s2 = 0.f;
   for (int i = warp * 2; i < n; i += NW * 2) {
     float d1[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f};
+    constexpr int MAXJ = 8;              // D <= 256
+    float eav[2][MAXJ], eiv[2][MAXJ];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (i + u < n) {
-        const float* ea = a.enc_a + ((size_t)b * Lt + t0 + i + u) * D;
-        const float* ei = a.enc_i + ((size_t)b * Lt + t0 + i + u) * D;
-        for (int d = lane; d < D; d += 32) {
-          d1[u] = fmaf(dc[d], ea[d], d1[u]);
-          d2[u] = fmaf(dc[D + d], ei[d], d2[u]);
-        }
+    for (int u = 0; u < 2; ++u) {        // loads first (memory-level parallelism)
+      const float* ea = a.enc_a + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
+      const float* ei = a.enc_i + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int d = lane + 32 * j;
+        eav[u][j] = d < D ? ea[d] : 0.f;
+        eiv[u][j] = d < D ? ei[d] : 0.f;
       }
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D) {
+          d1[u] = fmaf(dc[d], eav[u][j], d1[u]);
+          d2[u] = fmaf(dc[D + d], eiv[u][j], d2[u]);
+        }
+      }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const float x1 = warp_sum(d1[u]), x2 = warp_sum(d2[u]);

@@ -113,12 +113,11 @@ MMB_API int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* lengt
 
 /* Backward through time of the same layer.  `gates` (activated gates from the forward pass) is
  * overwritten with d(loss)/d(pre-activation) (zeros past each length); dout (B,L,ndir*H);
- * dh_n / dc_n (B,ndir,H) may be NULL.  db_part (B,ndir,4H), optional: the sum over time of d(pre-activation) per
- * sequence (its sum over B is the bias gradient).  dW_ih, dx and dW_hh are GEMMs over `gates` for the caller.
+ * dh_n / dc_n (B,ndir,H) may be NULL.  dW_ih, dx, db and dW_hh are GEMMs over `gates` for the caller.
  */
 MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, const int32_t* lengths,
-                           const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, float* db_part,
-                           int B, int L, int H, int ndir, mmb_stream_t stream);
+                           const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, int B, int L,
+                           int H, int ndir, mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
  * Multimodal attention decoder, one step (replaces attention.py:145-186).

@@ -30,7 +30,7 @@ SIGNATURES = {
     "mmb_bidaf_bwd": [c_void_p] * 11 + [c_float] + [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
     "mmb_bidaf_bwd_workspace_bytes": [c_int] * 5,
     "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
-    "mmb_bilstm_bwd": [c_void_p] * 9 + [c_int] * 4 + [c_void_p],
+    "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_chunks": [c_int, c_int],
     "mmb_decoder_attn_fwd": [c_void_p] * 17 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_attn_finish": [c_void_p] * 17 + [c_int] * 6 + [c_void_p],

@@ -45,7 +45,6 @@ struct LstmArgs {
   const float* dout;       // bwd: (B, L, ndir*H)
   const float* dh_n;       // bwd: (B, ndir, H) or nullptr
   const float* dc_n;       // bwd: (B, ndir, H) or nullptr
-  float* db_part;          // bwd: (B, ndir, 4H) per-sequence sums over time of d(pre-activation), or nullptr
   int B, L, H, ndir, save;
 };
 
@@ -284,10 +283,9 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmA
 #pragma unroll 1
   for (int s = 0; s < RING - 1; ++s) prefetch(s, s);
 
-  float dh_rec[NB], dc[NB], db0[NB], db1[NB];      // db: bias gradient of this lane's two gates, summed over time
+  float dh_rec[NB], dc[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
-    db0[n] = db1[n] = 0.f;
     dh_rec[n] = (live && seq[n] >= 0 && a.dh_n) ? a.dh_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
     dc[n] = (live && seq[n] >= 0 && a.dc_n) ? a.dc_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
   }
@@ -320,8 +318,6 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmA
       const float d1 = kp ? dh * tc * go * (1.f - go) : dct * cprev * gf * (1.f - gf);
       if (on) {
         dc[n] = dct * gf;
-        db0[n] += d0;
-        db1[n] += d1;
         dcur[(n * 4 + 2 * kp) * HP + j] = d0;
         dcur[(n * 4 + 2 * kp + 1) * HP + j] = d1;
         gp[n][0] = d0;
@@ -368,11 +364,6 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmA
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
     if (seq[n] < 0) continue;
-    if (a.db_part && live) {
-      float* dbp = a.db_part + ((size_t)seq[n] * ndir + dir) * 4 * H + (2 * kp) * H + j;
-      dbp[0] = db0[n];
-      dbp[H] = db1[n];
-    }
     for (int i = tid; i < (L - len[n]) * 4 * H; i += nthr) {
       const int t = len[n] + i / (4 * H), u = i % (4 * H);
       a.gates[(((size_t)seq[n] * L + t) * ndir + dir) * 4 * H + u] = 0.f;
@@ -423,17 +414,17 @@ extern "C" int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* le
   MMB_REQUIRE(!save || cell, MMB_ERR_INVALID, "mmb_bilstm_fwd: save=1 needs a cell buffer");
   MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID,
               "mmb_bilstm_fwd: B=%d L=%d H=%d ndir=%d", B, L, H, ndir);
-  mmb::LstmArgs a{gates, w_hh, lengths, order, out, h_n, c_n, cell, nullptr, nullptr, nullptr, nullptr, B, L, H, ndir, save};
+  mmb::LstmArgs a{gates, w_hh, lengths, order, out, h_n, c_n, cell, nullptr, nullptr, nullptr, B, L, H, ndir, save};
   return mmb::dispatch(a, false, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, const int32_t* lengths,
-                              const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, float* db_part,
-                              int B, int L, int H, int ndir, mmb_stream_t stream) {
+                              const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, int B, int L,
+                              int H, int ndir, mmb_stream_t stream) {
   MMB_REQUIRE(gates && cell && w_hh && lengths && dout, MMB_ERR_INVALID, "mmb_bilstm_bwd: null pointer");
   MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID,
               "mmb_bilstm_bwd: B=%d L=%d H=%d ndir=%d", B, L, H, ndir);
-  mmb::LstmArgs a{gates, w_hh, lengths, order, nullptr, nullptr, nullptr, const_cast<float*>(cell), dout, dh_n, dc_n, db_part,
+  mmb::LstmArgs a{gates, w_hh, lengths, order, nullptr, nullptr, nullptr, const_cast<float*>(cell), dout, dh_n, dc_n,
                   B, L, H, ndir, 1};
   return mmb::dispatch(a, true, static_cast<cudaStream_t>(stream));
 }

@@ -41,11 +41,11 @@ class _LstmLayer(torch.autograd.Function):
         B, L, H, ndir, fan_in = ctx.dims
         if d_out is None:
             d_out = torch.zeros_like(out)
-        da, db_part = ops.lstm_layer_bwd(gates, cell, w_hh, lengths, order, d_out, d_h_n, None, B, L, H, ndir)
+        da = ops.lstm_layer_bwd(gates, cell, w_hh, lengths, order, d_out, d_h_n, None, B, L, H, ndir)
         da2d = da.view(B * L, ndir * 4 * H)
         dx = (da2d @ w_ih).view(B, L, fan_in) if ctx.needs_input_grad[0] else None
         dw_ih = da2d.t() @ x2d                                                               # (ndir*4H, in)
-        db = db_part.sum(dim=0).reshape(ndir * 4 * H)      # (B, ndir, 4H) summed in the kernel over time: no pass over da
+        db = da2d.sum(dim=0)
         grads = []
         zero = out.new_zeros(B, 1, H)
         for d in range(ndir):

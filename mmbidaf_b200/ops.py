@@ -118,18 +118,16 @@ def lstm_layer_fwd(gates: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tenso
 
 def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor,
                    order: Optional[torch.Tensor], dout: torch.Tensor, dh_n: Optional[torch.Tensor],
-                   dc_n: Optional[torch.Tensor], B: int, L: int, H: int, ndir: int):
-    """BPTT of :func:`lstm_layer_fwd`; overwrites ``gates`` with d(pre-activation).  Returns (gates, db_part) with
-    db_part (B, ndir, 4H) the per-sequence sums over time of d(pre-activation) (bias gradient = its sum over B)."""
+                   dc_n: Optional[torch.Tensor], B: int, L: int, H: int, ndir: int) -> torch.Tensor:
+    """BPTT of :func:`lstm_layer_fwd`; overwrites ``gates`` with d(pre-activation) and returns it."""
     lib = _lib.lib()
     p = _lib.ptr
-    db_part = torch.empty(B, ndir, 4 * H, device=gates.device, dtype=torch.float32)
     _lib.check(lib.mmb_bilstm_bwd(p(gates), p(cell), p(w_hh), p(lengths), p(order), p(dout.contiguous()),
                                   p(None if dh_n is None else dh_n.contiguous()),
-                                  p(None if dc_n is None else dc_n.contiguous()), p(db_part), B, L, H, ndir,
-                                  _lib.stream()), "mmb_bilstm_bwd")
+                                  p(None if dc_n is None else dc_n.contiguous()), B, L, H, ndir, _lib.stream()),
+               "mmb_bilstm_bwd")
     _count(1)
-    return gates, db_part
+    return gates
 
 
 class DecoderSeq:

@@ -4,7 +4,7 @@
 // gathers around it, encoding.py:91-101) for one layer, both directions.  The input projection
 // x W_ih^T + b_ih + b_hh is a plain GEMM done by the caller; this kernel owns the serial part.
 //
-// One CTA = one direction x NB sequences, alive for the whole sequence.  Two lanes share a hidden
+// One CTA = one direction x NB sequences, alive for the whole sequence.  FORWARD kernel: two lanes share a hidden
 // unit j: lane kp (0/1) keeps in REGISTERS the recurrent weights of all four gate rows of unit j
 // restricted to half of the k range (4 x KS floats, KS = 52 at H = 100), so W_hh never leaves the
 // register file between time steps and the CTA is only 2H threads (7 warps at H = 100: <= 2 warps per
@@ -12,7 +12,7 @@
 // reads from shared memory), a 2-shuffle reduce-scatter (lane 0 ends with gates i,f; lane 1 with g,o),
 // two branch-free activations per lane, a 2-shuffle exchange, the cell update, one __syncthreads.
 // Input pre-activations are prefetched RING-1 steps ahead with cp.async; all addressing is by running
-// pointers (one add per step).
+// pointers (one add per step).  The BACKWARD kernel uses a different cut (a gate per warp pair), see its header.
 //
 // Semantics follow torch.nn.LSTM on a PackedSequence: gate order i,f,g,o; zero initial state;
 // the reverse direction starts at each sample's own last valid step; outputs past a sample's
@@ -209,69 +209,83 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
 
 // Backward through time.  `gates` holds the activated gates on entry and d(pre-activation) on exit
 // (zeros past each length), so dW_ih / dx / db / dW_hh are plain GEMMs for the caller.
-// Lane kp of unit j owns gates (2kp, 2kp+1): it loads and differentiates those two gates and keeps the
-// matching 2 x H slice of W_hh^T (column j) in registers for the recurrent product dh = W_hh^T da.
+//
+// The recurrent product dh[j] = sum_{g,r} W_hh[g H + r][j] da[g][r] reads FOUR H-vectors from shared memory per step
+// (the forward reads one), and a broadcast LDS.128 costs 2.3 cycles per warp (tools/micro/lds_bcast.cu), so the first
+// version (two lanes per unit, each reading the 2 x H values of its two gates: 52 LDS.128 per thread) spent ~820 of its
+// 1700 cycles per step in the shared-memory pipe.  Here a thread keeps the W_hh^T columns of TWO units restricted to
+// ONE gate (2 x HP weights, the same register budget) and the gate is uniform over a warp pair: 26 LDS.128 per thread,
+// all lanes of a warp on the same address.  The four per-gate partial sums of a unit meet in shared memory; the
+// point-wise part of a step is done by one thread per unit (threads 0..H-1), which also owns the cp.async ring.
+// Measured: 0.87 -> 0.61 us per step.  (The same cut of the FORWARD kernel doubles its shared-memory reads -- it only
+// needs the H values of h -- and adds a barrier: 0.75 us per step against 0.67 for the lane-pair design above.)
+constexpr int BWD_NT = 256, BWD_SL = 64;     // 8 warps = 4 gates x 64 unit slots; a slot covers units slot and slot + 64
+
 template <int KS, int NB>
-__global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmArgs a) {
+__global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
   constexpr int HP = 2 * KS;                       // >= H, multiple of 4
+  static_assert(HP <= 2 * BWD_SL, "two units per slot cover the hidden size");
   const int H = a.H, L = a.L, ndir = a.ndir;
   const int dir = blockIdx.y;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int j = tid >> 1, kp = tid & 1;
-  const bool live = j < H;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q = warp >> 1;                         // the gate whose rows this warp pair multiplies (warp-uniform)
+  const int slot = tid & (BWD_SL - 1);
+  const bool unit = tid < H;                       // point-wise owner of hidden unit j = tid
+  const int j = tid;
 
   extern __shared__ __align__(16) float smem[];
-  float* da_s = smem;                              // [2][NB][4][HP]
-  float* ring = da_s + 2 * NB * 4 * HP;            // [RING][NB][4][nthr]
+  float* da_s = smem;                              // [NB][4][HP]
+  float* part = da_s + NB * 4 * HP;                // [NB][4][2 * BWD_SL]
+  float* ring = part + NB * 4 * 2 * BWD_SL;        // [RING][NB][7][128]
 
   int seq[NB], len[NB];
   int max_len = 0;
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
-    const int slot = blockIdx.x * NB + n;
-    seq[n] = slot < a.B ? (a.order ? a.order[slot] : slot) : -1;
+    const int sl = blockIdx.x * NB + n;
+    seq[n] = sl < a.B ? (a.order ? a.order[sl] : sl) : -1;
     len[n] = seq[n] >= 0 ? min(max(a.lengths[seq[n]], 0), L) : 0;
     max_len = max(max_len, len[n]);
   }
 
-  float wt[2][HP];                                 // W_hh[(2kp+gg)*H + r][j]
+  float wt[2][HP];                                 // W_hh[q H + r][slot + 64 u]
   {
     const float* wd = a.w_hh + (size_t)dir * 4 * H * H;
 #pragma unroll
-    for (int gg = 0; gg < 2; ++gg)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int r = 0; r < HP; ++r) wt[gg][r] = (live && r < H) ? wd[(size_t)((2 * kp + gg) * H + r) * H + j] : 0.f;
+      for (int r = 0; r < HP; ++r) {
+        const int ju = slot + BWD_SL * u;
+        wt[u][r] = (ju < H && r < H) ? wd[(size_t)(q * H + r) * H + ju] : 0.f;
+      }
   }
-  for (int i = tid; i < 2 * NB * 4 * HP; i += nthr) da_s[i] = 0.f;
+  for (int i = tid; i < NB * 4 * HP + NB * 4 * 2 * BWD_SL; i += BWD_NT) da_s[i] = 0.f;
 
   // Backward step s visits the forward steps in reverse: time t = dir ? s : len-1-s.
   const long sign = dir ? 1 : -1;
   const long g_stride = sign * (long)ndir * 4 * H, o_stride = sign * (long)ndir * H;
   float* gp[NB];
-  const float *pg[NB], *pc[NB], *pd[NB];           // prefetch pointers: gates, cell, dout
+  const float *pg[NB], *pc[NB], *pd[NB];           // prefetch pointers: gates, cell, dout (unit threads)
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
     const size_t bt0 = (size_t)max(seq[n], 0) * L + (dir ? 0 : max(len[n] - 1, 0));
-    gp[n] = a.gates + (bt0 * ndir + dir) * 4 * H + (2 * kp) * H + j;
+    gp[n] = a.gates + (bt0 * ndir + dir) * 4 * H + (unit ? j : 0);
     pg[n] = gp[n];
-    pc[n] = a.cell + (bt0 * ndir + dir) * H + j;
-    pd[n] = a.dout + bt0 * ndir * H + dir * H + j;
+    pc[n] = a.cell + (bt0 * ndir + dir) * H + (unit ? j : 0);
+    pd[n] = a.dout + bt0 * ndir * H + dir * H + (unit ? j : 0);
   }
-  float* ring_t = ring + tid;
-  auto prefetch = [&](int s, int slot) {
-    if (live) {
+  float* ring_t = ring + (tid & 127);
+  auto prefetch = [&](int s, int sl) {
+    if (unit) {
 #pragma unroll
       for (int n = 0; n < NB; ++n) {
         if (s < len[n]) {
-          float* dst = ring_t + (slot * NB + n) * 4 * nthr;
-          cp_async4(dst, pg[n]);
-          cp_async4(dst + nthr, pg[n] + H);
-          if (kp == 0) {
-            cp_async4(dst + 2 * nthr, pc[n]);                                 // c_t
-            if (s + 1 < len[n]) cp_async4(dst + 3 * nthr, pc[n] + o_stride);  // c of the previous forward step
-          } else {
-            cp_async4(dst + 2 * nthr, pd[n]);                                 // d out
-          }
+          float* dst = ring_t + (sl * NB + n) * 7 * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) cp_async4(dst + g * 128, pg[n] + g * H);
+          cp_async4(dst + 4 * 128, pc[n]);                                    // c_t
+          if (s + 1 < len[n]) cp_async4(dst + 5 * 128, pc[n] + o_stride);     // c of the previous forward step
+          cp_async4(dst + 6 * 128, pd[n]);                                    // d out
         }
         pg[n] += g_stride;
         pc[n] += o_stride;
@@ -286,77 +300,79 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmA
   float dh_rec[NB], dc[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
-    dh_rec[n] = (live && seq[n] >= 0 && a.dh_n) ? a.dh_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
-    dc[n] = (live && seq[n] >= 0 && a.dc_n) ? a.dc_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
+    dh_rec[n] = (unit && seq[n] >= 0 && a.dh_n) ? a.dh_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
+    dc[n] = (unit && seq[n] >= 0 && a.dc_n) ? a.dc_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
   }
   __syncthreads();
-  float* dcur = da_s;
-  float* dnxt = da_s + NB * 4 * HP;
-  int slot = 0;
+  int sl = 0;
 
 #pragma unroll 1
   for (int s = 0; s < max_len; ++s) {
-    prefetch(s + RING - 1, (slot + RING - 1) & (RING - 1));
+    prefetch(s + RING - 1, (sl + RING - 1) & (RING - 1));
     cp_async_wait<RING - 1>();
 
+    // ---- point-wise part: one thread per hidden unit -----------------------------------------------------------------
+    if (unit) {
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      const bool on = live && s < len[n];
-      const float* rs = ring_t + (slot * NB + n) * 4 * nthr;
-      const float g0 = on ? rs[0] : 0.f, g1 = on ? rs[nthr] : 0.f;          // lane 0: i, f   lane 1: g, o
-      const float x2 = on ? rs[2 * nthr] : 0.f;                             // lane 0: c_t    lane 1: d out
-      const float x3 = (on && kp == 0 && s + 1 < len[n]) ? rs[3 * nthr] : 0.f;   // lane 0: c_prev
-      const float o0 = __shfl_xor_sync(0xffffffffu, g0, 1), o1 = __shfl_xor_sync(0xffffffffu, g1, 1);
-      const float y2 = __shfl_xor_sync(0xffffffffu, x2, 1), y3 = __shfl_xor_sync(0xffffffffu, x3, 1);
-      const float gi = kp ? o0 : g0, gf = kp ? o1 : g1, gg = kp ? g0 : o0, go = kp ? g1 : o1;
-      const float ct = kp ? y2 : x2, dy = kp ? x2 : y2, cprev = kp ? y3 : x3;
-      const float dh = dy + dh_rec[n];
-      const float tc = tanh_fast(ct);
-      const float dct = fmaf(dh * go, 1.f - tc * tc, dc[n]);
-      // lane 0: (d a_i, d a_f)   lane 1: (d a_g, d a_o)
-      const float d0 = kp ? dct * gi * (1.f - gg * gg) : dct * gg * gi * (1.f - gi);
-      const float d1 = kp ? dh * tc * go * (1.f - go) : dct * cprev * gf * (1.f - gf);
-      if (on) {
-        dc[n] = dct * gf;
-        dcur[(n * 4 + 2 * kp) * HP + j] = d0;
-        dcur[(n * 4 + 2 * kp + 1) * HP + j] = d1;
-        gp[n][0] = d0;
-        gp[n][H] = d1;
-      } else if (live) {
-        dcur[(n * 4 + 2 * kp) * HP + j] = 0.f;
-        dcur[(n * 4 + 2 * kp + 1) * HP + j] = 0.f;
+      for (int n = 0; n < NB; ++n) {
+        const bool on = s < len[n];
+        const float* rs = ring_t + (sl * NB + n) * 7 * 128;
+        float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
+        if (on) {
+          const float gi = rs[0], gf = rs[128], gg = rs[2 * 128], go = rs[3 * 128], ct = rs[4 * 128], dy = rs[6 * 128];
+          const float cprev = s + 1 < len[n] ? rs[5 * 128] : 0.f;
+          const float dh = dy + dh_rec[n];
+          const float tc = tanh_fast(ct);
+          const float dct = fmaf(dh * go, 1.f - tc * tc, dc[n]);
+          d_i = dct * gg * gi * (1.f - gi);
+          d_f = dct * cprev * gf * (1.f - gf);
+          d_g = dct * gi * (1.f - gg * gg);
+          d_o = dh * tc * go * (1.f - go);
+          dc[n] = dct * gf;
+          gp[n][0] = d_i;
+          gp[n][H] = d_f;
+          gp[n][2 * H] = d_g;
+          gp[n][3 * H] = d_o;
+        }
+        float* dn = da_s + n * 4 * HP + j;
+        dn[0] = d_i;
+        dn[HP] = d_f;
+        dn[2 * HP] = d_g;
+        dn[3 * HP] = d_o;
+        gp[n] += g_stride;
       }
-      gp[n] += g_stride;
     }
     __syncthreads();
-    // dh_rec[j] = sum_r W_hh[r][j] da[r]: this lane covers the rows of gates 2kp, 2kp+1
-    float part[NB][2];
-#pragma unroll
-    for (int n = 0; n < NB; ++n) part[n][0] = part[n][1] = 0.f;
-#pragma unroll
-    for (int r4 = 0; r4 < HP / 4; ++r4) {
-#pragma unroll
-      for (int n = 0; n < NB; ++n)
-#pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          const float4 dv = *reinterpret_cast<const float4*>(dcur + (n * 4 + 2 * kp + gg) * HP + r4 * 4);
-          part[n][gg] = fmaf(wt[gg][r4 * 4 + 0], dv.x, part[n][gg]);
-          part[n][gg] = fmaf(wt[gg][r4 * 4 + 1], dv.y, part[n][gg]);
-          part[n][gg] = fmaf(wt[gg][r4 * 4 + 2], dv.z, part[n][gg]);
-          part[n][gg] = fmaf(wt[gg][r4 * 4 + 3], dv.w, part[n][gg]);
-        }
-    }
+    // ---- dh_rec partials: this warp pair's gate, this thread's two units -------------------------------------------
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
-      const float p = part[n][0] + part[n][1];
-      dh_rec[n] = p + __shfl_xor_sync(0xffffffffu, p, 1);
+      float p0[2] = {0.f, 0.f}, p1[2] = {0.f, 0.f};
+      const float* dq = da_s + (n * 4 + q) * HP;
+#pragma unroll
+      for (int r4 = 0; r4 < HP / 4; ++r4) {
+        const float4 dv = *reinterpret_cast<const float4*>(dq + r4 * 4);
+        p0[0] = fmaf(wt[0][r4 * 4 + 0], dv.x, p0[0]);
+        p1[0] = fmaf(wt[1][r4 * 4 + 0], dv.x, p1[0]);
+        p0[1] = fmaf(wt[0][r4 * 4 + 1], dv.y, p0[1]);
+        p1[1] = fmaf(wt[1][r4 * 4 + 1], dv.y, p1[1]);
+        p0[0] = fmaf(wt[0][r4 * 4 + 2], dv.z, p0[0]);
+        p1[0] = fmaf(wt[1][r4 * 4 + 2], dv.z, p1[0]);
+        p0[1] = fmaf(wt[0][r4 * 4 + 3], dv.w, p0[1]);
+        p1[1] = fmaf(wt[1][r4 * 4 + 3], dv.w, p1[1]);
+      }
+      float* pn = part + (n * 4 + q) * 2 * BWD_SL + slot;
+      pn[0] = p0[0] + p0[1];
+      pn[BWD_SL] = p1[0] + p1[1];
     }
-    slot = (slot + 1) & (RING - 1);
-    {
-      float* t = dcur;
-      dcur = dnxt;
-      dnxt = t;
+    __syncthreads();
+    if (unit) {
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        const float* pn = part + n * 4 * 2 * BWD_SL + j;
+        dh_rec[n] = (pn[0] + pn[2 * BWD_SL]) + (pn[4 * BWD_SL] + pn[6 * BWD_SL]);
+      }
     }
+    sl = (sl + 1) & (RING - 1);
   }
   cp_async_wait<0>();
 
@@ -364,7 +380,7 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_bwd_kernel(const LstmA
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
     if (seq[n] < 0) continue;
-    for (int i = tid; i < (L - len[n]) * 4 * H; i += nthr) {
+    for (int i = tid; i < (L - len[n]) * 4 * H; i += BWD_NT) {
       const int t = len[n] + i / (4 * H), u = i % (4 * H);
       a.gates[(((size_t)seq[n] * L + t) * ndir + dir) * 4 * H + u] = 0.f;
     }
@@ -382,9 +398,9 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
     bilstm_fwd_kernel<KS, NB><<<grid, block, smem, stream>>>(a);
     return check_launch("bilstm_fwd_kernel");
   }
-  const size_t smem = sizeof(float) * (2 * NB * 4 * HP + (size_t)RING * NB * 4 * nthr);
+  const size_t smem = sizeof(float) * (NB * 4 * HP + NB * 4 * 2 * BWD_SL + (size_t)RING * NB * 7 * 128);
   MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bilstm_bwd_kernel<KS, NB><<<grid, block, smem, stream>>>(a);
+  bilstm_bwd_kernel<KS, NB><<<grid, BWD_NT, smem, stream>>>(a);
   return check_launch("bilstm_bwd_kernel");
 }
 

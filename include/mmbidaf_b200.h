@@ -126,7 +126,7 @@ MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, c
  * BLAS (they are plain (B x K) x (K x N) products over the whole batch):
  *   hw    (B,4*2H) = h [W2;W4;W_beta_2;W_beta_4]^T + [b2+bc1; b4+bc2; bb2; bb4]
  *   mmb_decoder_attn_fwd      energies + un-masked soft-max over the text axis + contexts c1,c2 (attention.py:147-156)
- *   pb    (2,B,2H) = c_k W_beta_{1,3}^T + bias
+ *   pb    (2,B,2H) = c_k W_beta_{1,3}^T (+ bias, unless the caller adds it with hw's third / fourth block: same tanh)
  *   mmb_decoder_attn_finish   2-way modality soft-max, attended context, att_cov, coverage (attention.py:161-177);
  *                             also assembles xcat (B, 2H+E+H) = [ctx | sent_embed | h]
  *   gates (B,4H)   = xcat [W_ih | W_hh]^T + b_ih + b_hh

@@ -124,6 +124,10 @@ class MMBiDAF(nn.Module):
         targets = batch_target_indices.reshape(B, -1).to(embedded_text.device).long()      # int(tensor), models.py:168
         out_distributions, step_losses = [], []
         steps = batch_target_indices.size(1) if self.training else max_dec_len
+        if self.training:
+            # teacher forcing (models.py:173): every step's next input is known up front -- one gather for the whole
+            # sequence, laid out (steps, B, E) so that a step's slice is contiguous, instead of a gather per step
+            next_inputs = embedded_text[rows.unsqueeze(0), targets[:, :steps].t()]
         for idx in range(steps):
             tgt = targets[:, idx]
             # the decoder kernels also emit this step's loss terms: -log(p[target] + 1e-12) (models.py:168-170)
@@ -131,8 +135,10 @@ class MMBiDAF(nn.Module):
             out_distribution, decoder_hidden, decoder_cell_state, att_cov_dist, coverage_vec, step_loss = \
                 self.multimodal_att_decoder.step(decoder_input, decoder_hidden, decoder_cell_state, mod_text_audio,
                                                  mod_text_image, coverage_vec, decoder_mask, target=tgt)
-            nxt = tgt if self.training else out_distribution.max(dim=1)[1]                  # models.py:173 / :184,:193
-            decoder_input = embedded_text[rows, nxt].unsqueeze(1)
+            if self.training:
+                decoder_input = next_inputs[idx].unsqueeze(1)                               # models.py:173
+            else:
+                decoder_input = embedded_text[rows, out_distribution.max(dim=1)[1]].unsqueeze(1)   # models.py:184,:193
             out_distributions.append(out_distribution)
             step_losses.append(step_loss)
         terms = torch.stack(step_losses)                                                    # (steps, 2, B)

@@ -144,9 +144,10 @@ class DecoderSeq:
         self.H, self.M = self.D // 2, out_size
         self.E = P["lstm_w_ih"].shape[1] - self.D
         self.Wh4 = torch.cat([P["W2"], P["W4"], P["Wb2"], P["Wb4"]], dim=0).contiguous()           # (4D, H)
-        self.bh4 = torch.cat([P["b2"] + P["bc1"], P["b4"] + P["bc2"], P["bb2"], P["bb4"]]).contiguous()
+        # every bias that ends up inside the same tanh is added once, with the h projection: W2 h + b2 + bc1 (attention.py:147),
+        # W_beta_2 h + bb2 + bb1 (the bias of W_beta_1 c_1, :161) -- so the c_k projection below is a bias-free GEMM
+        self.bh4 = torch.cat([P["b2"] + P["bc1"], P["b4"] + P["bc2"], P["bb2"] + P["bb1"], P["bb4"] + P["bb3"]]).contiguous()
         self.Wb13 = torch.stack([P["Wb1"], P["Wb3"]]).contiguous()                                 # (2, D, D)
-        self.bb13 = torch.stack([P["bb1"], P["bb3"]]).unsqueeze(1).contiguous()                    # (2, 1, D)
         self.Wcat = torch.cat([P["lstm_w_ih"], P["lstm_w_hh"]], dim=1).contiguous()                # (4H, D+E+H)
         self.bcat = (P["lstm_b_ih"] + P["lstm_b_hh"]).contiguous()
         self.out_w, self.out_b = P["out_w"].contiguous(), P["out_b"].contiguous()
@@ -175,7 +176,7 @@ def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_arg
     _lib.check(lib.mmb_decoder_attn_fwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
                                         p(seq.v1), p(seq.wc1), p(seq.v2), p(seq.wc2), p(seq.v1b), p(seq.v2b), p(alpha),
                                         p(stats), p(ctxp), p(ctx12), p(scale), B, Lt, D, nch, st), "mmb_decoder_attn_fwd")
-    pb = torch.baddbmm(seq.bb13, ctx12, seq.Wb13.transpose(1, 2))              # (2, B, D)  library GEMM
+    pb = torch.bmm(ctx12, seq.Wb13.transpose(1, 2))                            # (2, B, D)  library GEMM (bias: see DecoderSeq)
     xcat = torch.empty(B, D + E + H, **f32)
     att_cov, cov_out, beta = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32), torch.empty(B, 2, **f32)
     lossvec = torch.empty(2, B, **f32) if target is not None else None       # [nll | coverage term]

@@ -50,7 +50,11 @@ class MMBiDAF(nn.Module):
             return [job() for job in jobs]
         main = torch.cuda.current_stream()
         if getattr(self, "_streams", None) is None or self._streams[0].device != main.device:
-            object.__setattr__(self, "_streams", [torch.cuda.Stream(device=main.device) for _ in range(3)])
+            # the first job of a fork is the one on the critical path (the 1024-frame audio recurrence): its stream gets
+            # the high priority, so its 64 CTAs are not queued behind the shorter text / image recurrences (192 CTAs
+            # for 148 SMs) -- that ordering was a coin flip and made the step time bimodal
+            object.__setattr__(self, "_streams", [torch.cuda.Stream(device=main.device, priority=-1 if i == 0 else 0)
+                                                  for i in range(3)])
         results = []
         for stream, job in zip(self._streams, jobs):
             stream.wait_stream(main)
@@ -94,8 +98,8 @@ class MMBiDAF(nn.Module):
             feats = self.image_keyframes_emb(img).reshape(B, transformed_images.size(1), -1)
             return feats, self.image_enc(self.i_emb(feats), original_image_lengths)[0]
 
-        (text_emb, text_encoded), (audio_encoded,), (image_emb, image_encoded) = \
-            self._fork_join([text_branch, audio_branch, image_branch])
+        (audio_encoded,), (text_emb, text_encoded), (image_emb, image_encoded) = \
+            self._fork_join([audio_branch, text_branch, image_branch])
 
         text_mask = self.get_mask(embedded_text, original_text_lengths)
         audio_mask = self.get_mask(embedded_audio, original_audio_lengths)

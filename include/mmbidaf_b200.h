@@ -144,8 +144,8 @@ MMB_API int mmb_decoder_chunks(int B, int Lt);
 MMB_API int mmb_decoder_attn_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
                                  const float* hw, const float* coverage, const float* v1, const float* wc1,
                                  const float* v2, const float* wc2, const float* v1b, const float* v2b, float* p,
-                                 float* stats, float* ctxp, float* ctx12, float* scale, int B, int Lt, int D, int nch,
-                                 mmb_stream_t stream);
+                                 float* stats, float* ctxp, float* ctx12, float* scale, int* counters, int B, int Lt, int D,
+                                 int nch, mmb_stream_t stream);
 /* p_alpha: in = p from mmb_decoder_attn_fwd, out = the attention weights alpha (B,2,Lt). */
 MMB_API int mmb_decoder_attn_finish(const float* pb, const float* hw, const float* ctx12, const float* scale,
                                     const float* coverage, const float* sent, const float* h, const float* vb1,
@@ -171,6 +171,8 @@ MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long lon
  *   d_h    = d_xcat[:, 2H+E:] + d_hw4 [W2;W4;W_beta_2;W_beta_4]
  * vec_acc (B,6,2H) += [dWc1, dWc2, dv1, dv2, dv_beta_1, dv_beta_2]; scal_acc (B,4) += their scalar biases.
  * Scratch: d_alpha (B,2,Lt)  spart (B,nch,2)  colp (B,nch,2,3,2H)  separt (B,nch,2).
+ * counters (B) int32 of mmb_decoder_attn_fwd / _bwd: zero before the first call, left at zero by every call (the last chunk
+ * block of a video to finish merges that video's chunk partials, so neither function needs a second launch for it).
  */
 MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
                                         const float* g_nll, float* d_logits, int B, int M, mmb_stream_t stream);
@@ -188,8 +190,8 @@ MMB_API int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, const
                                  const float* datt, const float* d_ctx12, const float* d_cov_out, const float* d_pre_b,
                                  const float* v1, const float* wc1, const float* v2, const float* wc2, float* d_alpha,
                                  float* spart, float* d_proj_a, float* d_proj_i, float* d_cov, float* colp, float* separt,
-                                 float* d_hw4, float* vec_acc, float* scal_acc, int B, int Lt, int D, int nch,
-                                 mmb_stream_t stream);
+                                 float* d_hw4, float* vec_acc, float* scal_acc, int* counters, int B, int Lt, int D,
+                                 int nch, mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
  * masked_softmax over the last axis (attention.py:78-98): y = softmax(mask ? x : -1e30), or

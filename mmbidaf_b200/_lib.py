@@ -32,14 +32,14 @@ SIGNATURES = {
     "mmb_bilstm_fwd": [c_void_p] * 8 + [c_int] * 5 + [c_void_p],
     "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_chunks": [c_int, c_int],
-    "mmb_decoder_attn_fwd": [c_void_p] * 17 + [c_int] * 4 + [c_void_p],
+    "mmb_decoder_attn_fwd": [c_void_p] * 18 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_attn_finish": [c_void_p] * 17 + [c_int] * 6 + [c_void_p],
     "mmb_decoder_cell_fwd": [c_void_p] * 4 + [c_int] * 2 + [c_void_p],
     "mmb_decoder_out_softmax": [c_void_p] * 5 + [c_int] * 2 + [c_void_p],
     "mmb_decoder_out_softmax_bwd": [c_void_p] * 5 + [c_int] * 2 + [c_void_p],
     "mmb_decoder_cell_bwd": [c_void_p] * 7 + [c_int] * 2 + [c_void_p],
     "mmb_decoder_attn_finish_bwd": [c_void_p, c_int] + [c_void_p] * 18 + [c_int] * 3 + [c_void_p],
-    "mmb_decoder_attn_bwd": [c_void_p] * 26 + [c_int] * 4 + [c_void_p],
+    "mmb_decoder_attn_bwd": [c_void_p] * 27 + [c_int] * 4 + [c_void_p],
     "mmb_highway_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_highway_bwd": [c_void_p] * 5 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_masked_softmax_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p],

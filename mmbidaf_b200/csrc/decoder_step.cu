@@ -46,10 +46,58 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 //   e_k[t] = v_k . tanh(proj_k[t] + hw_k + cov[t] wc_k) + v_k bias                       (attention.py:147,153)
 //   p[b,k,t] = exp(e_k[t] - m_c),  stats[b,c,k] = (m_c, sum_t p),  ctxp[b,c,k,:] = sum_t p enc_k[t]
 // ----------------------------------------------------------------------------------------------------------
+// forward 2: merge the chunk partials -> contexts c1, c2 (2,B,D) and per-chunk scales (B,2,nch).  Run by the LAST chunk
+// block of a video to finish (see last_block_of_video), so the step needs no separate launch for it.
+__device__ __forceinline__ void combine_video(const float* stats, const float* ctxp,   /* other blocks' partials: no read-only path */
+                                              float* ctx12, float* scale, int b, int B, int D, int nch) {
+  const int tid = threadIdx.x;
+  __shared__ float w[2][64];
+  __shared__ float inv_l[2];
+  if (tid < 2) {
+    const int k = tid;
+    float m = -INFINITY;
+    for (int c = 0; c < nch; ++c) m = fmaxf(m, stats[((size_t)b * nch + c) * 4 + 2 * k]);
+    float l = 0.f;
+    for (int c = 0; c < nch; ++c) {
+      const float wc = expf(stats[((size_t)b * nch + c) * 4 + 2 * k] - m);
+      w[k][c] = wc;
+      l = fmaf(wc, stats[((size_t)b * nch + c) * 4 + 2 * k + 1], l);
+    }
+    inv_l[k] = 1.f / l;
+    for (int c = 0; c < nch; ++c) scale[((size_t)b * 2 + k) * nch + c] = w[k][c] / l;
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * D; i += NT) {
+    const int k = i / D, d = i - k * D;
+    float s = 0.f;
+    for (int c = 0; c < nch; ++c) s = fmaf(w[k][c], ctxp[(((size_t)b * nch + c) * 2 + k) * D + d], s);
+    ctx12[((size_t)k * B + b) * D + d] = s * inv_l[k];
+  }
+}
+
+// True in exactly one of the `nblk` blocks that call it for video b: the last one to arrive, after whose fence the global
+// writes of all the others are visible.  `counter` (one int per video, zero on entry) is left at zero again.
+__device__ __forceinline__ bool last_block_of_video(int* counter, int nblk) {
+  __shared__ int last;
+  __threadfence();                                   // this block's partials, device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(counter, 1);
+    last = prev == nblk - 1;
+    if (last) *counter = 0;
+  }
+  __syncthreads();
+  const bool is_last = last != 0;
+  if (is_last) __threadfence();
+  return is_last;
+}
+
 struct PartialArgs {
   const float *proj_a, *proj_i, *enc_a, *enc_i, *hw, *cov;   // hw (B,4D): [W2 h+b | W4 h+b | ...]
   const float *v1, *wc1, *v2, *wc2, *v1b, *v2b;
   float *p, *stats, *ctxp;
+  float *ctx12, *scale;      // written by the last chunk block of each video (combine_video)
+  int* counters;             // (B) zero on entry, zero on exit
   int B, Lt, D, chunk, nch;
 };
 
@@ -175,35 +223,7 @@ __global__ void __launch_bounds__(NT) dec_attn_partial_kernel(const PartialArgs 
     for (int g = 0; g < groups; ++g) s += part[(g * 2 + k) * D + dd];
     a.ctxp[(((size_t)b * a.nch + c) * 2 + k) * D + dd] = s;
   }
-}
-
-// forward 2: merge the chunk partials -> contexts c1, c2 (2,B,D) and per-chunk scales (B,2,nch)
-__global__ void __launch_bounds__(NT) dec_attn_combine_kernel(const float* __restrict__ stats, const float* __restrict__ ctxp,
-                                                              float* __restrict__ ctx12, float* __restrict__ scale, int B,
-                                                              int D, int nch) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  __shared__ float w[2][64];
-  __shared__ float inv_l[2];
-  if (tid < 2) {
-    const int k = tid;
-    float m = -INFINITY;
-    for (int c = 0; c < nch; ++c) m = fmaxf(m, stats[((size_t)b * nch + c) * 4 + 2 * k]);
-    float l = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      const float wc = expf(stats[((size_t)b * nch + c) * 4 + 2 * k] - m);
-      w[k][c] = wc;
-      l = fmaf(wc, stats[((size_t)b * nch + c) * 4 + 2 * k + 1], l);
-    }
-    inv_l[k] = 1.f / l;
-    for (int c = 0; c < nch; ++c) scale[((size_t)b * 2 + k) * nch + c] = w[k][c] / l;
-  }
-  __syncthreads();
-  for (int i = tid; i < 2 * D; i += NT) {
-    const int k = i / D, d = i - k * D;
-    float s = 0.f;
-    for (int c = 0; c < nch; ++c) s = fmaf(w[k][c], ctxp[(((size_t)b * nch + c) * 2 + k) * D + d], s);
-    ctx12[((size_t)k * B + b) * D + d] = s * inv_l[k];
-  }
+  if (last_block_of_video(a.counters + b, a.nch)) combine_video(a.stats, a.ctxp, a.ctx12, a.scale, b, a.B, D, a.nch);
 }
 
 // forward 3: modality soft-max, attended context, attention / coverage outputs         (attention.py:161-177)
@@ -420,6 +440,9 @@ struct SweepArgs {
   const float *v1, *wc1, *v2, *wc2;
   float *d_alpha, *spart;                                     // (B,2,Lt), (B,nch,2)
   float *d_proj_a, *d_proj_i, *d_cov, *colp, *separt;         // colp (B,nch,2,3,D), separt (B,nch,2)
+  const float* d_pre_b;                                       // reduce_video
+  float *d_hw4, *vec_acc, *scal_acc;
+  int* counters;                                              // (B) zero on entry, zero on exit
   int B, Lt, D, chunk, nch;
 };
 
@@ -480,6 +503,50 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep1_kernel(const SweepArgs a) 
     a.spart[((size_t)b * a.nch + c) * 2 + 1] = s2;
   }
 }
+
+// 6: reduce the chunk partials: d (W h + b) rows for the final GEMM, parameter-gradient accumulators.  Run by the LAST
+// sweep-2 block of a video to finish.
+__device__ __forceinline__ void reduce_video(int b, const float* colp, const float* separt,   /* other blocks' partials */
+                                                             const float* __restrict__ d_pre_b, float* __restrict__ d_hw4,
+                                                             float* __restrict__ vec_acc, float* __restrict__ scal_acc, int B,
+                                                             int D, int nch) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * D; i += NT) {
+    const int m = i / D, d = i - m * D;
+    float x = 0.f, y = 0.f, z = 0.f;
+    constexpr int CB = 8;                                                  // chunk partials in flight (the sum order is unchanged)
+    for (int c0 = 0; c0 < nch; c0 += CB) {
+      float xs[CB], ys[CB], zs[CB];
+#pragma unroll
+      for (int u = 0; u < CB; ++u) {
+        const float* q = colp + ((((size_t)b * nch + min(c0 + u, nch - 1)) * 2 + m) * 3) * D;
+        xs[u] = q[d];
+        ys[u] = q[D + d];
+        zs[u] = q[2 * D + d];
+      }
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+        if (c0 + u < nch) {
+          x += xs[u];
+          y += ys[u];
+          z += zs[u];
+        }
+    }
+    d_hw4[(size_t)b * 4 * D + m * D + d] = x;                             // d (W2 h) | d (W4 h)
+    d_hw4[(size_t)b * 4 * D + (2 + m) * D + d] = d_pre_b[((size_t)m * B + b) * D + d];   // d (W_beta_2 h) | d (W_beta_4 h)
+    vec_acc[((size_t)b * 6 + m) * D + d] += y;                            // d Wc weight
+    vec_acc[((size_t)b * 6 + 2 + m) * D + d] += z;                        // d v weight
+  }
+  if (tid < 64) {                                                          // warps 0, 1: lane pairs (chunk, k) loaded in parallel
+    const int warp = tid >> 5, lane = tid & 31;
+    float v0 = lane < nch ? separt[((size_t)b * nch + lane) * 2 + warp] : 0.f;
+    float v1 = lane + 32 < nch ? separt[((size_t)b * nch + lane + 32) * 2 + warp] : 0.f;
+    float s = 0.f;
+    for (int c = 0; c < nch; ++c) s += __shfl_sync(0xffffffffu, c < 32 ? v0 : v1, c & 31);   // fixed order
+    if (lane == 0) scal_acc[b * 4 + warp] += s;                           // d v bias (identically 0 up to rounding)
+  }
+}
+
 
 // 5: sweep 2 over the projections of a chunk: soft-max backward, tanh backward, d proj (+=), d cov, column partials
 __global__ void __launch_bounds__(NT) dec_attn_sweep2_kernel(const SweepArgs a) {
@@ -581,48 +648,8 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep2_kernel(const SweepArgs a) 
     __syncthreads();
   }
   for (int i = tid; i < n; i += NT) a.d_cov[(size_t)b * Lt + t0 + i] = rowacc[i];
-}
-
-// 6: reduce the chunk partials: d (W h + b) rows for the final GEMM, parameter-gradient accumulators
-__global__ void __launch_bounds__(NT) dec_attn_reduce_kernel(const float* __restrict__ colp, const float* __restrict__ separt,
-                                                             const float* __restrict__ d_pre_b, float* __restrict__ d_hw4,
-                                                             float* __restrict__ vec_acc, float* __restrict__ scal_acc, int B,
-                                                             int D, int nch) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < 2 * D; i += NT) {
-    const int m = i / D, d = i - m * D;
-    float x = 0.f, y = 0.f, z = 0.f;
-    constexpr int CB = 8;                                                  // chunk partials in flight (the sum order is unchanged)
-    for (int c0 = 0; c0 < nch; c0 += CB) {
-      float xs[CB], ys[CB], zs[CB];
-#pragma unroll
-      for (int u = 0; u < CB; ++u) {
-        const float* q = colp + ((((size_t)b * nch + min(c0 + u, nch - 1)) * 2 + m) * 3) * D;
-        xs[u] = q[d];
-        ys[u] = q[D + d];
-        zs[u] = q[2 * D + d];
-      }
-#pragma unroll
-      for (int u = 0; u < CB; ++u)
-        if (c0 + u < nch) {
-          x += xs[u];
-          y += ys[u];
-          z += zs[u];
-        }
-    }
-    d_hw4[(size_t)b * 4 * D + m * D + d] = x;                             // d (W2 h) | d (W4 h)
-    d_hw4[(size_t)b * 4 * D + (2 + m) * D + d] = d_pre_b[((size_t)m * B + b) * D + d];   // d (W_beta_2 h) | d (W_beta_4 h)
-    vec_acc[((size_t)b * 6 + m) * D + d] += y;                            // d Wc weight
-    vec_acc[((size_t)b * 6 + 2 + m) * D + d] += z;                        // d v weight
-  }
-  if (tid < 64) {                                                          // warps 0, 1: lane pairs (chunk, k) loaded in parallel
-    const int warp = tid >> 5, lane = tid & 31;
-    float v0 = lane < nch ? separt[((size_t)b * nch + lane) * 2 + warp] : 0.f;
-    float v1 = lane + 32 < nch ? separt[((size_t)b * nch + lane + 32) * 2 + warp] : 0.f;
-    float s = 0.f;
-    for (int c = 0; c < nch; ++c) s += __shfl_sync(0xffffffffu, c < 32 ? v0 : v1, c & 31);   // fixed order
-    if (lane == 0) scal_acc[b * 4 + warp] += s;                           // d v bias (identically 0 up to rounding)
-  }
+  if (last_block_of_video(a.counters + b, a.nch))
+    reduce_video(b, a.colp, a.separt, a.d_pre_b, a.d_hw4, a.vec_acc, a.scal_acc, a.B, D, a.nch);
 }
 
 }  // namespace
@@ -641,24 +668,23 @@ extern "C" int mmb_decoder_chunks(int B, int Lt) {
 extern "C" int mmb_decoder_attn_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
                                     const float* hw, const float* coverage, const float* v1, const float* wc1,
                                     const float* v2, const float* wc2, const float* v1b, const float* v2b, float* p,
-                                    float* stats, float* ctxp, float* ctx12, float* scale, int B, int Lt, int D, int nch,
-                                    mmb_stream_t stream) {
+                                    float* stats, float* ctxp, float* ctx12, float* scale, int* counters, int B, int Lt, int D,
+                                    int nch, mmb_stream_t stream) {
   MMB_REQUIRE(proj_a && proj_i && enc_a && enc_i && hw && coverage && v1 && wc1 && v2 && wc2 && v1b && v2b && p && stats &&
-                  ctxp && ctx12 && scale,
+                  ctxp && ctx12 && scale && counters,
               MMB_ERR_INVALID, "mmb_decoder_attn_fwd: null pointer");
   MMB_REQUIRE(B > 0 && Lt > 0 && D > 0 && nch > 0 && nch <= 64, MMB_ERR_INVALID, "mmb_decoder_attn_fwd: bad sizes");
   MMB_REQUIRE(D <= NT, MMB_ERR_UNSUPPORTED, "mmb_decoder_attn_fwd: 2H=%d > %d", D, NT);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = (Lt + nch - 1) / nch;
-  PartialArgs a{proj_a, proj_i, enc_a, enc_i, hw, coverage, v1, wc1, v2, wc2, v1b, v2b, p, stats, ctxp, B, Lt, D, chunk, nch};
+  PartialArgs a{proj_a, proj_i, enc_a, enc_i, hw, coverage, v1, wc1, v2, wc2, v1b, v2b, p, stats, ctxp, ctx12, scale, counters,
+                B, Lt, D, chunk, nch};
   const int groups = (D % 4 == 0) ? NT / (D / 4) : NT / D;
   const size_t smem = sizeof(float) * ((size_t)groups * 2 * D + 6 * D + 32 + 2 * chunk);
   MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_attn_fwd: chunk %d too large", chunk);
   MMB_CUDA(cudaFuncSetAttribute(dec_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dec_attn_partial_kernel<<<dim3(nch, B), NT, smem, st>>>(a);
-  if (int rc = check_launch("dec_attn_partial_kernel")) return rc;
-  dec_attn_combine_kernel<<<B, NT, 0, st>>>(stats, ctxp, ctx12, scale, B, D, nch);
-  return check_launch("dec_attn_combine_kernel");
+  return check_launch("dec_attn_partial_kernel");
 }
 
 extern "C" int mmb_decoder_attn_finish(const float* pb, const float* hw, const float* ctx12, const float* scale,
@@ -728,17 +754,18 @@ extern "C" int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, co
                                     const float* datt, const float* d_ctx12, const float* d_cov_out, const float* d_pre_b,
                                     const float* v1, const float* wc1, const float* v2, const float* wc2, float* d_alpha,
                                     float* spart, float* d_proj_a, float* d_proj_i, float* d_cov, float* colp, float* separt,
-                                    float* d_hw4, float* vec_acc, float* scal_acc, int B, int Lt, int D, int nch,
-                                    mmb_stream_t stream) {
+                                    float* d_hw4, float* vec_acc, float* scal_acc, int* counters, int B, int Lt, int D,
+                                    int nch, mmb_stream_t stream) {
   MMB_REQUIRE(proj_a && proj_i && enc_a && enc_i && hw && coverage && alpha && beta && datt && d_ctx12 && d_pre_b && v1 &&
                   wc1 && v2 && wc2 && d_alpha && spart && d_proj_a && d_proj_i && d_cov && colp && separt && d_hw4 &&
-                  vec_acc && scal_acc,
+                  vec_acc && scal_acc && counters,
               MMB_ERR_INVALID, "mmb_decoder_attn_bwd: null pointer");
   MMB_REQUIRE(D <= 256 && nch > 0 && nch <= 64, MMB_ERR_UNSUPPORTED, "mmb_decoder_attn_bwd: 2H=%d > 256 or bad chunks", D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = (Lt + nch - 1) / nch;
   SweepArgs a{proj_a, proj_i, enc_a, enc_i, hw, coverage, alpha, beta, datt, d_ctx12, d_cov_out, v1, wc1, v2, wc2,
-              d_alpha, spart, d_proj_a, d_proj_i, d_cov, colp, separt, B, Lt, D, chunk, nch};
+              d_alpha, spart, d_proj_a, d_proj_i, d_cov, colp, separt, d_pre_b, d_hw4, vec_acc, scal_acc, counters,
+              B, Lt, D, chunk, nch};
   {
     const size_t smem = sizeof(float) * (2 * (size_t)D + 32);
     dec_attn_sweep1_kernel<<<dim3(nch, B), NT, smem, st>>>(a);
@@ -749,8 +776,6 @@ extern "C" int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, co
     MMB_REQUIRE(smem <= 227 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_attn_bwd: chunk %d too large", chunk);
     MMB_CUDA(cudaFuncSetAttribute(dec_attn_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dec_attn_sweep2_kernel<<<dim3(nch, B), NT, smem, st>>>(a);
-    if (int rc = check_launch("dec_attn_sweep2_kernel")) return rc;
+    return check_launch("dec_attn_sweep2_kernel");
   }
-  dec_attn_reduce_kernel<<<B, NT, 0, st>>>(colp, separt, d_pre_b, d_hw4, vec_acc, scal_acc, B, D, nch);
-  return check_launch("dec_attn_reduce_kernel");
 }

@@ -156,6 +156,8 @@ class DecoderSeq:
         self.vb1, self.vb2 = flat("vb1"), flat("vb2")
         self.v1b, self.v2b, self.vb1b, self.vb2b = flat("v1b"), flat("v2b"), flat("vb1b"), flat("vb2b")
         self.nch = _lib.lib().mmb_decoder_chunks(self.B, self.Lt)
+        # per-video arrival counters of the chunk-parallel kernels (zero between launches): one set per direction
+        self.counters = torch.zeros(2, self.B, device=self.enc_a.device, dtype=torch.int32)
 
 
 def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_argmax: bool = False, target=None):
@@ -175,7 +177,8 @@ def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_arg
     ctx12, scale = torch.empty(2, B, D, **f32), torch.empty(B, 2, nch, **f32)
     _lib.check(lib.mmb_decoder_attn_fwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
                                         p(seq.v1), p(seq.wc1), p(seq.v2), p(seq.wc2), p(seq.v1b), p(seq.v2b), p(alpha),
-                                        p(stats), p(ctxp), p(ctx12), p(scale), B, Lt, D, nch, st), "mmb_decoder_attn_fwd")
+                                        p(stats), p(ctxp), p(ctx12), p(scale), p(seq.counters[0]), B, Lt, D, nch, st),
+               "mmb_decoder_attn_fwd")
     pb = torch.bmm(ctx12, seq.Wb13.transpose(1, 2))                            # (2, B, D)  library GEMM (bias: see DecoderSeq)
     xcat = torch.empty(B, D + E + H, **f32)
     att_cov, cov_out, beta = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32), torch.empty(B, 2, **f32)
@@ -191,7 +194,7 @@ def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_arg
     argmax = torch.empty(B, device=h.device, dtype=torch.int64) if want_argmax else None
     _lib.check(lib.mmb_decoder_out_softmax(p(probs), p(mask_u8), p(argmax), p(target),
                                            p(None if lossvec is None else lossvec[0]), B, M, st), "mmb_decoder_out_softmax")
-    _count(6)
+    _count(5)
     return probs, h_out, cell_out, att_cov, cov_out, argmax, (hw, alpha, beta, ctx12, pb, xcat, gates), lossvec
 
 
@@ -232,10 +235,11 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     _lib.check(lib.mmb_decoder_attn_bwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
                                         p(alpha), p(beta), p(datt), p(d_ctx12), p(dcov_tot), p(d_pre_b), p(seq.v1),
                                         p(seq.wc1), p(seq.v2), p(seq.wc2), p(d_alpha), p(spart), p(d_proj_a), p(d_proj_i),
-                                        p(d_cov), p(colp), p(separt), p(d_hw4), p(vec_acc), p(scal_acc), B, Lt, D, nch, st),
+                                        p(d_cov), p(colp), p(separt), p(d_hw4), p(vec_acc), p(scal_acc), p(seq.counters[1]), B, Lt, D, nch,
+                                        st),
                "mmb_decoder_attn_bwd")
     d_h = torch.addmm(d_xcat[:, D + E:], d_hw4, seq.Wh4)                       # (B, H)  library GEMM
-    _count(6)
+    _count(5)
     return d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b
 
 

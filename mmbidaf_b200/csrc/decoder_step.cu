@@ -658,8 +658,10 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep2_kernel(const SweepArgs a) 
 using namespace mmb;
 
 extern "C" int mmb_decoder_chunks(int B, int Lt) {
-  // enough (chunk, video) CTAs for ~2 waves of 148 SMs, at least 16 sentences per chunk, at most 64 chunks
-  int nch = (296 + B - 1) / B;
+  // as many (chunk, video) CTAs as fit in ONE wave at two CTAs per SM (sweep 2 needs 127 registers x 256 threads): 2 x 148
+  // slots, rounded DOWN -- 320 CTAs (10 chunks x 32 videos) ran as a full wave plus a 24-CTA tail that doubled the time;
+  // at least 16 sentences per chunk, at most 64 chunks
+  int nch = 296 / B;
   nch = nch < 1 ? 1 : nch > 64 ? 64 : nch;
   const int max_by_len = (Lt + 15) / 16;
   return nch < max_by_len ? nch : (max_by_len < 1 ? 1 : max_by_len);

@@ -140,6 +140,12 @@ class DecoderTape:
         self.seq = seq
         self.rows = {k: [] for k in ("h_prev", "xcat", "h_out", "alpha", "dlog", "da", "dctx12", "dhw4", "dpre", "ctx12")}
         self.d_proj_a = self.d_proj_i = self.vec_acc = self.scal_acc = None
+        self._zero = None
+
+    def zero_token(self, like):
+        if self._zero is None:
+            self._zero = like.new_zeros(1)
+        return self._zero
 
     def open_accumulators(self):
         if self.d_proj_a is None:
@@ -209,6 +215,7 @@ class _DecoderStep(torch.autograd.Function):
         probs, h_out, cell_out, att, cov_out, _, saved, lossvec = ops.decoder_step_fwd(
             tape.seq, sent, h, cell, cov, mask_u8, target=target)
         ctx.tape = tape
+        ctx.has_token = token is not None
         ctx.fused = target is not None
         extra = (target, att, cov_out) if ctx.fused else ()
         ctx.save_for_backward(h, cell, cov, probs, h_out, cell_out, *saved, *extra)
@@ -233,7 +240,8 @@ class _DecoderStep(torch.autograd.Function):
         r["h_prev"].append(h); r["xcat"].append(xcat); r["h_out"].append(h_out); r["alpha"].append(alpha)
         r["dlog"].append(d_logits); r["da"].append(d_gates); r["dctx12"].append(d_ctx12); r["dhw4"].append(d_hw4)
         r["dpre"].append(d_pre_b); r["ctx12"].append(ctx12)
-        return None, torch.zeros_like(d_h[:1, 0]), None, d_h, d_cell, d_cov, None, None
+        # the token only orders _DecoderOpen.backward after the steps: its gradient is a constant zero (made once per sequence)
+        return None, (tape.zero_token(d_h) if ctx.has_token else None), None, d_h, d_cell, d_cov, None, None
 
 
 def decoder_open(tape, proj_a, proj_i, enc_a, enc_i, params):

@@ -143,7 +143,7 @@ class MultimodalAttentionDecoder(nn.Module):
             return c
         proj_a, proj_i = self.W1(enc_a), self.W3(enc_i)              # hoisted: the reference recomputes them per step
         c = {"a": weakref.ref(enc_a), "i": weakref.ref(enc_i), "key": (enc_a._version, enc_i._version, grad),
-             "proj_a": proj_a, "proj_i": proj_i, "seq": None, "tape": None, "token": None}
+             "proj_a": proj_a, "proj_i": proj_i, "seq": None, "tape": None, "token": None, "last_h": None}
         params = {name: self._param_of(name) for name in _lib_fields()}
         c["seq"] = ops.DecoderSeq(params, enc_a, enc_i, proj_a, proj_i, self.output_size)
         needs_grad = grad and (proj_a.requires_grad or enc_a.requires_grad or enc_i.requires_grad)
@@ -177,8 +177,14 @@ class MultimodalAttentionDecoder(nn.Module):
         cov = coverage_vec.reshape(B, Lt).contiguous()
         tgt = None if target is None else target.reshape(B).to(torch.int64).contiguous()
         if seq["tape"] is not None:
-            probs, h, cell, att, cov, lossvec = Fn.decoder_step(seq["tape"], seq["token"], sent, h, cell, cov,
-                                                                ops._u8(mask), tgt)
+            # The token makes the sequence's closing backward (_DecoderOpen) run after this step's.  When the step continues
+            # the previous one (its hidden state is that step's output, as in models.py:163) the chain of hidden-state
+            # gradients already orders it behind a step that holds the token, so only the first step of a chain takes it:
+            # no per-step gradient accumulation on the token.
+            chained = seq["last_h"] is not None and h.data_ptr() == seq["last_h"]
+            probs, h, cell, att, cov, lossvec = Fn.decoder_step(seq["tape"], None if chained else seq["token"], sent, h, cell,
+                                                                cov, ops._u8(mask), tgt)
+            seq["last_h"] = h.data_ptr()
         else:
             probs, h, cell, att, cov, _, _, lossvec = ops.decoder_step_fwd(seq["seq"], sent, h, cell, cov, ops._u8(mask),
                                                                            target=tgt)

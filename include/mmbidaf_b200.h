@@ -160,14 +160,16 @@ MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long lon
 /* Backward of the step, same structure in reverse (GEMMs by the caller between the kernels):
  *   mmb_decoder_out_softmax_bwd   d_logits = p (d_probs - sum p d_probs)            [d_probs may be NULL = 0]
  *   d_h'   = d_h_out + d_logits out.weight
- *   mmb_decoder_cell_bwd          activated gates -> d pre-activations d_gates (B,4H), d_cell
+ *   mmb_decoder_cell_bwd          activated gates -> d pre-activations d_gates (B,4H; row stride ldg), d_cell; the hidden-state
+ *                                 gradient is d_h + d_h2 (d_h2 may be NULL)
  *   d_xcat = d_gates [W_ih | W_hh]                 (its first 2H columns are d ctx, row stride ldx)
  *   mmb_decoder_attn_finish_bwd   dcov_tot (B,Lt) = d_cov_out + d cov_loss, datt (B,Lt) = d_att_cov + d cov_loss + dcov_tot
  *                                 (g_cov (B) = gradient of the fused coverage-loss term; ties of min() split evenly),
  *                                 d_pre_b (2,B,2H) = d(W_beta tanh argument),
  *                                 d_ctx12 (2,B,2H) = beta_k d ctx   (the caller adds d_pre_b W_beta_{1,3})
  *   mmb_decoder_attn_bwd          (d_cov_out = dcov_tot) sweeps over the text chunks: d_alpha, soft-max / tanh backward, d_cov,
- *                                 d_proj_a / d_proj_i ACCUMULATED in place (+=), d_hw4 (B,4*2H) = d(hw)
+ *                                 d_proj_a / d_proj_i ACCUMULATED in place (+=), d_hw4 (B,4*2H; row stride ldhw) = d(hw)
+ *   (with d_gates and d_hw4 side by side in one (B, 4H + 4*2H) buffer, d_h is ONE GEMM against [W_hh ; Wh4])
  *   d_h    = d_xcat[:, 2H+E:] + d_hw4 [W2;W4;W_beta_2;W_beta_4]
  * vec_acc (B,6,2H) += [dWc1, dWc2, dv1, dv2, dv_beta_1, dv_beta_2]; scal_acc (B,4) += their scalar biases.
  * Scratch: d_alpha (B,2,Lt)  spart (B,nch,2)  colp (B,nch,2,3,2H)  separt (B,nch,2).
@@ -177,8 +179,8 @@ MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long lon
 MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
                                         const float* g_nll, float* d_logits, int B, int M, mmb_stream_t stream);
 MMB_API int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const float* cell_out, const float* d_h,
-                                 const float* d_cell_out, float* d_gates, float* d_cell, int B, int H,
-                                 mmb_stream_t stream);
+                                 const float* d_h2, const float* d_cell_out, float* d_gates, int ldg, float* d_cell,
+                                 int B, int H, mmb_stream_t stream);
 MMB_API int mmb_decoder_attn_finish_bwd(const float* d_xcat, int ldx, const float* d_att_cov, const float* d_cov_out,
                                         const float* alpha, const float* beta, const float* ctx12, const float* pb,
                                         const float* hw, const float* vb1, const float* vb2, float* datt, float* d_pre_b,
@@ -190,8 +192,8 @@ MMB_API int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, const
                                  const float* datt, const float* d_ctx12, const float* d_cov_out, const float* d_pre_b,
                                  const float* v1, const float* wc1, const float* v2, const float* wc2, float* d_alpha,
                                  float* spart, float* d_proj_a, float* d_proj_i, float* d_cov, float* colp, float* separt,
-                                 float* d_hw4, float* vec_acc, float* scal_acc, int* counters, int B, int Lt, int D,
-                                 int nch, mmb_stream_t stream);
+                                 float* d_hw4, int ldhw, float* vec_acc, float* scal_acc, int* counters, int B, int Lt,
+                                 int D, int nch, mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
  * masked_softmax over the last axis (attention.py:78-98): y = softmax(mask ? x : -1e30), or

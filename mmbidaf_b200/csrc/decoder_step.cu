@@ -360,17 +360,18 @@ __global__ void __launch_bounds__(NT) dec_out_softmax_bwd_kernel(const float* __
 // 2: LSTM cell backward (point-wise): activated gates -> d pre-activations (in place), d cell
 __global__ void __launch_bounds__(NT) dec_cell_bwd_kernel(float* __restrict__ gates, const float* __restrict__ cell_in,
                                                           const float* __restrict__ cell_out, const float* __restrict__ d_h,
-                                                          const float* __restrict__ d_cell_out, float* __restrict__ d_gates,
-                                                          float* __restrict__ d_cell, int B, int H) {
+                                                          const float* __restrict__ d_h2, const float* __restrict__ d_cell_out,
+                                                          float* __restrict__ d_gates, int ldg, float* __restrict__ d_cell, int B,
+                                                          int H) {
   const int i = blockIdx.x * NT + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, j = i - b * H;
   const float* g = gates + (size_t)b * 4 * H;
   const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
   const float tc = tanh_fast(cell_out[i]);
-  const float dh = d_h[i];
+  const float dh = d_h[i] + (d_h2 ? d_h2[i] : 0.f);      // e.g. d logits out.weight + the next step's d h
   const float dc = fmaf(dh * go, 1.f - tc * tc, d_cell_out ? d_cell_out[i] : 0.f);
-  float* o = d_gates + (size_t)b * 4 * H;
+  float* o = d_gates + (size_t)b * ldg;
   o[j] = dc * gg * gi * (1.f - gi);
   o[H + j] = dc * cell_in[i] * gf * (1.f - gf);
   o[2 * H + j] = dc * gi * (1.f - gg * gg);
@@ -443,6 +444,7 @@ struct SweepArgs {
   const float* d_pre_b;                                       // reduce_video
   float *d_hw4, *vec_acc, *scal_acc;
   int* counters;                                              // (B) zero on entry, zero on exit
+  int ldhw;                                                   // row stride of d_hw4 (>= 4D)
   int B, Lt, D, chunk, nch;
 };
 
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep1_kernel(const SweepArgs a) 
 __device__ __forceinline__ void reduce_video(int b, const float* colp, const float* separt,   /* other blocks' partials */
                                                              const float* __restrict__ d_pre_b, float* __restrict__ d_hw4,
                                                              float* __restrict__ vec_acc, float* __restrict__ scal_acc, int B,
-                                                             int D, int nch) {
+                                                             int D, int nch, int ldhw) {
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * D; i += NT) {
     const int m = i / D, d = i - m * D;
@@ -532,8 +534,8 @@ __device__ __forceinline__ void reduce_video(int b, const float* colp, const flo
           z += zs[u];
         }
     }
-    d_hw4[(size_t)b * 4 * D + m * D + d] = x;                             // d (W2 h) | d (W4 h)
-    d_hw4[(size_t)b * 4 * D + (2 + m) * D + d] = d_pre_b[((size_t)m * B + b) * D + d];   // d (W_beta_2 h) | d (W_beta_4 h)
+    d_hw4[(size_t)b * ldhw + m * D + d] = x;                              // d (W2 h) | d (W4 h)
+    d_hw4[(size_t)b * ldhw + (2 + m) * D + d] = d_pre_b[((size_t)m * B + b) * D + d];    // d (W_beta_2 h) | d (W_beta_4 h)
     vec_acc[((size_t)b * 6 + m) * D + d] += y;                            // d Wc weight
     vec_acc[((size_t)b * 6 + 2 + m) * D + d] += z;                        // d v weight
   }
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(NT) dec_attn_sweep2_kernel(const SweepArgs a) 
   }
   for (int i = tid; i < n; i += NT) a.d_cov[(size_t)b * Lt + t0 + i] = rowacc[i];
   if (last_block_of_video(a.counters + b, a.nch))
-    reduce_video(b, a.colp, a.separt, a.d_pre_b, a.d_hw4, a.vec_acc, a.scal_acc, a.B, D, a.nch);
+    reduce_video(b, a.colp, a.separt, a.d_pre_b, a.d_hw4, a.vec_acc, a.scal_acc, a.B, D, a.nch, a.ldhw);
 }
 
 }  // namespace
@@ -727,12 +729,12 @@ extern "C" int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_pr
 }
 
 extern "C" int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const float* cell_out, const float* d_h,
-                                    const float* d_cell_out, float* d_gates, float* d_cell, int B, int H,
-                                    mmb_stream_t stream) {
-  MMB_REQUIRE(gates && cell_in && cell_out && d_h && d_gates && d_cell && B > 0 && H > 0, MMB_ERR_INVALID,
+                                    const float* d_h2, const float* d_cell_out, float* d_gates, int ldg, float* d_cell, int B,
+                                    int H, mmb_stream_t stream) {
+  MMB_REQUIRE(gates && cell_in && cell_out && d_h && d_gates && d_cell && B > 0 && H > 0 && ldg >= 4 * H, MMB_ERR_INVALID,
               "mmb_decoder_cell_bwd: bad arguments");
-  dec_cell_bwd_kernel<<<(B * H + NT - 1) / NT, NT, 0, static_cast<cudaStream_t>(stream)>>>(gates, cell_in, cell_out, d_h,
-                                                                                          d_cell_out, d_gates, d_cell, B, H);
+  dec_cell_bwd_kernel<<<(B * H + NT - 1) / NT, NT, 0, static_cast<cudaStream_t>(stream)>>>(
+      gates, cell_in, cell_out, d_h, d_h2, d_cell_out, d_gates, ldg, d_cell, B, H);
   return check_launch("dec_cell_bwd_kernel");
 }
 
@@ -756,18 +758,19 @@ extern "C" int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, co
                                     const float* datt, const float* d_ctx12, const float* d_cov_out, const float* d_pre_b,
                                     const float* v1, const float* wc1, const float* v2, const float* wc2, float* d_alpha,
                                     float* spart, float* d_proj_a, float* d_proj_i, float* d_cov, float* colp, float* separt,
-                                    float* d_hw4, float* vec_acc, float* scal_acc, int* counters, int B, int Lt, int D,
-                                    int nch, mmb_stream_t stream) {
+                                    float* d_hw4, int ldhw, float* vec_acc, float* scal_acc, int* counters, int B, int Lt,
+                                    int D, int nch, mmb_stream_t stream) {
   MMB_REQUIRE(proj_a && proj_i && enc_a && enc_i && hw && coverage && alpha && beta && datt && d_ctx12 && d_pre_b && v1 &&
                   wc1 && v2 && wc2 && d_alpha && spart && d_proj_a && d_proj_i && d_cov && colp && separt && d_hw4 &&
                   vec_acc && scal_acc && counters,
               MMB_ERR_INVALID, "mmb_decoder_attn_bwd: null pointer");
   MMB_REQUIRE(D <= 256 && nch > 0 && nch <= 64, MMB_ERR_UNSUPPORTED, "mmb_decoder_attn_bwd: 2H=%d > 256 or bad chunks", D);
+  MMB_REQUIRE(ldhw >= 4 * D, MMB_ERR_INVALID, "mmb_decoder_attn_bwd: ldhw=%d < 4 * 2H", ldhw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = (Lt + nch - 1) / nch;
   SweepArgs a{proj_a, proj_i, enc_a, enc_i, hw, coverage, alpha, beta, datt, d_ctx12, d_cov_out, v1, wc1, v2, wc2,
               d_alpha, spart, d_proj_a, d_proj_i, d_cov, colp, separt, d_pre_b, d_hw4, vec_acc, scal_acc, counters,
-              B, Lt, D, chunk, nch};
+              ldhw, B, Lt, D, chunk, nch};
   {
     const size_t smem = sizeof(float) * (2 * (size_t)D + 32);
     dec_attn_sweep1_kernel<<<dim3(nch, B), NT, smem, st>>>(a);

@@ -149,6 +149,9 @@ class DecoderSeq:
         self.bh4 = torch.cat([P["b2"] + P["bc1"], P["b4"] + P["bc2"], P["bb2"] + P["bb1"], P["bb4"] + P["bb3"]]).contiguous()
         self.Wb13 = torch.stack([P["Wb1"], P["Wb3"]]).contiguous()                                 # (2, D, D)
         self.Wcat = torch.cat([P["lstm_w_ih"], P["lstm_w_hh"]], dim=1).contiguous()                # (4H, D+E+H)
+        # backward: d ctx = d_gates W_ih[:, :D]; d h = [d_gates | d_hw4] [W_hh ; Wh4] (one GEMM over the stacked gradients)
+        self.Wcat_ctx = P["lstm_w_ih"][:, :self.D].contiguous()                                    # (4H, D)
+        self.Wh_stack = torch.cat([P["lstm_w_hh"], self.Wh4], dim=0).contiguous()                   # (4H + 4D, H)
         self.bcat = (P["lstm_b_ih"] + P["lstm_b_hh"]).contiguous()
         self.out_w, self.out_b = P["out_w"].contiguous(), P["out_b"].contiguous()
         flat = lambda k: P[k].reshape(-1).contiguous()
@@ -216,14 +219,16 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(target if fused else None),
                                                p(g[0] if fused else None), p(d_logits), B, M, st),
                "mmb_decoder_out_softmax_bwd")
-    dh_tot = d_logits @ seq.out_w if d_h_out is None else torch.addmm(d_h_out, d_logits, seq.out_w)
-    d_gates, d_cell = torch.empty(B, 4 * H, **f32), torch.empty(B, H, **f32)
-    _lib.check(lib.mmb_decoder_cell_bwd(p(gates), p(cell), p(cell_out), p(dh_tot), p(c(d_cell_out)), p(d_gates), p(d_cell),
-                                        B, H, st), "mmb_decoder_cell_bwd")
-    d_xcat = d_gates @ seq.Wcat                                                # (B, D+E+H)  library GEMM
+    dh_logits = d_logits @ seq.out_w                                           # (B, H)  library GEMM
+    gbuf = torch.empty(B, 4 * H + 4 * D, **f32)                                # [d_gates | d_hw4] side by side
+    d_gates, d_hw4 = gbuf[:, :4 * H], gbuf[:, 4 * H:]
+    d_cell = torch.empty(B, H, **f32)
+    _lib.check(lib.mmb_decoder_cell_bwd(p(gates), p(cell), p(cell_out), p(dh_logits), p(c(d_h_out)), p(c(d_cell_out)),
+                                        gbuf.data_ptr(), 4 * H + 4 * D, p(d_cell), B, H, st), "mmb_decoder_cell_bwd")
+    d_xcat = d_gates @ seq.Wcat_ctx                                            # (B, D) = d ctx  library GEMM
     datt, d_pre_b, d_ctx12 = torch.empty(B, Lt, **f32), torch.empty(2, B, D, **f32), torch.empty(2, B, D, **f32)
     dcov_tot = torch.empty(B, Lt, **f32)
-    _lib.check(lib.mmb_decoder_attn_finish_bwd(p(d_xcat), D + E + H, p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
+    _lib.check(lib.mmb_decoder_attn_finish_bwd(p(d_xcat), D, p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
                                                p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(datt), p(d_pre_b),
                                                p(d_ctx12), p(vec_acc), p(scal_acc), p(att_cov if fused else None),
                                                p(cov_out if fused else None), p(g[1] if fused else None), p(dcov_tot),
@@ -231,14 +236,14 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     d_ctx12.baddbmm_(d_pre_b, seq.Wb13)                                        # += d_pre W_beta   library GEMM
     d_alpha, spart = torch.empty(B, 2, Lt, **f32), torch.empty(B, nch, 2, **f32)
     d_cov, colp = torch.empty(B, Lt, **f32), torch.empty(B, nch, 2, 3, D, **f32)
-    separt, d_hw4 = torch.empty(B, nch, 2, **f32), torch.empty(B, 4 * D, **f32)
+    separt = torch.empty(B, nch, 2, **f32)
     _lib.check(lib.mmb_decoder_attn_bwd(p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(hw), p(coverage),
                                         p(alpha), p(beta), p(datt), p(d_ctx12), p(dcov_tot), p(d_pre_b), p(seq.v1),
                                         p(seq.wc1), p(seq.v2), p(seq.wc2), p(d_alpha), p(spart), p(d_proj_a), p(d_proj_i),
-                                        p(d_cov), p(colp), p(separt), p(d_hw4), p(vec_acc), p(scal_acc), p(seq.counters[1]), B, Lt, D, nch,
-                                        st),
+                                        p(d_cov), p(colp), p(separt), d_hw4.data_ptr(), 4 * H + 4 * D, p(vec_acc), p(scal_acc),
+                                        p(seq.counters[1]), B, Lt, D, nch, st),
                "mmb_decoder_attn_bwd")
-    d_h = torch.addmm(d_xcat[:, D + E:], d_hw4, seq.Wh4)                       # (B, H)  library GEMM
+    d_h = gbuf @ seq.Wh_stack                                                  # (B, H)  library GEMM
     _count(5)
     return d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b
 

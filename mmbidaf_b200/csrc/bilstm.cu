@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
 // all lanes of a warp on the same address.  The four per-gate partial sums of a unit meet in shared memory; the
 // point-wise part of a step is done by one thread per unit (threads 0..H-1), which also owns the cp.async ring.
 // Measured: 0.87 -> 0.61 us per step.  (The same cut of the FORWARD kernel doubles its shared-memory reads -- it only
-// needs the H values of h -- and adds a barrier: 0.75 us per step against 0.67 for the lane-pair design above.)
+// needs the H values of h -- and adds a barrier: 0.75 us per step against 0.67 for the lane-pair design above.  Packed
+// fma.rn.f32x2 in place of the scalar FMAs halves the instruction count of both loops but is not faster: forward 0.66,
+// backward 0.69 us per step -- the FMA pipe takes an FFMA2 at half rate and the dependent chains get longer.)
 constexpr int BWD_NT = 256, BWD_SL = 64;     // 8 warps = 4 gates x 64 unit slots; a slot covers units slot and slot + 64
 
 template <int KS, int NB>

@@ -44,16 +44,23 @@ class _LstmLayer(torch.autograd.Function):
         da = ops.lstm_layer_bwd(gates, cell, w_hh, lengths, order, d_out, d_h_n, None, B, L, H, ndir)
         da2d = da.view(B * L, ndir * 4 * H)
         dx = (da2d @ w_ih).view(B, L, fan_in) if ctx.needs_input_grad[0] else None
-        dw_ih = da2d.t() @ x2d                                                               # (ndir*4H, in)
+        # Weight gradients are reductions over all B*L rows with small outputs (4H x in, 4H x H): as ONE GEMM they are a
+        # handful of output tiles looping over K = B*L (43 - 100 us each on 14 CTAs).  Batched over the videos instead --
+        # sum_b da_b^T x_b -- every video is its own set of tiles (B x more CTAs), and the B partial results are summed
+        # by a small reduction.  The recurrent weights take the hidden state that FED step t through shifted views
+        # (h[t-1] going forward, h[t+1] going backward; both operands are zero past each length): no concatenation.
+        da3 = da.view(B, L, ndir * 4 * H)
+        dw_ih = torch.bmm(da3.transpose(1, 2), x2d.view(B, L, fan_in)).sum(dim=0)            # (ndir*4H, in)
         db = da2d.sum(dim=0)
         grads = []
-        zero = out.new_zeros(B, 1, H)
         for d in range(ndir):
             h_dir = out[:, :, d * H:(d + 1) * H]
-            # state that fed step t: h[t-1] going forward, h[t+1] going backward (zero at the start)
-            h_prev = torch.cat([zero, h_dir[:, :-1]], dim=1) if d == 0 else torch.cat([h_dir[:, 1:], zero], dim=1)
-            da_dir = da2d[:, d * 4 * H:(d + 1) * 4 * H]
-            dw_hh = da_dir.t() @ h_prev.reshape(B * L, H)
+            da_dir = da3[:, :, d * 4 * H:(d + 1) * 4 * H]
+            if L > 1:
+                lhs, rhs = (da_dir[:, 1:], h_dir[:, :-1]) if d == 0 else (da_dir[:, :-1], h_dir[:, 1:])
+                dw_hh = torch.bmm(lhs.transpose(1, 2), rhs).sum(dim=0)                       # (4H, H)
+            else:
+                dw_hh = out.new_zeros(4 * H, H)
             b_d = db[d * 4 * H:(d + 1) * 4 * H]
             grads += [dw_ih[d * 4 * H:(d + 1) * 4 * H], dw_hh, b_d, b_d]
         return (dx, None, None, *grads)

@@ -13,6 +13,37 @@ import torch
 from . import ops
 
 
+def tall_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T b for tall a (N, p), b (N, q) with small p, q -- the shape of every weight gradient here.  As one GEMM that is a
+    handful of output tiles looping over K = N on a few CTAs; split into G row blocks it is G times more tiles (a batched
+    GEMM) followed by a small sum over the blocks."""
+    n = a.shape[0]
+    for g in (64, 32, 16, 8):
+        if n % g == 0 and n // g >= 128:
+            return torch.bmm(a.view(g, n // g, -1).transpose(1, 2), b.view(g, n // g, -1)).sum(dim=0)
+    return a.t() @ b
+
+
+class _TallLinear(torch.autograd.Function):
+    """y = x W^T without bias (the Embedding projection, encoding.py:22) whose weight gradient uses :func:`tall_tn`."""
+
+    @staticmethod
+    def forward(ctx, x2d, w):
+        ctx.save_for_backward(x2d, w)
+        return x2d @ w.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w = ctx.saved_tensors
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        return dx, tall_tn(dy.contiguous(), x2d)
+
+
+def tall_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    shape = x.shape
+    return _TallLinear.apply(x.reshape(-1, shape[-1]), weight).view(*shape[:-1], weight.shape[0])
+
+
 class _LstmLayer(torch.autograd.Function):
     """One (bi)directional LSTM layer over padded (B, L, in) with per-sample lengths."""
 
@@ -277,7 +308,7 @@ class _HighwayLayer(torch.autograd.Function):
         H = x2d.shape[1]
         d_pre, dx = ops.highway_bwd(pre, x2d, dy)
         dx = torch.addmm(dx, d_pre, w)                          # direct path + through both linears
-        dw = d_pre.t() @ x2d                                    # (2H, H)
+        dw = tall_tn(d_pre, x2d)                                # (2H, H)
         db = d_pre.sum(dim=0)
         return dx, dw[:H], db[:H], dw[H:], db[H:]
 

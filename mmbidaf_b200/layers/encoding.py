@@ -44,7 +44,10 @@ class Embedding(nn.Module):
         self.hwy = HighwayEncoder(2, hidden_size)
 
     def forward(self, x):
-        return self.hwy(self.proj(F.dropout(x, self.drop_prob, self.training)))
+        x = F.dropout(x, self.drop_prob, self.training)
+        if not x.is_cuda:
+            raise RuntimeError("mmbidaf_b200.layers.Embedding runs on a B200 only (no CPU fallback)")
+        return self.hwy(Fn.tall_linear(x, self.proj.weight))     # Linear(E -> H, no bias); batched weight gradient
 
 
 class _LengthCache:

@@ -17,10 +17,12 @@ def tall_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a^T b for tall a (N, p), b (N, q) with small p, q -- the shape of every weight gradient here.  As one GEMM that is a
     handful of output tiles looping over K = N on a few CTAs; split into G row blocks it is G times more tiles (a batched
     GEMM) followed by a small sum over the blocks."""
-    n = a.shape[0]
-    for g in (64, 32, 16, 8):
-        if n % g == 0 and n // g >= 128:
-            return torch.bmm(a.view(g, n // g, -1).transpose(1, 2), b.view(g, n // g, -1)).sum(dim=0)
+    n, p, q = a.shape[0], a.shape[1], b.shape[1]
+    tiles = -(-p // 64) * -(-q // 64)                  # output tiles of a typical 64 x 64 GEMM kernel
+    if tiles < 148:                                    # too few to fill the 148 SMs: split the reduction
+        for g in (8, 16, 32, 64):                      # fewest row blocks that give ~2 waves of tiles (small partials)
+            if n % g == 0 and n // g >= 128 and (tiles * g >= 296 or g == 64):
+                return torch.bmm(a.view(g, n // g, p).transpose(1, 2), b.view(g, n // g, q)).sum(dim=0)
     return a.t() @ b
 
 
@@ -81,7 +83,7 @@ class _LstmLayer(torch.autograd.Function):
         # by a small reduction.  The recurrent weights take the hidden state that FED step t through shifted views
         # (h[t-1] going forward, h[t+1] going backward; both operands are zero past each length): no concatenation.
         da3 = da.view(B, L, ndir * 4 * H)
-        dw_ih = torch.bmm(da3.transpose(1, 2), x2d.view(B, L, fan_in)).sum(dim=0)            # (ndir*4H, in)
+        dw_ih = tall_tn(da2d, x2d)                                                           # (ndir*4H, in)
         db = da2d.sum(dim=0)
         grads = []
         for d in range(ndir):

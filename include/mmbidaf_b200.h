@@ -159,6 +159,8 @@ MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long lon
 
 /* Backward of the step, same structure in reverse (GEMMs by the caller between the kernels):
  *   mmb_decoder_out_softmax_bwd   d_logits = p (d_probs - sum p d_probs)            [d_probs may be NULL = 0]
+ *                                 d_logits has row stride ldd >= M; columns M..ldd-1 are written as zeros (so that the
+ *                                 caller can keep the K of d_logits out.weight a multiple of 4 when M is odd)
  *   d_h'   = d_h_out + d_logits out.weight
  *   mmb_decoder_cell_bwd          activated gates -> d pre-activations d_gates (B,4H; row stride ldg), d_cell; the hidden-state
  *                                 gradient is d_h + d_h2 (d_h2 may be NULL)
@@ -177,7 +179,7 @@ MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long lon
  * block of a video to finish merges that video's chunk partials, so neither function needs a second launch for it).
  */
 MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
-                                        const float* g_nll, float* d_logits, int B, int M, mmb_stream_t stream);
+                                        const float* g_nll, float* d_logits, int ldd, int B, int M, mmb_stream_t stream);
 MMB_API int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const float* cell_out, const float* d_h,
                                  const float* d_h2, const float* d_cell_out, float* d_gates, int ldg, float* d_cell,
                                  int B, int H, mmb_stream_t stream);

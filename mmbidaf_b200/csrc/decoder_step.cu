@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(NT) dec_out_softmax_kernel(float* __restrict__
 // 1: masked soft-max backward: dlogit = p (dp - sum p dp); masked entries have p = 0
 __global__ void __launch_bounds__(NT) dec_out_softmax_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ d_probs,
                                                                  const long long* __restrict__ tgt, const float* __restrict__ g_nll,
-                                                                 float* __restrict__ d_logits, int M) {
+                                                                 float* __restrict__ d_logits, int ldd, int M) {
   __shared__ float red[32];
   const int b = blockIdx.x, tid = threadIdx.x;
   // optional sparse part: d(-log(p_tgt + eps)) = -g / (p_tgt + eps) at the target column only
@@ -353,8 +353,9 @@ __global__ void __launch_bounds__(NT) dec_out_softmax_bwd_kernel(const float* __
   if (tgt) dot = fmaf(probs[(size_t)b * M + tg], dp_t, dot);
   for (int m = tid; m < M; m += NT) {
     const float dp = (d_probs ? d_probs[(size_t)b * M + m] : 0.f) + (m == tg ? dp_t : 0.f);
-    d_logits[(size_t)b * M + m] = probs[(size_t)b * M + m] * (dp - dot);
+    d_logits[(size_t)b * ldd + m] = probs[(size_t)b * M + m] * (dp - dot);
   }
+  for (int m = M + tid; m < ldd; m += NT) d_logits[(size_t)b * ldd + m] = 0.f;   // row padding (keeps the next GEMM's K aligned)
 }
 
 // 2: LSTM cell backward (point-wise): activated gates -> d pre-activations (in place), d cell
@@ -721,10 +722,10 @@ extern "C" int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long 
 }
 
 extern "C" int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
-                                           const float* g_nll, float* d_logits, int B, int M, mmb_stream_t stream) {
-  MMB_REQUIRE(probs && d_logits && B > 0 && M > 0 && (!target || g_nll), MMB_ERR_INVALID,
+                                           const float* g_nll, float* d_logits, int ldd, int B, int M, mmb_stream_t stream) {
+  MMB_REQUIRE(probs && d_logits && B > 0 && M > 0 && ldd >= M && (!target || g_nll), MMB_ERR_INVALID,
               "mmb_decoder_out_softmax_bwd: bad arguments");
-  dec_out_softmax_bwd_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(probs, d_probs, target, g_nll, d_logits, M);
+  dec_out_softmax_bwd_kernel<<<B, NT, 0, static_cast<cudaStream_t>(stream)>>>(probs, d_probs, target, g_nll, d_logits, ldd, M);
   return check_launch("dec_out_softmax_bwd_kernel");
 }
 

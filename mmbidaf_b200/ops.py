@@ -154,6 +154,9 @@ class DecoderSeq:
         self.Wh_stack = torch.cat([P["lstm_w_hh"], self.Wh4], dim=0).contiguous()                   # (4H + 4D, H)
         self.bcat = (P["lstm_b_ih"] + P["lstm_b_hh"]).contiguous()
         self.out_w, self.out_b = P["out_w"].contiguous(), P["out_b"].contiguous()
+        # backward: d h = d_logits out.weight with K = M padded to a multiple of 8 (M = 409 is odd: an un-aligned GEMM otherwise)
+        self.Mp = (self.M + 7) // 8 * 8
+        self.out_w_pad = torch.cat([self.out_w, self.out_w.new_zeros(self.Mp - self.M, self.H)], dim=0).contiguous()
         flat = lambda k: P[k].reshape(-1).contiguous()
         self.v1, self.wc1, self.v2, self.wc2 = flat("v1"), flat("Wc1"), flat("v2"), flat("Wc2")
         self.vb1, self.vb2 = flat("vb1"), flat("vb2")
@@ -213,13 +216,14 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     p = _lib.ptr
     st = _lib.stream()
     c = lambda t: None if t is None else t.contiguous()
-    d_logits = torch.empty(B, M, **f32)
+    d_logits_pad = torch.empty(B, seq.Mp, **f32)                               # zero-padded columns: aligned K below
+    d_logits = d_logits_pad[:, :M]
     fused = target is not None and d_lossvec is not None
     g = c(d_lossvec) if fused else None                                        # (2, B): [d nll | d coverage term]
     _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(target if fused else None),
-                                               p(g[0] if fused else None), p(d_logits), B, M, st),
+                                               p(g[0] if fused else None), d_logits_pad.data_ptr(), seq.Mp, B, M, st),
                "mmb_decoder_out_softmax_bwd")
-    dh_logits = d_logits @ seq.out_w                                           # (B, H)  library GEMM
+    dh_logits = d_logits_pad @ seq.out_w_pad                                   # (B, H)  library GEMM
     gbuf = torch.empty(B, 4 * H + 4 * D, **f32)                                # [d_gates | d_hw4] side by side
     d_gates, d_hw4 = gbuf[:, :4 * H], gbuf[:, 4 * H:]
     d_cell = torch.empty(B, H, **f32)

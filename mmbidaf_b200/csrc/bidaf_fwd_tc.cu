@@ -522,7 +522,7 @@ struct FusedArgs {
   int* ready;            // (B) zeroed before the launch
   int nq, nc;            // X blocks per batch row of each pass
   int n_q2c;             // B * nq
-  long long* cta_times;  // debugging aid (MMB_BIDAF_FWD_CTA_TIMES: a device pointer, 4 x int64 per block) or null
+  long long* cta_times;  // debugging aid (MMB_BIDAF_FWD_CTA_TIMES: a device pointer, 12 x int64 per block) or null
 };
 
 // (separate launches: debugging aid, MMB_BIDAF_FWD_SPLIT=1)
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_kernel(const TcArgs a) {
 
 __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc_fused_kernel(const FusedArgs f) {
   const int blk = blockIdx.x;
-  long long* times = f.cta_times ? f.cta_times + 4 * (size_t)blk : nullptr;   // debugging aid: [start, loop end, end, SM id]
+  long long* times = f.cta_times ? f.cta_times + 12 * (size_t)blk : nullptr;   // debugging aid: [start, loop end, end, SM id, ...]
   if (times && threadIdx.x == 0) {
     times[0] = globaltimer_ns();
     uint32_t smid;

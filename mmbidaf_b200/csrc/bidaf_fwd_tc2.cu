@@ -90,6 +90,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (cta_times && tid == 0) cta_times[4] = globaltimer_ns();
 
   // Tiles past the last un-masked Y row contribute exp(-1e30 - m) = 0 to every soft-max: stop there.  (If nothing at
   // all is un-masked the soft-max is uniform over the whole range, attention.py:94, and every tile is needed.)
@@ -133,6 +134,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
   const uint32_t xs_lo = desc_lo(smem_u32(Xs), 128), ps_lo = desc_lo(smem_u32(Ps), 2048);
 
   if (warp_u == MMA_WARP) mbar_wait(bar_x, 0);
+  if (cta_times && tid == 0) { cta_times[5] = globaltimer_ns(); cta_times[7] = nty; }
   for (int t = 0; t < nty; ++t) {
     const int s = t % STAGES;
     const uint32_t st_addr = smem_u32(St + s * stage_bytes);
@@ -157,6 +159,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    if (cta_times && tid == 0 && t == 0) cta_times[6] = globaltimer_ns();
     if (KIND != Q2C && warp_u == TMA_WARP && t == nty - 1) {    // X operand no longer needed: fetch the plain text tile
       mbar_expect_tx(bar_x, X_BYTES, leader);
       tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x, leader);
@@ -302,6 +305,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
       __syncthreads();
       if ((warp >> 1) == hr) drain(stg + (row - 64 * hr) * STG_STRIDE);
       __syncthreads();
+      if (cta_times && tid == 0) cta_times[8 + 2 * hr] = globaltimer_ns();
 #pragma unroll 2
       for (int r = 64 * hr + warp; r < 64 * hr + 64; r += NW) {
         if (x0 + r >= a.LX) break;
@@ -325,6 +329,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
           }
         }
       }
+      if (cta_times && tid == 0) cta_times[9 + 2 * hr] = globaltimer_ns();
     }
   }
   tc_fence_before();
@@ -335,7 +340,8 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
 
 __global__ void __launch_bounds__(NTHREADS, 2) bidaf_tc2_kernel(const FusedArgs f) {
   const int blk = blockIdx.x;
-  long long* times = f.cta_times ? f.cta_times + 4 * (size_t)blk : nullptr;   // debugging aid: [start, loop end, end, SM id]
+  long long* times = f.cta_times ? f.cta_times + 12 * (size_t)blk : nullptr;   // debugging aid: [start, loop end, end, SM id, prologue end, X landed,
+                                                                               //  first S tile done, tiles]
   if (times && threadIdx.x == 0) {
     times[0] = globaltimer_ns();
     uint32_t smid;

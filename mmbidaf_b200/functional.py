@@ -6,11 +6,70 @@ a hand-written kernel reached through ops.py.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional, Tuple
 
 import torch
 
 from . import ops
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Leaf lanes.  Weight and bias gradients are LEAVES of the backward graph: nothing in the step waits for them except the
+# final gradient pack.  Computed inline they sit in stream order between a recurrence and the next op that depends on it
+# (tools/step_timeline.py: ~1.2 ms of the 5.9 ms step were such GEMMs and reductions on the critical path, with 84 SMs
+# idle beside a 64-CTA recurrence).  Inside ``leaf_lanes()`` every backward below computes what the chain needs (dx) on
+# its own stream and hands the leaf products to a side stream; the context joins the lanes on exit.  Outside it (plain
+# ``loss.backward()``) everything runs inline as before.
+# ---------------------------------------------------------------------------------------------------------------------
+class _Lanes:
+    enabled = False
+    n = 2
+    streams = {}          # device index -> [torch.cuda.Stream] * n
+    used = set()          # streams that took work since the context was entered
+    rr = 0
+
+
+@contextlib.contextmanager
+def leaf_lanes():
+    """Run the weight-gradient products of the backward functions in this module on side streams; on exit the CURRENT
+    stream waits for them (so the gradients may be consumed right after the ``with`` block).  CUDA-graph capturable."""
+    if not torch.cuda.is_available() or _Lanes.enabled:
+        yield
+        return
+    _Lanes.enabled = True
+    _Lanes.used = set()
+    try:
+        yield
+    finally:
+        _Lanes.enabled = False
+        cur = torch.cuda.current_stream()
+        for lane in _Lanes.used:
+            cur.wait_stream(lane)
+        _Lanes.used = set()
+
+
+@contextlib.contextmanager
+def _leaf(*inputs):
+    """Everything issued inside runs on a leaf lane, ordered after what the current stream has issued so far.  ``inputs``:
+    the tensors read inside that were allocated on other streams (their blocks must not be recycled under the lane)."""
+    live = [t for t in inputs if t is not None]
+    if not (_Lanes.enabled and live and live[0].is_cuda):
+        yield
+        return
+    cur = torch.cuda.current_stream()
+    dev = cur.device.index if cur.device.index is not None else torch.cuda.current_device()
+    lanes = _Lanes.streams.get(dev)
+    if lanes is None:
+        lanes = _Lanes.streams[dev] = [torch.cuda.Stream(device=cur.device) for _ in range(_Lanes.n)]
+    lane = lanes[_Lanes.rr % _Lanes.n]
+    _Lanes.rr += 1
+    _Lanes.used.add(lane)
+    lane.wait_stream(cur)
+    for t in live:
+        t.record_stream(lane)
+    with torch.cuda.stream(lane):
+        yield
 
 
 def tall_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -38,12 +97,39 @@ class _TallLinear(torch.autograd.Function):
     def backward(ctx, dy):
         x2d, w = ctx.saved_tensors
         dx = dy @ w if ctx.needs_input_grad[0] else None
-        return dx, tall_tn(dy.contiguous(), x2d)
+        with _leaf(dy, x2d):
+            dw = tall_tn(dy.contiguous(), x2d)
+        return dx, dw
 
 
 def tall_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     shape = x.shape
     return _TallLinear.apply(x.reshape(-1, shape[-1]), weight).view(*shape[:-1], weight.shape[0])
+
+
+class _TallLinearBias(torch.autograd.Function):
+    """y = x W^T + b over tall x (the decoder's hoisted projections W1 enc_a, W3 enc_i, attention.py:152-157): weight and
+    bias gradients through :func:`tall_tn` on a leaf lane instead of autograd's inline single GEMM + reduction."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, b):
+        ctx.save_for_backward(x2d, w)
+        return torch.addmm(b, x2d, w.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        with _leaf(dy, x2d):
+            dw = tall_tn(dy, x2d)
+            db = dy.sum(dim=0)
+        return dx, dw, db
+
+
+def tall_linear_bias(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    shape = x.shape
+    return _TallLinearBias.apply(x.reshape(-1, shape[-1]), weight, bias).view(*shape[:-1], weight.shape[0])
 
 
 class _LstmLayer(torch.autograd.Function):
@@ -83,19 +169,20 @@ class _LstmLayer(torch.autograd.Function):
         # by a small reduction.  The recurrent weights take the hidden state that FED step t through shifted views
         # (h[t-1] going forward, h[t+1] going backward; both operands are zero past each length): no concatenation.
         da3 = da.view(B, L, ndir * 4 * H)
-        dw_ih = tall_tn(da2d, x2d)                                                           # (ndir*4H, in)
-        db = da2d.sum(dim=0)
         grads = []
-        for d in range(ndir):
-            h_dir = out[:, :, d * H:(d + 1) * H]
-            da_dir = da3[:, :, d * 4 * H:(d + 1) * 4 * H]
-            if L > 1:
-                lhs, rhs = (da_dir[:, 1:], h_dir[:, :-1]) if d == 0 else (da_dir[:, :-1], h_dir[:, 1:])
-                dw_hh = torch.bmm(lhs.transpose(1, 2), rhs).sum(dim=0)                       # (4H, H)
-            else:
-                dw_hh = out.new_zeros(4 * H, H)
-            b_d = db[d * 4 * H:(d + 1) * 4 * H]
-            grads += [dw_ih[d * 4 * H:(d + 1) * 4 * H], dw_hh, b_d, b_d]
+        with _leaf(da, x2d, out):                       # leaves: off the chain that continues with dx
+            dw_ih = tall_tn(da2d, x2d)                                                       # (ndir*4H, in)
+            db = da2d.sum(dim=0)
+            for d in range(ndir):
+                h_dir = out[:, :, d * H:(d + 1) * H]
+                da_dir = da3[:, :, d * 4 * H:(d + 1) * 4 * H]
+                if L > 1:
+                    lhs, rhs = (da_dir[:, 1:], h_dir[:, :-1]) if d == 0 else (da_dir[:, :-1], h_dir[:, 1:])
+                    dw_hh = torch.bmm(lhs.transpose(1, 2), rhs).sum(dim=0)                   # (4H, H)
+                else:
+                    dw_hh = out.new_zeros(4 * H, H)
+                b_d = db[d * 4 * H:(d + 1) * 4 * H]
+                grads += [dw_ih[d * 4 * H:(d + 1) * 4 * H], dw_hh, b_d, b_d]
         return (dx, None, None, *grads)
 
 
@@ -212,6 +299,21 @@ class _DecoderOpen(torch.autograd.Function):
             return (None,) * (5 + len(ctx.shapes))
         s = tape.seq
         B, D, H, E = s.B, s.D, s.H, s.E
+        # what the rest of the backward pass waits for first: the gradients of the encoder outputs
+        alpha = torch.stack(r["alpha"], dim=0)                               # (S, B, 2, Lt)
+        dctx12 = torch.stack(r["dctx12"], dim=0)                             # (S, 2, B, D)
+        d_enc_a = torch.bmm(alpha[:, :, 0].permute(1, 2, 0), dctx12[:, 0].permute(1, 0, 2))
+        d_enc_i = torch.bmm(alpha[:, :, 1].permute(1, 2, 0), dctx12[:, 1].permute(1, 0, 2))
+        with _leaf(tape.vec_acc, tape.scal_acc, *(t for k in ("h_prev", "xcat", "h_out", "dlog", "da", "dhw4", "dpre", "ctx12")
+                                                    for t in r[k])):
+            grads = _DecoderOpen._param_grads(ctx, tape, r, s)
+        for v in r.values():
+            v.clear()
+        return (None, tape.d_proj_a, tape.d_proj_i, d_enc_a, d_enc_i, *grads)
+
+    @staticmethod
+    def _param_grads(ctx, tape, r, s):
+        B, D, H, E = s.B, s.D, s.H, s.E
         cat = lambda k: torch.cat(r[k], dim=0)
         h_prev, xcat, h_out, dlog, da, dhw4 = cat("h_prev"), cat("xcat"), cat("h_out"), cat("dlog"), cat("da"), cat("dhw4")
         S = len(r["dlog"])
@@ -235,15 +337,8 @@ class _DecoderOpen(torch.autograd.Function):
             "lstm_w_ih": d_wcat[:, :D + E], "lstm_w_hh": d_wcat[:, D + E:], "lstm_b_ih": gate_sum, "lstm_b_hh": gate_sum,
             "out_w": dlog.t() @ h_out, "out_b": dlog.sum(dim=0),
         }
-        alpha = torch.stack(r["alpha"], dim=0)                               # (S, B, 2, Lt)
-        dctx12 = torch.stack(r["dctx12"], dim=0)                             # (S, 2, B, D)
-        d_enc_a = torch.bmm(alpha[:, :, 0].permute(1, 2, 0), dctx12[:, 0].permute(1, 0, 2))
-        d_enc_i = torch.bmm(alpha[:, :, 1].permute(1, 2, 0), dctx12[:, 1].permute(1, 0, 2))
         from ._lib import DECODER_WEIGHT_FIELDS
-        grads = [g[name].reshape(shape) for name, shape in zip(DECODER_WEIGHT_FIELDS, ctx.shapes)]
-        for v in r.values():
-            v.clear()
-        return (None, tape.d_proj_a, tape.d_proj_i, d_enc_a, d_enc_i, *grads)
+        return [g[name].reshape(shape) for name, shape in zip(DECODER_WEIGHT_FIELDS, ctx.shapes)]
 
 
 class _DecoderStep(torch.autograd.Function):
@@ -310,8 +405,9 @@ class _HighwayLayer(torch.autograd.Function):
         H = x2d.shape[1]
         d_pre, dx = ops.highway_bwd(pre, x2d, dy)
         dx = torch.addmm(dx, d_pre, w)                          # direct path + through both linears
-        dw = tall_tn(d_pre, x2d)                                # (2H, H)
-        db = d_pre.sum(dim=0)
+        with _leaf(d_pre, x2d):
+            dw = tall_tn(d_pre, x2d)                            # (2H, H)
+            db = d_pre.sum(dim=0)
         return dx, dw[:H], db[:H], dw[H:], db[H:]
 
 

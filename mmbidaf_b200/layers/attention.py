@@ -141,7 +141,9 @@ class MultimodalAttentionDecoder(nn.Module):
         c = self._cache
         if c is not None and c["a"]() is enc_a and c["i"]() is enc_i and c["key"] == (enc_a._version, enc_i._version, grad):
             return c
-        proj_a, proj_i = self.W1(enc_a), self.W3(enc_i)              # hoisted: the reference recomputes them per step
+        # hoisted: the reference recomputes them per step (attention.py:152, 157)
+        proj_a = Fn.tall_linear_bias(enc_a, self.W1.weight, self.W1.bias)
+        proj_i = Fn.tall_linear_bias(enc_i, self.W3.weight, self.W3.bias)
         c = {"a": weakref.ref(enc_a), "i": weakref.ref(enc_i), "key": (enc_a._version, enc_i._version, grad),
              "proj_a": proj_a, "proj_i": proj_i, "seq": None, "tape": None, "token": None, "last_h": None}
         params = {name: self._param_of(name) for name in _lib_fields()}

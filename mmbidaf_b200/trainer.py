@@ -16,6 +16,7 @@ from typing import Iterable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from .functional import leaf_lanes
 from .synth import Batch
 
 
@@ -169,7 +170,9 @@ class Trainer:
                              batch.targets, batch.target_len, batch.max_dec_len)
         # functional backward: gradients are produced fresh and packed into the flat buffer with one copy
         # kernel (no per-parameter accumulation nodes, which also keeps the step CUDA-graph capturable)
-        grads = torch.autograd.grad(loss, self.grads.params, allow_unused=True)
+        # (weight-gradient products run on side streams next to the serial chains; joined when the block exits)
+        with leaf_lanes():
+            grads = torch.autograd.grad(loss, self.grads.params, allow_unused=True)
         self.grads.pack(grads)
         return loss.detach()
 

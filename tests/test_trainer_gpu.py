@@ -48,3 +48,37 @@ def test_training_reduces_the_loss_and_keeps_parameters_aligned():
     for _ in range(15):
         last = float(tr.step(batch))
     assert last < first
+
+
+@pytest.mark.parametrize("tier", ["fp32", "fast"])
+def test_leaf_lanes_give_the_same_gradients_as_the_inline_backward(tier):
+    """Inside ``functional.leaf_lanes()`` the weight-gradient products run on side streams (same kernels, same operands):
+    every gradient must be bit-identical to the plain single-stream backward, run after run."""
+    import contextlib
+    import mmbidaf_b200
+    from mmbidaf_b200 import functional as Fn
+    mmbidaf_b200.set_precision(tier)
+    try:
+        model = _make(drop=0.0)
+        model.train()
+        params = [p for p in model.parameters() if p.requires_grad]
+        b = make_batch(6, 40, 90, 11, 5, seed=21).to("cuda")
+
+        def grads(lanes):
+            _, loss = model(b.text, b.text_len, b.audio, b.audio_len, b.images, b.image_len, b.targets, b.target_len, b.max_dec_len)
+            with (Fn.leaf_lanes() if lanes else contextlib.nullcontext()):
+                g = torch.autograd.grad(loss, params, allow_unused=True)
+            out = [None if t is None else t.clone() for t in g]
+            torch.cuda.synchronize()
+            return out
+
+        want = grads(False)
+        assert sum(t is not None for t in want) > 40
+        for _ in range(4):
+            got = grads(True)
+            for w, g in zip(want, got):
+                assert (w is None) == (g is None)
+                if w is not None:
+                    assert torch.equal(w, g)
+    finally:
+        mmbidaf_b200.set_precision("fp32")

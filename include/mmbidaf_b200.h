@@ -216,6 +216,16 @@ MMB_API int mmb_highway_fwd(const float* pre, const float* x, float* y, long lon
 MMB_API int mmb_highway_bwd(const float* pre, const float* x, const float* dy, float* d_pre, float* dx_direct,
                             long long n, int H, mmb_stream_t stream);
 
+/* --------------------------------------------------------------------------------------
+ * Column sums of a tall matrix: out (p) = sum over the n rows of a (n, p).  Every bias gradient of the training step is one
+ * (the autograd gradient of nn.LSTM's b_ih / b_hh, encoding.py:76-81; of the highway biases, encoding.py:52-59; of the
+ * decoder's hoisted projections W1 / W3, attention.py:152-157) -- in the reference an ATen reduction inside
+ * loss.backward() (train.py:148).  Deterministic two-stage sum; partial: workspace of mmb_col_sum_blocks(n, p) * p floats.
+ * p % 4 == 0, a and partial 16-byte aligned.
+ */
+MMB_API int mmb_col_sum_blocks(long long n, int p);
+MMB_API int mmb_col_sum(const float* a, float* partial, float* out, long long n, int p, mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ from . import ops
 # ---------------------------------------------------------------------------------------------------------------------
 class _Lanes:
     enabled = False
-    n = 2
+    n = 4
     streams = {}          # device index -> [torch.cuda.Stream] * n
     used = set()          # streams that took work since the context was entered
     rr = 0
@@ -123,7 +123,8 @@ class _TallLinearBias(torch.autograd.Function):
         dx = dy @ w if ctx.needs_input_grad[0] else None
         with _leaf(dy, x2d):
             dw = tall_tn(dy, x2d)
-            db = dy.sum(dim=0)
+        with _leaf(dy):
+            db = ops.col_sum(dy)
         return dx, dw, db
 
 
@@ -170,10 +171,12 @@ class _LstmLayer(torch.autograd.Function):
         # (h[t-1] going forward, h[t+1] going backward; both operands are zero past each length): no concatenation.
         da3 = da.view(B, L, ndir * 4 * H)
         grads = []
-        with _leaf(da, x2d, out):                       # leaves: off the chain that continues with dx
+        with _leaf(da, x2d):                            # leaves: off the chain that continues with dx, each on its own lane
             dw_ih = tall_tn(da2d, x2d)                                                       # (ndir*4H, in)
-            db = da2d.sum(dim=0)
-            for d in range(ndir):
+        with _leaf(da):
+            db = ops.col_sum(da2d)
+        for d in range(ndir):
+            with _leaf(da, out):
                 h_dir = out[:, :, d * H:(d + 1) * H]
                 da_dir = da3[:, :, d * 4 * H:(d + 1) * 4 * H]
                 if L > 1:
@@ -181,8 +184,8 @@ class _LstmLayer(torch.autograd.Function):
                     dw_hh = torch.bmm(lhs.transpose(1, 2), rhs).sum(dim=0)                   # (4H, H)
                 else:
                     dw_hh = out.new_zeros(4 * H, H)
-                b_d = db[d * 4 * H:(d + 1) * 4 * H]
-                grads += [dw_ih[d * 4 * H:(d + 1) * 4 * H], dw_hh, b_d, b_d]
+            b_d = db[d * 4 * H:(d + 1) * 4 * H]
+            grads += [dw_ih[d * 4 * H:(d + 1) * 4 * H], dw_hh, b_d, b_d]
         return (dx, None, None, *grads)
 
 
@@ -407,7 +410,8 @@ class _HighwayLayer(torch.autograd.Function):
         dx = torch.addmm(dx, d_pre, w)                          # direct path + through both linears
         with _leaf(d_pre, x2d):
             dw = tall_tn(d_pre, x2d)                            # (2H, H)
-            db = d_pre.sum(dim=0)
+        with _leaf(d_pre):
+            db = ops.col_sum(d_pre)
         return dx, dw[:H], db[:H], dw[H:], db[H:]
 
 

@@ -272,6 +272,22 @@ def masked_softmax_bwd(y2d: torch.Tensor, dy2d: torch.Tensor, mask2d_u8: torch.T
     return dx
 
 
+def col_sum(a: torch.Tensor) -> torch.Tensor:
+    """out (p) = a.sum(dim=0) for a tall (n, p) fp32 matrix: the bias gradients of the step (deterministic two-stage
+    kernel, HBM-bound; ATen's dim-0 reduction runs at 0.4 - 1.3 TB/s on these shapes)."""
+    n, p = a.shape
+    if p % 4 != 0 or n == 0:
+        return a.sum(dim=0)                       # plain library reduction for shapes the kernel does not take
+    lib = _lib.lib()
+    a = a.contiguous()
+    R = lib.mmb_col_sum_blocks(n, p)
+    partial = torch.empty(R, p, device=a.device, dtype=torch.float32)
+    out = torch.empty(p, device=a.device, dtype=torch.float32)
+    _lib.check(lib.mmb_col_sum(_lib.ptr(a), _lib.ptr(partial), _lib.ptr(out), n, p, _lib.stream()), "mmb_col_sum")
+    _count(2)
+    return out
+
+
 def highway_fwd(pre: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """y = sigmoid(pre[:, :H]) * relu(pre[:, H:]) + (1 - sigmoid(pre[:, :H])) * x  (encoding.py:55-57)."""
     lib = _lib.lib()

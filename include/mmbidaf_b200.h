@@ -226,6 +226,18 @@ MMB_API int mmb_highway_bwd(const float* pre, const float* x, const float* dy, f
 MMB_API int mmb_col_sum_blocks(long long n, int p);
 MMB_API int mmb_col_sum(const float* a, float* partial, float* out, long long n, int p, mmb_stream_t stream);
 
+/* --------------------------------------------------------------------------------------
+ * Parameter update of the training step (train.py:154-155 with the optimiser of train.py:110): clip_grad_norm_ followed by
+ * one Adadelta step, fused into one pass over flat buffers of n floats (n % 4 == 0, 16-byte aligned):
+ *   coef = min(max_norm / (grad_norm[0] + 1e-6), 1); grad *= coef (written back); g = grad + weight_decay * param;
+ *   square_avg = rho square_avg + (1 - rho) g^2; delta = sqrt(acc_delta + eps) / sqrt(square_avg + eps) * g;
+ *   acc_delta = rho acc_delta + (1 - rho) delta^2; param -= lr * delta.
+ * grad_norm: device scalar, the 2-norm of grad (after the all-reduce when data parallel).
+ */
+MMB_API int mmb_adadelta_clip_step(float* param, float* grad, float* square_avg, float* acc_delta, const float* grad_norm,
+                                   float max_norm, float lr, float rho, float eps, float weight_decay, long long n,
+                                   mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,7 @@ SIGNATURES = {
     "mmb_highway_bwd": [c_void_p] * 5 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_col_sum_blocks": [ctypes.c_longlong, c_int],
     "mmb_col_sum": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_void_p],
+    "mmb_adadelta_clip_step": [c_void_p] * 5 + [c_float] * 5 + [ctypes.c_longlong, c_void_p],
     "mmb_masked_softmax_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p],
     "mmb_masked_softmax_bwd": [c_void_p] * 4 + [ctypes.c_longlong, c_int, c_int, c_void_p],
 }

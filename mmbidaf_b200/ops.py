@@ -288,6 +288,16 @@ def col_sum(a: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def adadelta_clip_step(param: torch.Tensor, grad: torch.Tensor, square_avg: torch.Tensor, acc_delta: torch.Tensor,
+                       grad_norm: torch.Tensor, max_norm: float, lr: float, rho: float, eps: float, weight_decay: float) -> None:
+    """clip_grad_norm_(max_norm) + one Adadelta step (train.py:154-155, :110) in one pass over the flat buffers, in place."""
+    lib = _lib.lib()
+    _lib.check(lib.mmb_adadelta_clip_step(_lib.ptr(param), _lib.ptr(grad), _lib.ptr(square_avg), _lib.ptr(acc_delta),
+                                          _lib.ptr(grad_norm), float(max_norm), float(lr), float(rho), float(eps),
+                                          float(weight_decay), param.numel(), _lib.stream()), "mmb_adadelta_clip_step")
+    _count(1)
+
+
 def highway_fwd(pre: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """y = sigmoid(pre[:, :H]) * relu(pre[:, H:]) + (1 - sigmoid(pre[:, :H])) * x  (encoding.py:55-57)."""
     lib = _lib.lib()

@@ -62,7 +62,8 @@ class FlatState:
         self.flat.zero_()
 
     def pack(self, grads) -> None:
-        """Copy a tuple of per-parameter gradients (None = zero) into the flat buffer with one kernel."""
+        """Copy a tuple of per-parameter gradients (None = zero) into the flat buffer with one kernel.  (One batched
+        concatenation: 40 us for the 12.8 MB; torch._foreach_copy_ falls back to ~110 separate copies here, 190 us.)"""
         pieces = []
         for g, p in zip(grads, self.params):
             n = p.numel()
@@ -177,7 +178,15 @@ class Trainer:
         return loss.detach()
 
     def _update(self) -> None:
-        self.last_grad_norm = self.grads.clip_(self.max_grad_norm)
+        if self.grads.flat.is_cuda:
+            # clip + Adadelta as one pass over the flat buffers (csrc/optimizer.cu); the norm stays a device scalar
+            from . import ops
+            o = self.optimizer
+            self.last_grad_norm = torch.linalg.vector_norm(self.grads.flat)
+            ops.adadelta_clip_step(self.grads.flat_param, self.grads.flat, o.square_avg, o.acc_delta, self.last_grad_norm,
+                                   self.max_grad_norm, o.lr, o.rho, o.eps, o.wd)
+            return
+        self.last_grad_norm = self.grads.clip_(self.max_grad_norm)        # host tensors (gloo tests): the same update in torch ops
         self.optimizer.step()
 
     def step(self, batch: Batch) -> torch.Tensor:

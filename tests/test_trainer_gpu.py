@@ -82,3 +82,31 @@ def test_leaf_lanes_give_the_same_gradients_as_the_inline_backward(tier):
                     assert torch.equal(w, g)
     finally:
         mmbidaf_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+@pytest.mark.parametrize("gscale", [1e-3, 5.0])        # norm below / above max_grad_norm: un-clipped and clipped
+def test_fused_clip_adadelta_matches_torch_semantics(wd, gscale):
+    """csrc/optimizer.cu against clip_grad_norm_ + torch.optim.Adadelta (train.py:154-155, :110) in fp64, three steps."""
+    from mmbidaf_b200 import ops
+    n, lr, rho, eps, max_norm = 40_004, 0.5, 0.9, 1e-6, 2.0
+    gen = torch.Generator().manual_seed(7)
+    p0 = torch.randn(n, generator=gen)
+    ref = torch.nn.Parameter(p0.double().clone())
+    opt = torch.optim.Adadelta([ref], lr=lr, rho=rho, eps=eps, weight_decay=wd)
+    param = p0.cuda()
+    sq, acc = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(3):
+        g = torch.randn(n, generator=gen) * gscale
+        ref.grad = g.double().clone()
+        torch.nn.utils.clip_grad_norm_([ref], max_norm)
+        opt.step()
+        grad = g.cuda()
+        norm = torch.linalg.vector_norm(grad)
+        ops.adadelta_clip_step(param, grad, sq, acc, norm, max_norm, lr, rho, eps, wd)
+        torch.cuda.synchronize()
+        assert torch.allclose(grad.cpu().double(), ref.grad, rtol=1e-5, atol=1e-9)            # clipped gradient written back
+        assert torch.allclose(param.cpu().double(), ref.detach(), rtol=1e-5, atol=1e-6)
+    st = opt.state[ref]
+    assert torch.allclose(sq.cpu().double(), st["square_avg"], rtol=1e-5, atol=1e-12)
+    assert torch.allclose(acc.cpu().double(), st["acc_delta"], rtol=1e-4, atol=1e-12)

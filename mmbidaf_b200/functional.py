@@ -382,6 +382,41 @@ class _DecoderStep(torch.autograd.Function):
         return None, (tape.zero_token(d_h) if ctx.has_token else None), None, d_h, d_cell, d_cov, None, None
 
 
+class _DecodeLoss(torch.autograd.Function):
+    """loss = (sum_s nll_s + w * coverage) / steps from the per-step loss terms (2, B) the decoder kernels emit
+    (models.py:168-179 in training: the coverage term of every step; :197-199 in evaluation: of the last step only).
+    One stack + one reduction forward and ONE (2, B) tensor shared by every step backward, instead of ~25 one-microsecond
+    select / sum / expand kernels between the decoder's forward and backward chains."""
+
+    _coef = {}
+
+    @staticmethod
+    def forward(ctx, steps, cov_weight, every_step, *terms):
+        t = torch.stack(terms)                                           # (S, 2, B)
+        sums = t.sum(dim=2)                                              # (S, 2)
+        nll = sums[:, 0].sum()
+        cov = sums[:, 1].sum() if every_step else sums[-1, 1]
+        ctx.meta = (len(terms), steps, cov_weight, every_step, t.shape[2])
+        return (nll + cov_weight * cov) / steps
+
+    @staticmethod
+    def backward(ctx, g):
+        S, steps, w, every_step, B = ctx.meta
+        key = (g.device, steps, w, B)
+        coef = _DecodeLoss._coef.get(key)
+        if coef is None:                                                 # made once (outside any graph capture: warm-up steps)
+            coef = _DecodeLoss._coef[key] = torch.tensor([[1.0 / steps], [w / steps]], device=g.device).expand(2, B).contiguous()
+        d = coef * g                                                     # (2, B): [d nll | d coverage term], the same for every step
+        if every_step:
+            return (None, None, None, *([d] * S))
+        d_nll_only = torch.stack([d[0], torch.zeros_like(d[0])])
+        return (None, None, None, *([d_nll_only] * (S - 1)), d)
+
+
+def decode_loss(step_losses, steps: int, cov_weight: float, every_step: bool) -> torch.Tensor:
+    return _DecodeLoss.apply(steps, cov_weight, every_step, *step_losses)
+
+
 def decoder_open(tape, proj_a, proj_i, enc_a, enc_i, params):
     return _DecoderOpen.apply(tape, proj_a, proj_i, enc_a, enc_i, *params)
 

@@ -134,6 +134,15 @@ class MultimodalAttentionDecoder(nn.Module):
         self.out = nn.Linear(hidden_size, output_size)
         self.softmax = nn.Softmax()
         self._cache = None
+        self._prepared = None
+
+    def prepare(self):
+        """Optional: lay this step's weights out for the decoder kernels NOW (on the current stream), e.g. while the
+        encoders still run; the next new sequence picks the result up (once) instead of building it in front of its
+        first step.  Must be called again after the weights change."""
+        if self.W1.weight.is_cuda:
+            params = {name: self._param_of(name) for name in _lib_fields()}
+            self._prepared = ops.DecoderWeights(params, self.output_size)
 
     # ---- per-sequence state: step-invariant projections (+ the autograd tape when training) ----------------
     def _sequence(self, enc_a, enc_i):
@@ -147,7 +156,8 @@ class MultimodalAttentionDecoder(nn.Module):
         c = {"a": weakref.ref(enc_a), "i": weakref.ref(enc_i), "key": (enc_a._version, enc_i._version, grad),
              "proj_a": proj_a, "proj_i": proj_i, "seq": None, "tape": None, "token": None, "last_h": None}
         params = {name: self._param_of(name) for name in _lib_fields()}
-        c["seq"] = ops.DecoderSeq(params, enc_a, enc_i, proj_a, proj_i, self.output_size)
+        prepared, self._prepared = self._prepared, None             # used at most once: the weights move every training step
+        c["seq"] = ops.DecoderSeq(params, enc_a, enc_i, proj_a, proj_i, self.output_size, weights=prepared)
         needs_grad = grad and (proj_a.requires_grad or enc_a.requires_grad or enc_i.requires_grad)
         if needs_grad:
             tape = Fn.DecoderTape(c["seq"])

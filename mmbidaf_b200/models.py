@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import functional as Fn
 from .layers import BiDAFAttention, Embedding, ImageEmbedding, MultimodalAttentionDecoder, RNNEncoder
 
 __all__ = ["MMBiDAF"]
@@ -45,9 +46,15 @@ class MMBiDAF(nn.Module):
     # the stream of its forward op, so the overlap carries over to the backward pass.
     use_streams = True
 
-    def _fork_join(self, jobs):
+    def _fork_join(self, jobs, meanwhile=None):
+        """Run ``jobs`` on side streams and join them into the current stream.  ``meanwhile`` (optional) is issued on the
+        current stream between the fork and the join: glue that does not depend on the jobs' results (masks, decoder
+        start state, per-step weight layouts) runs beside the recurrences instead of after them."""
         if not (self.use_streams and torch.cuda.is_available()):
-            return [job() for job in jobs]
+            results = [job() for job in jobs]
+            if meanwhile is not None:
+                meanwhile()
+            return results
         main = torch.cuda.current_stream()
         if getattr(self, "_streams", None) is None or self._streams[0].device != main.device:
             # the first job of a fork is the one on the critical path (the 1024-frame audio recurrence): its stream gets
@@ -60,6 +67,8 @@ class MMBiDAF(nn.Module):
             stream.wait_stream(main)
             with torch.cuda.stream(stream):
                 results.append(job())
+        if meanwhile is not None:
+            meanwhile()
         capturing = torch.cuda.is_current_stream_capturing()
         for stream, res in zip(self._streams, results):
             main.wait_stream(stream)
@@ -98,14 +107,19 @@ class MMBiDAF(nn.Module):
             feats = self.image_keyframes_emb(img).reshape(B, transformed_images.size(1), -1)
             return feats, self.image_enc(self.i_emb(feats), original_image_lengths)[0]
 
-        (audio_encoded,), (text_emb, text_encoded), (image_emb, image_encoded) = \
-            self._fork_join([audio_branch, text_branch, image_branch])
+        masks = {}
 
-        text_mask = self.get_mask(embedded_text, original_text_lengths)
-        audio_mask = self.get_mask(embedded_audio, original_audio_lengths)
-        image_mask = self.get_mask(image_emb, original_image_lengths)
-        decoder_mask = torch.zeros(B, self.max_transcript_length, dtype=torch.bool, device=text_mask.device)
-        decoder_mask[:, :Lt] = text_mask                                   # models.py:121-123
+        def make_masks():                        # needs only the lengths: issued beside the encoders
+            masks["text"] = self.get_mask(embedded_text, original_text_lengths)
+            masks["audio"] = self.get_mask(embedded_audio, original_audio_lengths)
+            masks["image"] = self.get_mask(transformed_images, original_image_lengths)     # (B, Li, ...): same (B, Li)
+            dm = torch.zeros(B, self.max_transcript_length, dtype=torch.bool, device=embedded_text.device)
+            dm[:, :Lt] = masks["text"]                                     # models.py:121-123
+            masks["decoder"] = dm
+
+        (audio_encoded,), (text_emb, text_encoded), (image_emb, image_encoded) = \
+            self._fork_join([audio_branch, text_branch, image_branch], meanwhile=make_masks)
+        text_mask, audio_mask, image_mask, decoder_mask = masks["text"], masks["audio"], masks["image"], masks["decoder"]
 
         def audio_aware():
             att = self.bidaf_att_audio(text_encoded, audio_encoded, text_mask, audio_mask)
@@ -115,23 +129,31 @@ class MMBiDAF(nn.Module):
             att = self.bidaf_att_image(text_encoded, image_encoded, text_mask, image_mask)
             return self.mod_t_i(att, original_text_lengths)
 
+        steps = batch_target_indices.size(1) if self.training else max_dec_len
+        start = {}
+
+        def decoder_start():                     # everything the decode loop needs that does not depend on the encoders' output
+            start["cell"] = embedded_text.new_zeros(1, B, self.mod_t_a.rnn.hidden_size)
+            start["input"] = embedded_text.new_zeros(B, 1, embedded_text.size(-1))
+            start["cov"] = embedded_text.new_zeros(B, Lt, 1)
+            start["rows"] = torch.arange(B, device=embedded_text.device)
+            start["targets"] = batch_target_indices.reshape(B, -1).to(embedded_text.device).long()   # int(tensor), models.py:168
+            if self.training:
+                # teacher forcing (models.py:173): every step's next input is known up front -- one gather for the whole
+                # sequence, laid out (steps, B, E) so that a step's slice is contiguous, instead of a gather per step
+                start["next"] = embedded_text[start["rows"].unsqueeze(0), start["targets"][:, :steps].t()]
+            self.multimodal_att_decoder.prepare()          # this step's weight layouts of the decoder's batched GEMMs
+
         (mod_text_audio, text_audio_hidden), (mod_text_image, text_img_hidden) = \
-            self._fork_join([audio_aware, image_aware])
+            self._fork_join([audio_aware, image_aware], meanwhile=decoder_start)
 
         # models.py:143-149 (the hidden-state rows are in descending-length order: reference quirk Q3)
         decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)
-        decoder_cell_state = text_emb.new_zeros(1, B, decoder_hidden.size(-1))
-        decoder_input = embedded_text.new_zeros(B, 1, embedded_text.size(-1))
-        coverage_vec = text_emb.new_zeros(B, Lt, 1)
-
-        rows = torch.arange(B, device=embedded_text.device)
-        targets = batch_target_indices.reshape(B, -1).to(embedded_text.device).long()      # int(tensor), models.py:168
+        decoder_cell_state, decoder_input, coverage_vec = start["cell"], start["input"], start["cov"]
+        rows, targets = start["rows"], start["targets"]
         out_distributions, step_losses = [], []
-        steps = batch_target_indices.size(1) if self.training else max_dec_len
         if self.training:
-            # teacher forcing (models.py:173): every step's next input is known up front -- one gather for the whole
-            # sequence, laid out (steps, B, E) so that a step's slice is contiguous, instead of a gather per step
-            next_inputs = embedded_text[rows.unsqueeze(0), targets[:, :steps].t()]
+            next_inputs = start["next"]
         for idx in range(steps):
             tgt = targets[:, idx]
             # the decoder kernels also emit this step's loss terms: -log(p[target] + 1e-12) (models.py:168-170)
@@ -145,9 +167,8 @@ class MMBiDAF(nn.Module):
                 decoder_input = embedded_text[rows, out_distribution.max(dim=1)[1]].unsqueeze(1)   # models.py:184,:193
             out_distributions.append(out_distribution)
             step_losses.append(step_loss)
-        terms = torch.stack(step_losses)                                                    # (steps, 2, B)
+        # training adds the coverage loss at every step (models.py:177-178), evaluation once after the loop (:197-198);
+        # loss = (sum of the steps' nll + cov_loss_wt * coverage) / steps (models.py:179 / :199)
         cov_loss_wt = 1.0
-        # training adds the coverage loss at every step (models.py:177-178), evaluation once after the loop (:197-198)
-        coverage_loss = terms[:, 1].sum() if self.training else terms[-1, 1].sum()
-        loss = (terms[:, 0].sum() + cov_loss_wt * coverage_loss) / steps                    # models.py:179 / :199
+        loss = Fn.decode_loss(step_losses, steps, cov_loss_wt, self.training)
         return torch.stack(out_distributions).transpose(0, 1), loss

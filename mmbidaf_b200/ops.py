@@ -130,18 +130,15 @@ def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, 
     return gates
 
 
-class DecoderSeq:
-    """Everything that is constant over the steps of one decode sequence (attention.py:145-186): the batched
-    weight matrices of the small GEMMs, the vectors the kernels read, the hoisted projections and the chunking.
+class DecoderWeights:
+    """The decoder's weights laid out for the batched GEMMs and kernels of a step (attention.py:110-143 parameters).
+    Depends on the parameters only, so it can be built beside the encoders (MMBiDAF.forward) instead of in front of the
+    first decoder step.  ``params`` maps the names of ``_lib.DECODER_WEIGHT_FIELDS`` to parameter tensors."""
 
-    ``params`` maps the names of ``_lib.DECODER_WEIGHT_FIELDS`` to (detached) parameter tensors."""
-
-    def __init__(self, params: dict, enc_a, enc_i, proj_a, proj_i, out_size: int):
+    def __init__(self, params: dict, out_size: int):
         P = {k: v.detach() for k, v in params.items()}
-        self.enc_a, self.enc_i = enc_a.detach().contiguous(), enc_i.detach().contiguous()
-        self.proj_a, self.proj_i = proj_a.detach().contiguous(), proj_i.detach().contiguous()
-        self.B, self.Lt, self.D = self.enc_a.shape
-        self.H, self.M = self.D // 2, out_size
+        self.D, self.H = P["W2"].shape
+        self.M = out_size
         self.E = P["lstm_w_ih"].shape[1] - self.D
         self.Wh4 = torch.cat([P["W2"], P["W4"], P["Wb2"], P["Wb4"]], dim=0).contiguous()           # (4D, H)
         # every bias that ends up inside the same tanh is added once, with the h projection: W2 h + b2 + bc1 (attention.py:147),
@@ -161,6 +158,20 @@ class DecoderSeq:
         self.v1, self.wc1, self.v2, self.wc2 = flat("v1"), flat("Wc1"), flat("v2"), flat("Wc2")
         self.vb1, self.vb2 = flat("vb1"), flat("vb2")
         self.v1b, self.v2b, self.vb1b, self.vb2b = flat("v1b"), flat("v2b"), flat("vb1b"), flat("vb2b")
+
+
+class DecoderSeq:
+    """Everything that is constant over the steps of one decode sequence (attention.py:145-186): the weight layouts
+    (:class:`DecoderWeights`, built here unless handed in), the hoisted projections and the chunking."""
+
+    def __init__(self, params: dict, enc_a, enc_i, proj_a, proj_i, out_size: int, weights: Optional[DecoderWeights] = None):
+        w = weights if weights is not None else DecoderWeights(params, out_size)
+        self.__dict__.update(w.__dict__)
+        self.enc_a, self.enc_i = enc_a.detach().contiguous(), enc_i.detach().contiguous()
+        self.proj_a, self.proj_i = proj_a.detach().contiguous(), proj_i.detach().contiguous()
+        self.B, self.Lt, D = self.enc_a.shape
+        if D != self.D or out_size != self.M:
+            raise RuntimeError(f"DecoderSeq: encoder width {D} / output size {out_size} do not match the weights ({self.D}, {self.M})")
         self.nch = _lib.lib().mmb_decoder_chunks(self.B, self.Lt)
         # per-video arrival counters of the chunk-parallel kernels (zero between launches): one set per direction
         self.counters = torch.zeros(2, self.B, device=self.enc_a.device, dtype=torch.int32)

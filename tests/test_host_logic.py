@@ -43,3 +43,32 @@ def test_layers_refuse_cpu_tensors():
                           torch.ones(1, 2, dtype=torch.bool))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         RNNEncoder(4, 4, 1)(torch.zeros(1, 2, 4), [2])
+
+
+def test_decode_loss_matches_the_reference_formula_and_its_gradient():
+    """functional.decode_loss against models.py:168-179 (training: coverage term of every step) and :197-199 (evaluation:
+    of the last step only), values and the gradient handed to every step (host tensors: the function is pure torch)."""
+    import pytest
+    from mmbidaf_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(3)
+    steps, B, w = 5, 4, 1.0
+    for every_step in (True, False):
+        terms = [torch.rand(2, B, generator=gen).double().requires_grad_(True) for _ in range(steps)]
+        ref_terms = [t.detach().clone().requires_grad_(True) for t in terms]
+        got = Fn.decode_loss(terms, steps, w, every_step)
+        stacked = torch.stack(ref_terms)                                  # (steps, 2, B)
+        cov = stacked[:, 1].sum() if every_step else stacked[-1, 1].sum()
+        want = (stacked[:, 0].sum() + w * cov) / steps
+        assert float(got) == pytest.approx(float(want), rel=1e-12)
+        (3.0 * got).backward()
+        (3.0 * want).backward()
+        for t, r in zip(terms, ref_terms):
+            assert torch.allclose(t.grad, r.grad, rtol=1e-6, atol=0)      # the shared coefficient tensor is fp32
+
+
+def test_leaf_lanes_is_a_no_op_without_cuda_work():
+    from mmbidaf_b200 import functional as Fn
+    with Fn.leaf_lanes():
+        with Fn._leaf(torch.zeros(3)):
+            x = torch.ones(2) + 1
+    assert x.tolist() == [2.0, 2.0] and not Fn._Lanes.enabled

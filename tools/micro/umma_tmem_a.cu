@@ -105,10 +105,12 @@ __global__ void __launch_bounds__(128, 1) tmem_a_kernel(const __nv_bfloat16* a_p
     for (int mode = 0; mode < 2; ++mode)
       for (int pass = 0; pass < 2; ++pass) {
         const long long t0 = clock64();
-        for (int r = 0; r < rep; ++r) {
-          const int k = r % KSTEPS;
-          if (mode == 0) umma_bf16_ts(tmem + COL_D, tmem + COL_A + k * 8, b_lo + k * 16, b_hi, idesc, 1, leader);
-          else           umma_bf16_lh(tmem + COL_D, a_lo + k * 16, a_hi, b_lo + k * 16, b_hi, idesc, 1, leader);
+        if (mode == 0) {                                   // (k = r & 7: no integer division in the issue loop)
+#pragma unroll 8
+          for (int r = 0; r < rep; ++r) umma_bf16_ts(tmem + COL_D, tmem + COL_A + (r & 7) * 8, b_lo + (r & 7) * 16, b_hi, idesc, 1, leader);
+        } else {
+#pragma unroll 8
+          for (int r = 0; r < rep; ++r) umma_bf16_lh(tmem + COL_D, a_lo + (r & 7) * 16, a_hi, b_lo + (r & 7) * 16, b_hi, idesc, 1, leader);
         }
         umma_commit(smem_u32(&bar), leader);
         mbar_wait(smem_u32(&bar), phase);

@@ -23,6 +23,9 @@ from . import ops
 # ``loss.backward()``) everything runs inline as before.
 # ---------------------------------------------------------------------------------------------------------------------
 class _Lanes:
+    # Process-wide on purpose: autograd runs the backward nodes on its own device thread, so the state cannot be thread-local.
+    # One training step at a time per process (the design is one process per GPU); a nested / concurrent ``leaf_lanes()`` is
+    # a no-op that leaves the products inline.
     enabled = False
     n = 4
     streams = {}          # device index -> [torch.cuda.Stream] * n

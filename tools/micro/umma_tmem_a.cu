@@ -33,14 +33,17 @@ constexpr int M = 128, K = DPAD, KSTEPS = K / 16;
 constexpr int COL_D = 0, COL_A = 256;            // accumulator (<= 208 columns), A operand (K / 2 = 104 columns)
 
 // a_pack / b_pack: core-matrix order [row/8][chunk][row%8][8 bf16] (tc_common.cuh); d: (M, n) fp32 row-major
+// m = 128: row i of A and D on lane i.  m = 64: hypothesis under test -- A uses the lanes the accumulator uses
+// (tools/micro/umma_m64_layout.cu: row i on lane (i / 16) * 32 + i % 16, the upper half of each 32-lane quarter idle).
 __global__ void __launch_bounds__(128, 1) tmem_a_kernel(const __nv_bfloat16* a_pack, const __nv_bfloat16* b_pack, float* d, int n,
-                                                        int rep, long long* cycles) {
+                                                        int rep, long long* cycles, int m) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   unsigned char* As = smem;                               // 16 groups x 3328 B
   unsigned char* Bs = smem + 64 * 1024;                   // n / 8 groups
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int arow = m == 128 ? tid : ((tid & 31) < 16 ? (tid >> 5) * 16 + (tid & 31) : -1);      // the A / D row this lane holds
   for (int i = tid; i < M / 8 * GROUP_BYTES / 16; i += 128) reinterpret_cast<uint4*>(As)[i] = reinterpret_cast<const uint4*>(a_pack)[i];
   for (int i = tid; i < n / 8 * GROUP_BYTES / 16; i += 128) reinterpret_cast<uint4*>(Bs)[i] = reinterpret_cast<const uint4*>(b_pack)[i];
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
@@ -53,11 +56,12 @@ __global__ void __launch_bounds__(128, 1) tmem_a_kernel(const __nv_bfloat16* a_p
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   // stage A into TMEM: thread = row, 32-bit column c of the operand <- bf16 pair (K = 2c, 2c + 1)
   {
-    const unsigned char* arow = As + (tid >> 3) * GROUP_BYTES + (tid & 7) * 16;     // chunk ch of this row at + ch * 128
+    const int sr = arow < 0 ? 0 : arow;
+    const unsigned char* arow_p = As + (sr >> 3) * GROUP_BYTES + (sr & 7) * 16;     // chunk ch of this row at + ch * 128
     for (int q = 0; q < K / 32; ++q) {                                              // 16 columns = 32 K elements = 4 chunks
       float v[16];
       for (int ch = 0; ch < 4; ++ch) {
-        const uint4 u = *reinterpret_cast<const uint4*>(arow + (q * 4 + ch) * 128);
+        const uint4 u = *reinterpret_cast<const uint4*>(arow_p + (q * 4 + ch) * 128);
         v[ch * 4 + 0] = __uint_as_float(u.x); v[ch * 4 + 1] = __uint_as_float(u.y);
         v[ch * 4 + 2] = __uint_as_float(u.z); v[ch * 4 + 3] = __uint_as_float(u.w);
       }
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) tmem_a_kernel(const __nv_bfloat16* a_p
     {                                                                               // K = 208: the last 16 elements (8 columns)
       float v[16] = {};
       for (int ch = 0; ch < 2; ++ch) {
-        const uint4 u = *reinterpret_cast<const uint4*>(arow + ((K / 32) * 4 + ch) * 128);
+        const uint4 u = *reinterpret_cast<const uint4*>(arow_p + ((K / 32) * 4 + ch) * 128);
         v[ch * 4 + 0] = __uint_as_float(u.x); v[ch * 4 + 1] = __uint_as_float(u.y);
         v[ch * 4 + 2] = __uint_as_float(u.z); v[ch * 4 + 3] = __uint_as_float(u.w);
       }
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(128, 1) tmem_a_kernel(const __nv_bfloat16* a_p
   tc_fence_after();
   const int warp_u = uniform_warp_idx();
   const uint32_t leader = elect_one();
-  const uint32_t idesc = idesc_bf16(n, 0);
+  const uint32_t idesc = idesc_bf16(n, 0, m);
   const uint32_t b_lo = desc_lo(smem_u32(Bs), 128), b_hi = desc_hi(GROUP_BYTES);
   const uint32_t a_lo = desc_lo(smem_u32(As), 128), a_hi = desc_hi(GROUP_BYTES);
   if (warp_u == 0) {
@@ -94,7 +98,8 @@ __global__ void __launch_bounds__(128, 1) tmem_a_kernel(const __nv_bfloat16* a_p
   for (int q = 0; q < n / 16; ++q) {
     float o[16];
     tmem_ld16(lane_base + COL_D + q * 16, o);
-    for (int i = 0; i < 16; ++i) d[(size_t)tid * n + q * 16 + i] = o[i];
+    if (arow >= 0)
+      for (int i = 0; i < 16; ++i) d[(size_t)arow * n + q * 16 + i] = o[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -141,6 +146,7 @@ int main() {
   cudaMalloc(&dd, M * 208 * 4);
   cudaMalloc(&dc, 16);
   cudaFuncSetAttribute(tmem_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  for (int m : {128, 64})
   for (int n : {32, 64, 128, 208}) {
     std::vector<float> a((size_t)M * K), b((size_t)n * K);
     srand(7 + n);
@@ -151,20 +157,20 @@ int main() {
     pack(b, n, bp);
     cudaMemcpy(da, ap.data(), ap.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(db, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice);
-    tmem_a_kernel<<<1, 128, 160 * 1024>>>(da, db, dd, n, rep, dc);
+    tmem_a_kernel<<<1, 128, 160 * 1024>>>(da, db, dd, n, rep, dc, m);
     std::vector<float> d((size_t)M * n);
     long long cyc[2];
     cudaError_t e = cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { printf("N=%d: %s\n", n, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(cyc, dc, 16, cudaMemcpyDeviceToHost);
     double err = 0;
-    for (int i = 0; i < M; ++i)
+    for (int i = 0; i < m; ++i)
       for (int j = 0; j < n; ++j) {
         double s = 0;
         for (int k = 0; k < K; ++k) s += (double)a[(size_t)i * K + k] * b[(size_t)j * K + k];
         err = fmax(err, fabs(s - d[(size_t)i * n + j]));
       }
-    printf("M128 N%-3d K-major B: layout check max |err| %.3g (%s); A from TMEM %.1f cycles/MMA, A from smem %.1f (floor %d)\n", n, err,
+    printf("M%-3d N%-3d K-major B: layout check max |err| %.3g (%s); A from TMEM %.1f cycles/MMA, A from smem %.1f (floor %d)\n", m, n, err,
            err < 1e-3 ? "ok" : "LAYOUT WRONG", (double)cyc[0] / rep, (double)cyc[1] / rep, 128 * n / 256);
   }
   return 0;

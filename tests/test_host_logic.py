@@ -72,3 +72,16 @@ def test_leaf_lanes_is_a_no_op_without_cuda_work():
         with Fn._leaf(torch.zeros(3)):
             x = torch.ones(2) + 1
     assert x.tolist() == [2.0, 2.0] and not Fn._Lanes.enabled
+
+
+def test_tall_tn_split_reduction_matches_the_plain_product():
+    """functional.tall_tn (every weight gradient of the step) splits the reduction over row blocks when the output has too
+    few tiles; both paths against a^T b in fp64."""
+    from mmbidaf_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(5)
+    for n, p, q in ((4096, 400, 100), (1024, 200, 100), (1000, 64, 32), (130, 8, 8), (2048, 800, 800)):
+        a, b = torch.randn(n, p, generator=gen), torch.randn(n, q, generator=gen)
+        got = Fn.tall_tn(a, b)
+        want = a.double().t() @ b.double()
+        assert got.shape == (p, q)
+        assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-4

@@ -557,6 +557,10 @@ size_t tc_smem_bytes(int nparts) {
 
 int bidaf_fwd_tc2_launch(const BidafPacks& pk, const float* bias, float* out, float* q2c, float* bm, float* lse_row,
                          float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
+int bidaf_fwd_tc3_launch(const BidafPacks& pk, const float* bias, float* out, float* q2c, float* bm, float* lse_row,
+                         float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
+int bidaf_fwd_tc4_launch(const BidafPacks& pk, const float* text, const float* bias, float* out, float* q2c, float* bm,
+                         float* lse_row, float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
 
 // Workspace (bytes): packed operands, mask words (layout: tc_common.cuh::bidaf_packs).
 size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout) { return bidaf_packs(nullptr, B, Lc, Lq, dropout != 0).bytes; }
@@ -587,6 +591,8 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   // one-block-per-SM cut below win (B=16, 4096 x 2048: 436 vs 477 us).  MMB_BIDAF_FWD_CUT=1|2 forces one.
   const char* cut = getenv("MMB_BIDAF_FWD_CUT");
   const bool two_per_sm = cut ? atoi(cut) == 2 : (Lc <= 512 && Lq <= 512);
+  if (cut && atoi(cut) == 4) return bidaf_fwd_tc4_launch(pk, text, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
+  if (cut && atoi(cut) == 3) return bidaf_fwd_tc3_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   if (two_per_sm) return bidaf_fwd_tc2_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   // Q2C: X = modality rows, Y = text rows (S operand cw, values cp)
   const TcArgs aq{qs, cw, cp, nullptr, c_words, bias, q2c, tp, lse_col, nullptr, trace, Lq, LqP, Lc, LcP, d};

@@ -1,9 +1,3 @@
-// DRAFT for round 2 -- NOT part of libmmbidaf_b200.so, never run on hardware yet.  Compile check only:
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr -I mmbidaf_b200/csrc \
-//        -c tools/draft/bidaf_fwd_tc3.cu -o /tmp/bidaf_fwd_tc3.o
-// To try it: move it to mmbidaf_b200/csrc/, declare bidaf_fwd_tc3_launch next to bidaf_fwd_tc2_launch in bidaf_fwd_tc.cu and
-// select it with MMB_BIDAF_FWD_CUT=3; tests/test_bidaf_gpu.py::test_bf16_tier_both_kernel_cuts gets cut "3".
-//
 // Third cut of the fused BiDAF forward, tensor-core tier (layers/attention.py:37-75), built on two measurements of round 1
 // (profiles/r01_bidaf_tc_ncu.md):
 //   * a 128 x N x 16 tcgen05.mma costs 17.4 / 33.4 cycles (N = 32 / 64) with the A operand in TENSOR MEMORY against 41.4 / 49.5
@@ -62,6 +56,7 @@ struct FusedArgs {
   int* ready;            // (B) zeroed before the launch
   int nq, nc;
   int n_q2c, n_c2q;
+  long long* cta_times;  // debugging aid (tools/bidaf_fwd_timeline.py) or null
 };
 
 // D[tmem] (+)= A[tmem] * B[smem] (tools/micro/umma_tmem_a.cu: row i of A = lane i, column c = bf16 pair K = 2c, 2c+1)
@@ -80,7 +75,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 
 template <int KIND>
-__device__ __forceinline__ void block_body(const BlockArgs& a, const int b, const int xblk, int* ready, const int ready_target) {
+__device__ __forceinline__ void block_body(const BlockArgs& a, const int b, const int xblk, int* ready, const int ready_target,
+                                           long long* cta_times) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* Sr = smem;                                       // S-operand ring: S_SLOTS x Y_BYTES
   unsigned char* Vr = Sr + S_SLOTS * Y_BYTES;                     // value-operand ring: V_SLOTS x Y_BYTES
@@ -110,6 +106,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (cta_times && tid == 0) cta_times[4] = globaltimer_ns();
 
   int nty = (a.LY + TY - 1) / TY;                                  // tiles past the last un-masked Y row add nothing
   {
@@ -149,6 +146,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
   //      4 bf16 pairs per 16-byte chunk -> 4 columns; half 1 has 10 real chunks, the rest of its 48 columns is zero padding.
   const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);
   mbar_wait(bar_x, 0);
+  if (cta_times && tid == 0) { cta_times[5] = globaltimer_ns(); cta_times[7] = nty; }
   {
     const unsigned char* xrow = Xs + (row >> 3) * GROUP_BYTES + (row & 7) * 16;
     const int nq16 = half == 0 ? 4 : 3;
@@ -201,6 +199,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
     const bool all_open = (words.x & words.y) == ~0ull;
     mbar_wait(bar_s0 + 8 * (t & 1), (t >> 1) & 1);
     tc_fence_after();
+    if (cta_times && tid == 0 && t == 0) cta_times[6] = globaltimer_ns();
 
     // ---- this thread's half row of S(t): masked streaming soft-max (base 2) ----------------------------------------
     float sv[HALF];
@@ -302,6 +301,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
   if (nty > 0) mbar_wait(bar_final, 0);
   tc_fence_after();
   __syncthreads();
+  if (cta_times && tid == 0) cta_times[1] = globaltimer_ns();
   if (KIND != Q2C && warp_u == TMA_WARP) {                        // the plain text tile for the products: over the value ring's tail
     mbar_expect_tx(bar_x, X_BYTES, leader);
     tma_bulk_g2s(smem_u32(Xs), reinterpret_cast<const char*>(a.x_plain) + x_off, X_BYTES, bar_x, leader);
@@ -324,6 +324,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
             make_float4(o[i] * inv_l, o[i + 1] * inv_l, o[i + 2] * inv_l, o[i + 3] * inv_l);
   }
   __syncthreads();
+  if (cta_times && tid == 0) cta_times[8] = globaltimer_ns();
   constexpr int NW = NTHREADS / 32;
   if (KIND == Q2C) {
 #pragma unroll 1
@@ -348,6 +349,7 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
     }
   } else {
     mbar_wait(bar_x, 1);                                          // the plain text tile
+    if (cta_times && tid == 0) cta_times[9] = globaltimer_ns();
 #pragma unroll 2
     for (int r = warp; r < TX; r += NW) {
       if (x0 + r >= a.LX) break;
@@ -380,15 +382,23 @@ __device__ __forceinline__ void block_body(const BlockArgs& a, const int b, cons
 
 __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc3_kernel(const FusedArgs f) {
   const int blk = blockIdx.x;
+  long long* times = f.cta_times ? f.cta_times + 12 * (size_t)blk : nullptr;
+  if (times && threadIdx.x == 0) {
+    times[0] = globaltimer_ns();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    times[3] = smid;
+  }
   if (blk < f.n_q2c) {
-    block_body<Q2C>(f.k[Q2C], blk / f.nq, blk % f.nq, f.ready, 0);
+    block_body<Q2C>(f.k[Q2C], blk / f.nq, blk % f.nq, f.ready, 0, times);
   } else if (blk < f.n_q2c + f.n_c2q) {
     const int i = blk - f.n_q2c;
-    block_body<C2QA>(f.k[C2QA], i / f.nc, i % f.nc, nullptr, 0);
+    block_body<C2QA>(f.k[C2QA], i / f.nc, i % f.nc, nullptr, 0, times);
   } else {
     const int i = blk - f.n_q2c - f.n_c2q;
-    block_body<C2QB>(f.k[C2QB], i / f.nc, i % f.nc, f.ready, f.nq);
+    block_body<C2QB>(f.k[C2QB], i / f.nc, i % f.nc, f.ready, f.nq, times);
   }
+  if (times && threadIdx.x == 0) times[2] = globaltimer_ns();
 }
 
 constexpr size_t SMEM_BYTES = (size_t)(S_SLOTS + V_SLOTS) * Y_BYTES + 2 * P_BYTES + (4 + 2 * (S_SLOTS + V_SLOTS)) * 8 + 16 + 2 * TX * 4;
@@ -411,6 +421,8 @@ int bidaf_fwd_tc3_launch(const BidafPacks& pk, const float* bias, float* out, fl
   f.nc = LcP / TX;
   f.n_q2c = B * f.nq;
   f.n_c2q = B * f.nc;
+  const char* ct = getenv("MMB_BIDAF_FWD_CTA_TIMES");
+  f.cta_times = ct ? reinterpret_cast<long long*>(strtoull(ct, nullptr, 0)) : nullptr;
   MMB_CUDA(cudaMemsetAsync(pk.ready, 0, sizeof(int) * (size_t)B, stream));
   MMB_CUDA(cudaFuncSetAttribute(bidaf_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   bidaf_tc3_kernel<<<f.n_q2c + 2 * f.n_c2q, NTHREADS, SMEM_BYTES, stream>>>(f);

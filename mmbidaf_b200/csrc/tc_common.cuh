@@ -204,7 +204,7 @@ struct BidafPacks {
   __nv_bfloat16 *qs, *qp;            // modality: S operand (dropped, term chunk) / plain values (== qs without dropout)
   __nv_bfloat16* tp;                 // packed T = s2^T c
   unsigned long long *c_words, *q_words;   // (B, LP/64, 2): [in-range bits, un-masked bits] per 64 rows
-  int* ready;                        // (B) Q2C -> C2Q dependency counters of the fused launch
+  int* ready;                        // (B) Q2C -> C2Q dependency counters of the fused launch, then the work-queue head of cut 4
   long long* trace;                  // 2 x 256 clock stamps (debugging aid), the last 4096 bytes
   int LcP, LqP;
   size_t c_pack, q_pack, bytes;
@@ -230,7 +230,7 @@ inline BidafPacks bidaf_packs(void* workspace, int B, int Lc, int Lq, bool modal
   p.q_words = p.c_words + (size_t)B * (p.LcP / 64) * 2;
   const size_t used = ((size_t)(next - ws) + 16 * (size_t)B * (p.LcP / 64 + p.LqP / 64) + 255) / 256 * 256;
   p.ready = reinterpret_cast<int*>(ws + used);
-  const size_t used2 = used + ((size_t)B * 4 + 255) / 256 * 256;
+  const size_t used2 = used + ((size_t)(B + 1) * 4 + 255) / 256 * 256;
   p.trace = reinterpret_cast<long long*>(ws + used2);
   p.bytes = used2 + 4096;
   return p;

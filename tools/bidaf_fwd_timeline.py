@@ -43,7 +43,11 @@ for name, sl in (("Q2C", slice(0, nq)), ("C2QA", slice(nq, nq + nc)), ("C2QB", s
         tl = (x[:, 1] - x[:, 6]).float()
         print(f"      prologue {pro.float().mean():.0f}; X tile wait {xl.float().mean():.0f}; first S tile {s0.float().mean():.0f}; "
               f"tiles {nt.mean():.1f}; rest of the loop {tl.mean():.0f} = {(tl / (nt - 1).clamp(min=1)).mean():.0f} ns per further tile")
-        if int(x[:, 8].max()) > 0:
+        if int(x[:, 8].max()) > 0 and int(x[:, 11].max()) == 0:      # cut 3: [8] drained into staging, [9] plain text tile landed
+            print("      epilogue: loop end -> drained %.0f; -> text tile %.0f; -> end %.0f" % (
+                (x[:, 8] - x[:, 1]).float().mean(), (x[:, 9] - x[:, 8]).clamp(min=0).float().mean(),
+                (x[:, 2] - torch.maximum(x[:, 8], x[:, 9])).float().mean()))
+        elif int(x[:, 8].max()) > 0:
             e = x[:, 8:12] - torch.cat([x[:, 1:2], x[:, 8:11]], 1)
             print("      epilogue: wait text tile + drain rows 0-63 %.0f; store %.0f; drain rows 64-127 %.0f; store %.0f"
                   % tuple(e.float().mean(0).tolist()))

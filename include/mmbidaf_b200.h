@@ -217,11 +217,22 @@ MMB_API int mmb_highway_bwd(const float* pre, const float* x, const float* dy, f
                             long long n, int H, mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
+ * Mask / length plumbing on the device.  Replaces models.py:86-92 (`get_mask`: arange < len on the CPU, then .to(device),
+ * models.py:126-129), models.py:119-123 (decoder mask: zeros + cast + cat on the CPU) and the scheduling use of the
+ * descending-length order of encoding.py:91.  One launch from an int32 device vector of lengths:
+ *   mask (B, L) uint8 = pos < len[b];  dec_mask (B, M) uint8 (optional, M >= L) = the same, zero beyond L;
+ *   order (B) int32 (optional) = videos by descending length, ties in batch order (stable) -- used only to schedule the
+ *   longest recurrences first; the hidden-state permutation of encoding.py:99-106 keeps coming from the host's torch.sort.
+ */
+MMB_API int mmb_length_plan(const int32_t* lengths, uint8_t* mask, uint8_t* dec_mask, int32_t* order, int B, int L, int M,
+                            mmb_stream_t stream);
+
+/* --------------------------------------------------------------------------------------
  * Column sums of a tall matrix: out (p) = sum over the n rows of a (n, p).  Every bias gradient of the training step is one
  * (the autograd gradient of nn.LSTM's b_ih / b_hh, encoding.py:76-81; of the highway biases, encoding.py:52-59; of the
  * decoder's hoisted projections W1 / W3, attention.py:152-157) -- in the reference an ATen reduction inside
  * loss.backward() (train.py:148).  Deterministic two-stage sum; partial: workspace of mmb_col_sum_blocks(n, p) * p floats.
- * p % 4 == 0, a and partial 16-byte aligned.
+ * Any p; the float4 kernel runs when p % 4 == 0 and a, partial are 16-byte aligned, a one-column-per-thread kernel otherwise.
  */
 MMB_API int mmb_col_sum_blocks(long long n, int p);
 MMB_API int mmb_col_sum(const float* a, float* partial, float* out, long long n, int p, mmb_stream_t stream);

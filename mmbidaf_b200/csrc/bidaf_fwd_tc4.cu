@@ -104,6 +104,12 @@ __device__ __forceinline__ int4 ld_item(const int4* p) {                   // (o
   return v;
 }
 
+// One count on a global dependency counter with release semantics: this thread's earlier writes, and those it has observed through
+// the __syncwarp before it, are visible to whoever acquires the counter.
+__device__ __forceinline__ void signal_release(int* counter) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
 struct Smem {
   unsigned char* X;        // X_BYTES
   unsigned char* Y;        // NST x STAGE_BYTES
@@ -132,13 +138,19 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
   const int wrows = max(0, min(32, a.LX - x0 - q4 * 32));           // valid rows among this warp's 32
   const size_t row0 = (size_t)b * a.LX + x0 + q4 * 32;              // global row of this warp's first row
   const int c4 = (lane & 7) * 4, rsub = lane >> 3;                  // transposed role: 8 lanes x float4 = one row's 32 columns
+  const int nvalid = (wrows - rsub + 3) >> 2;                       // rows rsub, rsub + 4, ... below wrows: rr < nvalid
   constexpr int NCHUNK = (DPAD + EPI_COLS - 1) / EPI_COLS;          // 7: columns 0..223, 208 allocated
   const int last_cc = ((NCHUNK - 1 - eh) & ~1) + eh;                // this warp's last chunk
-  char* tpack = nullptr;
-  if (KIND == Q2C)
-    tpack = reinterpret_cast<char*>(a.t_pack) + ((size_t)b * (a.LXP / 8) + (size_t)(x0 + q4 * 32) / 8 + (lane >> 3)) * GROUP_BYTES +
-            (lane & 7) * 16;
-  const size_t ostride = KIND == Q2C ? (size_t)d : (size_t)4 * d;   // floats per output row
+  // running pointers, made once per item: everything below is pointer + small constant (the first version rebuilt 64-bit
+  // row offsets for every access: ~35 integer instructions per load)
+  const uint32_t ostride = KIND == Q2C ? (uint32_t)d : 4u * (uint32_t)d;      // floats per output row
+  float* const obase = a.out ? a.out + (row0 + rsub) * ostride + (KIND == C2QA ? d : KIND == C2QB ? 3 * d : 0) + c4 : nullptr;
+  const float* const cbase = KIND != Q2C ? a.c_src + (row0 + rsub) * d + c4 : nullptr;
+  float* const bbase = (KIND == C2QB && a.bm) ? a.bm + (row0 + rsub) * d + c4 : nullptr;
+  char* const tpack = KIND == Q2C ? reinterpret_cast<char*>(a.t_pack) +
+                                        ((size_t)b * (a.LXP / 8) + (size_t)(x0 + q4 * 32) / 8 + (lane >> 3)) * GROUP_BYTES + (lane & 7) * 16
+                                  : nullptr;
+  const uint32_t oinc = 4u * ostride, cinc = 4u * (uint32_t)d;      // four rows further
 #pragma unroll 1
   for (int cc = eh; cc < NCHUNK; cc += 2) {
     const int col0 = cc * EPI_COLS;
@@ -156,9 +168,6 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free_bar);                       // the accumulator may be overwritten (item n + 2)
     }
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * inv_l;
     if (KIND == Q2C) {
       // packed bf16 T (value operand of the C2QB items): this thread's 8-column chunks go straight to their place --
       // 8 consecutive rows x 16 bytes = one 128-byte core matrix, so a warp writes whole 128-byte lines
@@ -171,33 +180,39 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) {
             const bool ok = row_ok && ch * 8 + 2 * e2 < d;
-            h[e2] = __floats2bfloat162_rn(ok ? v[j * 8 + 2 * e2] : 0.f, ok ? v[j * 8 + 2 * e2 + 1] : 0.f);
+            h[e2] = __floats2bfloat162_rn(ok ? __uint_as_float(raw[j * 8 + 2 * e2]) * inv_l : 0.f,
+                                          ok ? __uint_as_float(raw[j * 8 + 2 * e2 + 1]) * inv_l : 0.f);
           }
           *reinterpret_cast<uint4*>(tpack + ch * 128) = *reinterpret_cast<uint4*>(h);
         }
       }
-      if (a.out == nullptr) continue;                               // inference: the fp32 T is only saved for the backward pass
+      if (obase == nullptr) continue;                               // inference: the fp32 T is only saved for the backward pass
     }
     // transpose through this warp's buffer: thread = row  ->  8 lanes x float4 = 128 contiguous bytes of one row
 #pragma unroll
     for (int i = 0; i < 32; i += 4)
-      *reinterpret_cast<float4*>(ebuf + lane * EPI_STRIDE + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      *reinterpret_cast<float4*>(ebuf + lane * EPI_STRIDE + i) =
+          make_float4(__uint_as_float(raw[i]) * inv_l, __uint_as_float(raw[i + 1]) * inv_l, __uint_as_float(raw[i + 2]) * inv_l,
+                      __uint_as_float(raw[i + 3]) * inv_l);
     __syncwarp();
+    const int nv = col_ok ? nvalid : 0;
     float4 cv[8];
-    if (KIND != Q2C) {                                              // the c values this chunk multiplies (v's registers are free now)
-      const float* cp = a.c_src + (row0 + rsub) * d + col0 + c4;
+    if (KIND != Q2C) {                                              // the c values this chunk multiplies (raw's registers are free now)
+      const float* cp = cbase + col0;
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         cv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr * 4 + rsub < wrows && col_ok) cv[rr] = __ldg(reinterpret_cast<const float4*>(cp + (size_t)rr * 4 * d));
+        if (rr < nv) cv[rr] = __ldg(reinterpret_cast<const float4*>(cp));
+        cp += cinc;
       }
     }
-    float* op = a.out + (row0 + rsub) * ostride + (KIND == C2QA ? d : KIND == C2QB ? 3 * d : 0) + col0 + c4;
-    float* bp = (KIND == C2QB && a.bm) ? a.bm + (row0 + rsub) * d + col0 + c4 : nullptr;
+    float* op = obase + col0;
+    float* bp = bbase ? bbase + col0 : nullptr;
+    const float* erow = ebuf + rsub * EPI_STRIDE + c4;
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) {
-      if (rr * 4 + rsub < wrows && col_ok) {
-        const float4 o = *reinterpret_cast<const float4*>(ebuf + (rr * 4 + rsub) * EPI_STRIDE + c4);
+      if (rr < nv) {
+        const float4 o = *reinterpret_cast<const float4*>(erow + rr * 4 * EPI_STRIDE);
         if (KIND == Q2C) {
           *reinterpret_cast<float4*>(op) = o;                       // re-read by the backward pass: default cache policy
         } else {
@@ -212,8 +227,8 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
           }
         }
       }
-      op += 4 * ostride;
-      if (KIND == C2QB) bp = bp ? bp + 4 * d : bp;
+      op += oinc;
+      if (KIND == C2QB && bp) bp += cinc;
     }
     __syncwarp();
   }
@@ -284,10 +299,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
       if (leader) item = atomicAdd(f.queue, 1);
       item = __shfl_sync(0xffffffffu, item, __ffs(__ballot_sync(0xffffffffu, leader)) - 1);
       int kind = DONE, b = 0, xblk = 0, nty = 0;
+      int canon = 0;                                                // kind-major item number (trace index)
       if (item < n_items) {
-        if (item < f.n_q2c) { kind = Q2C; b = item / f.nq; xblk = item - b * f.nq; }
-        else if (item < f.n_q2c + f.n_c2q) { kind = C2QA; const int i = item - f.n_q2c; b = i / f.nc; xblk = i - b * f.nc; }
-        else { kind = C2QB; const int i = item - f.n_q2c - f.n_c2q; b = i / f.nc; xblk = i - b * f.nc; }
+        // Queue order: Q2C and C2QA items interleaved in proportion (neither depends on anything), then the C2QB items.  With all
+        // Q2C items first every SM ran the same kind at the same time and the store phases of all SMs coincided.
+        const int n1 = f.n_q2c + f.n_c2q;
+        if (item < n1) {
+          const int qb = (int)((long long)item * f.n_q2c / n1), qa = (int)((long long)(item + 1) * f.n_q2c / n1);
+          if (qa > qb) { kind = Q2C; b = qb / f.nq; xblk = qb - b * f.nq; canon = qb; }
+          else { kind = C2QA; const int i = item - qb; b = i / f.nc; xblk = i - b * f.nc; canon = f.n_q2c + i; }
+        } else {
+          kind = C2QB;
+          const int i = item - n1;
+          b = i / f.nc;
+          xblk = i - b * f.nc;
+          canon = item;
+        }
         const KindArgs& a = f.k[kind];
         // tiles past the last un-masked Y row contribute exp(-1e30 - m) = 0 to every soft-max: stop there.  (If nothing at
         // all is un-masked the soft-max is uniform over the whole range, attention.py:94, and every tile is needed.)
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
       mbar_wait(item_empty0 + 8 * slot, ((n / ITEM_SLOTS) & 1) ^ 1);
       if (lane == 0) {
         sm.items[slot] = make_int4(kind, b, xblk, nty);
-        if (f.trace && kind != DONE) f.trace[(size_t)item * 8 + 0] = globaltimer_ns();
+        if (f.trace && kind != DONE) f.trace[(size_t)canon * 8 + 0] = globaltimer_ns();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(item_full0 + 8 * slot);            // release semantics: the slot contents are visible
@@ -543,7 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
       else epilogue_item<C2QB>(f, acc, ebuf, b, xblk, q4, eh, lane, inv_l, o_free0 + 8 * ob);
       if (kind == Q2C) {                                            // this warp's part of the T rows is in memory: one count per warp
         __syncwarp();
-        if (lane == 0) signal_counter(f.ready + b);
+        if (lane == 0) signal_release(f.ready + b);
       }
       if (f.trace && e == 0 && lane == 0) {
         long long* tr = f.trace + ((size_t)(kind == Q2C ? b * f.nq + xblk

@@ -47,6 +47,27 @@ __global__ void __launch_bounds__(CS_TX * CS_TY) col_sum_partial_kernel(const fl
   }
 }
 
+// Same row-block partial sums for any p / alignment (one float column per thread): the shapes the float4 kernel does not take
+// (p % 4 != 0 only happens for toy hidden sizes; the result goes through the same fixed-order final sum).
+__global__ void __launch_bounds__(CS_TX * CS_TY) col_sum_partial_scalar_kernel(const float* __restrict__ a, float* __restrict__ partial,
+                                                                               long long n, int p, int rows_per_block) {
+  __shared__ float red[CS_TY][CS_TX];
+  const int tx = threadIdx.x % CS_TX, ty = threadIdx.x / CS_TX;
+  const int c = blockIdx.x * CS_TX + tx;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(n, r0 + rows_per_block);
+  float acc = 0.f;
+  if (c < p)
+    for (long long r = r0 + ty; r < r1; r += CS_TY) acc += __ldg(a + r * p + c);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < p) {
+#pragma unroll
+    for (int y = 1; y < CS_TY; ++y) acc += red[y][tx];
+    partial[(size_t)blockIdx.y * p + c] = acc;
+  }
+}
+
 // out[c] = sum_r partial[r][c]: 32 columns x 8 row lanes per block (a column's R partials are summed by 8 threads with
 // independent loads, then across the lanes in a fixed order) -- one thread per column walked its R rows serially in ~11 us.
 __global__ void __launch_bounds__(256) col_sum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int p, int R) {
@@ -84,13 +105,17 @@ extern "C" int mmb_col_sum_blocks(long long n, int p) {
 
 extern "C" int mmb_col_sum(const float* a, float* partial, float* out, long long n, int p, mmb_stream_t stream) {
   MMB_REQUIRE(a && partial && out && n > 0 && p > 0, MMB_ERR_INVALID, "mmb_col_sum: bad arguments");
-  MMB_REQUIRE(p % 4 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0,
-              MMB_ERR_UNSUPPORTED, "mmb_col_sum: p=%d must be a multiple of 4 and the buffers 16-byte aligned", p);
+  const bool vec = p % 4 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0;
   const int R = mmb_col_sum_blocks(n, p);
   const int rows_per_block = (int)((n + R - 1) / R);
-  const int col_blocks = (p + 4 * mmb::CS_TX - 1) / (4 * mmb::CS_TX);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  mmb::col_sum_partial_kernel<<<dim3(col_blocks, R), mmb::CS_TX * mmb::CS_TY, 0, st>>>(a, partial, n, p, rows_per_block);
+  if (vec) {
+    const int col_blocks = (p + 4 * mmb::CS_TX - 1) / (4 * mmb::CS_TX);
+    mmb::col_sum_partial_kernel<<<dim3(col_blocks, R), mmb::CS_TX * mmb::CS_TY, 0, st>>>(a, partial, n, p, rows_per_block);
+  } else {
+    const int col_blocks = (p + mmb::CS_TX - 1) / mmb::CS_TX;
+    mmb::col_sum_partial_scalar_kernel<<<dim3(col_blocks, R), mmb::CS_TX * mmb::CS_TY, 0, st>>>(a, partial, n, p, rows_per_block);
+  }
   if (int rc = mmb::check_launch("col_sum_partial_kernel")) return rc;
   mmb::col_sum_final_kernel<<<(p + 31) / 32, 256, 0, st>>>(partial, out, p, R);
   return mmb::check_launch("col_sum_final_kernel");

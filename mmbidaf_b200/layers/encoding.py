@@ -50,34 +50,127 @@ class Embedding(nn.Module):
         return self.hwy(Fn.tall_linear(x, self.proj.weight))     # Linear(E -> H, no bias); batched weight gradient
 
 
-class _LengthCache:
-    """Host list of lengths -> (int32 device lengths, int32 device order, int64 device sort index).
+class LengthPlan:
+    """Device-side view of ONE host list of lengths (the reference passes lengths as Python lists, datasets.py:300-302).
 
-    The sort index is computed exactly as the reference does (encoding.py:85,91: a CPU float tensor
-    sorted with torch.sort descending) because the rows of the returned hidden state keep that order."""
+    ``packed`` (2, B) int64 = [lengths, sort index]; the sort index is computed exactly as the reference does (encoding.py:85,91:
+    a CPU float tensor sorted with torch.sort descending) because the rows of the returned hidden state keep that order (quirk
+    Q3) and that sort's tie order is not reproducible elsewhere (it is not stable; csrc/length_plan.cu).  Everything else is made
+    on the device from the lengths by one small kernel per mask shape (``ops.length_plan``): int32 lengths, the longest-first
+    scheduling order of the recurrences, position masks and the decoder mask (models.py:86-92, :119-123).
+
+    A *static* plan keeps every device tensor at a fixed address: ``update`` rewrites the lengths (pinned host ring -> H2D) and
+    ``refresh`` re-launches the kernels, so a captured CUDA graph that contains the ``refresh`` launches serves any batch."""
+
+    RING = 4
+
+    def __init__(self, lengths, device, static: bool = False):
+        n = len(lengths)
+        self.device, self.static = device, static
+        self.packed = torch.empty(2, n, dtype=torch.int64, device=device)
+        self.len_i32 = torch.empty(n, dtype=torch.int32, device=device)
+        self.order_i32 = torch.empty(n, dtype=torch.int32, device=device)
+        self.masks = {}
+        self._host = [torch.empty(2, n, dtype=torch.int64).pin_memory() for _ in range(self.RING)] if static else None
+        self._events = [None] * self.RING
+        self._turn = 0
+        self.update(lengths)
+        self.refresh()
+
+    @property
+    def sort_idx(self):
+        return self.packed[1]
+
+    def update(self, lengths) -> None:
+        """Host side of a new list of lengths: the reference's own sort, then one small H2D copy (stream ordered)."""
+        vals = [int(v) for v in lengths]
+        if len(vals) != self.packed.shape[1]:
+            raise ValueError(f"LengthPlan.update: {len(vals)} lengths for a plan of {self.packed.shape[1]}")
+        sort_idx = torch.Tensor(vals).sort(0, descending=True)[1]                 # encoding.py:85, :91
+        if self.static:
+            slot = self._turn % self.RING
+            self._turn += 1
+            if self._events[slot] is not None:
+                self._events[slot].synchronize()                                   # the copy that last read this pinned slot
+            host = self._host[slot]
+            host[0] = torch.tensor(vals, dtype=torch.int64)
+            host[1] = sort_idx
+            self.packed.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._events[slot] = ev
+        else:
+            self.packed.copy_(torch.stack([torch.tensor(vals, dtype=torch.int64), sort_idx]), non_blocking=True)
+
+    def refresh(self) -> None:
+        """Device side: everything derived from the lengths, into the same tensors (capturable)."""
+        from .. import ops
+        self.len_i32.copy_(self.packed[0])
+        ops.length_plan(self.len_i32, 0, 0, out=(None, None, self.order_i32))
+        for (L, M), (mask, dec) in self.masks.items():
+            ops.length_plan(self.len_i32, L, M, out=(mask, dec, None))
+
+    def mask(self, L: int, M: int = 0):
+        """(mask (B, L) bool, decoder mask (B, M) bool or None); made once per shape, re-made by ``refresh``."""
+        from .. import ops
+        hit = self.masks.get((L, M))
+        if hit is None:
+            mask, dec, _ = ops.length_plan(self.len_i32, L, M)
+            hit = self.masks[(L, M)] = (mask, dec)
+        return hit
+
+
+class _LengthCache:
+    """Host list of lengths -> LengthPlan.  Plans are cached per distinct list of values; ``pin`` registers a static plan for one
+    particular list OBJECT (looked up by identity first), which is how a graph-captured step keeps its length tensors."""
 
     def __init__(self):
         self._store = {}
+        self._pins = {}
 
-    def get(self, lengths, device):
+    def get(self, lengths, device) -> LengthPlan:
+        pin = self._pins.get(id(lengths))
+        if pin is not None and pin[0] is lengths:
+            return pin[1]
         key = (tuple(int(v) for v in lengths), str(device))
         hit = self._store.get(key)
         if hit is None:
             if len(self._store) > 64:
                 self._store.clear()
-            sort_idx = torch.Tensor(list(key[0])).sort(0, descending=True)[1]
-            packed = torch.stack([torch.tensor(key[0], dtype=torch.int64), sort_idx]).to(device, non_blocking=True)
-            hit = (packed[0].to(torch.int32), packed[1].to(torch.int32), packed[1])
-            self._store[key] = hit
+            hit = self._store[key] = LengthPlan(key[0], device)
         return hit
+
+    def pin(self, lengths, device) -> LengthPlan:
+        pin = self._pins.get(id(lengths))
+        if pin is None or pin[0] is not lengths:
+            pin = self._pins[id(lengths)] = (lengths, LengthPlan(lengths, device, static=True))
+        return pin[1]
+
+    def unpin(self, lengths) -> None:
+        pin = self._pins.get(id(lengths))
+        if pin is not None and pin[0] is lengths:
+            del self._pins[id(lengths)]
 
 
 _lengths = _LengthCache()
 
 
+def length_plan(lengths, device) -> LengthPlan:
+    return _lengths.get(lengths, device)
+
+
+def pin_lengths(lengths, device) -> LengthPlan:
+    """A static plan for this list object (see LengthPlan); the caller keeps the returned plan alive."""
+    return _lengths.pin(lengths, device)
+
+
+def unpin_lengths(lengths) -> None:
+    _lengths.unpin(lengths)
+
+
 def device_lengths(lengths, device):
     """int32 device tensor of a host list of lengths (cached per distinct list)."""
-    return _lengths.get(lengths, device)[0]
+    return _lengths.get(lengths, device).len_i32
 
 
 class RNNEncoder(nn.Module):
@@ -103,15 +196,15 @@ class RNNEncoder(nn.Module):
     def forward(self, x, lengths):
         if not x.is_cuda:
             raise RuntimeError("mmbidaf_b200.layers.RNNEncoder runs on a B200 only (no CPU fallback)")
-        len_dev, order_dev, sort_idx = _lengths.get(lengths, x.device)
+        plan = _lengths.get(lengths, x.device)
         finals = []
         for k in range(self.num_layers):
-            x, h_n = Fn.lstm_layer(x, len_dev, order_dev, self._layer_weights(k))
+            x, h_n = Fn.lstm_layer(x, plan.len_i32, plan.order_i32, self._layer_weights(k))
             finals.append(h_n)
             if k + 1 < self.num_layers:                       # nn.LSTM's inter-layer dropout
                 x = F.dropout(x, self.rnn.dropout, self.training)
         x = F.dropout(x, self.drop_prob, self.training)       # encoding.py:104
-        x_hidden = torch.cat(finals, dim=1).index_select(0, sort_idx)
+        x_hidden = torch.cat(finals, dim=1).index_select(0, plan.sort_idx)
         return x, x_hidden
 
 

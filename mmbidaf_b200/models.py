@@ -87,9 +87,8 @@ class MMBiDAF(nn.Module):
 
     def get_mask(self, X, X_len):
         """bool (B, L): position < length, on X's device (reference models.py:86-92 builds it on the CPU)."""
-        from .layers.encoding import device_lengths
-        lens = device_lengths(X_len, X.device)        # cached: no host->device copy after the first call
-        return torch.arange(X.size(1), device=X.device).unsqueeze(0) < lens.unsqueeze(1)
+        from .layers.encoding import length_plan
+        return length_plan(X_len, X.device).mask(X.size(1))[0]      # one kernel from the device lengths (csrc/length_plan.cu)
 
     def forward(self, embedded_text, original_text_lengths, embedded_audio, original_audio_lengths, transformed_images,
                 original_image_lengths, batch_target_indices, original_target_len, max_dec_len):
@@ -110,12 +109,12 @@ class MMBiDAF(nn.Module):
         masks = {}
 
         def make_masks():                        # needs only the lengths: issued beside the encoders
-            masks["text"] = self.get_mask(embedded_text, original_text_lengths)
+            from .layers.encoding import length_plan
+            # text mask and decoder mask (the text mask zero-padded to max_transcript_length, models.py:119-123): one launch
+            masks["text"], masks["decoder"] = length_plan(original_text_lengths, embedded_text.device).mask(
+                Lt, self.max_transcript_length)
             masks["audio"] = self.get_mask(embedded_audio, original_audio_lengths)
             masks["image"] = self.get_mask(transformed_images, original_image_lengths)     # (B, Li, ...): same (B, Li)
-            dm = torch.zeros(B, self.max_transcript_length, dtype=torch.bool, device=embedded_text.device)
-            dm[:, :Lt] = masks["text"]                                     # models.py:121-123
-            masks["decoder"] = dm
 
         (audio_encoded,), (text_emb, text_encoded), (image_emb, image_encoded) = \
             self._fork_join([audio_branch, text_branch, image_branch], meanwhile=make_masks)

@@ -287,8 +287,8 @@ def col_sum(a: torch.Tensor) -> torch.Tensor:
     """out (p) = a.sum(dim=0) for a tall (n, p) fp32 matrix: the bias gradients of the step (deterministic two-stage
     kernel, HBM-bound; ATen's dim-0 reduction runs at 0.4 - 1.3 TB/s on these shapes)."""
     n, p = a.shape
-    if p % 4 != 0 or n == 0:
-        return a.sum(dim=0)                       # plain library reduction for shapes the kernel does not take
+    if n == 0 or p == 0:
+        raise RuntimeError(f"col_sum: empty matrix {tuple(a.shape)}")
     lib = _lib.lib()
     a = a.contiguous()
     R = lib.mmb_col_sum_blocks(n, p)
@@ -297,6 +297,24 @@ def col_sum(a: torch.Tensor) -> torch.Tensor:
     _lib.check(lib.mmb_col_sum(_lib.ptr(a), _lib.ptr(partial), _lib.ptr(out), n, p, _lib.stream()), "mmb_col_sum")
     _count(2)
     return out
+
+
+def length_plan(lengths: torch.Tensor, L: int, M: int = 0, want_order: bool = False, out=None):
+    """One launch from int32 device lengths (B): mask (B, L) bool, decoder mask (B, M) bool (if M), scheduling order (B) int32
+    (if want_order) -- models.py:86-92, :119-123.  ``out`` = (mask, dec_mask, order) re-uses existing tensors (graph replay)."""
+    lib = _lib.lib()
+    assert lengths.dtype == torch.int32 and lengths.is_cuda
+    B = lengths.numel()
+    if out is None:
+        mask = torch.empty(B, L, dtype=torch.bool, device=lengths.device)
+        dec = torch.empty(B, M, dtype=torch.bool, device=lengths.device) if M else None
+        order = torch.empty(B, dtype=torch.int32, device=lengths.device) if want_order else None
+    else:
+        mask, dec, order = out
+    _lib.check(lib.mmb_length_plan(_lib.ptr(lengths), _lib.ptr(mask), _lib.ptr(dec), _lib.ptr(order), B, L, M if dec is not None else 0,
+                                   _lib.stream()), "mmb_length_plan")
+    _count(1)
+    return mask, dec, order
 
 
 def adadelta_clip_step(param: torch.Tensor, grad: torch.Tensor, square_avg: torch.Tensor, acc_delta: torch.Tensor,

@@ -28,13 +28,18 @@ def shard_range(n_items: int, rank: int, world: int) -> range:
 
 
 def shard_batch(batch: Batch, rank: int, world: int) -> Batch:
-    """This rank's videos, re-padded to the shard's own maximum lengths (padding is masked / never visited)."""
+    """This rank's videos.  Audio and key-frames are re-padded to the shard's own maxima: their padding is masked in both
+    BiDAF soft-maxes (attention.py:43-44) and never visited by the recurrences.  Text and targets keep the GLOBAL batch's
+    padded widths: the decoder's two attention soft-maxes and its coverage term run over every padded text position
+    (attention.py:148,154, quirk Q2), and the loss is averaged over the padded number of decode steps with padded steps scoring
+    sentence 0 (models.py:168,179, quirk Q4) -- a narrower shard would change alpha, the loss and every gradient, and the summed
+    rank gradients would no longer be the single-process gradient of the global batch."""
     idx = list(shard_range(len(batch.text_len), rank, world))
     pick = lambda xs: [xs[i] for i in idx]
     tl, al, il, gl = pick(batch.text_len), pick(batch.audio_len), pick(batch.image_len), pick(batch.target_len)
     sel = torch.tensor(idx, dtype=torch.long)
-    return Batch(batch.text[sel, :max(tl)].contiguous(), tl, batch.audio[sel, :max(al)].contiguous(), al,
-                 batch.images[sel, :max(il)].contiguous(), il, batch.targets[sel, :max(gl)].contiguous(), gl, max(gl))
+    return Batch(batch.text[sel].contiguous(), tl, batch.audio[sel, :max(al)].contiguous(), al,
+                 batch.images[sel, :max(il)].contiguous(), il, batch.targets[sel].contiguous(), gl, batch.max_dec_len)
 
 
 class FlatState:
@@ -127,7 +132,11 @@ class Trainer:
         the captured input tensors and replays.  Dropout draws fresh masks on every replay (torch's generator
         is graph-aware)."""
         import gc
+        from .layers.encoding import pin_lengths
         self._static = batch
+        # static length tensors (kept alive here): the captured kernels read lengths, masks and orders from fixed addresses that
+        # step_graphed() rewrites for every new batch
+        self._plans = [pin_lengths(lst, batch.text.device) for lst in (batch.text_len, batch.audio_len, batch.image_len)]
         # drop per-sequence caches that still own tensors (and stream-usage records) from eager steps, so that
         # nothing created on another stream is released while the capture is in flight
         for m in self.model.modules():
@@ -153,9 +162,14 @@ class Trainer:
     def step_graphed(self, batch: Optional[Batch] = None) -> torch.Tensor:
         if batch is not None and batch is not self._static:
             s = self._static
-            if (batch.text_len, batch.audio_len, batch.image_len, batch.target_len) != \
-                    (s.text_len, s.audio_len, s.image_len, s.target_len):
-                raise ValueError("step_graphed: lengths differ from the captured batch; call capture() again")
+            same_bucket = all(a.shape == b.shape for a, b in ((batch.text, s.text), (batch.audio, s.audio),
+                                                              (batch.images, s.images), (batch.targets, s.targets)))
+            if not same_bucket or batch.max_dec_len != s.max_dec_len:
+                raise ValueError("step_graphed: padded shapes differ from the captured batch (another bucket); call capture() again")
+            # any lengths of the same bucket: the graph reads them from the static plans (datasets.py:298-302 pads every batch to
+            # its own maxima, so a training run needs one capture per padded-shape bucket, not per batch)
+            for plan, lens in zip(self._plans, (batch.text_len, batch.audio_len, batch.image_len)):
+                plan.update(lens)
             s.text.copy_(batch.text, non_blocking=True)
             s.audio.copy_(batch.audio, non_blocking=True)
             s.images.copy_(batch.images, non_blocking=True)
@@ -167,6 +181,9 @@ class Trainer:
 
     def _forward_backward(self, batch: Batch) -> torch.Tensor:
         self.model.train()
+        if batch is getattr(self, "_static", None):
+            for plan in self._plans:                     # inside the captured region: lengths -> int32, order, masks
+                plan.refresh()
         _, loss = self.model(batch.text, batch.text_len, batch.audio, batch.audio_len, batch.images, batch.image_len,
                              batch.targets, batch.target_len, batch.max_dec_len)
         # functional backward: gradients are produced fresh and packed into the flat buffer with one copy

@@ -35,13 +35,17 @@ def test_shard_range_is_a_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_shard_batch_repads_to_local_max():
+def test_shard_batch_keeps_text_and_target_padding_of_the_global_batch():
+    """Audio / key-frames are re-padded to the shard's own maxima (masked everywhere); text and targets keep the global widths:
+    the decoder's un-masked attention soft-maxes (attention.py:148,154) and the padded decode steps (models.py:168,179) see them."""
     batch = make_batch(5, 12, 20, 4, 3, seed=9)
     parts = [shard_batch(batch, r, 2) for r in range(2)]
     assert sum(len(p.text_len) for p in parts) == 5
     for p in parts:
-        assert p.text.shape[1] == max(p.text_len) and p.audio.shape[1] == max(p.audio_len)
-    assert torch.equal(parts[1].text[0, :parts[1].text_len[0]], batch.text[3, :batch.text_len[3]])
+        assert p.text.shape[1] == batch.text.shape[1] and p.targets.shape[1] == batch.targets.shape[1]
+        assert p.max_dec_len == batch.max_dec_len
+        assert p.audio.shape[1] == max(p.audio_len) and p.images.shape[1] == max(p.image_len)
+    assert torch.equal(parts[1].text[0], batch.text[3]) and torch.equal(parts[1].targets[0], batch.targets[3])
 
 
 def test_flat_grads_clip_matches_torch():

@@ -33,10 +33,73 @@ def test_graphed_step_is_bit_identical_to_eager(tier):
         assert torch.isfinite(loss_e) and torch.equal(loss_e, loss_g)
         for p, q in zip(eager.model.parameters(), graphed.model.parameters()):
             assert torch.equal(p, q)
-        with pytest.raises(ValueError, match="lengths differ"):
-            graphed.step_graphed(make_batch(5, 33, 70, 9, 4, seed=12).to("cuda"))
+        with pytest.raises(ValueError, match="another bucket"):
+            graphed.step_graphed(make_batch(5, 34, 70, 9, 4, seed=12).to("cuda"))
     finally:
         mmbidaf_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("tier", ["fp32", "fast"])
+def test_graph_captured_on_one_batch_replays_other_batches_bit_identically(tier):
+    """The collator pads every batch to its own maxima and lengths change every batch (datasets.py:298-302, train.py:126-146).
+    A graph captured on batch A must serve any batch of the same padded-shape bucket: lengths, orders and masks are static
+    device tensors rewritten in place (layers/encoding.py::LengthPlan).  Sequence A, B, C, B through the graph == eager."""
+    import mmbidaf_b200
+    from mmbidaf_b200.trainer import Trainer
+    mmbidaf_b200.set_precision(tier)
+    try:
+        batches = [make_batch(5, 33, 70, 9, 4, seed=s).to("cuda") for s in (11, 12, 13)]
+        assert batches[0].text_len != batches[1].text_len and batches[1].audio_len != batches[2].audio_len
+        for b in batches[1:]:                           # same bucket: make_batch forces sample 0 to the maximum lengths
+            assert b.text.shape == batches[0].text.shape and b.max_dec_len == batches[0].max_dec_len
+        order = [0, 1, 2, 1]
+        work = torch.cuda.Stream()
+        with torch.cuda.stream(work):
+            eager, graphed = Trainer(_make()), Trainer(_make())
+            graphed.capture(batches[0], warmup=2)        # (two warm-up steps on batch A)
+            for _ in range(2):
+                eager.step(batches[0])
+            losses_e = [eager.step(batches[i]).clone() for i in order]
+            losses_g = [graphed.step_graphed(batches[i]).clone() for i in order]
+            torch.cuda.synchronize()
+        for le, lg in zip(losses_e, losses_g):
+            assert torch.isfinite(le) and torch.equal(le, lg)
+        assert len({float(v) for v in losses_e}) > 1       # the batches really differ
+        for p, q in zip(eager.model.parameters(), graphed.model.parameters()):
+            assert torch.equal(p, q)
+    finally:
+        mmbidaf_b200.set_precision("fp32")
+
+
+def test_length_plan_kernel_bit_exact_masks_and_stable_order():
+    """csrc/length_plan.cu against models.py:86-92 (get_mask) and :119-123 (decoder mask), and the stable longest-first order."""
+    from mmbidaf_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    for B, L, M in ((1, 1, 0), (3, 7, 11), (32, 409, 409), (5, 33, 64), (64, 1024, 0), (257, 3, 5)):
+        lens = torch.randint(0, L + 1, (B,), generator=gen)
+        lens[0] = L
+        dev = lens.to(torch.int32).cuda()
+        mask, dec, order = ops.length_plan(dev, L, M, want_order=True)
+        idx = torch.arange(L).unsqueeze(0).expand(B, L)
+        want = idx < lens.unsqueeze(1)                                               # models.py:88-91
+        assert mask.dtype == torch.bool and torch.equal(mask.cpu(), want)
+        if M:
+            want_dec = torch.cat((want, torch.zeros(B, M - L).type(want.type())), dim=1)   # models.py:121-123
+            assert torch.equal(dec.cpu(), want_dec)
+        else:
+            assert dec is None
+        stable = sorted(range(B), key=lambda i: -int(lens[i]))
+        assert order.cpu().tolist() == stable
+
+
+def test_col_sum_any_width():
+    from mmbidaf_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    for n, p in ((1000, 10), (33, 7), (4096, 800), (5, 1), (70000, 12)):
+        a = torch.randn(n, p, generator=gen).cuda()
+        got = ops.col_sum(a)
+        want = a.double().sum(dim=0)
+        assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-4
 
 
 def test_training_reduces_the_loss_and_keeps_parameters_aligned():

@@ -40,6 +40,27 @@ __global__ void __launch_bounds__(256) k_bulk(float* out, long long nrows, int n
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
+// mode 4 / 5: the store pattern of the persistent forward's epilogue (csrc/bidaf_fwd_tc4.cu): a warp owns 32 rows and sweeps them in
+// 32-column chunks; one instruction writes 4 rows x 128 bytes (8 lanes x float4 per row); default (4) or .cs (5) stores.
+template <int CS>
+__global__ void __launch_bounds__(256) k_epi(float* out, long long nrows, int nblk) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
+  const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+  for (long long g = warp; g < nrows / 32; g += nwarps)
+    for (int cc = 0; cc < 7; ++cc) {
+      if (cc * 32 + c4 >= BLK_FLOATS) continue;
+      float* p = out + (g * 32 + rsub) * ROW_FLOATS + BLK_FLOATS + cc * 32 + c4;
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        for (int b = 0; b < nblk; ++b) {
+          if (CS) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + b * BLK_FLOATS), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
+          else *reinterpret_cast<float4*>(p + b * BLK_FLOATS) = make_float4(1.f, 2.f, 3.f, 4.f);
+        }
+        p += 4 * ROW_FLOATS;
+      }
+    }
+}
 __global__ void __launch_bounds__(256) k_fill(float4* out, long long n4) {
   const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) out[i] = v;
@@ -57,14 +78,16 @@ int main() {
   cudaFuncSetAttribute(k_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * BLK_FLOATS * 4);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int mode = 0; mode < 4; ++mode)
-    for (int ctas : {148, 296, 592, 1184, 2368}) {
+  for (int mode = 0; mode < 6; ++mode)
+    for (int ctas : {148, 592, 2368}) {
       float best = 1e9f;
       for (int it = 0; it < 4; ++it) {
         cudaEventRecord(e0);
         if (mode == 0) k_runs<<<ctas, 256>>>(out, nrows, 3);
         if (mode == 1) k_bulk<<<ctas, 256, 64 * BLK_FLOATS * 4>>>(out, nrows, 3);
         if (mode == 2) k_fill<<<ctas, 256>>>(reinterpret_cast<float4*>(out), nrows * ROW_FLOATS / 4);
+        if (mode == 4) k_epi<0><<<ctas, 256>>>(out, nrows, 3);
+        if (mode == 5) k_epi<1><<<ctas, 256>>>(out, nrows, 3);
         if (mode == 3) k_copy<<<ctas, 256>>>(reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(in), nrows * ROW_FLOATS / 4);
         cudaEventRecord(e1);
         cudaError_t e = cudaDeviceSynchronize();
@@ -73,10 +96,11 @@ int main() {
         cudaEventElapsedTime(&ms, e0, e1);
         if (it > 0 && ms < best) best = ms;
       }
-      const double bytes = mode <= 1 ? (double)nrows * 3 * BLK_FLOATS * 4 : (double)nrows * ROW_FLOATS * 4 * (mode == 3 ? 2 : 1);
+      const double bytes = (mode <= 1 || mode >= 4) ? (double)nrows * 3 * BLK_FLOATS * 4 : (double)nrows * ROW_FLOATS * 4 * (mode == 3 ? 2 : 1);
       printf("mode %d ctas %4d: %.1f us, %.2f TB/s (%s)\n", mode, ctas, best * 1e3, bytes / (best * 1e-3) / 1e12,
              mode == 0 ? "STG.128 800-byte runs x3 per 3200-byte row" : mode == 1 ? "cp.async.bulk 800-byte runs x3 per row"
-             : mode == 2 ? "contiguous fill" : "contiguous copy, read+write");
+             : mode == 2 ? "contiguous fill" : mode == 3 ? "contiguous copy, read+write" : mode == 4 ? "epilogue pattern: 4 rows x 128 B per instruction"
+             : "epilogue pattern, st.global.cs");
     }
   return 0;
 }

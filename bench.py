@@ -2,18 +2,26 @@
 """bench.py -- MMBiDAF training throughput on B200 (BASELINE.json metric) + fused-BiDAF roofline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                # our arm (N>1: launched by torchrun)
-    python bench.py --impl reference [--steps K] [--warmup W]          # the reference algorithm on the host CPU
+    python bench.py --impl reference [--steps K] [--warmup W]          # the reference's own code on the host CPU
 
 One "step" = one pass of the hot path over one batch of synthetic Coursera-shaped videos:
 forward -> loss.backward() -> gradient all-reduce(SUM) -> clip_grad_norm_(2.0) -> Adadelta(lr 0.5).step()
 (reference train.py:146-155) on BASELINE config 3 (B=32 videos per GPU, Lt<=409, La<=1024, Li<=128,
 T_dec<=12, hidden 100, text 300 / audio 128 / image 1000, drop 0.2).  At N GPUs every rank runs the same
-per-GPU batch (weak scaling; N=8 is BASELINE config 4's global batch of 256).
+per-GPU batch (weak scaling; N=8 is BASELINE config 4's global batch of 256); `cfg4_strong` in the same line is
+config 4 as stated: a global batch of 256 sharded 256/N per GPU.
 
-One JSON line on stdout (rank 0).  value = videos/s with inputs resident in HBM; e2e = the same step fed
-from pinned host memory with the loss read back every step; roofline = the fused BiDAF forward on BASELINE
-config 2 (B=64, Lc=512, Lq=256, d=200) timed with CUDA events in this run against the measured HBM peak;
-cpu_baseline = the oracle port of the reference algorithm timed on this box's host cores.
+One JSON line on stdout (rank 0).
+  value        videos/s, inputs resident in HBM, the step replayed from CUDA graphs over FOUR rotating batches with different
+               length draws (the collator pads every batch to its own maxima and lengths change every batch, datasets.py:298-302)
+  e2e          the same step fed from pinned host memory (H2D inside the timed region), loss read back every step
+  no_graph     the same step launched kernel by kernel from Python (no CUDA graph)
+  fp32_tier    the rel <= 1e-5 tier (fp32 FFMA BiDAF kernels, fp32 library GEMMs)
+  roofline     the fused BiDAF forward on BASELINE config 2 (B=64, Lc=512, Lq=256, d=200), CUDA events in this run, against
+               the measured HBM peak; its backward beside it
+  cfg5         long-lecture evaluate.py-style decoding (B=16, Lt=La=4096, Li=2048, 16 greedy steps, no_grad)
+  eager_cuda   the UNMODIFIED reference (oracle/_ref, staged by oracle/stage_ref.py) in torch eager on the same B200
+  cpu_baseline the unmodified reference on this box's host cores (bounded sample)
 """
 from __future__ import annotations
 
@@ -33,8 +41,11 @@ sys.path.insert(0, ROOT)
 HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, M = 100, 300, 128, 1000, 409
 CFG3 = dict(batch=32, lt=409, la=1024, li=128, t_dec=12)            # per GPU
 CFG2 = dict(batch=64, lc=512, lq=256, d=200)
+CFG4_GLOBAL = 256
+CFG5 = dict(batch=16, lt=4096, la=4096, li=2048, m=4096, steps=16)
 DROP = 0.2                                                           # train.py:209
 METRIC, UNIT = "mmbidaf_train_videos_per_s", "videos/s"
+N_ROTATE = 4
 
 
 def measured_peaks():
@@ -99,68 +110,116 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def workload_config(n_gpus: int, **over):
+    cfg = {"workload": "BASELINE config 3: full MMBiDAF training step (embedding->RNNEncoder->BiDAFx2->mod-LSTM->"
+                       "multimodal attention decoder->loss; backward; clip 2.0; Adadelta lr 0.5)",
+           "per_gpu_batch": CFG3["batch"], "global_batch": CFG3["batch"] * n_gpus, "max_text_len": CFG3["lt"],
+           "max_audio_len": CFG3["la"], "max_image_len": CFG3["li"], "max_dec_len": CFG3["t_dec"], "hidden": HIDDEN,
+           "embed": [E_TEXT, E_AUDIO, E_IMAGE], "max_transcript_length": M, "drop_prob": DROP,
+           "parallelism": f"dp{n_gpus}",
+           "launch": f"step captured once into CUDA graphs (one padded-shape bucket) and replayed over {N_ROTATE} rotating batches "
+                     "with different length draws",
+           "l2": "inputs+activations per step exceed L2 (126 MB); BiDAF microbench rotates 4 input sets (4 x 144 MB)"}
+    cfg.update(over)
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm (the reference is Python and cannot travel to the
-# GPU box).  The only place besides tests/ and smoke() that executes oracle/.
+# The reference itself (oracle/_ref: the unmodified models.py + layers/, staged by oracle/stage_ref.py) -- on the host CPU
+# (--impl reference, cpu_baseline) and in torch eager on the GPU (eager_cuda).  If the staged copy is missing the CPU legs
+# fall back to the oracle's functional port (kind "port").  The only place besides tests/ and smoke() that executes oracle/.
 # ------------------------------------------------------------------------------------------------------
-def cpu_training_throughput(videos_per_step: int, steps: int, warmup: int):
+def _reference_step_fn(device, batch_size: int, drop: float):
     from mmbidaf_b200.synth import make_batch
-    from oracle import mmbidaf_oracle as O
+    from oracle import ref_loader
+    torch.manual_seed(224)
+    model = ref_loader.build_model("reference", HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, device, drop, M)
+    model.train()
+    opt = torch.optim.Adadelta(model.parameters(), lr=0.5)                      # train.py:110
+    batches = [make_batch(batch_size, CFG3["lt"], CFG3["la"], CFG3["li"], CFG3["t_dec"], E_TEXT, E_AUDIO, E_IMAGE,
+                          seed=224 + i).to(device) for i in range(N_ROTATE)]
+    state = {"k": 0}
+
+    def step():
+        b = batches[state["k"] % N_ROTATE]
+        state["k"] += 1
+        opt.zero_grad()
+        _, loss = model(b.text, b.text_len, b.audio, b.audio_len, b.images, b.image_len, b.targets, b.target_len, b.max_dec_len)
+        loss.backward()                                                         # train.py:148
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 2.0)                 # train.py:154
+        opt.step()
+        return loss
+    return step
+
+
+def cpu_training_throughput(videos_per_step: int, steps: int, warmup: int):
+    """-> (videos/s, ms/step, cores, kind, sample description)."""
+    from oracle import ref_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = {k: v.clone().requires_grad_(True) for k, v in O.make_params(HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, M).items()}
-    plist = list(params.values())
-    opt = torch.optim.Adadelta(plist, lr=0.5)
-    batch = make_batch(videos_per_step, CFG3["lt"], CFG3["la"], CFG3["li"], CFG3["t_dec"], E_TEXT, E_AUDIO, E_IMAGE, seed=224)
-    img = batch.images.flatten(2)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        _, loss = O.mmbidaf_forward(params, batch.text, batch.text_len, batch.audio, batch.audio_len, img,
-                                    batch.image_len, batch.targets, batch.max_dec_len, M, training=True, fast_lstm=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(plist, 2.0)
-        opt.step()
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    total = sum(times)
-    sample = (f"{videos_per_step} videos/step of config 3 shapes (Lt<=409, La<=1024, Li<=128, T_dec<=12), "
-              f"{steps} timed + {warmup} warm-up steps, fwd+bwd+clip+Adadelta, fp32, dropout off, torch CPU {torch.__version__}")
-    return videos_per_step * steps / total, total / steps * 1e3, cores, sample
+    shapes = (f"{videos_per_step} videos/step of config 3 shapes (Lt<=409, La<=1024, Li<=128, T_dec<=12), {N_ROTATE} rotating batches, "
+              f"{steps} timed + {warmup} warm-up steps, fwd+bwd+clip+Adadelta, fp32, dropout {DROP}, torch CPU {torch.__version__}")
+    if ref_loader.available():
+        step = _reference_step_fn(torch.device("cpu"), videos_per_step, DROP)
+        kind, what = "reference", "the unmodified reference (oracle/_ref/models.py + layers/, nn.LSTM on PackedSequence): "
+    else:                                                                       # staged copy missing: the functional port
+        from mmbidaf_b200.synth import make_batch
+        from oracle import mmbidaf_oracle as O
+        params = {k: v.clone().requires_grad_(True) for k, v in O.make_params(HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, M).items()}
+        plist = list(params.values())
+        opt = torch.optim.Adadelta(plist, lr=0.5)
+        batch = make_batch(videos_per_step, CFG3["lt"], CFG3["la"], CFG3["li"], CFG3["t_dec"], E_TEXT, E_AUDIO, E_IMAGE, seed=224)
+        img = batch.images.flatten(2)
+
+        def step():
+            opt.zero_grad()
+            _, loss = O.mmbidaf_forward(params, batch.text, batch.text_len, batch.audio, batch.audio_len, img, batch.image_len,
+                                        batch.targets, batch.max_dec_len, M, training=True, fast_lstm=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(plist, 2.0)
+            opt.step()
+        kind, what = "port", "oracle port (oracle/_ref not staged; dropout off): "
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    total = time.perf_counter() - t0
+    return videos_per_step * steps / total, total / steps * 1e3, cores, kind, what + shapes
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vps, ms, cores, sample = cpu_training_throughput(4, args.steps, args.warmup)
+    vps, ms, cores, kind, sample = cpu_training_throughput(CFG3["batch"], args.steps, max(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": round(vps, 4), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": round(vps, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.gpus, parallelism="host CPU, one process", global_batch=CFG3["batch"],
+                                      launch="torch eager on the host CPU (the reference's own code path), all host threads",
+                                      l2="n/a (CPU)"),
+            "cpu_baseline": {"value": round(vps, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(vps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(n_gpus: int):
-    return {"workload": "BASELINE config 3: full MMBiDAF training step (embedding->RNNEncoder->BiDAFx2->mod-LSTM->"
-                        "multimodal attention decoder->loss; backward; clip 2.0; Adadelta lr 0.5)",
-            "per_gpu_batch": CFG3["batch"], "global_batch": CFG3["batch"] * n_gpus, "max_text_len": CFG3["lt"],
-            "max_audio_len": CFG3["la"], "max_image_len": CFG3["li"], "max_dec_len": CFG3["t_dec"], "hidden": HIDDEN,
-            "embed": [E_TEXT, E_AUDIO, E_IMAGE], "max_transcript_length": M, "drop_prob": DROP,
-            "parallelism": f"dp{n_gpus}", "launch": "whole step captured once into a CUDA graph and replayed", "l2": "inputs+activations per step exceed L2 (126 MB); BiDAF microbench rotates 4 input sets"}
 
 
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
-def bidaf_microbench(device, iters: int, warmup: int, precision: int, backward: bool = False):
-    """Fused BiDAF forward (or backward) on BASELINE config 2; returns (avg seconds per call, algorithmic bytes)."""
-    from mmbidaf_b200 import ops
+def _event_time(fn, iters: int) -> float:
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(iters):
+        fn()
+    end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / 1e3 / iters
+
+
+def _cfg2_sets(device, gen):
     B, Lc, Lq, d = CFG2["batch"], CFG2["lc"], CFG2["lq"], CFG2["d"]
-    gen = torch.Generator().manual_seed(224)
     sets = []
     for _ in range(4):                                      # 4 x 144 MB > L2: every timed forward reads cold data
         c = torch.randn(B, Lc, d, generator=gen).to(device)
@@ -170,6 +229,17 @@ def bidaf_microbench(device, iters: int, warmup: int, precision: int, backward: 
         cm = (torch.arange(Lc).unsqueeze(0) < c_len.unsqueeze(1)).to(device)
         qm = (torch.arange(Lq).unsqueeze(0) < q_len.unsqueeze(1)).to(device)
         sets.append((c, q, cm, qm))
+    return sets
+
+
+def bidaf_microbench(device, rounds: int, warmup: int, precision: int, backward: bool = False):
+    """Fused BiDAF forward (or backward) on BASELINE config 2; returns (avg seconds per call, algorithmic bytes).
+    The four calls over the four rotating input sets are captured into ONE CUDA graph and the graph is replayed: at ~50 us per
+    call the Python / ctypes overhead of launching from the host (~40 us) would otherwise be part of the measurement."""
+    from mmbidaf_b200 import ops
+    B, Lc, Lq, d = CFG2["batch"], CFG2["lc"], CFG2["lq"], CFG2["d"]
+    gen = torch.Generator().manual_seed(224)
+    sets = _cfg2_sets(device, gen)
     w = [torch.randn(d, generator=gen).to(device) * 0.1 for _ in range(3)]
     bias = torch.zeros(1, device=device)
     if backward:                                             # saved forward state + an upstream gradient per input set
@@ -183,26 +253,116 @@ def bidaf_microbench(device, iters: int, warmup: int, precision: int, backward: 
                                       s[8], s[10], precision)
     else:
         run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision)
-    for i in range(warmup):
-        run(sets[i % 4])
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(max(warmup, 3)):
+            run(sets[i % 4])
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    start.record()
-    for i in range(iters):
-        run(sets[i % 4])
-    end.record()
-    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = [run(s) for s in sets]                        # outputs stay alive in the graph's pool
+    for _ in range(3):
+        graph.replay()
+    seconds = _event_time(graph.replay, rounds) / 4
+    del keep
     algo_bytes = 4 * B * (Lc * d + Lq * d + Lc * 4 * d) + B * (Lc + Lq)
     if backward:                                            # read dX (4 Lc d), c, q; write dc, dq
         algo_bytes = 4 * B * (4 * Lc * d + 2 * Lc * d + 2 * Lq * d)
-    return start.elapsed_time(end) / 1e3 / iters, algo_bytes
+    return seconds, algo_bytes
+
+
+def measured_traffic(name: str):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu capture of this round (profiles/*.json written by
+    tools/ncu_traffic.py from `ncu --set full`), or None: never a literal in this file."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        blob = json.load(f)
+    return int(blob["dram_bytes_read"] + blob["dram_bytes_write"])
+
+
+def cfg5_timing(device):
+    """BASELINE config 5: long-lecture stress, evaluate.py:107-126 flow (eval mode, no_grad, 16 greedy steps)."""
+    from mmbidaf_b200.models import MMBiDAF
+    from mmbidaf_b200.synth import make_batch
+    c = CFG5
+    torch.manual_seed(224)
+    model = MMBiDAF(HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, device, drop_prob=DROP, max_transcript_length=c["m"]).to(device)
+    model.eval()
+    batch = make_batch(c["batch"], c["lt"], c["la"], c["li"], c["steps"], E_TEXT, E_AUDIO, E_IMAGE, seed=224).to(device)
+
+    def run():
+        with torch.no_grad():
+            return model(batch.text, batch.text_len, batch.audio, batch.audio_len, batch.images, batch.image_len, batch.targets,
+                         batch.target_len, c["steps"])
+    for _ in range(2):
+        run()
+    seconds = _event_time(run, 3)
+    d = 2 * HIDDEN
+    bidaf_bytes = sum(4 * c["batch"] * (c["lt"] * d + lq * d + c["lt"] * 4 * d) + c["batch"] * (c["lt"] + lq)
+                      for lq in (c["la"], c["li"]))
+    return {"workload": "BASELINE config 5: B=16, Lt=La=4096, Li=2048, M=4096, eval, 16 greedy steps, no_grad",
+            "ms": round(seconds * 1e3, 2), "videos_per_s": round(c["batch"] / seconds, 1),
+            "bidaf_algorithmic_bytes": bidaf_bytes}
+
+
+def eager_cuda_baselines(device):
+    """The unmodified reference modules (oracle/_ref) in torch eager on this GPU (cuBLAS + cuDNN + ATen): the library bar of
+    SURVEY.md section 2.2 -- the full config-3 training step and the BiDAF op at config 2.  PyTorch's default precision flags
+    (fp32 matmul, TF32 allowed inside cuDNN)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "oracle/_ref is not staged"}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = False, True
+    try:
+        step = _reference_step_fn(device, CFG3["batch"], DROP)
+        for _ in range(2):
+            step()
+        t_step = _event_time(step, 4)
+        _, ref_att, _ = ref_loader.load("reference")
+        gen = torch.Generator().manual_seed(224)
+        sets = _cfg2_sets(device, gen)
+        mod = ref_att.BiDAFAttention(CFG2["d"], drop_prob=DROP).to(device)
+        mod.eval()
+        k = {"i": 0}
+
+        def fwd():
+            s = sets[k["i"] % 4]
+            k["i"] += 1
+            with torch.no_grad():
+                return mod(*s)
+        for _ in range(3):
+            fwd()
+        t_fwd = _event_time(fwd, 12)
+        mod.train()
+        grads = [torch.randn(CFG2["batch"], CFG2["lc"], 4 * CFG2["d"], device=device)]
+        leaves = [(s[0].clone().requires_grad_(True), s[1].clone().requires_grad_(True), s[2], s[3]) for s in sets]
+
+        def fwd_bwd():
+            s = leaves[k["i"] % 4]
+            k["i"] += 1
+            out = mod(*s)
+            torch.autograd.grad(out, (s[0], s[1], *mod.parameters()), grads[0])
+        for _ in range(3):
+            fwd_bwd()
+        t_fb = _event_time(fwd_bwd, 8)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    return {"what": "the unmodified reference (oracle/_ref) in torch eager on the same GPU, fp32 matmul / cuDNN LSTM",
+            "step_videos_per_s": round(CFG3["batch"] / t_step, 2), "step_ms": round(t_step * 1e3, 2),
+            "bidaf_cfg2_fwd_us": round(t_fwd * 1e6, 1), "bidaf_cfg2_fwd_bwd_us": round(t_fb * 1e6, 1), "torch": torch.__version__}
 
 
 def run_gpu_arm(args):
     import torch.distributed as dist
+    import mmbidaf_b200
     from mmbidaf_b200 import ops
     from mmbidaf_b200.models import MMBiDAF
-    from mmbidaf_b200.synth import make_batch
+    from mmbidaf_b200.synth import Batch, make_batch
     from mmbidaf_b200.trainer import Trainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,15 +382,8 @@ def run_gpu_arm(args):
         finally:
             os.dup2(saved, 1)
             os.close(saved)
-    import mmbidaf_b200
     mmbidaf_b200.set_precision(args.precision)
-
-    torch.manual_seed(224)                                   # args.py:43-46
-    model = MMBiDAF(HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, device, drop_prob=DROP, max_transcript_length=M).to(device)
-    trainer = Trainer(model)
-    host = make_batch(CFG3["batch"], CFG3["lt"], CFG3["la"], CFG3["li"], CFG3["t_dec"], E_TEXT, E_AUDIO, E_IMAGE,
-                      seed=224 + rank).pin()
-    resident = host.to(device)
+    sections = set(args.sections.split(","))
 
     def barrier():
         if world > 1:
@@ -250,38 +403,70 @@ def run_gpu_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)        # max over ranks
         return float(ms.item()) / 1e3
 
+    def new_trainer(seed=224):
+        torch.manual_seed(seed)                              # args.py:43-46
+        model = MMBiDAF(HIDDEN, E_TEXT, E_AUDIO, E_IMAGE, device, drop_prob=DROP, max_transcript_length=M).to(device)
+        return Trainer(model)
+
+    def batches_of(per_gpu):
+        hosts = [make_batch(per_gpu, CFG3["lt"], CFG3["la"], CFG3["li"], CFG3["t_dec"], E_TEXT, E_AUDIO, E_IMAGE,
+                            seed=224 + 101 * rank + i).pin() for i in range(N_ROTATE)]
+        return hosts, [h.to(device) for h in hosts]
+
     work = torch.cuda.Stream(device)                         # never the legacy stream: the step is graph-captured
     torch.cuda.set_stream(work)
+    trainer = new_trainer()
+    hosts, residents = batches_of(CFG3["batch"])
+    assert len({(tuple(h.text_len), tuple(h.audio_len)) for h in hosts}) == N_ROTATE      # different length draws ...
+    assert all(h.text.shape == hosts[0].text.shape and h.max_dec_len == hosts[0].max_dec_len for h in hosts)   # ... one bucket
     launches0 = ops.launch_count
-    for _ in range(args.warmup):
-        trainer.step(resident)
+    for i in range(args.warmup):
+        trainer.step(residents[i % N_ROTATE])
     launches_per_step = (ops.launch_count - launches0) // max(args.warmup, 1)
     graphed = not args.no_graph
+    turn = {"k": 0}
     if graphed:
-        # the step is ~1200 launches (launch-bound): capture forward+backward+all-reduce+clip+Adadelta once and
-        # replay; every replay executes the same kernels (counted above) and draws fresh dropout masks
-        trainer.capture(resident, warmup=1)
-        run_resident = lambda: trainer.step_graphed()
-    else:
-        run_resident = lambda: trainer.step(resident)
-    for _ in range(2):
+        # the step is ~1200 launches (launch-bound): forward + backward + gradient pack are captured once, clip + Adadelta once
+        # (the NCCL all-reduce sits between the two graphs); every replay takes the NEXT batch: its tensors are copied into the
+        # graph's static inputs and its lengths into the static length plans (layers/encoding.py::LengthPlan)
+        trainer.capture(residents[0], warmup=1)
+
+    def run_resident():
+        b = residents[turn["k"] % N_ROTATE]
+        turn["k"] += 1
+        return trainer.step_graphed(b) if graphed else trainer.step(b)
+
+    for _ in range(N_ROTATE):
         run_resident()
     with ClockSampler(local) as clocks:
         seconds = timed(run_resident, args.steps)
     launches = launches_per_step * args.steps
     videos = CFG3["batch"] * world * args.steps
 
+    # kernel-by-kernel launch from Python of the same step (no CUDA graph), same rotating batches
+    no_graph = None
+    if graphed and "step" in sections:
+        def run_eager():
+            b = residents[turn["k"] % N_ROTATE]
+            turn["k"] += 1
+            return trainer.step(b)
+        run_eager()
+        n_eager = max(3, min(args.steps, 8))
+        t = timed(run_eager, n_eager)
+        no_graph = {"value": round(CFG3["batch"] * world * n_eager / t, 2), "unit": UNIT, "ms_per_step": round(t / n_eager * 1e3, 3),
+                    "steps": n_eager}
+
     # End-to-end: every step's inputs start in pinned host memory and its loss is read back by the host.  The copy
     # of step k+1 is issued on a side stream while step k computes (a two-slot device staging area), the way an
     # input pipeline would feed the model; all of it happens inside the timed region.
     copy_stream = torch.cuda.Stream(device)
-    slots = [host.to(device), host.to(device)]
+    slots = [hosts[0].to(device), hosts[0].to(device)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"k": 0}
 
     def prefetch(k):
-        slot = slots[k & 1]
+        slot, host = slots[k & 1], hosts[k % N_ROTATE]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[k & 1])                       # the step that last read this slot is done
             for dst, src in ((slot.text, host.text), (slot.audio, host.audio), (slot.images, host.images),
@@ -291,54 +476,121 @@ def run_gpu_arm(args):
 
     def e2e_step():
         k = state["k"]
+        slot, host = slots[k & 1], hosts[k % N_ROTATE]
         torch.cuda.current_stream().wait_event(ready[k & 1])
-        loss = trainer.step_graphed(slots[k & 1]) if graphed else trainer.step(slots[k & 1])
+        feed = Batch(slot.text, host.text_len, slot.audio, host.audio_len, slot.images, host.image_len, slot.targets,
+                     host.target_len, host.max_dec_len)
+        loss = trainer.step_graphed(feed) if graphed else trainer.step(feed)
         consumed[k & 1].record()
         prefetch(k + 1)
         state["k"] = k + 1
         return float(loss.item())                                        # D2H read of the step's loss
 
-    for ev in consumed:
-        ev.record()
-    prefetch(0)
-    sections = set(args.sections.split(","))
     e2e_seconds = float("nan")
     if "e2e" in sections:
-        for _ in range(max(1, args.warmup // 2)):
+        for ev in consumed:
+            ev.record()
+        prefetch(0)
+        for _ in range(max(2, args.warmup // 2)):
             e2e_step()
         e2e_seconds = timed(e2e_step, args.steps)
+
+    # BASELINE config 4 as stated: a global batch of 256 videos sharded over the ranks (strong scaling)
+    cfg4 = None
+    per_gpu4 = CFG4_GLOBAL // world
+    if "cfg4" in sections and graphed and per_gpu4 * world == CFG4_GLOBAL:
+        if per_gpu4 == CFG3["batch"]:
+            cfg4 = {"global_batch": CFG4_GLOBAL, "per_gpu_batch": per_gpu4, "value": round(videos / seconds, 2), "unit": UNIT,
+                    "ms_per_step": round(seconds / args.steps * 1e3, 3), "note": "identical to the main measurement at this N"}
+        else:
+            tr4 = new_trainer()
+            _, res4 = batches_of(per_gpu4)
+            for i in range(2):
+                tr4.step(res4[i])
+            tr4.capture(res4[0], warmup=1)
+            k4 = {"k": 0}
+
+            def run4():
+                k4["k"] += 1
+                return tr4.step_graphed(res4[k4["k"] % N_ROTATE])
+            for _ in range(2):
+                run4()
+            n4 = max(3, min(args.steps, 6))
+            t4 = timed(run4, n4)
+            cfg4 = {"global_batch": CFG4_GLOBAL, "per_gpu_batch": per_gpu4, "value": round(CFG4_GLOBAL * n4 / t4, 2), "unit": UNIT,
+                    "ms_per_step": round(t4 / n4 * 1e3, 3), "steps": n4, "scaling": "strong"}
+            del tr4, res4
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         fast = args.precision == "fast"
-        t_bidaf, algo = bidaf_microbench(device, 20, 5, ops.PREC_BF16 if fast else ops.PREC_FP32) \
-            if "bidaf" in sections else (float("nan"), 1)
-        achieved = algo / t_bidaf / 1e9
-        t_bwd, algo_bwd = bidaf_microbench(device, 20, 5, ops.PREC_BF16, backward=True) \
-            if "bidaf" in sections and fast else (float("nan"), 1)
+        prec = ops.PREC_BF16 if fast else ops.PREC_FP32
         line = {"metric": METRIC, "value": round(videos / seconds, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16 tcgen05 BiDAF + tf32 library GEMMs, fp32 accumulate / soft-max / LSTM" if fast else "f32",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks.summary(),
-                "e2e": {"value": round(videos / e2e_seconds, 2), "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(),
+                "e2e": {"value": round(videos / e2e_seconds, 2), "unit": UNIT, "h2d_bytes_per_step": hosts[0].h2d_bytes(),
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_seconds / args.steps * 1e3, 3)},
-                "gpu_launches": launches,
-                "roofline": {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel + bidaf_tc2_kernel: Q2C, "
-                                        "C2QA and C2QB blocks in one launch, two per SM)" if fast else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
-                                       + ", BASELINE config 2 (B=64, Lc=512, Lq=256, d=200)",
-                             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4),
-                             "traffic": 151061248 if fast else None,      # dram read+write per forward, ncu (profiles/r01_bidaf_tc_ncu.md)
-                             "peak_source": peak_src,
-                             "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1),
-                             # the fused backward (prep + P^T pass + two dS passes + reduce) of the same op, same method
-                             "backward": {"us": round(t_bwd * 1e6, 1), "algorithmic_bytes": algo_bwd,
-                                          "achieved": round(algo_bwd / t_bwd / 1e9, 1),
-                                          "frac": round(algo_bwd / t_bwd / 1e9 / peak, 4)}}}
+                "gpu_launches": launches}
+        if not graphed:
+            line["config"]["launch"] = "every kernel launched from Python (--no-graph)"
+        if no_graph is not None:
+            line["no_graph"] = no_graph
+        if cfg4 is not None:
+            line["cfg4_strong"] = cfg4
+        if "bidaf" in sections:
+            t_bidaf, algo = bidaf_microbench(device, 10, 5, prec)
+            achieved = algo / t_bidaf / 1e9
+            roof = {"kernel": ("fused BiDAF forward, tcgen05 bf16 tier (bidaf_pack_kernel + the main tcgen05 launch)" if fast
+                               else "fused BiDAF forward, fp32 tier (bidaf_pass_f32 x2)")
+                              + ", BASELINE config 2 (B=64, Lc=512, Lq=256, d=200)",
+                    "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": measured_traffic("r02_bidaf_fwd_traffic.json") if fast else None,
+                    "peak_source": peak_src, "algorithmic_bytes": algo, "us_per_forward": round(t_bidaf * 1e6, 1),
+                    "timing": "CUDA events around replays of one CUDA graph holding the 4 calls over 4 rotating input sets"}
+            if fast:
+                t_bwd, algo_bwd = bidaf_microbench(device, 10, 5, ops.PREC_BF16, backward=True)
+                roof["backward"] = {"us": round(t_bwd * 1e6, 1), "algorithmic_bytes": algo_bwd,
+                                    "achieved": round(algo_bwd / t_bwd / 1e9, 1), "frac": round(algo_bwd / t_bwd / 1e9 / peak, 4),
+                                    "traffic": measured_traffic("r02_bidaf_bwd_traffic.json")}
+                fb = (algo + algo_bwd) / (t_bidaf + t_bwd) / 1e9
+                roof["forward_backward"] = {"us": round((t_bidaf + t_bwd) * 1e6, 1), "algorithmic_bytes": algo + algo_bwd,
+                                            "achieved": round(fb, 1), "frac": round(fb / peak, 4)}
+            line["roofline"] = roof
+        if "cfg5" in sections:
+            line["cfg5"] = cfg5_timing(device)
+        if "fp32" in sections and fast and graphed and world == 1:
+            mmbidaf_b200.set_precision("fp32")
+            try:
+                tr32 = new_trainer()
+                for i in range(2):
+                    tr32.step(residents[i])
+                tr32.capture(residents[0], warmup=1)
+                k32 = {"k": 0}
+
+                def run32():
+                    k32["k"] += 1
+                    return tr32.step_graphed(residents[k32["k"] % N_ROTATE])
+                for _ in range(2):
+                    run32()
+                n32 = max(3, min(args.steps, 6))
+                t32 = _event_time(run32, n32)
+                line["fp32_tier"] = {"value": round(CFG3["batch"] / t32, 2), "unit": UNIT, "ms_per_step": round(t32 * 1e3, 3),
+                                     "dtype": "f32 (FFMA BiDAF kernels, fp32 library GEMMs): rel <= 1e-5 tier", "steps": n32}
+                del tr32
+            finally:
+                mmbidaf_b200.set_precision(args.precision)
+        if world == 1 and "eager" in sections:
+            try:
+                line["eager_cuda"] = eager_cuda_baselines(device)
+            except Exception as exc:                                     # the bar must not take the bench line down with it
+                line["eager_cuda"] = {"unavailable": repr(exc)[:200]}
         if world == 1 and not args.no_cpu_baseline:
-            vps, _, cores, sample = cpu_training_throughput(4, 3, 1)
-            line["cpu_baseline"] = {"value": round(vps, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            # bounded sample: a reference CPU step at the full batch of 32 takes ~8 s, so 1 warm-up + 3 timed steps (~30 s)
+            vps, _, cores, kind, sample = cpu_training_throughput(CFG3["batch"], 3, 1)
+            line["cpu_baseline"] = {"value": round(vps, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -355,7 +607,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--precision", default="fast", choices=["fast", "fp32"],
                     help="fast: bf16 tensor-core BiDAF + TF32 GEMMs (rel<=2e-2); fp32: rel<=1e-5 tier")
-    ap.add_argument("--sections", default="step,e2e,bidaf", help="profiling aid: which GPU sections to run")
+    ap.add_argument("--sections", default="step,e2e,cfg4,bidaf,cfg5,fp32,eager", help="profiling aid: which GPU sections to run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

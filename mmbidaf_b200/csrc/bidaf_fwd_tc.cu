@@ -62,15 +62,20 @@ constexpr int PACK_CHUNK_STRIDE = 144;   // 128-byte core matrix + 16 bytes: spr
 
 struct PackPair { PackArgs side[2]; };
 
-__global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackPair pp) {
+// One warp per 8-row group (one 3328-byte run of each pack).  Round 1 kept the converted chunks of all eight rows in registers
+// (s_out / v_out: 64 registers, 119 in total -> two 256-thread blocks per SM, warps active 21 %, 25.7 us at config 2); here every
+// row's chunks go to the warp's shared-memory staging as soon as they are made, so a thread holds four rows of loads at a time
+// and seven 128-thread blocks (28 warps) fit per SM: the pass is a stream of independent load -> convert -> store chains and wants them in flight.
+__global__ void __launch_bounds__(128, 7) bidaf_pack_kernel(const PackPair pp) {
   const PackArgs& a = pp.side[blockIdx.z];
-  if ((int)blockIdx.x * 64 >= a.LP) return;
-  __shared__ __align__(16) unsigned char stage[8][CHUNKS * PACK_CHUNK_STRIDE];
+  if ((int)blockIdx.x * 32 >= a.LP) return;
+  __shared__ __align__(16) unsigned char stage[4][2][CHUNKS * PACK_CHUNK_STRIDE];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * 8 + warp;                 // 8-row group (LP is a multiple of 64: always in range)
+  const int g = blockIdx.x * 4 + warp;                 // 8-row group (LP is a multiple of 128: always in range)
   const int d = a.d, nchunk = d >> 3;
   const float* src = a.src + (size_t)b * a.L * d;
   const uint8_t* keep = a.keep ? a.keep + (size_t)b * a.L * d : nullptr;
+  const bool two_packs = a.v_pack != a.s_pack;
   float wt[8], wf[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -78,89 +83,92 @@ __global__ void __launch_bounds__(256) bidaf_pack_kernel(const PackPair pp) {
     wt[e] = (lane < nchunk) ? a.w_term[k] : 0.f;
     wf[e] = (lane < nchunk && a.w_fold) ? a.w_fold[k] : 1.f;
   }
-  uint4 s_out[8], v_out[8];
-  // phase 1: every global load of the 8-row group is issued before any is used
-  float4 raw[8][2];
-  uint2 kraw[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = g * 8 + r;
-    raw[r][0] = raw[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    kraw[r] = make_uint2(0u, 0u);
-    if (row < a.L && lane < nchunk) {
-      raw[r][0] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8));
-      raw[r][1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8 + 4));
-      if (keep) kraw[r] = __ldg(reinterpret_cast<const uint2*>(keep + (size_t)row * d + lane * 8));
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = g * 8 + r;
-    float v[8], vd[8];
-    {
-      const float4 lo = raw[r][0], hi = raw[r][1];
-      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-    }
-    if (a.out_copy && row < a.L && lane < nchunk) {     // out[:, :, 0:d] = text, exact fp32
-      float* o = a.out_copy + ((size_t)b * a.L + row) * 4 * d + lane * 8;
-      *reinterpret_cast<float4*>(o) = raw[r][0];
-      *reinterpret_cast<float4*>(o + 4) = raw[r][1];
-    }
-    float dot = 0.f;
-    if (keep && row < a.L && lane < nchunk) {
-      const uint2 kk = kraw[r];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t word = e < 4 ? kk.x : kk.y;
-        vd[e] = ((word >> (8 * (e & 3))) & 0xffu) ? v[e] * a.keep_scale : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) vd[e] = v[e];
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dot = fmaf(vd[e], wt[e], dot);
-    dot = warp_sum(dot);
-    __nv_bfloat162 sp[4], vp[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      sp[e] = __floats2bfloat162_rn(vd[2 * e] * wf[2 * e], vd[2 * e + 1] * wf[2 * e + 1]);
-      vp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    }
-    s_out[r] = *reinterpret_cast<uint4*>(sp);
-    v_out[r] = *reinterpret_cast<uint4*>(vp);
-    if (lane == CHUNKS - 1) {                           // the K-padding chunk carries the additive term
-      const bool in = row < a.L;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(dot);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(dot - __bfloat162float(hi));
-      const __nv_bfloat16 one = __float2bfloat16_rn(in ? 1.f : 0.f), zero = __float2bfloat16_rn(0.f);
-      __nv_bfloat16 t[8] = {zero, zero, zero, zero, zero, zero, zero, zero};
-      if (a.text_side) { t[0] = in ? hi : zero; t[1] = in ? lo : zero; t[2] = one; t[3] = one; }
-      else             { t[0] = one; t[1] = one; t[2] = in ? hi : zero; t[3] = in ? lo : zero; }
-      s_out[r] = *reinterpret_cast<uint4*>(t);
-      v_out[r] = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
-  // phase 3: transpose through shared memory so the 3328-byte group leaves as contiguous 512-byte bursts
-  unsigned char* buf = stage[warp];
-  const size_t base = ((size_t)b * (a.LP / 8) + g) * GROUP_BYTES;
+  unsigned char* sbuf = stage[warp][0] + lane * PACK_CHUNK_STRIDE;      // this lane's chunk: 8 rows x 16 bytes
+  unsigned char* vbuf = stage[warp][1] + lane * PACK_CHUNK_STRIDE;
 #pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    if (which == 1 && a.v_pack == a.s_pack) break;
-    if (lane < CHUNKS) {
+  for (int half = 0; half < 2; ++half) {
+    // every global load of four rows is issued before any is used
+    float4 raw[4][2];
+    uint2 kraw[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-        *reinterpret_cast<uint4*>(buf + lane * PACK_CHUNK_STRIDE + r * 16) = which == 0 ? s_out[r] : v_out[r];
+    for (int r = 0; r < 4; ++r) {
+      const int row = g * 8 + half * 4 + r;
+      raw[r][0] = raw[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      kraw[r] = make_uint2(0u, 0u);
+      if (row < a.L && lane < nchunk) {
+        raw[r][0] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8));
+        raw[r][1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8 + 4));
+        if (keep) kraw[r] = __ldg(reinterpret_cast<const uint2*>(keep + (size_t)row * d + lane * 8));
+      }
     }
-    __syncwarp();
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(which == 0 ? a.s_pack : a.v_pack) + base);
-    for (int i = lane; i < CHUNKS * 8; i += 32)
-      dst[i] = *reinterpret_cast<const uint4*>(buf + (i >> 3) * PACK_CHUNK_STRIDE + (i & 7) * 16);
-    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = g * 8 + half * 4 + r;
+      float v[8], vd[8];
+      {
+        const float4 lo = raw[r][0], hi = raw[r][1];
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+      }
+      if (a.out_copy && row < a.L && lane < nchunk) {     // out[:, :, 0:d] = text, exact fp32
+        float* o = a.out_copy + ((size_t)b * a.L + row) * 4 * d + lane * 8;
+        *reinterpret_cast<float4*>(o) = raw[r][0];
+        *reinterpret_cast<float4*>(o + 4) = raw[r][1];
+      }
+      float dot = 0.f;
+      if (keep && row < a.L && lane < nchunk) {
+        const uint2 kk = kraw[r];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t word = e < 4 ? kk.x : kk.y;
+          vd[e] = ((word >> (8 * (e & 3))) & 0xffu) ? v[e] * a.keep_scale : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vd[e] = v[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot = fmaf(vd[e], wt[e], dot);
+      dot = warp_sum(dot);
+      __nv_bfloat162 sp[4], vp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sp[e] = __floats2bfloat162_rn(vd[2 * e] * wf[2 * e], vd[2 * e + 1] * wf[2 * e + 1]);
+        vp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      }
+      uint4 s_out = *reinterpret_cast<uint4*>(sp), v_out = *reinterpret_cast<uint4*>(vp);
+      if (lane == CHUNKS - 1) {                           // the K-padding chunk carries the additive term
+        const bool in = row < a.L;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(dot);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(dot - __bfloat162float(hi));
+        const __nv_bfloat16 one = __float2bfloat16_rn(in ? 1.f : 0.f), zero = __float2bfloat16_rn(0.f);
+        __nv_bfloat16 t[8] = {zero, zero, zero, zero, zero, zero, zero, zero};
+        if (a.text_side) { t[0] = in ? hi : zero; t[1] = in ? lo : zero; t[2] = one; t[3] = one; }
+        else             { t[0] = one; t[1] = one; t[2] = in ? hi : zero; t[3] = in ? lo : zero; }
+        s_out = *reinterpret_cast<uint4*>(t);
+        v_out = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (lane < CHUNKS) {
+        *reinterpret_cast<uint4*>(sbuf + (half * 4 + r) * 16) = s_out;
+        if (two_packs) *reinterpret_cast<uint4*>(vbuf + (half * 4 + r) * 16) = v_out;
+      }
+    }
   }
-  // mask words of this block's 64-row tile
-  if (warp == 0) {
-    const int tile = blockIdx.x;
+  __syncwarp();
+  // the 3328-byte group leaves as contiguous 512-byte bursts
+  const size_t base = ((size_t)b * (a.LP / 8) + g) * GROUP_BYTES;
+  {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.s_pack) + base);
+    const unsigned char* buf = stage[warp][0];
+    for (int i = lane; i < CHUNKS * 8; i += 32) dst[i] = *reinterpret_cast<const uint4*>(buf + (i >> 3) * PACK_CHUNK_STRIDE + (i & 7) * 16);
+  }
+  if (two_packs) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.v_pack) + base);
+    const unsigned char* buf = stage[warp][1];
+    for (int i = lane; i < CHUNKS * 8; i += 32) dst[i] = *reinterpret_cast<const uint4*>(buf + (i >> 3) * PACK_CHUNK_STRIDE + (i & 7) * 16);
+  }
+  // mask words of the 64-row tile this block starts
+  if (warp == 0 && (blockIdx.x & 1) == 0) {
+    const int tile = blockIdx.x >> 1;
     const int r0 = tile * 64 + lane, r1 = r0 + 32;
     const unsigned v0 = __ballot_sync(0xffffffffu, r0 < a.L), v1 = __ballot_sync(0xffffffffu, r1 < a.L);
     const unsigned o0 = __ballot_sync(0xffffffffu, r0 < a.L && a.mask[(size_t)b * a.L + min(r0, a.L - 1)] != 0);
@@ -582,7 +590,7 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   pp.side[0] = PackArgs{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
   pp.side[1] = PackArgs{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, nullptr, keep_scale,
                         Lq, LqP, d, 0};
-  bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 64, B, 2), 256, 0, stream>>>(pp);
+  bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 32, B, 2), 128, 0, stream>>>(pp);
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
   // Two cuts of the same algorithm.  Short sequences are store-heavy (few tiles per 128-row block): the two-blocks-

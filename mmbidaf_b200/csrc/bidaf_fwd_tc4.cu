@@ -49,7 +49,8 @@ constexpr int EPI_COLS = 32, EPI_STRIDE = 36;   // per-warp transpose buffer: 32
 constexpr int EPI_WARP_BYTES = 32 * EPI_STRIDE * 4;
 constexpr int NSOFT = 8, NEPI = 8;
 constexpr int EPI_WARP0 = 8, MMA_WARP = 16, TMA_WARP = 17, XLOAD_WARP = 18, NTHREADS = 19 * 32;
-constexpr int COL_S = 0, COL_O = 64;            // S: 2 x 32 columns; O: 2 x 208 columns
+constexpr int NSB = 3;                          // S buffers in TMEM = P buffers in shared memory
+constexpr int COL_S = 0, COL_O = NSB * TY;      // S: 3 x 32 columns; O: 2 x 208 columns (96 + 416 = 512)
 constexpr int ITEM_SLOTS = 4;
 constexpr float TAU2 = 11.0f;
 constexpr float NEG2 = kNegFill * LOG2E;
@@ -78,6 +79,7 @@ struct Args {
   int n_q2c, n_c2q;      // B * nq, B * nc
   int d;
   long long* trace;      // debugging aid: 8 x int64 per item, or null
+  int dbg;               // debugging aid (MMB_TC4_DEBUG): 1 no global stores, 2 no c loads, 4 no TMEM drain, 8 no transpose
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -113,7 +115,7 @@ __device__ __forceinline__ void signal_release(int* counter) {
 struct Smem {
   unsigned char* X;        // X_BYTES
   unsigned char* Y;        // NST x STAGE_BYTES
-  unsigned char* P;        // 2 x P_BYTES
+  unsigned char* P;        // NSB x P_BYTES
   unsigned char* E;        // NEPI x EPI_WARP_BYTES
   float* xbuf;             // [2][2][TX] row-max exchange between the two threads of a row
   float* stat;             // [2][3][TX] m_ref, l (half 0), l (half 1)
@@ -121,8 +123,8 @@ struct Smem {
   uint64_t* bars;
   uint32_t* tmem_slot;
 };
-constexpr int NBARS = 2 * ITEM_SLOTS + 2 + 2 + 2 * NST + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2;
-constexpr size_t SMEM_BYTES = (size_t)X_BYTES + NST * STAGE_BYTES + 2 * P_BYTES + NEPI * EPI_WARP_BYTES + 2 * 2 * TX * 4 +
+constexpr int NBARS = 2 * ITEM_SLOTS + 2 + 2 + 2 * NST + 4 * NSB + 2 + 2 + 2 + 2;
+constexpr size_t SMEM_BYTES = (size_t)X_BYTES + NST * STAGE_BYTES + NSB * P_BYTES + NEPI * EPI_WARP_BYTES + 2 * 2 * TX * 4 +
                               2 * 3 * TX * 4 + ITEM_SLOTS * 16 + NBARS * 8 + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
 
@@ -156,9 +158,14 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
     const int col0 = cc * EPI_COLS;
     const bool col_ok = col0 + c4 < d;
     uint32_t raw[32];
-    tmem_ld16_nowait(acc + col0, raw);
-    if (cc < NCHUNK - 1) tmem_ld16_nowait(acc + col0 + 16, raw + 16);
-    tmem_wait_ld();
+    if (!(f.dbg & 4)) {
+      tmem_ld16_nowait(acc + col0, raw);
+      if (cc < NCHUNK - 1) tmem_ld16_nowait(acc + col0 + 16, raw + 16);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) raw[i] = 0x3f800000u;
+    }
     if (cc == NCHUNK - 1) {
 #pragma unroll
       for (int i = 16; i < 32; ++i) raw[i] = 0u;
@@ -183,7 +190,7 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
             h[e2] = __floats2bfloat162_rn(ok ? __uint_as_float(raw[j * 8 + 2 * e2]) * inv_l : 0.f,
                                           ok ? __uint_as_float(raw[j * 8 + 2 * e2 + 1]) * inv_l : 0.f);
           }
-          *reinterpret_cast<uint4*>(tpack + ch * 128) = *reinterpret_cast<uint4*>(h);
+          if (!(f.dbg & 1)) *reinterpret_cast<uint4*>(tpack + ch * 128) = *reinterpret_cast<uint4*>(h);
         }
       }
       if (obase == nullptr) continue;                               // inference: the fp32 T is only saved for the backward pass
@@ -202,7 +209,7 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         cv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < nv) cv[rr] = __ldg(reinterpret_cast<const float4*>(cp));
+        if (rr < nv && !(f.dbg & 2)) cv[rr] = __ldg(reinterpret_cast<const float4*>(cp));
         cp += cinc;
       }
     }
@@ -211,7 +218,7 @@ __device__ __forceinline__ void epilogue_item(const Args& f, const uint32_t acc,
     const float* erow = ebuf + rsub * EPI_STRIDE + c4;
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) {
-      if (rr < nv) {
+      if (rr < nv && !(f.dbg & 1)) {
         const float4 o = *reinterpret_cast<const float4*>(erow + rr * 4 * EPI_STRIDE);
         if (KIND == Q2C) {
           *reinterpret_cast<float4*>(op) = o;                       // re-read by the backward pass: default cache policy
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
   sm.X = smem_raw;
   sm.Y = sm.X + X_BYTES;
   sm.P = sm.Y + NST * STAGE_BYTES;
-  sm.E = sm.P + 2 * P_BYTES;
+  sm.E = sm.P + NSB * P_BYTES;
   sm.xbuf = reinterpret_cast<float*>(sm.E + NEPI * EPI_WARP_BYTES);
   sm.stat = sm.xbuf + 2 * 2 * TX;
   sm.items = reinterpret_cast<int4*>(sm.stat + 2 * 3 * TX);
@@ -256,9 +263,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
   const uint32_t item_full0 = b0, item_empty0 = item_full0 + 8 * ITEM_SLOTS;
   const uint32_t x_full0 = item_empty0 + 8 * ITEM_SLOTS, x_free0 = x_full0 + 16;
   const uint32_t y_full0 = x_free0 + 16, y_free0 = y_full0 + 8 * NST;
-  const uint32_t s_full0 = y_free0 + 8 * NST, s_free0 = s_full0 + 16;
-  const uint32_t p_full0 = s_free0 + 16, p_free0 = p_full0 + 16;
-  const uint32_t o_full0 = p_free0 + 16, o_free0 = o_full0 + 16;
+  const uint32_t s_full0 = y_free0 + 8 * NST, s_free0 = s_full0 + 8 * NSB;
+  const uint32_t p_full0 = s_free0 + 8 * NSB, p_free0 = p_full0 + 8 * NSB;
+  const uint32_t o_full0 = p_free0 + 8 * NSB, o_free0 = o_full0 + 16;
   const uint32_t st_full0 = o_free0 + 16, st_free0 = st_full0 + 16;
 
   if (tid == 0) {
@@ -269,10 +276,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(x_full0 + 8 * i, 1);
       mbar_init(x_free0 + 8 * i, 1);
-      mbar_init(s_full0 + 8 * i, 1);
-      mbar_init(s_free0 + 8 * i, NSOFT);
-      mbar_init(p_full0 + 8 * i, NSOFT);
-      mbar_init(p_free0 + 8 * i, 1);
       mbar_init(o_full0 + 8 * i, 1);
       mbar_init(o_free0 + 8 * i, NEPI);
       mbar_init(st_full0 + 8 * i, NSOFT);
@@ -281,6 +284,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(y_full0 + 8 * i, 1);
       mbar_init(y_free0 + 8 * i, 1);
+    }
+    for (int i = 0; i < NSB; ++i) {
+      mbar_init(s_full0 + 8 * i, 1);
+      mbar_init(s_free0 + 8 * i, NSOFT);
+      mbar_init(p_full0 + 8 * i, NSOFT);
+      mbar_init(p_free0 + 8 * i, 1);
     }
     fence_barrier_init();
   }
@@ -371,11 +380,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
       mbar_wait(x_full0, n & 1);
       tc_fence_after();
       const uint32_t xs_lo = desc_lo(smem_u32(sm.X), 128);
-      auto issue_s = [&](int t) {                                   // S(t) = X Y_t^T into S buffer (g0 + t) & 1
+      auto issue_s = [&](int t) {                                   // S(t) = X Y_t^T into S buffer (g + t) % NSB
         const uint32_t gt = g + t;
-        const int s = gt % NST, sb = gt & 1;
+        const int s = gt % NST, sb = gt % NSB;
         mbar_wait(y_full0 + 8 * s, (gt / NST) & 1);
-        mbar_wait(s_free0 + 8 * sb, ((gt >> 1) & 1) ^ 1);
+        mbar_wait(s_free0 + 8 * sb, ((gt / NSB) & 1) ^ 1);
         tc_fence_after();
         const uint32_t y_lo = desc_lo(smem_u32(sm.Y + s * STAGE_BYTES), 128);
 #pragma unroll
@@ -383,15 +392,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
           umma_bf16_lh(tmem + COL_S + sb * TY, xs_lo + k * 16, desc_hi(GROUP_BYTES), y_lo + k * 16, desc_hi(GROUP_BYTES), IDESC_S,
                        k > 0, leader);
         umma_commit(s_full0 + 8 * sb, leader);
-        if (t == nty - 1) umma_commit(x_free0, leader);    // the X tile is dead after the item's last S product
+        if (t == nty - 1) umma_commit(x_free0, leader);             // the X tile is dead after the item's last S product
       };
-      issue_s(0);
+      int s_issued = 0;
       for (int t = 0; t < nty; ++t) {
-        if (t + 1 < nty) issue_s(t + 1);                            // runs on the tensor pipe under the soft-max of S(t)
+        // the S products run ahead of the soft-max by up to NSB - 1 tiles: the tensor pipe always has the next S queued, and a
+        // soft-max warp that finishes a tile finds the next one waiting
+        while (s_issued < nty && s_issued < t + NSB) issue_s(s_issued++);
         const uint32_t gt = g + t;
-        const int s = gt % NST, pb = gt & 1;
+        const int s = gt % NST, pb = gt % NSB;
         if (t == 0) mbar_wait(o_free0 + 8 * ob, ((n >> 1) & 1) ^ 1);   // the accumulator of item n - 2 has been drained
-        mbar_wait(p_full0 + 8 * pb, (gt >> 1) & 1);
+        mbar_wait(p_full0 + 8 * pb, (gt / NSB) & 1);
         tc_fence_after();
         const uint32_t v_lo = desc_lo(smem_u32(sm.Y + s * STAGE_BYTES + (same_v ? 0 : Y_BYTES)), GROUP_BYTES);
         const uint32_t ps_lo = desc_lo(smem_u32(sm.P + pb * P_BYTES), 2048);
@@ -441,12 +452,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
       float m_ref = -INFINITY, l_part = 0.f;                        // log2 domain; l over this thread's columns
       ulonglong2 words = *reinterpret_cast<const ulonglong2*>(words_b);
       for (int t = 0; t < nty; ++t, ++g) {
-        const int sb = g & 1;
+        const int sb = g % NSB;
+        const uint32_t sk = (g / NSB) & 1;                          // parity of this use of buffer sb
         const uint32_t sh = (t & 1) * 32 + half * 16;
         const uint32_t wvalid = (uint32_t)(words.x >> sh) & 0xffffu, wopen = (uint32_t)(words.y >> sh) & 0xffffu;
         const bool all_open = (wvalid & wopen) == 0xffffu;
         if (t + 1 < nty) words = *reinterpret_cast<const ulonglong2*>(words_b + (size_t)((t + 1) >> 1) * 2);   // next tile's masks
-        mbar_wait(s_full0 + 8 * sb, (g >> 1) & 1);
+        mbar_wait(s_full0 + 8 * sb, sk);
         tc_fence_after();
         float sv[16];
         tmem_ld16(lane_base + COL_S + sb * TY + half * 16, sv);
@@ -503,14 +515,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc4_kernel(const Args f) {
           }
         }
         l_part = l_part * alpha + psum;
-        mbar_wait(p_free0 + 8 * sb, ((g >> 1) & 1) ^ 1);            // P V(t - 2) has read this P buffer
+        mbar_wait(p_free0 + 8 * sb, sk ^ 1);                        // P V(t - NSB) has read this P buffer
         {
           unsigned char* prow = sm.P + sb * P_BYTES + (2 * half) * 2048 + row * 16;
           *reinterpret_cast<uint4*>(prow) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           *reinterpret_cast<uint4*>(prow + 2048) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
         if (__any_sync(0xffffffffu, bump && t > 0)) {               // lazy rescale of this warp's rows (alpha = 1 where no bump)
-          mbar_wait(p_free0 + 8 * (sb ^ 1), ((g - 1) >> 1) & 1);    // P V(t - 1) has landed in the accumulator
+          mbar_wait(p_free0 + 8 * ((g - 1) % NSB), ((g - 1) / NSB) & 1);   // P V(t - 1) has landed in the accumulator
           tc_fence_after();
 #pragma unroll 1
           for (int qq = half; qq < DPAD / 16; qq += 2) {            // the two threads of a row split the columns
@@ -610,6 +622,8 @@ int bidaf_fwd_tc4_launch(const BidafPacks& pk, const float* text, const float* b
   f.n_q2c = B * f.nq;
   f.n_c2q = B * f.nc;
   f.d = d;
+  static const char* dbg_env = getenv("MMB_TC4_DEBUG");
+  f.dbg = dbg_env ? atoi(dbg_env) : 0;
   static const char* trace_env = getenv("MMB_BIDAF_FWD_ITEM_TRACE");     // debugging aid (tools/bidaf_fwd_timeline.py)
   f.trace = trace_env ? reinterpret_cast<long long*>(strtoull(trace_env, nullptr, 0)) : nullptr;
   static int num_sms = 0;

@@ -8,12 +8,16 @@ import torch
 
 def greedy_search(out_distributions: torch.Tensor, original_text_length: int) -> List[int]:
     """Sentence indices picked for one video: arg-max per timestep until it hits the EOS row
-    ``original_text_length - 1`` (evaluate.py:185-202, minus the on-disk sentence look-ups)."""
+    ``original_text_length - 1`` (evaluate.py:185-202).  The reference looks every pick up in the transcript on disk
+    (``get_source_sentence``, :236-259): an index past the transcript yields no sentence and is skipped, not a stop
+    (:195, :255-256) -- reproduced here from the length alone (the transcript has ``original_text_length - 1`` sentences)."""
     picks = out_distributions.argmax(dim=1).tolist()
     chosen = []
     for k in picks:
         if k == original_text_length - 1:
             break
+        if k > original_text_length - 1:
+            continue
         chosen.append(int(k))
     return chosen
 

@@ -302,13 +302,18 @@ def mmbidaf_forward(p: Params, text: Tensor, text_len: Sequence[int], audio: Ten
 
 
 def greedy_indices(out_distributions: Tensor, text_len: int) -> List[int]:
-    """Selected sentence indices of one video.  evaluate.py:185-202 without the disk
-    look-ups: stop when the arg-max equals the EOS row ``text_len - 1``."""
+    """Selected sentence indices of one video.  evaluate.py:185-202 with the disk look-up of
+    ``get_source_sentence`` (:236-259) reduced to what it decides: the transcript has ``text_len - 1``
+    sentences (the text length includes the EOS row, datasets.py:70); stop when the arg-max equals the EOS
+    row ``text_len - 1`` (:188, :253-254), SKIP an index beyond it (:255-256 returns None, :195), keep the rest.
+    Pinned by tests/golden/greedy_search.pt (made by the reference's own evaluate.py)."""
     picked = []
     for row in out_distributions.detach().cpu().numpy():
         k = int(row.argmax())
         if k == text_len - 1:
             break
+        if k > text_len - 1:
+            continue
         picked.append(k)
     return picked
 

@@ -181,3 +181,18 @@ def test_greedy_indices_stop_at_eos():
     dist[3, 1] = 1
     assert O.greedy_indices(dist, 5) == [2, 0]
     assert O.greedy_indices(dist, 6) == [2, 0, 4, 1]
+
+
+def test_greedy_search_matches_the_reference_evaluate_py():
+    """Selected sentence indices pinned to the reference's own evaluate.py:167-202, :236-259 (tests/golden/make_golden_greedy.py
+    imports it unmodified and runs it against pickled transcripts): EOS at the first step, an index beyond the transcript
+    (skipped, not a stop), the same sentence picked repeatedly."""
+    from mmbidaf_b200.decode import get_generated_indices, greedy_search
+    g = load_golden("greedy_search.pt")
+    assert len(g["cases"]) == 3
+    for case in g["cases"]:
+        dist, lengths, want = case["dist"], case["lengths"], case["indices"]
+        assert [O.greedy_indices(dist[b], lengths[b]) for b in range(len(lengths))] == want
+        assert [greedy_search(dist[b], lengths[b]) for b in range(len(lengths))] == want
+        assert get_generated_indices(dist, lengths) == want
+    assert any(len(w) == 0 for c in g["cases"] for w in c["indices"])

@@ -569,6 +569,8 @@ int bidaf_fwd_tc3_launch(const BidafPacks& pk, const float* bias, float* out, fl
                          float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
 int bidaf_fwd_tc4_launch(const BidafPacks& pk, const float* text, const float* bias, float* out, float* q2c, float* bm,
                          float* lse_row, float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
+int bidaf_fwd_tc5_launch(const BidafPacks& pk, const float* text, const float* bias, float* out, float* q2c, float* bm,
+                         float* lse_row, float* lse_col, int B, int Lc, int Lq, int d, cudaStream_t stream);
 
 // Workspace (bytes): packed operands, mask words (layout: tc_common.cuh::bidaf_packs).
 size_t bidaf_tc_workspace_bytes(int B, int Lc, int Lq, int dropout) { return bidaf_packs(nullptr, B, Lc, Lq, dropout != 0).bytes; }
@@ -593,12 +595,14 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 32, B, 2), 128, 0, stream>>>(pp);
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
-  // Two cuts of the same algorithm.  Short sequences are store-heavy (few tiles per 128-row block): the two-blocks-
-  // per-SM launch of bidaf_fwd_tc2.cu hides one block's stores under the other's MMAs (cfg2: 96.6 vs 103 us).  Long
-  // sequences are tile-heavy: there the 64-column S tiles and the single S evaluation per c2q block of the
-  // one-block-per-SM cut below win (B=16, 4096 x 2048: 436 vs 477 us).  MMB_BIDAF_FWD_CUT=1|2 forces one.
+  // Cuts of the same algorithm (profiles/r02_bidaf_fwd.md).  The default is cut 5 (csrc/bidaf_fwd_tc5.cu: one persistent warp-
+  // specialised CTA per SM, 64-column tiles, P through TMEM, split accumulator): the fastest on every shape measured (config 2:
+  // 94 vs 98 us; text x audio of config 3: 97 vs 109; config 5: 329 vs 431).  MMB_BIDAF_FWD_CUT=1..4 forces an earlier cut (kept
+  // as cross-checks of each other in tests/test_bidaf_gpu.py): 1 one block per SM, 2 two blocks per SM, 3 X operand in TMEM,
+  // 4 persistent with 32-column tiles.
   const char* cut = getenv("MMB_BIDAF_FWD_CUT");
-  const bool two_per_sm = cut ? atoi(cut) == 2 : (Lc <= 512 && Lq <= 512);
+  const bool two_per_sm = cut && atoi(cut) == 2;
+  if (!cut || atoi(cut) == 5) return bidaf_fwd_tc5_launch(pk, text, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   if (cut && atoi(cut) == 4) return bidaf_fwd_tc4_launch(pk, text, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   if (cut && atoi(cut) == 3) return bidaf_fwd_tc3_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   if (two_per_sm) return bidaf_fwd_tc2_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);

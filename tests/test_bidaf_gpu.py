@@ -259,7 +259,7 @@ def test_bf16_backward_matches_oracle_ragged(shape, dropout):
                  bias_slack=w_floor if min(lc, lq) == 1 else 0.0)
 
 
-@pytest.mark.parametrize("cut", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("cut", ["1", "2", "3", "4", "5"])
 @pytest.mark.parametrize("shape", [(2, 130, 257, 200), (2, 600, 70, 200), (3, 409, 1024, 200)])
 def test_bf16_tier_both_kernel_cuts(shape, cut, monkeypatch):
     """The forward has two cuts of the tcgen05 kernels (one / two blocks per SM) chosen by shape; force each on every

@@ -42,8 +42,8 @@ per_tile = []
 for smid in sorted(set(t[:, 4].tolist()))[:4]:
     x = t[t[:, 4] == smid]
     x = x[x[:, 0].argsort()]
-    print(f"SM {smid}: " + "  ".join(f"{('Q', 'A', 'B')[int(r[3])]}{int(r[5])}t pub {int(r[0]) - t0} acc {int(r[1]) - t0} end {int(r[2]) - t0}"
-                                     for r in x))
+    print(f"SM {smid}: " + "  ".join(f"{('Q', 'A', 'B')[int(r[3])]}{int(r[5])}t pub {int(r[0]) - t0}" + (f" mma {int(r[7]) - t0}" if int(r[7]) else "")
+                                     + f" acc {int(r[1]) - t0} end {int(r[2]) - t0}" for r in x))
 for smid in set(t[:, 4].tolist()):
     x = t[t[:, 4] == smid]
     x = x[x[:, 1].argsort()]

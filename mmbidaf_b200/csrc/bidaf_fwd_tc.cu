@@ -62,120 +62,168 @@ constexpr int PACK_CHUNK_STRIDE = 144;   // 128-byte core matrix + 16 bytes: spr
 
 struct PackPair { PackArgs side[2]; };
 
-// One warp per 8-row group (one 3328-byte run of each pack).  Round 1 kept the converted chunks of all eight rows in registers
-// (s_out / v_out: 64 registers, 119 in total -> two 256-thread blocks per SM, warps active 21 %, 25.7 us at config 2); here every
-// row's chunks go to the warp's shared-memory staging as soon as they are made, so a thread holds four rows of loads at a time
-// and seven 128-thread blocks (28 warps) fit per SM: the pass is a stream of independent load -> convert -> store chains and wants them in flight.
-__global__ void __launch_bounds__(128, 7) bidaf_pack_kernel(const PackPair pp) {
-  const PackArgs& a = pp.side[blockIdx.z];
-  if ((int)blockIdx.x * 32 >= a.LP) return;
-  __shared__ __align__(16) unsigned char stage[4][2][CHUNKS * PACK_CHUNK_STRIDE];
-  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * 4 + warp;                 // 8-row group (LP is a multiple of 128: always in range)
-  const int d = a.d, nchunk = d >> 3;
-  const float* src = a.src + (size_t)b * a.L * d;
-  const uint8_t* keep = a.keep ? a.keep + (size_t)b * a.L * d : nullptr;
-  const bool two_packs = a.v_pack != a.s_pack;
-  float wt[8], wf[8];
+// 256-bit global accesses (sm_100): one instruction per lane and row instead of two 128-bit ones whose halves of every 32-byte
+// sector arrived at L2 as separate requests (ncu: 2.3 M read sectors for 1.2 M sectors of input).
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// A persistent grid of warps, each streaming over "units" of four consecutive rows of one side (lane = 16-byte chunk = 8 columns): the
+// loads of the next unit are in flight while the current one is converted and stored.
+// Rounds 1-2: one warp per 8-row group in small blocks (1 536 blocks of 128 threads in 1.7 waves, every block a serial
+// load -> convert -> store chain behind a prologue of weight loads): two 128-bit loads per row and lane whose halves of every
+// 32-byte sector arrived at L2 as separate requests, the converted group staged in shared memory; 25.7 - 31 us at config 2 for
+// 99 MB of traffic.  Now: 256-bit loads / copies, the 16-byte pieces go straight to their place in the pack (a 128-byte core matrix
+// is completed by eight rows handled by the same warp back to back, so L2 sees whole lines), no shared memory.
+struct PackUnit {
+  int side, b, row0;       // four rows row0 .. row0 + 3 of batch row b
+};
+__device__ __forceinline__ PackUnit pack_unit(const PackPair& pp, const int u, const int units0, const int per_b0, const int per_b1) {
+  PackUnit r;
+  r.side = u >= units0;
+  const int v = r.side ? u - units0 : u, per_b = r.side ? per_b1 : per_b0;
+  r.b = v / per_b;
+  r.row0 = (v - r.b * per_b) * 4;
+  return r;
+}
+__device__ __forceinline__ void pack_load4(const PackArgs& a, const PackUnit& un, const int lane, float (*v)[8], uint2* kraw) {
+  const bool data_lane = lane < (a.d >> 3);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {                         // every global load of four rows is issued before any is used
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[r][e] = 0.f;
+    kraw[r] = make_uint2(0u, 0u);
+    const int row = un.row0 + r;
+    if (row < a.L && data_lane) {
+      const size_t off = ((size_t)un.b * a.L + row) * a.d + lane * 8;
+      ldg256(a.src + off, v[r]);
+      if (a.keep) kraw[r] = __ldg(reinterpret_cast<const uint2*>(a.keep + off));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, const int B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_b0 = pp.side[0].LP / 4, per_b1 = pp.side[1].LP / 4;          // units per batch row (LP is a multiple of 128)
+  const int units0 = B * per_b0, n_units = units0 + B * per_b1;
+  const int n_warps = gridDim.x * 4;
+  int u = blockIdx.x * 4 + warp;
+  if (u >= n_units) return;
+  // weights of both sides stay in registers (lane = chunk): 8 + 8 + 8 floats
+  float wt0[8], wf0[8], wt1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int k = lane * 8 + e;
-    wt[e] = (lane < nchunk) ? a.w_term[k] : 0.f;
-    wf[e] = (lane < nchunk && a.w_fold) ? a.w_fold[k] : 1.f;
+    const bool in0 = lane < (pp.side[0].d >> 3), in1 = lane < (pp.side[1].d >> 3);
+    wt0[e] = in0 ? pp.side[0].w_term[lane * 8 + e] : 0.f;
+    wf0[e] = (in0 && pp.side[0].w_fold) ? pp.side[0].w_fold[lane * 8 + e] : 1.f;
+    wt1[e] = in1 ? pp.side[1].w_term[lane * 8 + e] : 0.f;
   }
-  unsigned char* sbuf = stage[warp][0] + lane * PACK_CHUNK_STRIDE;      // this lane's chunk: 8 rows x 16 bytes
-  unsigned char* vbuf = stage[warp][1] + lane * PACK_CHUNK_STRIDE;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  float v[4][8], vn[4][8];
+  uint2 kraw[4], kn[4];
+  PackUnit un = pack_unit(pp, u, units0, per_b0, per_b1);
+  pack_load4(pp.side[un.side], un, lane, v, kraw);
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    // every global load of four rows is issued before any is used
-    float4 raw[4][2];
-    uint2 kraw[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int row = g * 8 + half * 4 + r;
-      raw[r][0] = raw[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      kraw[r] = make_uint2(0u, 0u);
-      if (row < a.L && lane < nchunk) {
-        raw[r][0] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8));
-        raw[r][1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * d + lane * 8 + 4));
-        if (keep) kraw[r] = __ldg(reinterpret_cast<const uint2*>(keep + (size_t)row * d + lane * 8));
-      }
+  for (;;) {
+    const int u_next = u + n_warps;
+    const bool more = u_next < n_units;
+    PackUnit nx = un;
+    if (more) {
+      nx = pack_unit(pp, u_next, units0, per_b0, per_b1);
+      pack_load4(pp.side[nx.side], nx, lane, vn, kn);
     }
+    const PackArgs& a = pp.side[un.side];
+    const int d = a.d;
+    const bool data_lane = lane < (d >> 3);
+    const bool two_packs = a.v_pack != a.s_pack;
+    const size_t pack_off = ((size_t)un.b * (a.LP / 8) + (un.row0 >> 3)) * GROUP_BYTES + lane * 128 + (un.row0 & 7) * 16;
+    char* const s_dst = reinterpret_cast<char*>(a.s_pack) + pack_off;
+    char* const v_dst = reinterpret_cast<char*>(a.v_pack) + pack_off;
+    float dot[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int row = g * 8 + half * 4 + r;
-      float v[8], vd[8];
-      {
-        const float4 lo = raw[r][0], hi = raw[r][1];
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-      }
-      if (a.out_copy && row < a.L && lane < nchunk) {     // out[:, :, 0:d] = text, exact fp32
-        float* o = a.out_copy + ((size_t)b * a.L + row) * 4 * d + lane * 8;
-        *reinterpret_cast<float4*>(o) = raw[r][0];
-        *reinterpret_cast<float4*>(o + 4) = raw[r][1];
-      }
-      float dot = 0.f;
-      if (keep && row < a.L && lane < nchunk) {
-        const uint2 kk = kraw[r];
+      const int row = un.row0 + r;
+      const bool in = row < a.L;
+      if (a.out_copy && in && data_lane) stg256(a.out_copy + ((size_t)un.b * a.L + row) * 4 * d + lane * 8, v[r]);   // out[:, :, 0:d] = text
+      __nv_bfloat162 vp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) vp[e] = __floats2bfloat162_rn(v[r][2 * e], v[r][2 * e + 1]);
+      if (two_packs && lane < CHUNKS) *reinterpret_cast<uint4*>(v_dst + r * 16) = lane < CHUNKS - 1 ? *reinterpret_cast<uint4*>(vp) : make_uint4(0u, 0u, 0u, 0u);
+      if (a.keep) {                                     // dropout (attention.py:66-67): the S operand sees the dropped values
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const uint32_t word = e < 4 ? kk.x : kk.y;
-          vd[e] = ((word >> (8 * (e & 3))) & 0xffu) ? v[e] * a.keep_scale : 0.f;
+          const uint32_t word = e < 4 ? kraw[r].x : kraw[r].y;
+          v[r][e] = ((word >> (8 * (e & 3))) & 0xffu) ? v[r][e] * a.keep_scale : 0.f;
         }
+      }
+      float dt = 0.f;
+      __nv_bfloat162 sp[4];
+      if (un.side == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dt = fmaf(v[r][e], wt0[e], dt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sp[e] = __floats2bfloat162_rn(v[r][2 * e] * wf0[2 * e], v[r][2 * e + 1] * wf0[2 * e + 1]);
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) vd[e] = v[e];
-      }
+        for (int e = 0; e < 8; ++e) dt = fmaf(v[r][e], wt1[e], dt);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dot = fmaf(vd[e], wt[e], dot);
-      dot = warp_sum(dot);
-      __nv_bfloat162 sp[4], vp[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        sp[e] = __floats2bfloat162_rn(vd[2 * e] * wf[2 * e], vd[2 * e + 1] * wf[2 * e + 1]);
-        vp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        for (int e = 0; e < 4; ++e) sp[e] = __floats2bfloat162_rn(v[r][2 * e], v[r][2 * e + 1]);
       }
-      uint4 s_out = *reinterpret_cast<uint4*>(sp), v_out = *reinterpret_cast<uint4*>(vp);
-      if (lane == CHUNKS - 1) {                           // the K-padding chunk carries the additive term
-        const bool in = row < a.L;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(dot);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(dot - __bfloat162float(hi));
-        const __nv_bfloat16 one = __float2bfloat16_rn(in ? 1.f : 0.f), zero = __float2bfloat16_rn(0.f);
+      dot[r] = dt;
+      if (lane < CHUNKS - 1) *reinterpret_cast<uint4*>(s_dst + r * 16) = *reinterpret_cast<uint4*>(sp);
+    }
+    // the four row sums at once: two exchange steps halve the number of values a lane carries, three more finish them
+    {
+      const bool up16 = lane & 16, up8 = lane & 8;
+      const float a0 = (up16 ? dot[2] : dot[0]) + __shfl_xor_sync(0xffffffffu, up16 ? dot[0] : dot[2], 16);   // rows {0,1} on lanes 0-15, {2,3} on 16-31
+      const float a1 = (up16 ? dot[3] : dot[1]) + __shfl_xor_sync(0xffffffffu, up16 ? dot[1] : dot[3], 16);
+      float sm = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);                             // one row per 8-lane group
+      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) dot[r] = __shfl_sync(0xffffffffu, sm, ((r >> 1) * 16) + ((r & 1) * 8));
+    }
+    if (lane == CHUNKS - 1) {                           // the K-padding chunk carries the additive term
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool in = un.row0 + r < a.L;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(dot[r]);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(dot[r] - __bfloat162float(hi));
+        const __nv_bfloat16 one = __float2bfloat16_rn(in ? 1.f : 0.f);
         __nv_bfloat16 t[8] = {zero, zero, zero, zero, zero, zero, zero, zero};
         if (a.text_side) { t[0] = in ? hi : zero; t[1] = in ? lo : zero; t[2] = one; t[3] = one; }
         else             { t[0] = one; t[1] = one; t[2] = in ? hi : zero; t[3] = in ? lo : zero; }
-        s_out = *reinterpret_cast<uint4*>(t);
-        v_out = make_uint4(0u, 0u, 0u, 0u);
-      }
-      if (lane < CHUNKS) {
-        *reinterpret_cast<uint4*>(sbuf + (half * 4 + r) * 16) = s_out;
-        if (two_packs) *reinterpret_cast<uint4*>(vbuf + (half * 4 + r) * 16) = v_out;
+        *reinterpret_cast<uint4*>(s_dst + r * 16) = *reinterpret_cast<uint4*>(t);
       }
     }
-  }
-  __syncwarp();
-  // the 3328-byte group leaves as contiguous 512-byte bursts
-  const size_t base = ((size_t)b * (a.LP / 8) + g) * GROUP_BYTES;
-  {
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.s_pack) + base);
-    const unsigned char* buf = stage[warp][0];
-    for (int i = lane; i < CHUNKS * 8; i += 32) dst[i] = *reinterpret_cast<const uint4*>(buf + (i >> 3) * PACK_CHUNK_STRIDE + (i & 7) * 16);
-  }
-  if (two_packs) {
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.v_pack) + base);
-    const unsigned char* buf = stage[warp][1];
-    for (int i = lane; i < CHUNKS * 8; i += 32) dst[i] = *reinterpret_cast<const uint4*>(buf + (i >> 3) * PACK_CHUNK_STRIDE + (i & 7) * 16);
-  }
-  // mask words of the 64-row tile this block starts
-  if (warp == 0 && (blockIdx.x & 1) == 0) {
-    const int tile = blockIdx.x >> 1;
-    const int r0 = tile * 64 + lane, r1 = r0 + 32;
-    const unsigned v0 = __ballot_sync(0xffffffffu, r0 < a.L), v1 = __ballot_sync(0xffffffffu, r1 < a.L);
-    const unsigned o0 = __ballot_sync(0xffffffffu, r0 < a.L && a.mask[(size_t)b * a.L + min(r0, a.L - 1)] != 0);
-    const unsigned o1 = __ballot_sync(0xffffffffu, r1 < a.L && a.mask[(size_t)b * a.L + min(r1, a.L - 1)] != 0);
-    if (lane == 0) {
-      a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 0] = ((unsigned long long)v1 << 32) | v0;
-      a.mask_words[((size_t)b * (a.LP / 64) + tile) * 2 + 1] = ((unsigned long long)o1 << 32) | o0;
+    // mask words of the 64-row tile this unit starts
+    if ((un.row0 & 63) == 0) {
+      const int tile = un.row0 >> 6;
+      const int r0 = un.row0 + lane, r1 = r0 + 32;
+      const unsigned v0 = __ballot_sync(0xffffffffu, r0 < a.L), v1 = __ballot_sync(0xffffffffu, r1 < a.L);
+      const unsigned o0 = __ballot_sync(0xffffffffu, r0 < a.L && a.mask[(size_t)un.b * a.L + min(r0, a.L - 1)] != 0);
+      const unsigned o1 = __ballot_sync(0xffffffffu, r1 < a.L && a.mask[(size_t)un.b * a.L + min(r1, a.L - 1)] != 0);
+      if (lane == 0) {
+        a.mask_words[((size_t)un.b * (a.LP / 64) + tile) * 2 + 0] = ((unsigned long long)v1 << 32) | v0;
+        a.mask_words[((size_t)un.b * (a.LP / 64) + tile) * 2 + 1] = ((unsigned long long)o1 << 32) | o0;
+      }
+    }
+    if (!more) break;
+    u = u_next;
+    un = nx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      kraw[r] = kn[r];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[r][e] = vn[r][e];
     }
   }
 }
@@ -592,7 +640,17 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   pp.side[0] = PackArgs{text, keep_text, text_mask, w_text, w_cross, cw, cp, c_words, out, keep_scale, Lc, LcP, d, 1};
   pp.side[1] = PackArgs{modality, keep_modality, modality_mask, w_modality, nullptr, qs, qp, q_words, nullptr, keep_scale,
                         Lq, LqP, d, 0};
-  bidaf_pack_kernel<<<dim3(max(LcP, LqP) / 32, B, 2), 128, 0, stream>>>(pp);
+  {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      MMB_CUDA(cudaGetDevice(&dev));
+      MMB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int n_units = B * (LcP + LqP) / 4;
+    const int blocks = min((n_units + 3) / 4, num_sms * 4);         // 16 warps per SM, each streaming over its units
+    bidaf_pack_kernel<<<blocks, 128, 0, stream>>>(pp, B);
+  }
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 
   // Cuts of the same algorithm (profiles/r02_bidaf_fwd.md).  The default is cut 5 (csrc/bidaf_fwd_tc5.cu: one persistent warp-

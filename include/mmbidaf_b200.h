@@ -141,6 +141,25 @@ MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, c
  *   p (B,2,Lt)  stats (B,nch,4)  ctxp (B,nch,2,2H)  ctx12 (2,B,2H)  scale (B,2,nch)
  */
 MMB_API int mmb_decoder_chunks(int B, int Lt);
+/*
+ * The same step as ONE kernel (north_star item 3; csrc/decoder_fused.cu): a thread-block cluster per video splits the text axis and
+ * the output neurons of the step's mat-vecs and exchanges the small vectors through distributed shared memory.  Takes the weights in
+ * the TRANSPOSED layouts of ops.DecoderWeights (consecutive threads read consecutive output neurons): Wh4t (H,4D) = [W2; W4; W_beta_2;
+ * W_beta_4]^T with bh4 (4D) = the biases that land in the same tanh, Wb13t (2,D,D) = [W_beta_1^T; W_beta_3^T], Wcatt (D+E+H, 4H) =
+ * [lstm.weight_ih | lstm.weight_hh]^T with bcat = b_ih + b_hh, out_wt (H,M) = out.weight^T.
+ * Writes the step's outputs and everything mmb_decoder_*_bwd wants saved: hw (B,4D), alpha (B,2,Lt), beta (B,2), ctx12 (2,B,D),
+ * pb (2,B,D), xcat (B,D+E+H) = [c3 | sent | h], gates (B,4H) activated.  argmax, target / nll and cov_loss may be NULL.
+ */
+MMB_API int mmb_decoder_step_fused_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
+                                       const float* Wh4t, const float* bh4, const float* v1, const float* wc1, const float* v2,
+                                       const float* wc2, const float* v1b, const float* v2b, const float* Wb13t, const float* vb1,
+                                       const float* vb2, const float* vb1b, const float* vb2b, const float* Wcatt, const float* bcat,
+                                       const float* out_wt, const float* out_b, const float* sent, const float* h, const float* cell,
+                                       const float* cov, const uint8_t* mask, const long long* target, float* probs, float* h_out,
+                                       float* cell_out, float* att_cov, float* cov_out, long long* argmax, float* nll,
+                                       float* cov_loss, float* hw, float* alpha, float* beta, float* ctx12, float* pb, float* xcat,
+                                       float* gates, int B, int Lt, int D, int H, int E, int M, mmb_stream_t stream);
+
 MMB_API int mmb_decoder_attn_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
                                  const float* hw, const float* coverage, const float* v1, const float* wc1,
                                  const float* v2, const float* wc2, const float* v1b, const float* v2b, float* p,

@@ -1,0 +1,564 @@
+// Multimodal-attention decoder step (layers/attention.py:145-186), forward, as ONE kernel: north_star (3) -- "the multimodal
+// attention and output-layer masked soft-max are fused into one kernel".
+//
+// The chunk-parallel cut (decoder_step.cu) is five kernels around four library GEMMs: nine dependent launches per step, ~48 us
+// of which ~5 us per launch is dependency latency.  Here one thread-block CLUSTER owns one video for the whole step: the CTAs of
+// the cluster split the text axis (energies, soft-max partials, contexts, coverage) and the output neurons of the five mat-vecs
+// (W2 / W4 / W_beta_2 / W_beta_4 h;  W_beta_1 c1, W_beta_3 c2;  the LSTM gates;  out(h')), and exchange the small vectors in between
+// through distributed shared memory (six cluster barriers per step).  Nothing goes through global memory between the stages
+// except what the backward pass wants saved.  Videos never interact, so there is no grid-wide synchronisation.
+//
+//   A  hw = [W2 | W4 | W_beta_2 | W_beta_4] h + folded biases                        (4D outputs, split over the cluster)
+//   B  e_k[t] = v_k . tanh(proj_k[t] + hw_k + cov[t] wc_k) + v_k bias; chunk-local soft-max partials and weighted contexts
+//      (the un-masked soft-max over the text axis, attention.py:148,154, quirk Q2), merged over the cluster
+//   C  pb_k = W_beta_{1,3} c_k (split); beta = soft-max_2; c3 = beta . c; att_cov, coverage', coverage-loss term
+//   D  LSTM gates = [W_ih | W_hh] [c3 | sent | h] + b (split by hidden unit), cell update
+//   E  logits = out(h') (split), masked soft-max over the M sentences, first-max arg-max, NLL term
+//
+// fp32 FFMA throughout (warp-per-output mat-vecs with 128-bit loads, warp-shuffle reductions): the step is latency bound, not
+// FLOP bound (~0.6 MFLOP per video), and fp32 keeps it inside the 1e-5 tier.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mmb {
+namespace {
+
+constexpr int NT = 512;        // 16 warps: the step is a chain of latency-bound stages, one CTA per SM
+constexpr int NW = NT / 32;
+constexpr int MAXC = 8;        // cluster sizes 4 and 8
+
+__device__ long long* g_dec_trace = nullptr;   // debugging aid (MMB_DEC_TRACE): clock64 stamps of block 0 at the stage boundaries
+#define DEC_STAMP(i)                                                          \
+  do {                                                                        \
+    if (g_dec_trace && blockIdx.x == 0 && threadIdx.x == 0) g_dec_trace[i] = clock64(); \
+  } while (0)
+
+struct FusedArgs {
+  // per sequence
+  const float *proj_a, *proj_i, *enc_a, *enc_i;            // (B, Lt, D)
+  // weights
+  const float *Wh4t, *bh4;                                  // (H, 4D) = Wh4^T, (4D)
+  const float *v1, *wc1, *v2, *wc2, *v1b, *v2b;             // (D) x4, (1) x2
+  const float *Wb13t;                                       // (2, D, D): [W_beta_1^T; W_beta_3^T]
+  const float *vb1, *vb2, *vb1b, *vb2b;
+  const float *Wcatt, *bcat;                                // (D+E+H, 4H) = Wcat^T, (4H)
+  const float *out_wt, *out_b;                              // (H, M) = out.weight^T, (M)
+  // per step inputs
+  const float *sent, *h, *cell, *cov;                       // (B,E), (B,H), (B,H), (B,Lt)
+  const uint8_t* mask;                                      // (B, M)
+  const long long* target;                                  // (B) or null
+  // outputs
+  float *probs, *h_out, *cell_out, *att_cov, *cov_out;      // (B,M), (B,H), (B,H), (B,Lt), (B,Lt)
+  long long* argmax;                                        // (B) or null
+  float *nll, *cov_loss;                                    // (B) or null
+  // saved for the backward pass (all required)
+  float *hw, *alpha, *beta, *ctx12, *pb, *xcat, *gates;     // (B,4D), (B,2,Lt), (B,2), (2,B,D), (2,B,D), (B,D+E+H), (B,4H)
+  int B, Lt, D, H, E, M, chunk;
+};
+
+// y[i] = sum_k Wt[k][col_of(i)] x[k] + bias[col_of(i)] for i < n_out, with the weights TRANSPOSED (Wt (K, ldn): consecutive threads read
+// consecutive outputs, no shuffle reductions).  The K axis is split over NT / n_out thread groups whose partial sums meet in shared
+// memory (`scratch`, NT floats).  One thread per (output, K slice): K / S independent coalesced loads and FMAs -- the warp-per-output
+// form (row-major weights, 5 shuffle steps per output) cost four times the instructions and the stage was issue bound.
+template <typename ColOf, typename Emit>
+__device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, const int ldn, const float* __restrict__ bias, const float* x,
+                                               const int K, const int n_out, float* scratch, ColOf col_of, Emit emit) {
+  const int tid = threadIdx.x;
+  if (n_out <= 0) return;
+  const int S = max(1, min(NT / n_out, 8));                        // K slices
+  const int i = tid % n_out, sl = tid / n_out;
+  float acc = 0.f;
+  if (sl < S) {
+    const int per = (K + S - 1) / S, k0 = sl * per, k1 = min(K, k0 + per);
+    const float* w = Wt + (size_t)k0 * ldn + col_of(i);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = k0;
+    for (; k + 16 <= k1; k += 16) {                                 // sixteen independent loads in flight per thread
+      float wv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (size_t)u * ldn);
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        a0 = fmaf(wv[u], x[k + u], a0); a1 = fmaf(wv[u + 1], x[k + u + 1], a1);
+        a2 = fmaf(wv[u + 2], x[k + u + 2], a2); a3 = fmaf(wv[u + 3], x[k + u + 3], a3);
+      }
+      w += (size_t)16 * ldn;
+    }
+    if (k + 8 <= k1) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)u * ldn);
+#pragma unroll
+      for (int u = 0; u < 8; u += 4) {
+        a0 = fmaf(wv[u], x[k + u], a0); a1 = fmaf(wv[u + 1], x[k + u + 1], a1);
+        a2 = fmaf(wv[u + 2], x[k + u + 2], a2); a3 = fmaf(wv[u + 3], x[k + u + 3], a3);
+      }
+      w += (size_t)8 * ldn;
+      k += 8;
+    }
+    for (; k < k1; ++k) {
+      a0 = fmaf(__ldg(w), x[k], a0);
+      w += ldn;
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();                                                  // scratch may still be read from the previous use
+  if (sl < S && S > 1) scratch[sl * n_out + i] = acc;
+  __syncthreads();
+  if (tid < n_out) {
+    float v = acc;                                                  // slice 0 (sl == 0 for tid < n_out)
+    for (int q = 1; q < S; ++q) v += scratch[q * n_out + tid];
+    const int c = col_of(tid);
+    emit(tid, v + (bias ? __ldg(bias + c) : 0.f));
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = lane < NW ? red[lane] : 0.f;
+  return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = lane < NW ? red[lane] : -INFINITY;
+  return warp_max(r);
+}
+
+__global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), R = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = a.D, H = a.H, E = a.E, M = a.M, Lt = a.Lt, K = D + E + H;
+
+  extern __shared__ __align__(16) float smem[];
+  auto up4 = [](int v) { return (v + 3) & ~3; };        // every array starts 16-byte aligned
+  float* s_hw = smem;                       // [4D]   full, gathered over the cluster
+  float* s_x = s_hw + up4(4 * D);           // [K]    xcat = [c3 | sent | h]
+  float* s_ctx = s_x + up4(K);              // [2D]   merged contexts
+  float* s_pb = s_ctx + up4(2 * D);         // [2D]   gathered
+  float* s_hn = s_pb + up4(2 * D);          // [H]    h', gathered
+  float* s_part = s_hn + up4(H);            // [MAXC][4 + 2D] soft-max partials of every rank (written remotely)
+  float* s_ex = s_part + up4(MAXC * (4 + 2 * D));   // [MAXC][8] small exchanges: coverage loss, soft-max (max, sum), arg-max (p, index)
+  float* s_g = s_ex + MAXC * 8;             // [4][ceil(H / CL) + 1] gate pre-activations of this rank's units
+  float* s_red = s_g + up4(4 * ((H + MAXC / 2 - 1) / (MAXC / 2) + 1));   // [32]   (sized for the smaller cluster)
+  float* s_scr = s_red + 32;                // [NT]   K-slice partial sums of the mat-vecs
+  float* s_vec = s_scr + NT;                // [4D]   v1 | wc1 | v2 | wc2
+  float* s_e = s_vec + up4(4 * D);          // [2][chunk] energies -> p -> alpha of this rank's rows
+  float* s_cpart = s_e + up4(2 * a.chunk);  // [groups][2][D] context partials inside the block; later this rank's logits
+
+  DEC_STAMP(0);
+  // ---- stage 0: this video's step inputs -----------------------------------------------------------------------------------
+  for (int i = tid; i < H; i += NT) s_x[D + E + i] = a.h[(size_t)b * H + i];
+  for (int i = tid; i < E; i += NT) s_x[D + i] = a.sent[(size_t)b * E + i];
+  for (int i = tid; i < D; i += NT) {
+    s_vec[i] = a.v1[i];
+    s_vec[D + i] = a.wc1[i];
+    s_vec[2 * D + i] = a.v2[i];
+    s_vec[3 * D + i] = a.wc2[i];
+  }
+  __syncthreads();
+
+  DEC_STAMP(1);
+  // ---- stage A: hw = Wh4 h + bh4, outputs split over the ranks, gathered in every rank ------------------------------------
+  {
+    const int per = (4 * D + CL - 1) / CL, o0 = R * per, o1 = min(4 * D, o0 + per);
+    block_matvec_t(a.Wh4t, 4 * D, a.bh4, s_x + D + E, H, o1 - o0, s_scr, [&](int i) { return o0 + i; }, [&](int i, float v) {
+      const int o = o0 + i;
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_hw, r)[o] = v;
+      a.hw[(size_t)b * 4 * D + o] = v;
+    });
+  }
+  DEC_STAMP(2);
+  cluster.sync();
+  DEC_STAMP(3);
+
+  // ---- stage B: energies of this rank's rows, chunk-local soft-max partials and contexts ----------------------------------
+  const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk), n = t1 - t0;
+  {
+    const float v1b = a.v1b[0], v2b = a.v2b[0];
+    constexpr int MAXJ = 8;                // D <= 256
+    constexpr int RU = 4;                  // rows per warp iteration: all their loads are in flight before the first tanh
+    for (int i = warp * RU; i < n; i += NW * RU) {
+      float s[RU][2];
+      float pav[RU][MAXJ], piv[RU][MAXJ], cvs[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {         // loads first (memory-level parallelism)
+        s[u][0] = s[u][1] = 0.f;
+        const int t = t0 + min(i + u, n - 1);
+        const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
+        const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
+        cvs[u] = a.cov[(size_t)b * Lt + t];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          if (32 * j < D) {                                      // (uniform: D = 200 has no work for j = 7)
+            pav[u][j] = d < D ? pa[d] : 0.f;
+            piv[u][j] = d < D ? pi[d] : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const float cv = cvs[u];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          if (32 * j < D && d < D) {
+            s[u][0] = fmaf(s_vec[d], tanh_fast((pav[u][j] + s_hw[d]) + cv * s_vec[D + d]), s[u][0]);
+            s[u][1] = fmaf(s_vec[2 * D + d], tanh_fast((piv[u][j] + s_hw[D + d]) + cv * s_vec[3 * D + d]), s[u][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const float x1 = warp_sum(s[u][0]), x2 = warp_sum(s[u][1]);
+        if (lane == 0 && i + u < n) {
+          s_e[i + u] = x1 + v1b;
+          s_e[a.chunk + i + u] = x2 + v2b;
+        }
+      }
+    }
+    __syncthreads();
+    DEC_STAMP(4);
+    float m1 = -INFINITY, m2 = -INFINITY;
+    for (int i = tid; i < n; i += NT) {
+      m1 = fmaxf(m1, s_e[i]);
+      m2 = fmaxf(m2, s_e[a.chunk + i]);
+    }
+    m1 = block_max(m1, s_red);
+    m2 = block_max(m2, s_red);
+    float l1 = 0.f, l2 = 0.f;
+    for (int i = tid; i < n; i += NT) {
+      const float p1 = expf(s_e[i] - m1), p2 = expf(s_e[a.chunk + i] - m2);
+      s_e[i] = p1;
+      s_e[a.chunk + i] = p2;
+      l1 += p1;
+      l2 += p2;
+    }
+    l1 = block_sum(l1, s_red);
+    l2 = block_sum(l2, s_red);
+    __syncthreads();
+    DEC_STAMP(5);
+    // weighted contexts of this rank's rows
+    const float* ea = a.enc_a + ((size_t)b * Lt + t0) * D;
+    const float* ei = a.enc_i + ((size_t)b * Lt + t0) * D;
+    const bool vec4 = (D & 3) == 0;
+    const int groups = vec4 ? NT / (D >> 2) : NT / D;
+    if (vec4) {
+      const int dv4 = D >> 2;
+      const int g = tid / dv4, c4 = tid - g * dv4;
+      if (g < groups) {
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll 8
+        for (int i = g; i < n; i += groups) {
+          const float w1 = s_e[i], w2 = s_e[a.chunk + i];
+          const float4 x1 = *reinterpret_cast<const float4*>(ea + (size_t)i * D + c4 * 4);
+          const float4 x2 = *reinterpret_cast<const float4*>(ei + (size_t)i * D + c4 * 4);
+          s1.x = fmaf(w1, x1.x, s1.x); s1.y = fmaf(w1, x1.y, s1.y); s1.z = fmaf(w1, x1.z, s1.z); s1.w = fmaf(w1, x1.w, s1.w);
+          s2.x = fmaf(w2, x2.x, s2.x); s2.y = fmaf(w2, x2.y, s2.y); s2.z = fmaf(w2, x2.z, s2.z); s2.w = fmaf(w2, x2.w, s2.w);
+        }
+        *reinterpret_cast<float4*>(s_cpart + (g * 2 + 0) * D + c4 * 4) = s1;
+        *reinterpret_cast<float4*>(s_cpart + (g * 2 + 1) * D + c4 * 4) = s2;
+      }
+    } else {
+      const int g = tid / D, d = tid - g * D;
+      if (g < groups) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = g; i < n; i += groups) {
+          s1 = fmaf(s_e[i], ea[(size_t)i * D + d], s1);
+          s2 = fmaf(s_e[a.chunk + i], ei[(size_t)i * D + d], s2);
+        }
+        s_cpart[(g * 2 + 0) * D + d] = s1;
+        s_cpart[(g * 2 + 1) * D + d] = s2;
+      }
+    }
+    __syncthreads();
+    // this rank's partials -> slot R of every rank
+    for (int d = tid; d < 2 * D; d += NT) {
+      const int k = d / D, dd = d - k * D;
+      float s = 0.f;
+      for (int g = 0; g < groups; ++g) s += s_cpart[(g * 2 + k) * D + dd];
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_part, r)[R * (4 + 2 * D) + 4 + d] = s;
+    }
+    if (tid < CL) {
+      float* dst = cluster.map_shared_rank(s_part, tid) + R * (4 + 2 * D);
+      dst[0] = m1; dst[1] = l1; dst[2] = m2; dst[3] = l2;
+    }
+  }
+  DEC_STAMP(6);
+  cluster.sync();
+  DEC_STAMP(7);
+
+  // merge (every rank, redundantly): contexts c1, c2; the scale that turns this rank's p into alpha
+  float scale_own[2];
+  {
+    float* s_w = s_scr;                                           // [2][MAXC] merge weights w_r / l, then [2 MAXC .. ] own scales
+    if (tid < 2) {
+      const int k = tid;
+      float m = -INFINITY;
+      for (int r = 0; r < CL; ++r)
+        if (min(Lt, r * a.chunk) < Lt) m = fmaxf(m, s_part[r * (4 + 2 * D) + 2 * k]);     // (a rank without rows: m = -inf, l = 0)
+      float l = 0.f, w[MAXC];
+#pragma unroll
+      for (int r = 0; r < MAXC; ++r) {
+        w[r] = (r < CL && min(Lt, r * a.chunk) < Lt) ? expf(s_part[r * (4 + 2 * D) + 2 * k] - m) : 0.f;
+        l = fmaf(w[r], r < CL ? s_part[r * (4 + 2 * D) + 2 * k + 1] : 0.f, l);
+      }
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int r = 0; r < MAXC; ++r) s_w[k * MAXC + r] = w[r] * inv;
+    }
+    __syncthreads();
+    scale_own[0] = s_w[R];
+    scale_own[1] = s_w[MAXC + R];
+    for (int i = tid; i < 2 * D; i += NT) {
+      const int k = i / D;
+      float sum = 0.f;
+      for (int r = 0; r < CL; ++r) sum = fmaf(s_w[k * MAXC + r], s_part[r * (4 + 2 * D) + 4 + i], sum);
+      s_ctx[i] = sum;
+      if (R == 0) a.ctx12[((size_t)k * a.B + b) * D + (i - k * D)] = sum;
+    }
+  }
+  __syncthreads();
+  DEC_STAMP(8);
+
+  // ---- stage C: pb_k = W_beta_{1,3} c_k (split), gathered; beta; c3; attention / coverage outputs of this rank's rows ------
+  {
+    const int per = (2 * D + CL - 1) / CL, o0 = R * per, o1 = min(2 * D, o0 + per);
+    // outputs below D take c1 (W_beta_1), the others c2 (W_beta_3); a rank's range may straddle the two
+    for (int k = 0; k < 2; ++k) {
+      const int lo = max(o0, k * D), hi = min(o1, (k + 1) * D);
+      block_matvec_t(a.Wb13t + (size_t)k * D * D, D, nullptr, s_ctx + k * D, D, hi - lo, s_scr, [&](int i) { return lo - k * D + i; },
+                     [&](int i, float v) {
+                       const int o = lo + i;
+                       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_pb, r)[o] = v;
+                       a.pb[((size_t)k * a.B + b) * D + (o - k * D)] = v;
+                     });
+    }
+  }
+  DEC_STAMP(9);
+  cluster.sync();
+  DEC_STAMP(10);
+  float beta1, beta2;
+  {
+    float eb1 = 0.f, eb2 = 0.f;
+    for (int d = tid; d < D; d += NT) {
+      eb1 = fmaf(a.vb1[d], tanh_fast(s_pb[d] + s_hw[2 * D + d]), eb1);
+      eb2 = fmaf(a.vb2[d], tanh_fast(s_pb[D + d] + s_hw[3 * D + d]), eb2);
+    }
+    eb1 = block_sum(eb1, s_red) + a.vb1b[0];
+    eb2 = block_sum(eb2, s_red) + a.vb2b[0];
+    const float mb = fmaxf(eb1, eb2);
+    const float x1 = expf(eb1 - mb), x2 = expf(eb2 - mb);
+    beta1 = x1 / (x1 + x2);
+    beta2 = x2 / (x1 + x2);
+    for (int d = tid; d < D; d += NT) s_x[d] = s_ctx[d] * beta1 + s_ctx[D + d] * beta2;
+    float closs = 0.f;
+    for (int i = tid; i < n; i += NT) {
+      const int t = t0 + i;
+      const float a1 = s_e[i] * scale_own[0], a2 = s_e[a.chunk + i] * scale_own[1];
+      a.alpha[((size_t)b * 2 + 0) * Lt + t] = a1;
+      a.alpha[((size_t)b * 2 + 1) * Lt + t] = a2;
+      const float att = a1 * beta1 + a2 * beta2;                 // bmm([a1 a2], beta), attention.py:167
+      const float cnew = a.cov[(size_t)b * Lt + t] + att;
+      a.att_cov[(size_t)b * Lt + t] = att;
+      a.cov_out[(size_t)b * Lt + t] = cnew;
+      closs += fminf(att, cnew);
+    }
+    closs = block_sum(closs, s_red);
+    if (tid == 0) cluster.map_shared_rank(s_ex, 0)[R * 8 + 0] = closs;      // summed by rank 0 after the next cluster barrier
+    if (R == 0 && tid == 0) {
+      a.beta[b * 2 + 0] = beta1;
+      a.beta[b * 2 + 1] = beta2;
+    }
+  }
+  __syncthreads();
+  if (R == 0)
+    for (int i = tid; i < K; i += NT) a.xcat[(size_t)b * K + i] = s_x[i];
+
+  DEC_STAMP(11);
+  // ---- stage D: LSTM gates of this rank's hidden units, cell update; h' gathered -------------------------------------------
+  {
+    const int per = (H + CL - 1) / CL, j0 = R * per, j1 = min(H, j0 + per), nj = max(0, j1 - j0);
+    block_matvec_t(a.Wcatt, 4 * H, a.bcat, s_x, K, 4 * nj, s_scr, [&](int i) { return (i / nj) * H + j0 + (i % nj); },
+                   [&](int i, float v) { s_g[(i / nj) * (per + 1) + (i % nj)] = v; });
+    __syncthreads();
+    if (tid < nj) {
+      const int j = j0 + tid;
+      const float gi = gate_act(s_g[tid], 1.f), gf = gate_act(s_g[(per + 1) + tid], 1.f), gg = tanh_fast(s_g[2 * (per + 1) + tid]),
+                  go = gate_act(s_g[3 * (per + 1) + tid], 1.f);
+      const float c = fmaf(gf, a.cell[(size_t)b * H + j], gi * gg);
+      const float hn = go * tanh_fast(c);
+      a.cell_out[(size_t)b * H + j] = c;
+      a.h_out[(size_t)b * H + j] = hn;
+      float* gs = a.gates + (size_t)b * 4 * H;                  // activated gates, kept for the backward pass
+      gs[j] = gi; gs[H + j] = gf; gs[2 * H + j] = gg; gs[3 * H + j] = go;
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_hn, r)[j] = hn;
+    }
+  }
+  DEC_STAMP(12);
+  cluster.sync();
+  DEC_STAMP(13);
+  if (R == 0 && tid == 0 && a.cov_loss) {
+    float s = 0.f;
+    for (int r = 0; r < CL; ++r) s += s_ex[r * 8 + 0];
+    a.cov_loss[b] = s;
+  }
+
+  // ---- stage E: logits of this rank's sentences, masked soft-max over M, arg-max, NLL ---------------------------------------
+  {
+    const int per = (M + CL - 1) / CL, m0 = min(M, R * per), m1 = min(M, m0 + per);
+    float* const lg = s_cpart;                                   // this rank's logits (the context partials are dead)
+    block_matvec_t(a.out_wt, M, a.out_b, s_hn, H, m1 - m0, s_scr, [&](int i) { return m0 + i; }, [&](int i, float v) { lg[i] = v; });
+    __syncthreads();
+    for (int m = m0 + tid; m < m1; m += NT)
+      if (!a.mask[(size_t)b * M + m]) lg[m - m0] = kNegFill;     // attention.py:184 (masked_softmax)
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int m = m0 + tid; m < m1; m += NT) mx = fmaxf(mx, lg[m - m0]);
+    mx = block_max(mx, s_red);
+    float sum = 0.f;
+    for (int m = m0 + tid; m < m1; m += NT) sum += expf(lg[m - m0] - mx);
+    sum = block_sum(sum, s_red);
+    if (tid < CL) {
+      float* dst = cluster.map_shared_rank(s_ex, tid) + R * 8;
+      dst[1] = mx;
+      dst[2] = sum;
+    }
+    DEC_STAMP(14);
+    cluster.sync();
+    DEC_STAMP(15);
+    float gmx = -INFINITY;
+    for (int r = 0; r < CL; ++r)
+      if (min(M, r * per) < M) gmx = fmaxf(gmx, s_ex[r * 8 + 1]);
+    float gsum = 0.f;
+    for (int r = 0; r < CL; ++r)
+      if (min(M, r * per) < M) gsum = fmaf(s_ex[r * 8 + 2], expf(s_ex[r * 8 + 1] - gmx), gsum);
+    const float inv = 1.f / gsum;
+    float best = -INFINITY;
+    int best_i = M;
+    const int tg = a.target ? (int)a.target[b] : -1;
+    for (int m = m0 + tid; m < m1; m += NT) {
+      const float p = expf(lg[m - m0] - gmx) * inv;
+      a.probs[(size_t)b * M + m] = p;
+      if (p > best) { best = p; best_i = m; }
+      if (m == tg && a.nll) a.nll[b] = -logf(p + 1e-12f);         // models.py:168-170
+    }
+    if (a.argmax) {                                               // first maximal index, as torch.max(dim) documents
+      const float bbest = block_max(best, s_red);
+      int cand = best == bbest ? best_i : M;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+      __shared__ int redi[NW];
+      __syncthreads();
+      if (lane == 0) redi[warp] = cand;
+      __syncthreads();
+      if (tid == 0) {
+        int r = M;
+        for (int w = 0; w < NW; ++w) r = min(r, redi[w]);
+        float* dst = cluster.map_shared_rank(s_ex, 0) + R * 8;
+        dst[3] = bbest;
+        dst[4] = __int_as_float(r);
+      }
+      cluster.sync();
+      if (R == 0 && tid == 0) {
+        float gb = -INFINITY;
+        int gi = M;
+        for (int r = 0; r < CL; ++r) {
+          if (min(M, r * per) >= M) continue;
+          const float pb_ = s_ex[r * 8 + 3];
+          const int ib = __float_as_int(s_ex[r * 8 + 4]);
+          if (pb_ > gb || (pb_ == gb && ib < gi)) { gb = pb_; gi = ib; }
+        }
+        a.argmax[b] = gi;
+      }
+    }
+  }
+  DEC_STAMP(16);
+  cluster.sync();      // no rank exits while another may still write into its shared memory
+  DEC_STAMP(17);
+}
+
+}  // namespace
+
+// bytes of dynamic shared memory for the launch below
+static size_t fused_smem_bytes(int Lt, int D, int H, int E, int M, int CL, int* chunk_out) {
+  const int chunk = (Lt + CL - 1) / CL;
+  const int K = D + E + H;
+  const int groups = (D & 3) == 0 ? NT / (D >> 2) : NT / D;
+  const int per_m = (M + CL - 1) / CL;
+  int cpart = groups * 2 * D;
+  if (cpart < per_m) cpart = per_m;
+  auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
+  const size_t floats = up4(4 * D) + up4(K) + 2 * up4(2 * D) + up4(H) + up4((size_t)MAXC * (4 + 2 * D)) + MAXC * 8 +
+                        up4(4 * ((H + MAXC / 2 - 1) / (MAXC / 2) + 1)) + 32 + NT + up4(4 * D) + up4(2 * (size_t)chunk) + up4(cpart);
+  if (chunk_out) *chunk_out = chunk;
+  return floats * sizeof(float) + 64;
+}
+
+}  // namespace mmb
+
+extern "C" int mmb_decoder_step_fused_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
+                                          const float* Wh4t, const float* bh4, const float* v1, const float* wc1, const float* v2,
+                                          const float* wc2, const float* v1b, const float* v2b, const float* Wb13t, const float* vb1,
+                                          const float* vb2, const float* vb1b, const float* vb2b, const float* Wcatt,
+                                          const float* bcat, const float* out_wt, const float* out_b, const float* sent,
+                                          const float* h, const float* cell, const float* cov, const uint8_t* mask,
+                                          const long long* target, float* probs, float* h_out, float* cell_out, float* att_cov,
+                                          float* cov_out, long long* argmax, float* nll, float* cov_loss, float* hw, float* alpha,
+                                          float* beta, float* ctx12, float* pb, float* xcat, float* gates, int B, int Lt, int D,
+                                          int H, int E, int M, mmb_stream_t stream) {
+  using namespace mmb;
+  MMB_REQUIRE(proj_a && proj_i && enc_a && enc_i && Wh4t && bh4 && v1 && wc1 && v2 && wc2 && v1b && v2b && Wb13t && vb1 && vb2 &&
+                  vb1b && vb2b && Wcatt && bcat && out_wt && out_b && sent && h && cell && cov && mask && probs && h_out &&
+                  cell_out && att_cov && cov_out && hw && alpha && beta && ctx12 && pb && xcat && gates,
+              MMB_ERR_INVALID, "mmb_decoder_step_fused_fwd: null pointer");
+  MMB_REQUIRE(B > 0 && Lt > 0 && D > 0 && H > 0 && E >= 0 && M > 0, MMB_ERR_INVALID,
+              "mmb_decoder_step_fused_fwd: B=%d Lt=%d D=%d H=%d E=%d M=%d", B, Lt, D, H, E, M);
+  MMB_REQUIRE(D <= 256, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fused_fwd: D=%d > 256", D);
+  // few videos: eight CTAs per video keep more of the chip busy on the text sweep
+  const int CL = (long long)B * 4 * 2 <= 160 ? 8 : 4;
+  FusedArgs a{proj_a, proj_i, enc_a, enc_i, Wh4t, bh4, v1, wc1, v2, wc2, v1b, v2b, Wb13t, vb1, vb2, vb1b, vb2b, Wcatt, bcat, out_wt, out_b,
+              sent, h, cell, cov, mask, target, probs, h_out, cell_out, att_cov, cov_out, argmax, nll, cov_loss, hw, alpha, beta,
+              ctx12, pb, xcat, gates, B, Lt, D, H, E, M, 0};
+  const size_t smem = fused_smem_bytes(Lt, D, H, E, M, CL, &a.chunk);
+  MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fused_fwd: %zu B of shared memory (Lt=%d)", smem, Lt);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    MMB_CUDA(cudaFuncSetAttribute(dec_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  static const char* trace_env = getenv("MMB_DEC_TRACE");
+  static bool trace_set = false;
+  if (trace_env && !trace_set) {
+    long long* ptr = reinterpret_cast<long long*>(strtoull(trace_env, nullptr, 0));
+    MMB_CUDA(cudaMemcpyToSymbol(g_dec_trace, &ptr, sizeof(ptr)));
+    trace_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMB_CUDA(cudaLaunchKernelEx(&cfg, dec_step_fused_kernel, a));
+  return check_launch("dec_step_fused_kernel");
+}

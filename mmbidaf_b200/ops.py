@@ -151,6 +151,9 @@ class DecoderWeights:
         self.Wh_stack = torch.cat([P["lstm_w_hh"], self.Wh4], dim=0).contiguous()                   # (4H + 4D, H)
         self.bcat = (P["lstm_b_ih"] + P["lstm_b_hh"]).contiguous()
         self.out_w, self.out_b = P["out_w"].contiguous(), P["out_b"].contiguous()
+        # transposed copies for the one-kernel step (csrc/decoder_fused.cu): consecutive threads read consecutive output neurons
+        self.Wh4t, self.Wcatt, self.out_wt = self.Wh4.t().contiguous(), self.Wcat.t().contiguous(), self.out_w.t().contiguous()
+        self.Wb13t = self.Wb13.transpose(1, 2).contiguous()
         # backward: d h = d_logits out.weight with K = M padded to a multiple of 8 (M = 409 is odd: an un-aligned GEMM otherwise)
         self.Mp = (self.M + 7) // 8 * 8
         self.out_w_pad = torch.cat([self.out_w, self.out_w.new_zeros(self.Mp - self.M, self.H)], dim=0).contiguous()
@@ -188,6 +191,29 @@ def decoder_step_fwd(seq: DecoderSeq, sent, h, cell, coverage, mask_u8, want_arg
     f32 = dict(device=h.device, dtype=torch.float32)
     p = _lib.ptr
     st = _lib.stream()
+    cut = os.environ.get("MMB_DECODER_CUT")
+    if cut is None:
+        # a cluster (4 or 8 CTAs) per video: at most ~1000 CTAs worth of text rows per launch keeps every CTA's share of the text sweep
+        # short; long lectures (config 5: 16 x 4096 rows) are better spread over the (chunks x B) grid of the five-kernel cut
+        cut = "fused" if B * Lt <= 20000 else "chunks"
+    if cut != "chunks":
+        # the whole step as one cluster kernel (csrc/decoder_fused.cu); MMB_DECODER_CUT=chunks forces the five-kernel cut below
+        hw, alpha, beta = torch.empty(B, 4 * D, **f32), torch.empty(B, 2, Lt, **f32), torch.empty(B, 2, **f32)
+        ctx12, pb = torch.empty(2, B, D, **f32), torch.empty(2, B, D, **f32)
+        xcat, gates = torch.empty(B, D + E + H, **f32), torch.empty(B, 4 * H, **f32)
+        probs, h_out, cell_out = torch.empty(B, M, **f32), torch.empty(B, H, **f32), torch.empty(B, H, **f32)
+        att_cov, cov_out = torch.empty(B, Lt, **f32), torch.empty(B, Lt, **f32)
+        argmax = torch.empty(B, device=h.device, dtype=torch.int64) if want_argmax else None
+        lossvec = torch.empty(2, B, **f32) if target is not None else None       # [nll | coverage term]
+        _lib.check(lib.mmb_decoder_step_fused_fwd(
+            p(seq.proj_a), p(seq.proj_i), p(seq.enc_a), p(seq.enc_i), p(seq.Wh4t), p(seq.bh4), p(seq.v1), p(seq.wc1), p(seq.v2),
+            p(seq.wc2), p(seq.v1b), p(seq.v2b), p(seq.Wb13t), p(seq.vb1), p(seq.vb2), p(seq.vb1b), p(seq.vb2b), p(seq.Wcatt),
+            p(seq.bcat), p(seq.out_wt), p(seq.out_b), p(sent), p(h), p(cell), p(coverage), p(mask_u8), p(target), p(probs), p(h_out),
+            p(cell_out), p(att_cov), p(cov_out), p(argmax), p(None if lossvec is None else lossvec[0]),
+            p(None if lossvec is None else lossvec[1]), p(hw), p(alpha), p(beta), p(ctx12), p(pb), p(xcat), p(gates),
+            B, Lt, D, H, E, M, st), "mmb_decoder_step_fused_fwd")
+        _count(1)
+        return probs, h_out, cell_out, att_cov, cov_out, argmax, (hw, alpha, beta, ctx12, pb, xcat, gates), lossvec
     hw = torch.addmm(seq.bh4, h, seq.Wh4.t())                                  # (B, 4D)  library GEMM
     alpha = torch.empty(B, 2, Lt, **f32)
     stats, ctxp = torch.empty(B, nch, 4, **f32), torch.empty(B, nch, 2, D, **f32)

@@ -146,3 +146,43 @@ def test_fused_step_loss_terms_and_gradients_match_torch_composition():
     assert grad_err(af, ap) < 1e-5 and grad_err(if_, ip) < 1e-5 and grad_err(hf, hp) < 1e-5
     for a, b in zip(pf, pp):
         assert grad_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(3, 24, 100, 300, 409), (32, 409, 100, 300, 409), (2, 700, 100, 300, 1024), (5, 13, 6, 10, 17),
+                                 (1, 1, 4, 3, 2), (2, 5, 100, 300, 9), (40, 37, 100, 300, 64)])
+def test_fused_cluster_step_matches_the_chunk_parallel_cut(cfg, monkeypatch):
+    """The one-kernel step (csrc/decoder_fused.cu, a thread-block cluster per video: cluster of 8 for few videos, of 4 otherwise;
+    ranks without text rows when Lt < cluster size) against the five-kernel cut on the same inputs: outputs, the state saved for the
+    backward pass, the fused loss terms (1e-5) and the selected sentence index (bit-exact)."""
+    from mmbidaf_b200 import ops
+    bsz, lt, hid, e, m = cfg
+    m = max(m, lt)
+    gen = torch.Generator().manual_seed(9000 + lt * 3 + bsz)
+    d = 2 * hid
+    shapes = {"W2": (d, hid), "b2": (d,), "Wc1": (d, 1), "bc1": (d,), "v1": (1, d), "v1b": (1,), "W4": (d, hid), "b4": (d,),
+              "Wc2": (d, 1), "bc2": (d,), "v2": (1, d), "v2b": (1,), "Wb1": (d, d), "bb1": (d,), "Wb2": (d, hid), "bb2": (d,),
+              "Wb3": (d, d), "bb3": (d,), "Wb4": (d, hid), "bb4": (d,), "vb1": (1, d), "vb1b": (1,), "vb2": (1, d), "vb2b": (1,),
+              "lstm_w_ih": (4 * hid, e + d), "lstm_w_hh": (4 * hid, hid), "lstm_b_ih": (4 * hid,), "lstm_b_hh": (4 * hid,),
+              "out_w": (m, hid), "out_b": (m,)}
+    held = {k: (torch.randn(*s, generator=gen) * 0.2).cuda() for k, s in shapes.items()}
+    enc_a, enc_i = torch.randn(bsz, lt, d, generator=gen).cuda(), torch.randn(bsz, lt, d, generator=gen).cuda()
+    proj_a, proj_i = torch.randn(bsz, lt, d, generator=gen).cuda(), torch.randn(bsz, lt, d, generator=gen).cuda()
+    sent, h, cell = (torch.randn(bsz, n, generator=gen).cuda() for n in (e, hid, hid))
+    cov = torch.rand(bsz, lt, generator=gen).cuda()
+    lens = torch.randint(1, m + 1, (bsz,), generator=gen)
+    mask = (torch.arange(m).unsqueeze(0) < lens.unsqueeze(1)).to(torch.uint8).cuda()
+    target = torch.stack([torch.randint(0, int(n), (1,), generator=gen)[0] for n in lens]).cuda()
+    seq = ops.DecoderSeq(held, enc_a, enc_i, proj_a, proj_i, m)
+    outs = {}
+    for cut in ("chunks", "fused"):
+        monkeypatch.setenv("MMB_DECODER_CUT", cut)
+        outs[cut] = ops.decoder_step_fwd(seq, sent, h, cell, cov, mask, want_argmax=True, target=target)
+        torch.cuda.synchronize()
+    want, got = outs["chunks"], outs["fused"]
+    for name, w, g in zip(("probs", "h", "cell", "att_cov", "coverage"), want[:5], got[:5]):
+        assert torch.isfinite(g).all() and rel_err(g, w) < TOL, name
+    assert torch.equal(got[5], want[5])                                    # arg-max: bit-exact
+    for name, w, g in zip(("hw", "alpha", "beta", "ctx12", "pb", "xcat", "gates"), want[6], got[6]):
+        assert rel_err(g, w) < TOL, name
+    assert rel_err(got[7], want[7]) < TOL                                  # [nll | coverage term]
+    assert (got[0][mask == 0] == 0).all()

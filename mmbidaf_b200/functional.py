@@ -160,6 +160,12 @@ class _LstmLayer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, d_h_n, _d_c_n):
+        # the backward kernel overwrites the saved activated gates in place with d(pre-activation) (one buffer, three roles):
+        # a second backward over the same graph (retain_graph=True) would read garbage -- refuse it instead
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("mmbidaf_b200: the LSTM layer's backward ran twice over one forward (retain_graph=True is not "
+                               "supported: its saved gates are overwritten in place)")
+        ctx.consumed = True
         x2d, gates, cell, out, w_ih, w_hh, lengths, order = ctx.saved_tensors
         B, L, H, ndir, fan_in = ctx.dims
         if d_out is None:
@@ -301,8 +307,12 @@ class _DecoderOpen(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _g):
         tape, r = ctx.tape, ctx.tape.rows
+        if getattr(tape, "closed", False):
+            raise RuntimeError("mmbidaf_b200: the decoder sequence's backward ran twice over one forward (retain_graph=True is not "
+                               "supported: the step tape is consumed and its accumulators are handed out)")
         if not r["dlog"]:
             return (None,) * (5 + len(ctx.shapes))
+        tape.closed = True
         s = tape.seq
         B, D, H, E = s.B, s.D, s.H, s.E
         # what the rest of the backward pass waits for first: the gradients of the encoder outputs
@@ -315,7 +325,9 @@ class _DecoderOpen(torch.autograd.Function):
             grads = _DecoderOpen._param_grads(ctx, tape, r, s)
         for v in r.values():
             v.clear()
-        return (None, tape.d_proj_a, tape.d_proj_i, d_enc_a, d_enc_i, *grads)
+        d_proj_a, d_proj_i = tape.d_proj_a, tape.d_proj_i
+        tape.d_proj_a = tape.d_proj_i = tape.vec_acc = tape.scal_acc = None      # handed out: never accumulated into again
+        return (None, d_proj_a, d_proj_i, d_enc_a, d_enc_i, *grads)
 
     @staticmethod
     def _param_grads(ctx, tape, r, s):
@@ -368,6 +380,9 @@ class _DecoderStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_probs, d_h_out, d_cell_out, d_att, d_cov_out, d_lossvec):
         tape = ctx.tape
+        if getattr(tape, "closed", False) or getattr(ctx, "consumed", False):
+            raise RuntimeError("mmbidaf_b200: a decoder step's backward ran twice over one forward (retain_graph=True is not supported)")
+        ctx.consumed = True
         h, cell, cov, probs, h_out, cell_out, *rest = ctx.saved_tensors
         saved, extra = rest[:7], rest[7:]
         target, att, cov_new = extra if ctx.fused else (None, None, None)

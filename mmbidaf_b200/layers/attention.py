@@ -193,10 +193,13 @@ class MultimodalAttentionDecoder(nn.Module):
             # the previous one (its hidden state is that step's output, as in models.py:163) the chain of hidden-state
             # gradients already orders it behind a step that holds the token, so only the first step of a chain takes it:
             # no per-step gradient accumulation on the token.
-            chained = seq["last_h"] is not None and h.data_ptr() == seq["last_h"]
+            # (decided by tensor identity -- the step's hidden state is the previous step's output or a view of it -- not by address:
+            # the caching allocator can hand an unrelated tensor the address of a freed one)
+            prev = seq["last_h"]
+            chained = prev is not None and (h is prev or h._base is prev)
             probs, h, cell, att, cov, lossvec = Fn.decoder_step(seq["tape"], None if chained else seq["token"], sent, h, cell,
                                                                 cov, ops._u8(mask), tgt)
-            seq["last_h"] = h.data_ptr()
+            seq["last_h"] = h
         else:
             probs, h, cell, att, cov, _, _, lossvec = ops.decoder_step_fwd(seq["seq"], sent, h, cell, cov, ops._u8(mask),
                                                                            target=tgt)

@@ -173,3 +173,18 @@ def test_fused_clip_adadelta_matches_torch_semantics(wd, gscale):
     st = opt.state[ref]
     assert torch.allclose(sq.cpu().double(), st["square_avg"], rtol=1e-5, atol=1e-12)
     assert torch.allclose(acc.cpu().double(), st["acc_delta"], rtol=1e-4, atol=1e-12)
+
+
+def test_second_backward_over_one_forward_raises():
+    """The LSTM backward overwrites its saved gates in place and the decoder tape is consumed by its closing backward: a second
+    backward over the same graph must raise, not return silently wrong gradients."""
+    import pytest as _pytest
+    from mmbidaf_b200.layers import RNNEncoder
+    torch.manual_seed(0)
+    enc = RNNEncoder(8, 6, 1).cuda()
+    x = torch.randn(3, 5, 8, device="cuda", requires_grad=True)
+    out, _ = enc(x, [5, 3, 2])
+    loss = out.sum()
+    loss.backward(retain_graph=True)
+    with _pytest.raises(RuntimeError, match="ran twice"):
+        loss.backward()

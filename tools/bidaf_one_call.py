@@ -19,6 +19,9 @@ bias = torch.zeros(1, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for it in range(3):
     flush.zero_()                                           # the inputs are cold in L2, as between two steps of a training run
+    if "--bwd" not in sys.argv:                             # what bench.py's roofline section times: nothing saved for a backward pass
+        ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, precision=ops.PREC_BF16)
+        continue
     out, q2c, lr, lc_, bm, ws = ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, precision=ops.PREC_BF16, save=True)
     if "--bwd" in sys.argv:
         g = torch.randn_like(out) if it == 0 else g

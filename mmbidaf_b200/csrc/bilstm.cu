@@ -18,6 +18,7 @@
 // the reverse direction starts at each sample's own last valid step; outputs past a sample's
 // length are exactly zero (pad_packed_sequence, encoding.py:99); h_n / c_n are the states after
 // each sample's last valid step.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mmb {
@@ -203,6 +204,199 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
     for (int i = tid; i < (L - len[n]) * H; i += nthr) {
       const int t = len[n] + i / H, u = i % H;
       a.out[((size_t)seq[n] * L + t) * ndir * H + dir * H + u] = 0.f;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Forward, two CTAs per (sequence, direction): a thread-block CLUSTER of two splits the hidden units.
+//
+// A step of the kernel above is ISSUE bound, not FMA bound: one CTA runs the whole 4H x H mat-vec of its sequence, 7 warps on 4
+// schedulers (2, 2, 2, 1) at ~355 instructions per warp and step -> >= 710 issue slots on the busy schedulers, ~1 300 cycles measured.
+// Here each CTA of the pair owns half of the hidden units (same lane-pair layout, same per-thread work: 4 warps, ONE per scheduler)
+// and the two halves of h meet in both CTAs' shared memory: every new h value is stored locally and -- st.async with
+// mbarrier::complete_tx -- into the partner's buffer, whose threads wait on their own mbarrier for the partner's bytes.  The exchange
+// costs one DSMEM latency (~215 cycles) per step, the issue-bound part halves.  The h buffers are double buffered: a CTA can only be
+// one step ahead of its partner (it needs the partner's h(t) to run step t), which is exactly what two buffers allow.
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned map_to_cta(const void* local_smem, unsigned rank) {
+  const unsigned l = static_cast<unsigned>(__cvta_generic_to_shared(local_smem));
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(unsigned remote_addr, float v, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(__float_as_uint(v)),
+               "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void pair_bar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pair_bar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pair_bar_wait(unsigned bar, unsigned parity) {
+#pragma unroll 1
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+    unsigned done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int KS>
+__global__ void __launch_bounds__(threads_for(KS / 2 + 1)) bilstm_fwd_pair_kernel(const LstmArgs a) {
+  constexpr int HP = 2 * KS;                       // padded hidden size
+  const int H = a.H, L = a.L, ndir = a.ndir;
+  const int dir = blockIdx.y;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const unsigned rank = cluster_ctarank();
+  const int UH = (H + 1) / 2;                      // units per CTA
+  const int jj = tid >> 1, kp = tid & 1;
+  const int j = (int)rank * UH + jj;
+  const bool live = jj < UH && j < H;
+
+  extern __shared__ __align__(16) float smem[];
+  float* h_s = smem;                               // [2][HP]  the full hidden state, both halves
+  float* ring = h_s + 2 * HP;                      // [RING][2][nthr]
+  __shared__ __align__(8) unsigned long long bars[2];
+
+  const int slot_b = blockIdx.x >> 1;
+  const int seq = slot_b < a.B ? (a.order ? a.order[slot_b] : slot_b) : -1;
+  const int len = seq >= 0 ? min(max(a.lengths[seq], 0), L) : 0;
+
+  float w[4][KS];
+  {
+    const float* wd = a.w_hh + (size_t)dir * 4 * H * H;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const int k = kp * KS + kk;
+        w[g][kk] = (live && k < H) ? wd[(size_t)(g * H + j) * H + k] : 0.f;
+      }
+  }
+  for (int i = tid; i < 2 * HP; i += nthr) h_s[i] = 0.f;
+  const unsigned bar0 = static_cast<unsigned>(__cvta_generic_to_shared(&bars[0]));
+  if (tid == 0) {
+    pair_bar_init(bar0, 1);
+    pair_bar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the partner's units and the bytes it sends per step
+  const int other_units = max(0, min(UH, H - (int)(rank ^ 1u) * UH));
+  const unsigned rbar0 = map_to_cta(&bars[0], rank ^ 1u);
+  const unsigned rh0 = map_to_cta(h_s, rank ^ 1u);
+
+  const long sign = dir ? -1 : 1;
+  const long g_stride = sign * (long)ndir * 4 * H, o_stride = sign * (long)ndir * H;
+  const size_t bt0 = (size_t)max(seq, 0) * L + (dir ? max(len - 1, 0) : 0);
+  const int jc = live ? j : 0;
+  float* gp = a.gates + (bt0 * ndir + dir) * 4 * H + (2 * kp) * H + jc;
+  float* op = a.out + bt0 * ndir * H + dir * H + jc;
+  float* cp = a.cell ? a.cell + (bt0 * ndir + dir) * H + jc : nullptr;
+  const float* pf = gp;
+  float* ring_t = ring + tid;
+  auto prefetch = [&](int s, int slot) {
+    if (live) {
+      if (s < len) {
+        cp_async4(ring_t + (slot * 2 + 0) * nthr, pf);
+        cp_async4(ring_t + (slot * 2 + 1) * nthr, pf + H);
+      }
+      pf += g_stride;
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int s = 0; s < RING - 1; ++s) prefetch(s, s);
+  __syncthreads();
+  cluster_sync_all();                              // both CTAs' barriers and zeroed buffers exist before any remote store
+
+  float c_reg = 0.f, h_reg = 0.f;
+  const float k_first = kp ? 2.0f : 1.0f;          // lane 0: (i, f) both sigmoid; lane 1: (g = tanh, o = sigmoid)
+  const bool save = a.save != 0;
+  int cur = 0, slot = 0;
+
+#pragma unroll 1
+  for (int s = 0; s < len; ++s) {
+    const int nxt = cur ^ 1;
+    if (tid == 0) pair_bar_expect(bar0 + 8 * nxt, 4u * (unsigned)other_units);   // the partner's half of h(s + 1)
+    prefetch(s + RING - 1, (slot + RING - 1) & (RING - 1));
+    cp_async_wait<RING - 1>();
+    const float* hk = h_s + cur * HP + kp * KS;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k4 = 0; k4 < KS / 4; ++k4) {
+      const float4 hv = *reinterpret_cast<const float4*>(hk + k4 * 4);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        acc[g] = fmaf(w[g][k4 * 4 + 0], hv.x, acc[g]);
+        acc[g] = fmaf(w[g][k4 * 4 + 1], hv.y, acc[g]);
+        acc[g] = fmaf(w[g][k4 * 4 + 2], hv.z, acc[g]);
+        acc[g] = fmaf(w[g][k4 * 4 + 3], hv.w, acc[g]);
+      }
+    }
+    // reduce-scatter over the lane pair: lane 0 keeps gates (i, f), lane 1 keeps (g, o)
+    float m0 = kp ? acc[2] : acc[0], m1 = kp ? acc[3] : acc[1];
+    m0 += __shfl_xor_sync(0xffffffffu, kp ? acc[0] : acc[2], 1);
+    m1 += __shfl_xor_sync(0xffffffffu, kp ? acc[1] : acc[3], 1);
+    const float* rs = ring_t + slot * 2 * nthr;
+    const float a0 = gate_act(m0 + (live ? rs[0] : 0.f), k_first);   // i | g
+    const float a1 = gate_act(m1 + (live ? rs[nthr] : 0.f), 1.0f);   // f | o
+    const float b0 = __shfl_xor_sync(0xffffffffu, a0, 1);
+    const float b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
+    const float gi = kp ? b0 : a0, gf = kp ? b1 : a1, gg = kp ? a0 : b0, go = kp ? a1 : b1;
+    if (live) {
+      c_reg = fmaf(gf, c_reg, gi * gg);
+      h_reg = go * tanh_fast(c_reg);
+      if (kp == 0) {
+        h_s[nxt * HP + j] = h_reg;
+        st_async_f32(rh0 + (unsigned)(nxt * HP + j) * 4u, h_reg, rbar0 + 8u * (unsigned)nxt);
+        *op = h_reg;
+      }
+      if (save) {
+        gp[0] = a0;
+        gp[H] = a1;
+        if (kp == 1) *cp = c_reg;
+      }
+    }
+    gp += g_stride;
+    op += o_stride;
+    if (save) cp += o_stride;
+    slot = (slot + 1) & (RING - 1);
+    __syncthreads();                                                  // this CTA's half of h(s + 1) is in its buffer
+    pair_bar_wait(bar0 + 8 * nxt, (unsigned)(s >> 1) & 1u);           // ... and so is the partner's
+    cur = nxt;
+  }
+  cp_async_wait<0>();
+  cluster_sync_all();                              // neither CTA exits while the other may still store into it
+
+  if (seq >= 0) {
+    if (live && kp == 0) a.h_n[((size_t)seq * ndir + dir) * H + j] = h_reg;
+    if (live && kp == 1) a.c_n[((size_t)seq * ndir + dir) * H + j] = c_reg;
+    // pad_packed_sequence: zeros past the sample's length (each CTA of the pair clears its own units)
+    const int u0 = (int)rank * UH, nu = max(0, min(UH, H - u0));
+    for (int i = tid; i < (L - len) * nu; i += nthr) {
+      const int t = len + i / nu, u = u0 + i % nu;
+      a.out[((size_t)seq * L + t) * ndir * H + dir * H + u] = 0.f;
     }
   }
 }
@@ -394,6 +588,35 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
   constexpr int HP = 2 * KS;
   const int nthr = max(((2 * a.H + 31) / 32) * 32, 64);
   dim3 grid((a.B + NB - 1) / NB, a.ndir), block(nthr);
+  // Opt-in (MMB_LSTM_PAIR=1).  Measured (B = 32, H = 100): 0.62 instead of 0.67 us per step for ONE layer alone -- the step is bound by
+  // its dependent chain (LDS -> 52-deep FMA chains -> shuffles -> activations -> barrier), not by issue slots, so halving the warps per
+  // scheduler buys 7 % -- but a pair takes 128 SMs per layer and the training step runs three encoders side by side (384 CTAs on 296
+  // slots): 5 870 instead of 6 186 videos/s.  Kept as a measured alternative, off by default.
+  static const char* pair_env = getenv("MMB_LSTM_PAIR");
+  const bool pair_ok = pair_env && atoi(pair_env) != 0;
+  if (!backward && NB == 1 && pair_ok && a.H >= 32 && 2 * a.B * a.ndir <= 2 * 148) {
+    // two CTAs per (sequence, direction): see bilstm_fwd_pair_kernel
+    const int pthr = threads_for(KS / 2 + 1);
+    const int UH = (a.H + 1) / 2;
+    if (2 * UH <= pthr) {
+      const size_t smem = sizeof(float) * (2 * HP + (size_t)RING * 2 * pthr);
+      MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_pair_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(2 * a.B), (unsigned)a.ndir);
+      cfg.blockDim = dim3((unsigned)pthr);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      MMB_CUDA(cudaLaunchKernelEx(&cfg, bilstm_fwd_pair_kernel<KS>, a));
+      return check_launch("bilstm_fwd_pair_kernel");
+    }
+  }
   if (!backward) {
     const size_t smem = sizeof(float) * (2 * NB * HP + (size_t)RING * NB * 2 * nthr);
     MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

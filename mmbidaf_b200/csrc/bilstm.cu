@@ -592,7 +592,7 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
   // its dependent chain (LDS -> 52-deep FMA chains -> shuffles -> activations -> barrier), not by issue slots, so halving the warps per
   // scheduler buys 7 % -- but a pair takes 128 SMs per layer and the training step runs three encoders side by side (384 CTAs on 296
   // slots): 5 870 instead of 6 186 videos/s.  Kept as a measured alternative, off by default.
-  static const char* pair_env = getenv("MMB_LSTM_PAIR");
+  const char* pair_env = getenv("MMB_LSTM_PAIR");
   const bool pair_ok = pair_env && atoi(pair_env) != 0;
   if (!backward && NB == 1 && pair_ok && a.H >= 32 && 2 * a.B * a.ndir <= 2 * 148) {
     // two CTAs per (sequence, direction): see bilstm_fwd_pair_kernel

@@ -52,9 +52,13 @@ def test_encoder_matches_reference_golden(name):
             assert grad_err(w.grad, g["grad_params"][nm.format(k=k)], nm) < 1e-4, (k, nm)
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
 @pytest.mark.parametrize("cfg", [(1, 1, 3, 4), (7, 33, 20, 16), (5, 50, 100, 100), (40, 19, 100, 100),
-                                 (90, 12, 64, 100), (3, 300, 800, 100), (4, 9, 104, 104), (2, 6, 10, 60)])
-def test_encoder_matches_oracle(cfg):
+                                 (90, 12, 64, 100), (3, 300, 800, 100), (4, 9, 104, 104), (2, 6, 10, 60), (3, 21, 16, 33)])
+def test_encoder_matches_oracle(cfg, pair, monkeypatch):
+    """pair = 1: the forward recurrence on a two-CTA cluster per (sequence, direction) (bilstm_fwd_pair_kernel; hidden sizes >= 32, odd
+    sizes split 17 / 16), pair = 0: one CTA."""
+    monkeypatch.setenv("MMB_LSTM_PAIR", pair)
     bsz, max_len, fan_in, hid = cfg
     gen = torch.Generator().manual_seed(31 * bsz + max_len)
     lengths = torch.randint(1, max_len + 1, (bsz,), generator=gen).tolist()

@@ -90,7 +90,7 @@ class ClockSampler:
                 self.reasons.update(k for k, v in names.items() if bits & v)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.nv is not None:

@@ -197,6 +197,18 @@ MMB_API int mmb_decoder_out_softmax(float* logits, const uint8_t* mask, long lon
  * counters (B) int32 of mmb_decoder_attn_fwd / _bwd: zero before the first call, left at zero by every call (the last chunk
  * block of a video to finish merges that video's chunk partials, so neither function needs a second launch for it).
  */
+/* The head of a backward step as ONE cluster kernel (csrc/decoder_fused.cu): mmb_decoder_out_softmax_bwd, d h = d_logits out.weight,
+ * mmb_decoder_cell_bwd, d c3 = d_gates W_ih[:, :D], mmb_decoder_attn_finish_bwd and d c_k += W_beta_k^T d_pre_k -- same arguments and
+ * results as those calls and the three library GEMMs between them (out_w (M,H), Wcat_ctx (4H,D), Wb13 (2,D,D) row-major).  The text
+ * sweeps (mmb_decoder_attn_bwd) and the final d h GEMM follow it unchanged. */
+MMB_API int mmb_decoder_bwd_head(const float* probs, const float* d_probs, const long long* target, const float* g_nll,
+                                 const float* g_cov, const float* out_w, const float* gates, const float* cell_in,
+                                 const float* cell_out, const float* d_h_out, const float* d_cell_out, const float* Wcat_ctx,
+                                 const float* d_att_cov, const float* d_cov_out, const float* alpha, const float* beta,
+                                 const float* ctx12, const float* pb, const float* hw, const float* vb1, const float* vb2,
+                                 const float* att, const float* cov_out, const float* Wb13, float* d_logits, int ldd, float* d_gates,
+                                 int ldg, float* d_cell, float* datt, float* dcov_tot, float* d_pre_b, float* d_ctx12, float* vec_acc,
+                                 float* scal_acc, int B, int Lt, int D, int H, int M, mmb_stream_t stream);
 MMB_API int mmb_decoder_out_softmax_bwd(const float* probs, const float* d_probs, const long long* target,
                                         const float* g_nll, float* d_logits, int ldd, int B, int M, mmb_stream_t stream);
 MMB_API int mmb_decoder_cell_bwd(float* gates, const float* cell_in, const float* cell_out, const float* d_h,

@@ -33,6 +33,7 @@ SIGNATURES = {
     "mmb_bilstm_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_chunks": [c_int, c_int],
     "mmb_decoder_step_fused_fwd": [c_void_p] * 42 + [c_int] * 6 + [c_void_p],
+    "mmb_decoder_bwd_head": [c_void_p] * 25 + [c_int] + [c_void_p] + [c_int] + [c_void_p] * 7 + [c_int] * 5 + [c_void_p],
     "mmb_decoder_attn_fwd": [c_void_p] * 18 + [c_int] * 4 + [c_void_p],
     "mmb_decoder_attn_finish": [c_void_p] * 17 + [c_int] * 6 + [c_void_p],
     "mmb_decoder_cell_fwd": [c_void_p] * 4 + [c_int] * 2 + [c_void_p],

@@ -493,6 +493,198 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
 
 }  // namespace
 
+// ----------------------------------------------------------------------------------------------------------------------------------
+// Backward, the "head" of a step: everything between the previous step's text sweeps and this step's -- the masked soft-max backward,
+// d h = d_logits out.weight, the LSTM cell backward, d c3 = d_gates W_ih[:, :D], the modality soft-max / W_beta tanh backward and
+// d c_k += W_beta_k^T d_pre_k -- as ONE cluster kernel per step instead of three kernels and three library GEMMs (25 us of the 63 us of a
+// backward step inside a CUDA graph: each of the six is a 2 - 5 us launch on a few CTAs).  Same cut as the forward: a cluster per video,
+// mat-vecs split over the ranks with the weights read so that consecutive threads read consecutive outputs, small vectors through DSMEM.
+// The two sweeps over the text axis (decoder_step.cu: dec_attn_sweep1 / sweep2) and the final d h GEMM keep their kernels.
+// ----------------------------------------------------------------------------------------------------------------------------------
+struct HeadArgs {
+  const float *probs, *d_probs;                             // (B,M); d_probs may be null
+  const long long* target;                                  // (B) or null
+  const float *g_nll, *g_cov;                               // (B) or null: d loss / d [nll | coverage term]
+  const float* out_w;                                       // (M, H) row-major (rows past M are never read)
+  const float *gates, *cell_in, *cell_out;                  // (B,4H) activated gates, (B,H), (B,H)
+  const float *d_h_out, *d_cell_out;                        // (B,H) or null
+  const float* Wcat_ctx;                                    // (4H, D) = lstm.weight_ih[:, :D]
+  const float *d_att_cov, *d_cov_out;                       // (B,Lt) or null
+  const float *alpha, *beta, *ctx12, *pb, *hw;              // (B,2,Lt), (B,2), (2,B,D), (2,B,D), (B,4D)
+  const float *vb1, *vb2;                                   // (D)
+  const float *att, *cov_out;                               // (B,Lt): the step's att_cov / coverage' (fused coverage loss) or null
+  const float* Wb13;                                        // (2, D, D) row-major
+  float* d_logits;                                          // (B, ldd), columns M..ldd-1 zeroed
+  float* d_gates;                                           // (B, ldg): first 4H columns
+  float *d_cell, *datt, *dcov_tot, *d_pre_b, *d_ctx12;      // (B,H), (B,Lt), (B,Lt), (2,B,D), (2,B,D)
+  float *vec_acc, *scal_acc;                                // (B,6,D), (B,4): accumulated in place (rows 4, 5; columns 2, 3)
+  int B, Lt, D, H, M, ldd, ldg, chunk;
+};
+
+__global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), R = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL;
+  const int tid = threadIdx.x;
+  const int D = a.D, H = a.H, M = a.M, Lt = a.Lt;
+
+  extern __shared__ __align__(16) float smem[];
+  auto up4 = [](int v) { return (v + 3) & ~3; };
+  float* s_dl = smem;                                   // [per_m]  this rank's slice of d_logits (first: p dp)
+  const int per_m = (M + CL - 1) / CL;
+  float* s_dhp = s_dl + up4(per_m);                     // [MAXC][H]  partial d h of every rank (written remotely)
+  float* s_dg = s_dhp + up4(MAXC * H);                  // [4H]     d_gates
+  float* s_dctx = s_dg + up4(4 * H);                    // [D]      d c3, gathered
+  float* s_dpre = s_dctx + up4(D);                      // [2D]     d_pre_b
+  float* s_ex = s_dpre + up4(2 * D);                    // [MAXC][4] scalar exchanges
+  float* s_red = s_ex + MAXC * 4;                       // [32]
+  float* s_scr = s_red + 32;                            // [NT]
+
+  // ---- 1: masked soft-max backward: d_logit = p (dp - sum p dp); masked entries have p = 0 ---------------------------------
+  const int m0 = min(M, R * per_m), m1 = min(M, m0 + per_m);
+  const int tg = a.target ? (int)a.target[b] : -1;
+  const float dp_t = a.target ? -a.g_nll[b] / (a.probs[(size_t)b * M + tg] + 1e-12f) : 0.f;   // d(-log(p_tgt + eps)) at the target column
+  {
+    float dot = 0.f;
+    if (a.d_probs)
+      for (int m = m0 + tid; m < m1; m += NT) dot = fmaf(a.probs[(size_t)b * M + m], a.d_probs[(size_t)b * M + m], dot);
+    dot = block_sum(dot, s_red);
+    if (tid < CL) cluster.map_shared_rank(s_ex, tid)[R * 4 + 0] = dot;
+  }
+  cluster.sync();
+  {
+    float dot = 0.f;
+    for (int r = 0; r < CL; ++r) dot += s_ex[r * 4 + 0];
+    if (a.target) dot = fmaf(a.probs[(size_t)b * M + tg], dp_t, dot);
+    for (int m = m0 + tid; m < m1; m += NT) {
+      const float dp = (a.d_probs ? a.d_probs[(size_t)b * M + m] : 0.f) + (m == tg ? dp_t : 0.f);
+      const float v = a.probs[(size_t)b * M + m] * (dp - dot);
+      s_dl[m - m0] = v;
+      a.d_logits[(size_t)b * a.ldd + m] = v;
+    }
+    if (R == 0)
+      for (int m = M + tid; m < a.ldd; m += NT) a.d_logits[(size_t)b * a.ldd + m] = 0.f;   // row padding (keeps the weight-gradient GEMM aligned)
+  }
+  __syncthreads();
+  // ---- 2: d h (from the logits) = d_logits out.weight: this rank's rows of out.weight, all H outputs; partials summed over the ranks
+  block_matvec_t(a.out_w + (size_t)m0 * H, H, nullptr, s_dl, m1 - m0, H, s_scr, [](int i) { return i; }, [&](int i, float v) {
+    for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dhp, r)[R * H + i] = v;
+  });
+  if (m1 - m0 <= 0 && tid < H)
+    for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dhp, r)[R * H + tid] = 0.f;
+  cluster.sync();
+  // ---- 3: LSTM cell backward (every rank, redundantly: H elements) ------------------------------------------------------------
+  if (tid < H) {
+    const int j = tid;
+    float dh = 0.f;
+    for (int r = 0; r < CL; ++r) dh += s_dhp[r * H + j];
+    if (a.d_h_out) dh += a.d_h_out[(size_t)b * H + j];
+    const float* g = a.gates + (size_t)b * 4 * H;
+    const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+    const float tc = tanh_fast(a.cell_out[(size_t)b * H + j]);
+    const float dc = fmaf(dh * go, 1.f - tc * tc, a.d_cell_out ? a.d_cell_out[(size_t)b * H + j] : 0.f);
+    const float di = dc * gg * gi * (1.f - gi), df = dc * a.cell_in[(size_t)b * H + j] * gf * (1.f - gf);
+    const float dg = dc * gi * (1.f - gg * gg), dO = dh * tc * go * (1.f - go);
+    s_dg[j] = di; s_dg[H + j] = df; s_dg[2 * H + j] = dg; s_dg[3 * H + j] = dO;
+    if (R == 0) {
+      float* o = a.d_gates + (size_t)b * a.ldg;
+      o[j] = di; o[H + j] = df; o[2 * H + j] = dg; o[3 * H + j] = dO;
+      a.d_cell[(size_t)b * H + j] = dc * gf;
+    }
+  }
+  __syncthreads();
+  // ---- 4: d c3 = d_gates W_ih[:, :D]: outputs split over the ranks, gathered -----------------------------------------------------
+  {
+    const int per = (D + CL - 1) / CL, d0 = min(D, R * per), d1 = min(D, d0 + per);
+    block_matvec_t(a.Wcat_ctx, D, nullptr, s_dg, 4 * H, d1 - d0, s_scr, [&](int i) { return d0 + i; }, [&](int i, float v) {
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dctx, r)[d0 + i] = v;
+    });
+  }
+  cluster.sync();
+  // ---- 5: modality soft-max + W_beta tanh backward; datt / dcov_tot of this rank's text rows ---------------------------------------
+  const float beta1 = a.beta[b * 2 + 0], beta2 = a.beta[b * 2 + 1];
+  {
+    float db1 = 0.f, db2 = 0.f;
+    if (R == 0)
+      for (int d = tid; d < D; d += NT) {
+        db1 = fmaf(a.ctx12[(size_t)b * D + d], s_dctx[d], db1);
+        db2 = fmaf(a.ctx12[((size_t)a.B + b) * D + d], s_dctx[d], db2);
+      }
+    const float gc = a.g_cov ? a.g_cov[b] : 0.f;
+    const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk);
+    for (int t = t0 + tid; t < t1; t += NT) {
+      float dcv = a.d_cov_out ? a.d_cov_out[(size_t)b * Lt + t] : 0.f;
+      float g = a.d_att_cov ? a.d_att_cov[(size_t)b * Lt + t] : 0.f;
+      if (a.g_cov) {                                              // d sum min(att, cov'): ties split evenly (torch.minimum)
+        const float av = a.att[(size_t)b * Lt + t], cv = a.cov_out[(size_t)b * Lt + t];
+        const float tie = av == cv ? 0.5f * gc : 0.f;
+        g += av < cv ? gc : tie;
+        dcv += cv < av ? gc : tie;
+      }
+      a.dcov_tot[(size_t)b * Lt + t] = dcv;
+      g += dcv;                                                   // coverage' = coverage + att
+      a.datt[(size_t)b * Lt + t] = g;
+      db1 = fmaf(a.alpha[((size_t)b * 2 + 0) * Lt + t], g, db1);
+      db2 = fmaf(a.alpha[((size_t)b * 2 + 1) * Lt + t], g, db2);
+    }
+    db1 = block_sum(db1, s_red);
+    db2 = block_sum(db2, s_red);
+    if (tid < CL) {
+      float* dst = cluster.map_shared_rank(s_ex, tid) + R * 4;
+      dst[1] = db1;
+      dst[2] = db2;
+    }
+  }
+  cluster.sync();
+  {
+    float db1 = 0.f, db2 = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      db1 += s_ex[r * 4 + 1];
+      db2 += s_ex[r * 4 + 2];
+    }
+    const float mix = beta1 * db1 + beta2 * db2;
+    const float deb1 = beta1 * (db1 - mix), deb2 = beta2 * (db2 - mix);
+    for (int d = tid; d < D; d += NT) {
+      const float t1 = tanh_fast(a.pb[(size_t)b * D + d] + a.hw[(size_t)b * 4 * D + 2 * D + d]);
+      const float t2 = tanh_fast(a.pb[((size_t)a.B + b) * D + d] + a.hw[(size_t)b * 4 * D + 3 * D + d]);
+      const float p1 = deb1 * a.vb1[d] * (1.f - t1 * t1), p2 = deb2 * a.vb2[d] * (1.f - t2 * t2);
+      s_dpre[d] = p1;
+      s_dpre[D + d] = p2;
+      if (R == 0) {
+        a.d_pre_b[(size_t)b * D + d] = p1;
+        a.d_pre_b[((size_t)a.B + b) * D + d] = p2;
+        a.vec_acc[((size_t)b * 6 + 4) * D + d] += deb1 * t1;        // d v_beta_1 weight
+        a.vec_acc[((size_t)b * 6 + 5) * D + d] += deb2 * t2;
+      }
+    }
+    if (R == 0 && tid == 0) {
+      a.scal_acc[b * 4 + 2] += deb1;
+      a.scal_acc[b * 4 + 3] += deb2;
+    }
+  }
+  __syncthreads();
+  // ---- 6: d c_k = beta_k d c3 + W_beta_k^T d_pre_k: the 2D outputs split over the ranks --------------------------------------------
+  {
+    const int per = (2 * D + CL - 1) / CL, o0 = min(2 * D, R * per), o1 = min(2 * D, o0 + per);
+    for (int k = 0; k < 2; ++k) {
+      const int lo = max(o0, k * D), hi = min(o1, (k + 1) * D);
+      const float bk = k == 0 ? beta1 : beta2;
+      block_matvec_t(a.Wb13 + (size_t)k * D * D, D, nullptr, s_dpre + k * D, D, hi - lo, s_scr, [&](int i) { return lo - k * D + i; },
+                     [&](int i, float v) {
+                       const int dd = lo - k * D + i;
+                       a.d_ctx12[((size_t)k * a.B + b) * D + dd] = fmaf(bk, s_dctx[dd], v);
+                     });
+    }
+  }
+  cluster.sync();      // no rank exits while another may still write into its shared memory
+}
+
+static size_t head_smem_bytes(int D, int H, int M, int CL) {
+  auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
+  const size_t per_m = (M + CL - 1) / CL;
+  return (up4(per_m) + up4((size_t)MAXC * H) + up4(4 * H) + up4(D) + up4(2 * D) + MAXC * 4 + 32 + NT) * sizeof(float) + 64;
+}
+
 // bytes of dynamic shared memory for the launch below
 static size_t fused_smem_bytes(int Lt, int D, int H, int E, int M, int CL, int* chunk_out) {
   const int chunk = (Lt + CL - 1) / CL;
@@ -561,4 +753,46 @@ extern "C" int mmb_decoder_step_fused_fwd(const float* proj_a, const float* proj
   cfg.numAttrs = 1;
   MMB_CUDA(cudaLaunchKernelEx(&cfg, dec_step_fused_kernel, a));
   return check_launch("dec_step_fused_kernel");
+}
+
+extern "C" int mmb_decoder_bwd_head(const float* probs, const float* d_probs, const long long* target, const float* g_nll,
+                                    const float* g_cov, const float* out_w, const float* gates, const float* cell_in,
+                                    const float* cell_out, const float* d_h_out, const float* d_cell_out, const float* Wcat_ctx,
+                                    const float* d_att_cov, const float* d_cov_out, const float* alpha, const float* beta,
+                                    const float* ctx12, const float* pb, const float* hw, const float* vb1, const float* vb2,
+                                    const float* att, const float* cov_out, const float* Wb13, float* d_logits, int ldd, float* d_gates,
+                                    int ldg, float* d_cell, float* datt, float* dcov_tot, float* d_pre_b, float* d_ctx12, float* vec_acc,
+                                    float* scal_acc, int B, int Lt, int D, int H, int M, mmb_stream_t stream) {
+  using namespace mmb;
+  MMB_REQUIRE(probs && out_w && gates && cell_in && cell_out && Wcat_ctx && alpha && beta && ctx12 && pb && hw && vb1 && vb2 && Wb13 &&
+                  d_logits && d_gates && d_cell && datt && dcov_tot && d_pre_b && d_ctx12 && vec_acc && scal_acc,
+              MMB_ERR_INVALID, "mmb_decoder_bwd_head: null pointer");
+  MMB_REQUIRE((!target || g_nll) && (!g_cov || (att && cov_out)), MMB_ERR_INVALID, "mmb_decoder_bwd_head: loss-term pointers");
+  MMB_REQUIRE(B > 0 && Lt > 0 && D > 0 && H > 0 && M > 0 && ldd >= M && ldg >= 4 * H && H <= NT, MMB_ERR_INVALID,
+              "mmb_decoder_bwd_head: B=%d Lt=%d D=%d H=%d M=%d ldd=%d ldg=%d", B, Lt, D, H, M, ldd, ldg);
+  const int CL = (long long)B * 4 * 2 <= 160 ? 8 : 4;
+  HeadArgs a{probs, d_probs, target, g_nll, g_cov, out_w, gates, cell_in, cell_out, d_h_out, d_cell_out, Wcat_ctx, d_att_cov, d_cov_out,
+             alpha, beta, ctx12, pb, hw, vb1, vb2, att, cov_out, Wb13, d_logits, d_gates, d_cell, datt, dcov_tot, d_pre_b, d_ctx12,
+             vec_acc, scal_acc, B, Lt, D, H, M, ldd, ldg, (Lt + CL - 1) / CL};
+  const size_t smem = head_smem_bytes(D, H, M, CL);
+  MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_bwd_head: %zu B of shared memory", smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    MMB_CUDA(cudaFuncSetAttribute(dec_bwd_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMB_CUDA(cudaLaunchKernelEx(&cfg, dec_bwd_head_kernel, a));
+  return check_launch("dec_bwd_head_kernel");
 }

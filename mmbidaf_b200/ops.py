@@ -257,24 +257,38 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     d_logits = d_logits_pad[:, :M]
     fused = target is not None and d_lossvec is not None
     g = c(d_lossvec) if fused else None                                        # (2, B): [d nll | d coverage term]
-    _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(target if fused else None),
-                                               p(g[0] if fused else None), d_logits_pad.data_ptr(), seq.Mp, B, M, st),
-               "mmb_decoder_out_softmax_bwd")
-    dh_logits = d_logits_pad @ seq.out_w_pad                                   # (B, H)  library GEMM
     gbuf = torch.empty(B, 4 * H + 4 * D, **f32)                                # [d_gates | d_hw4] side by side
     d_gates, d_hw4 = gbuf[:, :4 * H], gbuf[:, 4 * H:]
     d_cell = torch.empty(B, H, **f32)
-    _lib.check(lib.mmb_decoder_cell_bwd(p(gates), p(cell), p(cell_out), p(dh_logits), p(c(d_h_out)), p(c(d_cell_out)),
-                                        gbuf.data_ptr(), 4 * H + 4 * D, p(d_cell), B, H, st), "mmb_decoder_cell_bwd")
-    d_xcat = d_gates @ seq.Wcat_ctx                                            # (B, D) = d ctx  library GEMM
     datt, d_pre_b, d_ctx12 = torch.empty(B, Lt, **f32), torch.empty(2, B, D, **f32), torch.empty(2, B, D, **f32)
     dcov_tot = torch.empty(B, Lt, **f32)
-    _lib.check(lib.mmb_decoder_attn_finish_bwd(p(d_xcat), D, p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
-                                               p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(datt), p(d_pre_b),
-                                               p(d_ctx12), p(vec_acc), p(scal_acc), p(att_cov if fused else None),
-                                               p(cov_out if fused else None), p(g[1] if fused else None), p(dcov_tot),
-                                               B, Lt, D, st), "mmb_decoder_attn_finish_bwd")
-    d_ctx12.baddbmm_(d_pre_b, seq.Wb13)                                        # += d_pre W_beta   library GEMM
+    cut = os.environ.get("MMB_DECODER_CUT")
+    if cut is None:
+        cut = "fused" if B * Lt <= 20000 else "chunks"
+    if cut != "chunks":
+        # everything up to the text sweeps as ONE cluster kernel (csrc/decoder_fused.cu: dec_bwd_head_kernel)
+        _lib.check(lib.mmb_decoder_bwd_head(p(probs), p(c(d_probs)), p(target if fused else None), p(g[0] if fused else None),
+                                            p(g[1] if fused else None), p(seq.out_w), p(gates), p(cell), p(cell_out), p(c(d_h_out)),
+                                            p(c(d_cell_out)), p(seq.Wcat_ctx), p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
+                                            p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(att_cov if fused else None),
+                                            p(cov_out if fused else None), p(seq.Wb13), d_logits_pad.data_ptr(), seq.Mp,
+                                            gbuf.data_ptr(), 4 * H + 4 * D, p(d_cell), p(datt), p(dcov_tot), p(d_pre_b), p(d_ctx12),
+                                            p(vec_acc), p(scal_acc), B, Lt, D, H, M, st), "mmb_decoder_bwd_head")
+        _count(-2)                                                             # (one kernel where the chunk cut counts three)
+    else:
+        _lib.check(lib.mmb_decoder_out_softmax_bwd(p(probs), p(c(d_probs)), p(target if fused else None),
+                                                   p(g[0] if fused else None), d_logits_pad.data_ptr(), seq.Mp, B, M, st),
+                   "mmb_decoder_out_softmax_bwd")
+        dh_logits = d_logits_pad @ seq.out_w_pad                               # (B, H)  library GEMM
+        _lib.check(lib.mmb_decoder_cell_bwd(p(gates), p(cell), p(cell_out), p(dh_logits), p(c(d_h_out)), p(c(d_cell_out)),
+                                            gbuf.data_ptr(), 4 * H + 4 * D, p(d_cell), B, H, st), "mmb_decoder_cell_bwd")
+        d_xcat = d_gates @ seq.Wcat_ctx                                        # (B, D) = d ctx  library GEMM
+        _lib.check(lib.mmb_decoder_attn_finish_bwd(p(d_xcat), D, p(c(d_att_cov)), p(c(d_cov_out)), p(alpha), p(beta),
+                                                   p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(datt), p(d_pre_b),
+                                                   p(d_ctx12), p(vec_acc), p(scal_acc), p(att_cov if fused else None),
+                                                   p(cov_out if fused else None), p(g[1] if fused else None), p(dcov_tot),
+                                                   B, Lt, D, st), "mmb_decoder_attn_finish_bwd")
+        d_ctx12.baddbmm_(d_pre_b, seq.Wb13)                                    # += d_pre W_beta   library GEMM
     d_alpha, spart = torch.empty(B, 2, Lt, **f32), torch.empty(B, nch, 2, **f32)
     d_cov, colp = torch.empty(B, Lt, **f32), torch.empty(B, nch, 2, 3, D, **f32)
     separt = torch.empty(B, nch, 2, **f32)

@@ -186,3 +186,47 @@ def test_fused_cluster_step_matches_the_chunk_parallel_cut(cfg, monkeypatch):
         assert rel_err(g, w) < TOL, name
     assert rel_err(got[7], want[7]) < TOL                                  # [nll | coverage term]
     assert (got[0][mask == 0] == 0).all()
+
+
+@pytest.mark.parametrize("cfg", [(3, 24, 100, 300, 409, 3), (32, 409, 100, 300, 409, 3), (2, 7, 6, 10, 17, 2), (24, 130, 100, 300, 256, 2)])
+@pytest.mark.parametrize("fused_loss", [True, False])
+def test_cluster_kernels_match_the_chunk_parallel_cut_through_autograd(cfg, fused_loss, monkeypatch):
+    """Both cluster kernels (the one-kernel forward step and the head of the backward step: soft-max / LSTM cell / modality
+    soft-max backward with their three mat-vecs) against the five-kernel cut + library GEMMs, through the module and autograd:
+    a chain of steps, loss, every gradient."""
+    from conftest import grad_err
+    from mmbidaf_b200.layers import MultimodalAttentionDecoder
+    bsz, lt, hid, e, m, steps = cfg
+    results = []
+    for cut in ("chunks", "fused"):
+        monkeypatch.setenv("MMB_DECODER_CUT", cut)
+        torch.manual_seed(77)
+        mod = MultimodalAttentionDecoder(e, hid, m, num_layers=1).cuda().train()
+        gen = torch.Generator().manual_seed(1234 + lt)
+        enc_a = torch.randn(bsz, lt, 2 * hid, generator=gen).cuda().requires_grad_(True)
+        enc_i = torch.randn(bsz, lt, 2 * hid, generator=gen).cuda().requires_grad_(True)
+        h = torch.randn(bsz, 1, hid, generator=gen).cuda().requires_grad_(True)
+        state = (h, torch.randn(1, bsz, hid, generator=gen).cuda(), torch.rand(bsz, lt, 1, generator=gen).cuda())
+        lens = torch.randint(1, m + 1, (bsz,), generator=gen)
+        mask = (torch.arange(m).unsqueeze(0) < lens.unsqueeze(1)).cuda()
+        sents = [torch.randn(bsz, 1, e, generator=gen).cuda() for _ in range(steps)]
+        tgts = [torch.stack([torch.randint(0, int(n), (1,), generator=gen)[0] for n in lens]).cuda() for _ in range(steps)]
+        loss = 0
+        for k in range(steps):
+            if fused_loss:
+                probs, h1, c1, att, cov, terms = mod.step(sents[k], state[0], state[1], enc_a, enc_i, state[2], mask, target=tgts[k])
+                loss = loss + terms.sum()
+            else:
+                probs, h1, c1, att, cov = mod(sents[k], state[0], state[1], enc_a, enc_i, state[2], mask)
+                loss = loss - torch.log(probs.gather(1, tgts[k].unsqueeze(1)) + 1e-12).sum() + torch.min(att, cov).sum() + (probs * probs).sum()
+            state = (h1, c1, cov)
+        loss.backward()
+        results.append((loss.detach(), enc_a.grad, enc_i.grad, h.grad, {n: p.grad for n, p in mod.named_parameters()}))
+    (lw, aw, iw, hw_, pw), (lg, ag, ig, hg, pg) = results
+    assert rel_err(lg, lw) < 1e-5
+    assert grad_err(ag, aw) < 2e-5 and grad_err(ig, iw) < 2e-5 and grad_err(hg, hw_) < 2e-5
+    for name in pw:
+        # the four scalar bias gradients (v1 / v2: identically zero, v_beta_1 / v_beta_2: beta_k (db_k - mix), a difference of
+        # nearly equal sums over the text axis) are cancellation noise at the 1e-4 level in both cuts: the summation orders differ
+        tol = 5e-4 if name in ("v1.bias", "v2.bias", "v_beta_1.bias", "v_beta_2.bias") else 5e-5
+        assert grad_err(pg[name], pw[name], name) < tol, name

@@ -68,9 +68,21 @@ class BiDAFAttention(nn.Module):
             nn.init.xavier_uniform_(weight)
         self.bias = nn.Parameter(torch.zeros(1))
 
+    def predraw_dropout(self, text_shape, modality_shape, device):
+        """Optional: draw this call's keep-masks NOW (on the current stream) -- they depend on shapes only, so a caller that knows
+        the shapes ahead (mmbidaf_b200/models.py: while the encoders still run) takes two mask draws off the serial chain between
+        the encoders and the fused kernel.  Consumed by the next ``forward`` with matching shapes; same draw order (text, modality)."""
+        self._predrawn = None
+        if self.training and self.drop_prob > 0:
+            self._predrawn = tuple(torch.empty(tuple(shape), dtype=torch.uint8, device=device).bernoulli_(1.0 - self.drop_prob)
+                                   for shape in (text_shape, modality_shape))
+
     def _dropout_masks(self, text, modality):
+        pre, self._predrawn = getattr(self, "_predrawn", None), None
         if not self.training or self.drop_prob <= 0:
             return None, None, 1.0
+        if pre is not None and pre[0].shape == text.shape and pre[1].shape == modality.shape:
+            return pre[0], pre[1], 1.0 / (1.0 - self.drop_prob)
         # same draw order as the reference: text first, then modality (attention.py:66-67)
         return _keep_mask(text, self.drop_prob), _keep_mask(modality, self.drop_prob), 1.0 / (1.0 - self.drop_prob)
 

@@ -116,16 +116,12 @@ class MMBiDAF(nn.Module):
             masks["audio"] = self.get_mask(embedded_audio, original_audio_lengths)
             masks["image"] = self.get_mask(transformed_images, original_image_lengths)     # (B, Li, ...): same (B, Li)
 
-        (audio_encoded,), (text_emb, text_encoded), (image_emb, image_encoded) = \
-            self._fork_join([audio_branch, text_branch, image_branch], meanwhile=make_masks)
-        text_mask, audio_mask, image_mask, decoder_mask = masks["text"], masks["audio"], masks["image"], masks["decoder"]
-
         def audio_aware():
-            att = self.bidaf_att_audio(text_encoded, audio_encoded, text_mask, audio_mask)
+            att = self.bidaf_att_audio(branch["text"], branch["audio"], masks["text"], masks["audio"])
             return self.mod_t_a(att, original_text_lengths)
 
         def image_aware():
-            att = self.bidaf_att_image(text_encoded, image_encoded, text_mask, image_mask)
+            att = self.bidaf_att_image(branch["text"], branch["image"], masks["text"], masks["image"])
             return self.mod_t_i(att, original_text_lengths)
 
         steps = batch_target_indices.size(1) if self.training else max_dec_len
@@ -143,8 +139,73 @@ class MMBiDAF(nn.Module):
                 start["next"] = embedded_text[start["rows"].unsqueeze(0), start["targets"][:, :steps].t()]
             self.multimodal_att_decoder.prepare()          # this step's weight layouts of the decoder's batched GEMMs
 
-        (mod_text_audio, text_audio_hidden), (mod_text_image, text_img_hidden) = \
-            self._fork_join([audio_aware, image_aware], meanwhile=decoder_start)
+        branch = {}
+        if not (self.use_streams and torch.cuda.is_available()):
+            # reference order of the calls (and of the dropout draws): models.py:95-135
+            branch["text"] = text_branch()[1]
+            branch["audio"] = audio_branch()[0]
+            branch["image"] = image_branch()[1]
+            make_masks()
+            mod_text_audio, text_audio_hidden = audio_aware()
+            mod_text_image, text_img_hidden = image_aware()
+            decoder_start()
+        else:
+            # Dependency-driven: the text x image chain (BiDAF + two modality-LSTM layers, ~0.6 ms) needs the text and image encoders
+            # only, which finish ~0.3 ms before the 1024-frame audio recurrence -- it runs beside the rest of that recurrence instead of
+            # behind a join of all three encoders (which is what two successive fork-joins did: 160 us on the critical path).
+            main = torch.cuda.current_stream()
+            if getattr(self, "_streams", None) is None or self._streams[0].device != main.device:
+                # stream 0 carries the critical path (audio): high priority, so that its 64 CTAs are never queued behind the others
+                object.__setattr__(self, "_streams", [torch.cuda.Stream(device=main.device, priority=-1 if i == 0 else 0)
+                                                      for i in range(3)])
+            s_audio, s_text, s_image = self._streams
+            capturing = torch.cuda.is_current_stream_capturing()
+
+            def keep(t, stream):                  # a tensor made on one stream and read on another (no-op inside a graph's pool)
+                if not capturing and isinstance(t, torch.Tensor):
+                    t.record_stream(stream)
+
+            for st in self._streams:
+                st.wait_stream(main)
+            with torch.cuda.stream(s_audio):
+                branch["audio"] = audio_branch()[0]
+            with torch.cuda.stream(s_text):
+                branch["text"] = text_branch()[1]
+                text_done = torch.cuda.Event()
+                text_done.record(s_text)
+            with torch.cuda.stream(s_image):
+                branch["image"] = image_branch()[1]
+            make_masks()                          # on the main stream, beside the encoders: needs only the lengths
+            # ... and so do the keep-masks of the two BiDAF blocks (shapes only): two mask draws less between the audio recurrence and
+            # the fused kernel, on the critical path
+            d2 = 2 * self.text_enc.rnn.hidden_size
+            dev = embedded_text.device
+            self.bidaf_att_audio.predraw_dropout((B, Lt, d2), (B, embedded_audio.size(1), d2), dev)
+            self.bidaf_att_image.predraw_dropout((B, Lt, d2), (B, transformed_images.size(1), d2), dev)
+            for att, st in ((self.bidaf_att_audio, s_audio), (self.bidaf_att_image, s_image)):
+                for t in (getattr(att, "_predrawn", None) or ()):
+                    keep(t, st)
+            masks_done = torch.cuda.Event()
+            masks_done.record(main)
+            with torch.cuda.stream(s_image):
+                s_image.wait_event(text_done)
+                s_image.wait_event(masks_done)
+                mod_text_image, text_img_hidden = image_aware()
+            with torch.cuda.stream(s_audio):
+                s_audio.wait_event(text_done)
+                s_audio.wait_event(masks_done)
+                mod_text_audio, text_audio_hidden = audio_aware()
+            decoder_start()                       # on the main stream, beside the recurrences
+            for st in self._streams:
+                main.wait_stream(st)
+            keep(branch["text"], s_audio)
+            keep(branch["text"], s_image)
+            for m in masks.values():
+                keep(m, s_audio)
+                keep(m, s_image)
+            for t in (mod_text_audio, text_audio_hidden, mod_text_image, text_img_hidden, branch["text"], branch["audio"], branch["image"]):
+                keep(t, main)
+        decoder_mask = masks["decoder"]
 
         # models.py:143-149 (the hidden-state rows are in descending-length order: reference quirk Q3)
         decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)

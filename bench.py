@@ -252,7 +252,8 @@ def bidaf_microbench(device, rounds: int, warmup: int, precision: int, backward:
         run = lambda s: ops.bidaf_bwd(s[4], s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, None, None, 1.0, s[5], s[9], s[6], s[7],
                                       s[8], s[10], precision)
     else:
-        run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision)
+        # aux=False: the forward as the layer runs it under no_grad (only `out`; T and the log-sum-exps are saved for a backward pass only)
+        run = lambda s: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=precision, aux=False)
     side = torch.cuda.Stream(device)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):

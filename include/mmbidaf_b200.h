@@ -68,6 +68,7 @@ MMB_API int mmb_device_supported(void);
  *   soft-max -- saved for the backward pass; bm (B,Lc,d) = s1 q2c (the b of attention.py:50 before the
  *   product with c), optional (NULL in inference), also for the backward pass.  MMB_PREC_FP32: d % 4 == 0, d <= 256 (workspace may be NULL).
  *   MMB_PREC_BF16 (tcgen05 + TMEM + TMA): d % 8 == 0, d <= 200, workspace of mmb_bidaf_workspace_bytes().
+  * On the bf16 tier q2c, lse_row and lse_col may be NULL (inference: only `out` is written).
  */
 MMB_API int mmb_bidaf_fwd(const float* text, const float* modality, const uint8_t* text_mask, const uint8_t* modality_mask,
                   const float* w_text, const float* w_modality, const float* w_cross, const float* bias,

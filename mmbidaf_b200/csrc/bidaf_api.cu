@@ -37,9 +37,11 @@ extern "C" int mmb_bidaf_fwd(const float* text, const float* modality, const uin
                              const uint8_t* keep_modality, float keep_scale, float* out, float* q2c, float* bm,
                              float* lse_row, float* lse_col, void* workspace, int B, int Lc, int Lq, int d, int precision,
                              mmb_stream_t stream) {
-  MMB_REQUIRE(text && modality && text_mask && modality_mask && w_text && w_modality && w_cross && bias && out && q2c &&
-                  lse_row && lse_col,
-              MMB_ERR_INVALID, "mmb_bidaf_fwd: null pointer");
+  MMB_REQUIRE(text && modality && text_mask && modality_mask && w_text && w_modality && w_cross && bias && out, MMB_ERR_INVALID,
+              "mmb_bidaf_fwd: null pointer");
+  // q2c, lse_row and lse_col (what the backward pass wants saved) may be NULL on the bf16 tier: inference writes `out` only
+  MMB_REQUIRE(precision == MMB_PREC_BF16 || (q2c && lse_row && lse_col), MMB_ERR_INVALID,
+              "mmb_bidaf_fwd: q2c / lse_row / lse_col are required on the fp32 tier");
   MMB_REQUIRE(B > 0 && Lc > 0 && Lq > 0 && d > 0, MMB_ERR_INVALID, "mmb_bidaf_fwd: B=%d Lc=%d Lq=%d d=%d", B, Lc, Lq, d);
   MMB_REQUIRE(d % 4 == 0 && d <= 256, MMB_ERR_UNSUPPORTED, "mmb_bidaf_fwd: d=%d (need d %% 4 == 0, d <= 256)", d);
   MMB_REQUIRE(B <= 65535, MMB_ERR_UNSUPPORTED, "mmb_bidaf_fwd: B=%d > 65535", B);

@@ -661,6 +661,7 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
   const char* cut = getenv("MMB_BIDAF_FWD_CUT");
   const bool two_per_sm = cut && atoi(cut) == 2;
   if (!cut || atoi(cut) == 5) return bidaf_fwd_tc5_launch(pk, text, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
+  MMB_REQUIRE(q2c && lse_row && lse_col, MMB_ERR_INVALID, "mmb_bidaf_fwd: forward cuts 1 - 4 need q2c / lse_row / lse_col");
   if (cut && atoi(cut) == 4) return bidaf_fwd_tc4_launch(pk, text, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   if (cut && atoi(cut) == 3) return bidaf_fwd_tc3_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);
   if (two_per_sm) return bidaf_fwd_tc2_launch(pk, bias, out, q2c, bm, lse_row, lse_col, B, Lc, Lq, d, stream);

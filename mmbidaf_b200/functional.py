@@ -216,7 +216,7 @@ class _BidafAttention(torch.autograd.Function):
                 keep_text, keep_modality, keep_scale, precision):
         save = any(ctx.needs_input_grad)
         res = ops.bidaf_fwd(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,
-                            keep_text, keep_modality, keep_scale, precision, save=save)
+                            keep_text, keep_modality, keep_scale, precision, save=save, aux=False)
         if save:
             out, q2c, lse_row, lse_col, bm, ws = res
             ctx.save_for_backward(text, modality, text_mask, modality_mask, w_text, w_modality, w_cross, bias,

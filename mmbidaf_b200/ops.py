@@ -33,9 +33,11 @@ def _u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tensor, modality_mask: torch.Tensor,
               w_text: torch.Tensor, w_modality: torch.Tensor, w_cross: torch.Tensor, bias: torch.Tensor,
               keep_text: Optional[torch.Tensor] = None, keep_modality: Optional[torch.Tensor] = None,
-              keep_scale: float = 1.0, precision: int = PREC_FP32, save: bool = False):
+              keep_scale: float = 1.0, precision: int = PREC_FP32, save: bool = False, aux: bool = True):
     """Fused BiDAF forward (attention.py:37-75).  Returns (out (B,Lc,4d), q2c (B,Lq,d), lse_row (B,Lc),
-    lse_col (B,Lq)); with ``save`` also (bm (B,Lc,d), workspace) -- everything the backward pass needs."""
+    lse_col (B,Lq)); with ``save`` also (bm (B,Lc,d), workspace) -- everything the backward pass needs.  ``aux=False`` (bf16 tier,
+    default kernel cut, no ``save``): only ``out`` is computed and written (inference: the reference's forward returns nothing else);
+    the other three results are None."""
     L = _lib.lib()
     assert text.dtype == torch.float32 and modality.dtype == torch.float32
     B, Lc, d = text.shape
@@ -45,10 +47,11 @@ def bidaf_fwd(text: torch.Tensor, modality: torch.Tensor, text_mask: torch.Tenso
     kt, km = _u8(keep_text), _u8(keep_modality)
     wt, wm, wc = (w.detach().reshape(-1).contiguous() for w in (w_text, w_modality, w_cross))
     out = torch.empty(B, Lc, 4 * d, device=text.device, dtype=torch.float32)
-    q2c = torch.empty(B, Lq, d, device=text.device, dtype=torch.float32)
+    want_aux = aux or save or precision != PREC_BF16 or os.environ.get("MMB_BIDAF_FWD_CUT", "5") != "5"
+    q2c = torch.empty(B, Lq, d, device=text.device, dtype=torch.float32) if want_aux else None
     bm = torch.empty(B, Lc, d, device=text.device, dtype=torch.float32) if save else None
-    lse_row = torch.empty(B, Lc, device=text.device, dtype=torch.float32)
-    lse_col = torch.empty(B, Lq, device=text.device, dtype=torch.float32)
+    lse_row = torch.empty(B, Lc, device=text.device, dtype=torch.float32) if want_aux else None
+    lse_col = torch.empty(B, Lq, device=text.device, dtype=torch.float32) if want_aux else None
     p = _lib.ptr
     ws_bytes = L.mmb_bidaf_workspace_bytes(B, Lc, Lq, d, int(precision), int(km is not None))
     ws = torch.empty(ws_bytes, device=text.device, dtype=torch.uint8) if ws_bytes else None

@@ -380,3 +380,19 @@ def test_full_size_config2_tiers_agree_and_backward_is_linear():
     for b_, n in enumerate(q_len.tolist()):
         if n < lq:
             assert (dq[b_, n:] == 0).all()
+
+
+def test_bf16_inference_path_writes_only_out():
+    """aux=False (what the layer runs under no_grad): T and the log-sum-exps are neither allocated nor written; `out` is bit-identical
+    to the full call."""
+    from mmbidaf_b200 import ops
+    gen = torch.Generator().manual_seed(99)
+    c, q = torch.randn(3, 140, 200, generator=gen).cuda(), torch.randn(3, 75, 200, generator=gen).cuda()
+    cm = (torch.arange(140).unsqueeze(0) < torch.tensor([[140], [17], [90]])).cuda()
+    qm = (torch.arange(75).unsqueeze(0) < torch.tensor([[75], [75], [3]])).cuda()
+    w = [(torch.randn(200, generator=gen) * 0.1).cuda() for _ in range(3)]
+    bias = torch.tensor([0.2]).cuda()
+    full = ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, precision=ops.PREC_BF16)
+    lean = ops.bidaf_fwd(c, q, cm, qm, w[0], w[1], w[2], bias, precision=ops.PREC_BF16, aux=False)
+    assert lean[1] is None and lean[2] is None and lean[3] is None
+    assert torch.equal(full[0], lean[0])

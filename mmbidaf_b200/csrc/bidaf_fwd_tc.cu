@@ -62,15 +62,17 @@ constexpr int PACK_CHUNK_STRIDE = 144;   // 128-byte core matrix + 16 bytes: spr
 
 struct PackPair { PackArgs side[2]; };
 
+// (The inputs are read once and block 0 of the output is not re-read by this pass: evict-first loads and streaming stores leave L2 to the
+// bf16 packs, which the main kernel streams several times.)
 // 256-bit global accesses (sm_100): one instruction per lane and row instead of two 128-bit ones whose halves of every 32-byte
 // sector arrived at L2 as separate requests (ncu: 2.3 M read sectors for 1.2 M sectors of input).
 __device__ __forceinline__ void ldg256(const float* p, float* v) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
 __device__ __forceinline__ void stg256(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+  asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }

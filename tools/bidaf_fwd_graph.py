@@ -30,7 +30,7 @@ for _ in range(4):
     sets.append((c, q, cm, qm))
 w = [torch.randn(d, generator=gen).to(dev) * 0.1 for _ in range(3)]
 bias = torch.full((1,), 0.3, device=dev)
-run = lambda s, prec: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=prec)
+run = lambda s, prec, aux=True: ops.bidaf_fwd(s[0], s[1], s[2], s[3], w[0], w[1], w[2], bias, precision=prec, aux=aux)
 if not a.no_check:
     s = sets[0]
     got = run(s, ops.PREC_BF16)
@@ -43,12 +43,12 @@ side = torch.cuda.Stream(dev)
 side.wait_stream(torch.cuda.current_stream())
 with torch.cuda.stream(side):
     for i in range(4):
-        run(sets[i], ops.PREC_BF16)
+        run(sets[i], ops.PREC_BF16, False)
 torch.cuda.current_stream().wait_stream(side)
 torch.cuda.synchronize()
 graph = torch.cuda.CUDAGraph()
 with torch.cuda.graph(graph):
-    keep = [run(s, ops.PREC_BF16) for s in sets]
+    keep = [run(s, ops.PREC_BF16, False) for s in sets]                   # as bench.py: the inference path (only out)
 for _ in range(3):
     graph.replay()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

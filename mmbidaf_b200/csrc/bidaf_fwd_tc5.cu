@@ -92,26 +92,8 @@ struct EvLog {                       // lane 0 of one warp of CTA 0 appends (cod
   }
 };
 
-// A wait that is expected to be long (microseconds): back off between polls instead of spinning -- a spinning warp competes for
-// the issue slots of its scheduler with the three warps it shares it with.
-__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    __nanosleep(200);
-  }
-  __trap();
-}
+// (A back-off variant of mbar_wait -- __nanosleep between polls for the waits that are expected to be long -- was measured: it does not
+// free anything the working warps need, and the coarser wake-up costs ~1.5 us per forward; every wait polls.)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -348,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
         if (last > 0) nty = min(nty, last);
       }
       const int slot = n & (ITEM_SLOTS - 1);
-      mbar_wait_long(item_empty0 + 8 * slot, ((n / ITEM_SLOTS) & 1) ^ 1);
+      mbar_wait(item_empty0 + 8 * slot, ((n / ITEM_SLOTS) & 1) ^ 1);
       if (lane == 0) {
         sItems[slot] = make_int4(kind, b, xblk, nty);
         if (f.trace && kind != DONE) {
@@ -375,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
 #pragma unroll 1
         for (int part = 0; part < (same_v ? 1 : 2); ++part, ++g) {
           const int s = g % NSLOT;
-          mbar_wait_long(slot_free0 + 8 * s, ((g / NSLOT) & 1) ^ 1);
+          mbar_wait(slot_free0 + 8 * s, ((g / NSLOT) & 1) ^ 1);
           if (part == 0) ev(100 + t);
           mbar_expect_tx(slot_full0 + 8 * s, SLOT_BYTES, leader);
           tma_bulk_g2s(smem_u32(sY + s * SLOT_BYTES), reinterpret_cast<const char*>(part == 0 ? a.s_pack : a.v_pack) + off, SLOT_BYTES,
@@ -393,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
     EvLog ev{(f.ev && blockIdx.x == 0 && lane == 0) ? f.ev : nullptr, 0};
     for (uint32_t n = 0;; ++n) {
       const int slot = n & (ITEM_SLOTS - 1);
-      mbar_wait_long(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
+      mbar_wait(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
       const int4 it = ld_item(sItems + slot);
       __syncwarp();
       if (lane == 0) mbar_arrive(item_empty0 + 8 * slot);
@@ -403,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
       const uint32_t per = same_v ? 1u : 2u;
       const int ob = n & 1;
       ev(kind);
-      mbar_wait_long(x_full, nx & 1);
+      mbar_wait(x_full, nx & 1);
       ++nx;
       ev(10);
       tc_fence_after();
@@ -432,8 +414,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
         const uint32_t gg = g + per * t + (per - 1), tt = gt + t;
         const int s = gg % NSLOT, pb = tt & 1;
         if (t == 0) {                                               // the accumulators this pass writes have been drained
-          mbar_wait_long(lo_free0 + 8 * ob, ((n >> 1) & 1) ^ 1);
-          mbar_wait_long(hi_free, (n & 1) ^ 1);
+          mbar_wait(lo_free0 + 8 * ob, ((n >> 1) & 1) ^ 1);
+          mbar_wait(hi_free, (n & 1) ^ 1);
         }
         if (!same_v) mbar_wait(slot_full0 + 8 * s, (gg / NSLOT) & 1);
         mbar_wait(p_full0 + 8 * pb, (tt >> 1) & 1);
@@ -460,14 +442,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
     uint32_t nx = 0;
     for (uint32_t n = 0;; ++n) {
       const int slot = n & (ITEM_SLOTS - 1);
-      mbar_wait_long(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
+      mbar_wait(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
       const int4 it = ld_item(sItems + slot);
       __syncwarp();
       if (lane == 0) mbar_arrive(item_empty0 + 8 * slot);
       if (it.x == DONE) break;
       const PassArgs& a = f.p[it.x];
       const size_t x_off = ((size_t)it.y * (a.LXP / 8) + (size_t)it.z * (TX / 8)) * GROUP_BYTES;
-      mbar_wait_long(x_free, (nx & 1) ^ 1);                              // the previous item's last S product has read the tile
+      mbar_wait(x_free, (nx & 1) ^ 1);                              // the previous item's last S product has read the tile
       ++nx;
       mbar_expect_tx(x_full, X_BYTES, leader);
       tma_bulk_g2s(smem_u32(sX), reinterpret_cast<const char*>(f.x_pack[it.x]) + x_off, X_BYTES, x_full, leader);
@@ -481,7 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
     EvLog ev{(f.ev && blockIdx.x == 0 && tid == 0) ? f.ev + 2048 : nullptr, 0};
     for (uint32_t n = 0;; ++n) {
       const int slot = n & (ITEM_SLOTS - 1);
-      mbar_wait_long(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
+      mbar_wait(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
       const int4 it = ld_item(sItems + slot);
       __syncwarp();
       if (lane == 0) mbar_arrive(item_empty0 + 8 * slot);
@@ -601,7 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
         ev(600 + t);
       }
       // row statistics -> epilogue warps; log-sum-exp of the row (natural log) for the backward pass
-      mbar_wait_long(st_free0 + 8 * ob, ((n >> 1) & 1) ^ 1);
+      mbar_wait(st_free0 + 8 * ob, ((n >> 1) & 1) ^ 1);
       sStat[ob * TX + row] = l_run;
       __syncwarp();
       if (lane == 0) mbar_arrive(st_full0 + 8 * ob);
@@ -616,7 +598,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
     EvLog ev{(f.ev && blockIdx.x == 0 && e == (f.dbg >> 8) && lane == 0) ? f.ev + 3 * 2048 : nullptr, 0};
     for (uint32_t n = 0;; ++n) {
       const int slot = n & (ITEM_SLOTS - 1);
-      mbar_wait_long(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
+      mbar_wait(item_full0 + 8 * slot, (n / ITEM_SLOTS) & 1);
       const int4 it = ld_item(sItems + slot);
       __syncwarp();
       if (lane == 0) mbar_arrive(item_empty0 + 8 * slot);
@@ -648,11 +630,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
       const bool ld_hi = lane < n4_hi && kind != PQ && !(f.dbg & 1), ld_lo = lane < n4_lo && kind != PQ && !(f.dbg & 1);
       uint2 cva[16], cvb[16];
       load_c16(cva, c_row + (N_LO / 8) * 128, ld_hi ? cnt0 : 0);    // in flight while the tile loop of this pass still runs
-      mbar_wait_long(st_full0 + 8 * ob, par);
+      mbar_wait(st_full0 + 8 * ob, par);
       const float inv_l = 1.f / sStat[ob * TX + q4 * 32 + lane];
       __syncwarp();
       if (lane == 0) mbar_arrive(st_free0 + 8 * ob);
-      mbar_wait_long(o_full0 + 8 * ob, par);
+      mbar_wait(o_full0 + 8 * ob, par);
       tc_fence_after();
       long long t_acc = 0;
       if (f.trace && e == 0 && lane == 0) t_acc = globaltimer_ns();

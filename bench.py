@@ -14,7 +14,8 @@ config 4 as stated: a global batch of 256 sharded 256/N per GPU.
 One JSON line on stdout (rank 0).
   value        videos/s, inputs resident in HBM, the step replayed from CUDA graphs over FOUR rotating batches with different
                length draws (the collator pads every batch to its own maxima and lengths change every batch, datasets.py:298-302)
-  e2e          the same step fed from pinned host memory (H2D inside the timed region), loss read back every step
+  e2e          the same step fed from pinned host memory (H2D inside the timed region), every step's loss copied to the host and read
+               there (one step late, under the next step; the last one inside the timed region)
   no_graph     the same step launched kernel by kernel from Python (no CUDA graph)
   fp32_tier    the rel <= 1e-5 tier (fp32 FFMA BiDAF kernels, fp32 library GEMMs)
   roofline     the fused BiDAF forward on BASELINE config 2 (B=64, Lc=512, Lq=256, d=200), CUDA events in this run, against
@@ -475,7 +476,21 @@ def run_gpu_arm(args):
                 dst.copy_(src, non_blocking=True)                        # H2D from pinned memory
             ready[k & 1].record(copy_stream)
 
-    def e2e_step():
+    # The loss of every step is copied to pinned host memory and read by the host -- one step late: the copy of step k is awaited after
+    # step k + 1 has been enqueued, so the host never idles the GPU between two graph replays waiting for four bytes.  The last step's
+    # loss is read inside the timed region too (`flush`).
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    pending = {"k": None, "seen": []}
+
+    def read_pending():
+        if pending["k"] is not None:
+            j = pending["k"] & 1
+            loss_ready[j].synchronize()
+            pending["seen"].append(float(loss_host[j][0]))               # the host reads the step's loss
+            pending["k"] = None
+
+    def e2e_step(last=False):
         k = state["k"]
         slot, host = slots[k & 1], hosts[k % N_ROTATE]
         torch.cuda.current_stream().wait_event(ready[k & 1])
@@ -483,9 +498,14 @@ def run_gpu_arm(args):
                      host.target_len, host.max_dec_len)
         loss = trainer.step_graphed(feed) if graphed else trainer.step(feed)
         consumed[k & 1].record()
+        loss_host[k & 1].copy_(loss.detach().reshape(1), non_blocking=True)      # D2H read of the step's loss
+        loss_ready[k & 1].record()
         prefetch(k + 1)
         state["k"] = k + 1
-        return float(loss.item())                                        # D2H read of the step's loss
+        read_pending()                                                   # step k - 1's loss, while step k runs
+        pending["k"] = k
+        if last:
+            read_pending()
 
     e2e_seconds = float("nan")
     if "e2e" in sections:
@@ -494,7 +514,14 @@ def run_gpu_arm(args):
         prefetch(0)
         for _ in range(max(2, args.warmup // 2)):
             e2e_step()
-        e2e_seconds = timed(e2e_step, args.steps)
+        read_pending()
+        calls = {"n": 0}
+
+        def e2e_timed():
+            calls["n"] += 1
+            e2e_step(last=calls["n"] == args.steps)
+        e2e_seconds = timed(e2e_timed, args.steps)
+        assert len(pending["seen"]) >= args.steps and all(v == v for v in pending["seen"])    # every step's loss reached the host
 
     # BASELINE config 4 as stated: a global batch of 256 videos sharded over the ranks (strong scaling)
     cfg4 = None

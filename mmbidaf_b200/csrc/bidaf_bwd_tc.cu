@@ -45,6 +45,13 @@ constexpr float NEG2 = kNegFill * LOG2E;
 
 enum Mode { PT = 0, DC = 1, DQ = 2 };
 
+// Ask L2 for [p, p + bytes) (16-byte granules inside the range): the epilogue's fp32 rows are requested when the block starts, so
+// that a whole tile loop later they are L2 hits instead of a burst of DRAM reads issued by every SM at the same moment.
+__device__ __forceinline__ void l2_prefetch(const void* p, size_t bytes) {
+  const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15), hi = (reinterpret_cast<uintptr_t>(p) + bytes) & ~uintptr_t(15);
+  if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 1. prep
 // ---------------------------------------------------------------------------------------------------------
@@ -149,6 +156,7 @@ struct BwdArgs {
   long long* trace;                    // debugging aid: clock64() stamps of CTA (0,0), or null
   float keep_scale;
   int LX, LXP, LY, LYP, d;
+  int prefetch;                        // request the epilogue's rows from L2 at block start
 };
 
 // One X block of one pass.  `ready` (per batch row) orders the passes inside ONE launch: a PT block bumps ready[b]
@@ -216,6 +224,16 @@ __device__ __forceinline__ void bwd_block(const BwdArgs& a, const int b, const i
   }
   const size_t x_off = ((size_t)b * (a.LXP / 8) + x0 / 8) * GROUP_BYTES;
   const size_t y_batch = (size_t)b * (a.LYP / 8) * GROUP_BYTES;
+  if (a.prefetch && tid == 32 * 5) {                     // (a warp that issues neither MMAs nor TMA loads)
+    const size_t e0 = ((size_t)b * a.LX + x0) * a.d, ne = (size_t)min(ROWS, a.LX - x0) * a.d;
+    if (IS_PT) {
+      l2_prefetch(a.t_feat + e0, ne * 4);
+    } else {
+      l2_prefetch(a.x_feat + e0, ne * 4);
+      l2_prefetch(a.dx + e0, ne * 4);
+      if (a.x_keep) l2_prefetch(a.x_keep + e0, ne);
+    }
+  }
   const float log2_lx = log2f((float)a.LX);
   // per-column scalars of tile t -> ycol[t & 1], by one warp (an idle one in DC/DQ), in two steps so that the global
   // loads are issued a whole tile before their values are stored (visible after the next __syncthreads)
@@ -628,24 +646,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_tc_kernel(const BwdArgs
 
 // All three passes in one launch: PT blocks first in block order, then the DC and DQ blocks, each of which starts as
 // soon as the PT blocks of ITS batch row are done -- no launch boundaries, no partially filled waves in between.
+// Block order: PT, then the LONGER of the two dependent kinds first (a DQ block streams Lc / 32 tiles, a DC block Lq / 32): with the
+// long blocks at the end of the grid the launch ended on a few SMs running one of them alone (config 2: 6 waves of 148, DQ blocks of
+// 35 us last).
 struct BwdFusedArgs {
   BwdArgs k[3];
   int* ready;                  // (B) zeroed before the launch
-  int n_pt, n_dc;              // blocks of PT and DC (B * blocks per batch row)
+  int n_pt, n_dc, n_dq;        // blocks of PT, DC and DQ (B * blocks per batch row)
   int nb[3];                   // X blocks per batch row of PT, DC, DQ
+  int dq_first;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) bidaf_bwd_fused_kernel(const BwdFusedArgs f) {
   const int blk = blockIdx.x;
   if (blk < f.n_pt) {
     bwd_block<PT>(f.k[PT], blk / f.nb[PT], blk % f.nb[PT], f.nb[PT], f.ready, 0);
-  } else if (blk < f.n_pt + f.n_dc) {
-    const int i = blk - f.n_pt;
-    bwd_block<DC>(f.k[DC], i / f.nb[DC], i % f.nb[DC], f.nb[DC], f.ready, f.nb[PT]);
-  } else {
-    const int i = blk - f.n_pt - f.n_dc;
-    bwd_block<DQ>(f.k[DQ], i / f.nb[DQ], i % f.nb[DQ], f.nb[DQ], f.ready, f.nb[PT]);
+    return;
   }
+  int i = blk - f.n_pt;
+  bool is_dq;
+  if (f.dq_first) {
+    is_dq = i < f.n_dq;
+    if (!is_dq) i -= f.n_dq;
+  } else {
+    is_dq = i >= f.n_dc;
+    if (is_dq) i -= f.n_dc;
+  }
+  if (is_dq) bwd_block<DQ>(f.k[DQ], i / f.nb[DQ], i % f.nb[DQ], f.nb[DQ], f.ready, f.nb[PT]);
+  else bwd_block<DC>(f.k[DC], i / f.nb[DC], i % f.nb[DC], f.nb[DC], f.ready, f.nb[PT]);
 }
 
 template <int MODE>
@@ -795,14 +823,18 @@ int bidaf_bwd_tc(const float* grad_out, const float* text, const float* modality
     a.LX = Lq; a.LXP = LqP; a.LY = Lc; a.LYP = LcP; a.d = d;
     a.trace = tracing ? w.trace + 512 : nullptr;
   }
+  static const char* pf_env = getenv("MMB_BIDAF_BWD_PREFETCH");
+  pt.prefetch = dc.prefetch = dq.prefetch = pf_env ? atoi(pf_env) : 1;
   constexpr size_t smem_pt = bwd_smem_bytes<PT>(), smem_dc = bwd_smem_bytes<DC>(), smem_dq = bwd_smem_bytes<DQ>();
   static_assert(smem_dc <= 227 * 1024 && smem_dq <= 227 * 1024 && smem_pt <= 227 * 1024, "shared memory");
   if (!env) {   // the normal path: one launch for the three tensor-core passes
     constexpr size_t smem = smem_dc > smem_pt ? (smem_dc > smem_dq ? smem_dc : smem_dq) : (smem_pt > smem_dq ? smem_pt : smem_dq);
-    BwdFusedArgs f{{pt, dc, dq}, w.ready, B * (LqP / 128), B * (LcP / 64), {LqP / 128, LcP / 64, LqP / 64}};
+    static const char* ord_env = getenv("MMB_BIDAF_BWD_ORDER");         // 0: PT, DC, DQ (round 1); default: longest kind first
+    const int dq_first = ord_env ? atoi(ord_env) : (Lc >= Lq ? 1 : 0);
+    BwdFusedArgs f{{pt, dc, dq}, w.ready, B * (LqP / 128), B * (LcP / 64), B * (LqP / 64), {LqP / 128, LcP / 64, LqP / 64}, dq_first};
     MMB_CUDA(cudaMemsetAsync(w.ready, 0, sizeof(int) * (size_t)B, stream));
     MMB_CUDA(cudaFuncSetAttribute(bidaf_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bidaf_bwd_fused_kernel<<<f.n_pt + f.n_dc + B * (LqP / 64), NTHREADS, smem, stream>>>(f);
+    bidaf_bwd_fused_kernel<<<f.n_pt + f.n_dc + f.n_dq, NTHREADS, smem, stream>>>(f);
     if (int rc = check_launch("bidaf_bwd_fused_kernel")) return rc;
   } else {
     if (stages & 2) {

@@ -34,6 +34,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// 1 - k / (1 + 2^z): sigma(x) for k = 1, z = x log2 e; tanh(x) for k = 2, z = 2 x log2 e.  ex2 / rcp in their flush-to-zero forms (one
+// MUFU each, no range fix-ups: 2^z -> inf gives 1, 2^z -> 0 gives 1 - k).
+__device__ __forceinline__ float gate_act2(float z, float k) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(-k, r, 1.0f);
+}
+
+// Predicated memory operations: the loop body of the recurrence must stay ONE basic block (ptxas does not schedule across the branches
+// that `if (on) *p = v;` compiles to, and every instruction of a step that is not FMA work has to be interleaved with the FMAs).
+__device__ __forceinline__ void st_global_if(float* p, float v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void st_shared_if(float* p, float v, bool pred) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(sa), "f"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(float* smem_dst, const float* gsrc, bool pred) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(sa), "l"(gsrc), "r"((int)pred) : "memory");
+}
+
 struct LstmArgs {
   float* gates;            // (B, L, ndir, 4H): in = input pre-activations, out (save) = activated gates / d pre-act
   const float* w_hh;       // (ndir, 4H, H)
@@ -47,22 +70,47 @@ struct LstmArgs {
   const float* dh_n;       // bwd: (B, ndir, H) or nullptr
   const float* dc_n;       // bwd: (B, ndir, H) or nullptr
   int B, L, H, ndir, save;
+  long long* trace;        // debugging aid (MMB_LSTM_TRACE, tools/lstm_trace.py): clock64 stamps of CTA (0, 0), or null
 };
 
 constexpr int threads_for(int KS) { return (4 * KS + 31) / 32 * 32 < 64 ? 64 : (4 * KS + 31) / 32 * 32; }
 
-template <int KS, int NB>
+// Stamp that cannot be scheduled before the values it names are computed.
+__device__ __forceinline__ long long clock_after(float x, float y) {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(x), "f"(y) : "memory");
+  return t;
+}
+constexpr int TRACE_S0 = 64, TRACE_NS = 32, TRACE_PTS = 5;   // steps [64, 96): 5 stamps per step, lane 0 of each warp
+
+constexpr int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
+
+// The loop body is written for INSTRUCTION COUNT and as one basic block (tools/lstm_trace.py, round 2: a step is issue bound -- two
+// warps per scheduler, ~380 instructions each, of which 211 are the FFMAs; the serial tail after them is ~320 cycles):
+//  * the weights are PRE-SCALED by log2(e) (2 log2(e) for the tanh gate g) so that the accumulated pre-activation is the argument of
+//    ex2 directly: sigma(x) = 1 - 1 / (1 + 2^(x log2 e)), tanh(x) = 1 - 2 / (1 + 2^(2 x log2 e));
+//  * a lane keeps its weight rows in the order (kept gate 0, kept gate 1, sent gate 0, sent gate 1) -- lane 0 keeps (i, f), lane 1
+//    (g, o) -- so the reduce-scatter over the pair needs no selects, and the input pre-activations SEED the two kept accumulators;
+//  * the global stores of a step (out, saved gates, cell state) are issued one step LATE, from registers, inside the next step's FMA
+//    stream, and every memory operation is predicated rather than branched around;
+//  * the cp.async ring has a power-of-two slot stride: one add + one and per step for both ring positions.
+template <int KS, int NB, bool TRACE = false>
 __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmArgs a) {
   constexpr int HP = 2 * KS;                       // padded hidden size
+  constexpr int NT = threads_for(KS);              // == blockDim.x
+  constexpr int RSLOT = pow2_ceil(NB * 2 * NT);    // floats per ring slot: [NB][2][NT], padded to a power of two
+  constexpr int RMASK = RING * RSLOT - 1;
   const int H = a.H, L = a.L, ndir = a.ndir;
   const int dir = blockIdx.y;
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x;
   const int j = tid >> 1, kp = tid & 1;
   const bool live = j < H;
+  const int jj = min(j, H - 1);                    // threads past the last unit MIRROR it: same weights, same values, same addresses,
+                                                   // so nothing in the loop is predicated on the thread
 
   extern __shared__ __align__(16) float smem[];
   float* h_s = smem;                               // [2][NB][HP]
-  float* ring = h_s + 2 * NB * HP;                 // [RING][NB][2][nthr]
+  float* ring = h_s + 2 * NB * HP;                 // [RING][RSLOT]
 
   int seq[NB], len[NB];
   int max_len = 0;
@@ -74,23 +122,27 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
     max_len = max(max_len, len[n]);
   }
 
-  // recurrent weights of unit j, gates 0..3, k in [kp*KS, kp*KS + KS)
+  // recurrent weights of unit j, k in [kp*KS, kp*KS + KS); slot q of w holds gate (q < 2 ? 2 kp + q : 2 (1 - kp) + q - 2)
+  constexpr float LOG2E_F = 1.4426950408889634f;
   float w[4][KS];
   {
     const float* wd = a.w_hh + (size_t)dir * 4 * H * H;
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+    for (int q = 0; q < 4; ++q) {
+      const int g = q < 2 ? 2 * kp + q : 2 * (1 - kp) + (q - 2);
+      const float sc = g == 2 ? 2.f * LOG2E_F : LOG2E_F;
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
         const int k = kp * KS + kk;
-        w[g][kk] = (live && k < H) ? wd[(size_t)(g * H + j) * H + k] : 0.f;
+        w[q][kk] = k < H ? wd[(size_t)(g * H + jj) * H + k] * sc : 0.f;
       }
+    }
   }
-  for (int i = tid; i < 2 * NB * HP; i += nthr) h_s[i] = 0.f;
+  for (int i = tid; i < 2 * NB * HP; i += NT) h_s[i] = 0.f;
 
-  // Running pointers: this lane's two pre-activation / saved-gate slots (gates 2kp, 2kp+1 of unit j), the
-  // output slot and the cell slot of sequence n at the current step, and the prefetch pointer RING-1
-  // steps ahead.  Forward walks t = 0.., the reverse direction t = len-1 ...
+  // Running pointers: this lane's two pre-activation / saved-gate slots (gates 2kp, 2kp+1 of unit j), the output slot and the cell slot
+  // of sequence n at the step being STORED (one behind the step being computed), and the prefetch pointer RING-1 steps ahead.
+  // Forward walks t = 0.., the reverse direction t = len-1 ...
   const long sign = dir ? -1 : 1;
   const long g_stride = sign * (long)ndir * 4 * H, o_stride = sign * (long)ndir * H;
   float *gp[NB], *op[NB], *cp[NB];
@@ -98,49 +150,57 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
     const size_t bt0 = (size_t)max(seq[n], 0) * L + (dir ? max(len[n] - 1, 0) : 0);
-    gp[n] = a.gates + (bt0 * ndir + dir) * 4 * H + (2 * kp) * H + j;
-    op[n] = a.out + bt0 * ndir * H + dir * H + j;
-    cp[n] = a.cell ? a.cell + (bt0 * ndir + dir) * H + j : nullptr;
+    gp[n] = a.gates + (bt0 * ndir + dir) * 4 * H + (2 * kp) * H + jj;
+    op[n] = a.out + bt0 * ndir * H + dir * H + jj;
+    cp[n] = (a.cell ? a.cell : a.out) + (bt0 * ndir + dir) * H + jj;   // (never dereferenced without a cell buffer)
     pf[n] = gp[n];
   }
-  float* ring_t = ring + tid;
-  auto prefetch = [&](int s, int slot) {
-    if (live) {
+  float* const ring_t = ring + tid;
+  auto prefetch = [&](int s, int off) {            // off: float offset of the ring slot
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        if (s < len[n]) {
-          cp_async4(ring_t + ((slot * NB + n) * 2 + 0) * nthr, pf[n]);
-          cp_async4(ring_t + ((slot * NB + n) * 2 + 1) * nthr, pf[n] + H);
-        }
-        pf[n] += g_stride;
-      }
+    for (int n = 0; n < NB; ++n) {
+      const bool p = s < len[n];
+      cp_async4_if(ring_t + off + (n * 2 + 0) * NT, pf[n], p);
+      cp_async4_if(ring_t + off + (n * 2 + 1) * NT, pf[n] + H, p);
+      pf[n] += g_stride;
     }
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int s = 0; s < RING - 1; ++s) prefetch(s, s);
+  for (int s = 0; s < RING - 1; ++s) prefetch(s, s * RSLOT);
   __syncthreads();
 
-  float c_reg[NB], h_reg[NB];
+  float c_reg[NB], h_reg[NB], a0_reg[NB], a1_reg[NB];
 #pragma unroll
-  for (int n = 0; n < NB; ++n) c_reg[n] = h_reg[n] = 0.f;
+  for (int n = 0; n < NB; ++n) c_reg[n] = h_reg[n] = a0_reg[n] = a1_reg[n] = 0.f;
   const float k_first = kp ? 2.0f : 1.0f;          // lane 0: (i, f) both sigmoid; lane 1: (g = tanh, o = sigmoid)
+  const float pre_first = k_first * LOG2E_F;
   const bool save = a.save != 0;
-  const float* hc = h_s;
-  float* hn = h_s + NB * HP;
-  int slot = 0;
+  // (both lanes of a pair hold the same h and c: both store them -- same address, same value -- rather than predicate on the lane)
+  int hoff = 0;                                    // float offset of the current h buffer (0 or NB * HP)
+  int roff = 0;                                    // float offset of the current ring slot
+  __shared__ long long tr_s[TRACE ? TRACE_NS * 8 * TRACE_PTS : 1];
+  const bool tr_on = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && (tid & 31) == 0;
 
 #pragma unroll 1
   for (int s = 0; s < max_len; ++s) {
-    prefetch(s + RING - 1, (slot + RING - 1) & (RING - 1));
+    const bool tr_now = TRACE && tr_on && s >= TRACE_S0 && s < TRACE_S0 + TRACE_NS;
+    long long* const tr = tr_s + ((s - TRACE_S0) * 8 + (tid >> 5)) * TRACE_PTS;
+    if (tr_now) tr[0] = clock_after(0.f, 0.f);
+    prefetch(s + RING - 1, (roff + (RING - 1) * RSLOT) & RMASK);
     cp_async_wait<RING - 1>();
-    const float* hk = hc + kp * KS;
+    const float* hk = h_s + hoff + kp * KS;
 
+    // the input pre-activations of this step (scaled like the weights) seed the two kept accumulators.  A sequence that has ended
+    // (NB = 2 only) reads a stale ring slot: its values are never stored.
     float acc[NB][4];
 #pragma unroll
-    for (int n = 0; n < NB; ++n)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) acc[n][g] = 0.f;
+    for (int n = 0; n < NB; ++n) {
+      const float* rs = ring_t + roff + n * 2 * NT;
+      acc[n][0] = rs[0] * pre_first;
+      acc[n][1] = rs[NT] * LOG2E_F;
+      acc[n][2] = acc[n][3] = 0.f;
+    }
 #pragma unroll
     for (int k4 = 0; k4 < KS / 4; ++k4) {
 #pragma unroll
@@ -155,45 +215,60 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
         }
       }
     }
+    // the previous step's values go to memory now: independent of this step's chain, interleaved with it by the scheduler
+    {
+      const bool prev = s > 0;
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        const bool on = prev && (NB == 1 || s - 1 < len[n]), on_sv = on && save;
+        st_global_if(op[n], h_reg[n], on);
+        st_global_if(gp[n], a0_reg[n], on_sv);
+        st_global_if(gp[n] + H, a1_reg[n], on_sv);
+        st_global_if(cp[n], c_reg[n], on_sv);
+        gp[n] += prev ? g_stride : 0;
+        op[n] += prev ? o_stride : 0;
+        cp[n] += prev ? o_stride : 0;
+      }
+    }
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
-      // reduce-scatter over the lane pair: lane 0 keeps gates (i, f), lane 1 keeps (g, o)
-      float m0 = kp ? acc[n][2] : acc[n][0], m1 = kp ? acc[n][3] : acc[n][1];
-      m0 += __shfl_xor_sync(0xffffffffu, kp ? acc[n][0] : acc[n][2], 1);
-      m1 += __shfl_xor_sync(0xffffffffu, kp ? acc[n][1] : acc[n][3], 1);
-      const bool on = live && s < len[n];                           // s < len[n] is uniform over the CTA
-      const float* rs = ring_t + (slot * NB + n) * 2 * nthr;
-      const float a0 = gate_act(m0 + (on ? rs[0] : 0.f), k_first);   // i | g
-      const float a1 = gate_act(m1 + (on ? rs[nthr] : 0.f), 1.0f);   // f | o
+      const bool on = NB == 1 || s < len[n];                       // uniform over the CTA
+      if (tr_now && n == 0) tr[1] = clock_after(acc[n][0] + acc[n][1], acc[n][2] + acc[n][3]);
+      // reduce-scatter over the lane pair: lane 0 ends with gates (i, f), lane 1 with (g, o)
+      const float m0 = acc[n][0] + __shfl_xor_sync(0xffffffffu, acc[n][2], 1);
+      const float m1 = acc[n][1] + __shfl_xor_sync(0xffffffffu, acc[n][3], 1);
+      const float a0 = gate_act2(m0, k_first);                     // i | g
+      const float a1 = gate_act2(m1, 1.0f);                        // f | o
+      if (tr_now && n == 0) tr[2] = clock_after(a0, a1);
       const float b0 = __shfl_xor_sync(0xffffffffu, a0, 1);
       const float b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
-      const float gi = kp ? b0 : a0, gf = kp ? b1 : a1, gg = kp ? a0 : b0, go = kp ? a1 : b1;
-      if (on) {
-        c_reg[n] = fmaf(gf, c_reg[n], gi * gg);
-        h_reg[n] = go * tanh_fast(c_reg[n]);
-        if (kp == 0) {
-          hn[n * HP + j] = h_reg[n];
-          *op[n] = h_reg[n];
-        }
-        if (save) {
-          gp[n][0] = a0;
-          gp[n][H] = a1;
-          if (kp == 1) *cp[n] = c_reg[n];
-        }
-      }
-      gp[n] += g_stride;
-      op[n] += o_stride;
-      if (save) cp[n] += o_stride;
+      const float gf = kp ? b1 : a1, go = kp ? a1 : b1;            // (i g = a0 b0 on both lanes)
+      const float c_new = fmaf(gf, c_reg[n], a0 * b0);
+      const float h_new = go * gate_act2(c_new * (2.f * LOG2E_F), 2.0f);
+      if (tr_now && n == 0) tr[3] = clock_after(h_new, 0.f);
+      st_shared_if(h_s + (hoff ^ (NB * HP)) + n * HP + jj, h_new, on);
+      c_reg[n] = on ? c_new : c_reg[n];
+      h_reg[n] = on ? h_new : h_reg[n];
+      a0_reg[n] = a0;
+      a1_reg[n] = a1;
     }
-    slot = (slot + 1) & (RING - 1);
-    {                                                               // swap the double-buffered hidden state
-      const float* t = hc;
-      hc = hn;
-      hn = const_cast<float*>(t);
-    }
+    roff = (roff + RSLOT) & RMASK;
+    hoff ^= NB * HP;
+    if (tr_now) tr[4] = clock_after(0.f, 0.f);
     __syncthreads();
   }
+  // the last step's values
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    const bool on = max_len > 0 && max_len - 1 < len[n], on_sv = on && save;
+    st_global_if(op[n], h_reg[n], on);
+    st_global_if(gp[n], a0_reg[n], on_sv);
+    st_global_if(gp[n] + H, a1_reg[n], on_sv);
+    st_global_if(cp[n], c_reg[n], on_sv);
+  }
   cp_async_wait<0>();
+  if (TRACE && blockIdx.x == 0 && blockIdx.y == 0 && a.trace)
+    for (int i = tid; i < TRACE_NS * 8 * TRACE_PTS; i += NT) a.trace[i] = tr_s[i];
 
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
@@ -201,7 +276,7 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
     if (live && kp == 0) a.h_n[((size_t)seq[n] * ndir + dir) * H + j] = h_reg[n];
     if (live && kp == 1) a.c_n[((size_t)seq[n] * ndir + dir) * H + j] = c_reg[n];
     // pad_packed_sequence: zeros past the sample's length
-    for (int i = tid; i < (L - len[n]) * H; i += nthr) {
+    for (int i = tid; i < (L - len[n]) * H; i += NT) {
       const int t = len[n] + i / H, u = i % H;
       a.out[((size_t)seq[n] * L + t) * ndir * H + dir * H + u] = 0.f;
     }
@@ -618,9 +693,15 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
     }
   }
   if (!backward) {
-    const size_t smem = sizeof(float) * (2 * NB * HP + (size_t)RING * NB * 2 * nthr);
+    constexpr int NT = threads_for(KS);
+    const size_t smem = sizeof(float) * (2 * NB * HP + (size_t)RING * pow2_ceil(NB * 2 * NT));
+    if (NB == 1 && a.trace) {
+      MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_kernel<KS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bilstm_fwd_kernel<KS, 1, true><<<grid, NT, smem, stream>>>(a);
+      return check_launch("bilstm_fwd_kernel<trace>");
+    }
     MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bilstm_fwd_kernel<KS, NB><<<grid, block, smem, stream>>>(a);
+    bilstm_fwd_kernel<KS, NB><<<grid, NT, smem, stream>>>(a);
     return check_launch("bilstm_fwd_kernel");
   }
   const size_t smem = sizeof(float) * (NB * 4 * HP + NB * 4 * 2 * BWD_SL + (size_t)RING * NB * 7 * 128);
@@ -655,7 +736,9 @@ extern "C" int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* le
   MMB_REQUIRE(!save || cell, MMB_ERR_INVALID, "mmb_bilstm_fwd: save=1 needs a cell buffer");
   MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID,
               "mmb_bilstm_fwd: B=%d L=%d H=%d ndir=%d", B, L, H, ndir);
-  mmb::LstmArgs a{gates, w_hh, lengths, order, out, h_n, c_n, cell, nullptr, nullptr, nullptr, B, L, H, ndir, save};
+  mmb::LstmArgs a{gates, w_hh, lengths, order, out, h_n, c_n, cell, nullptr, nullptr, nullptr, B, L, H, ndir, save, nullptr};
+  static const char* trace_env = getenv("MMB_LSTM_TRACE");                 // debugging aid (tools/lstm_trace.py)
+  a.trace = trace_env ? reinterpret_cast<long long*>(strtoull(trace_env, nullptr, 0)) : nullptr;
   return mmb::dispatch(a, false, static_cast<cudaStream_t>(stream));
 }
 
@@ -666,6 +749,6 @@ extern "C" int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh
   MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID,
               "mmb_bilstm_bwd: B=%d L=%d H=%d ndir=%d", B, L, H, ndir);
   mmb::LstmArgs a{gates, w_hh, lengths, order, nullptr, nullptr, nullptr, const_cast<float*>(cell), dout, dh_n, dc_n,
-                  B, L, H, ndir, 1};
+                  B, L, H, ndir, 1, nullptr};
   return mmb::dispatch(a, true, static_cast<cudaStream_t>(stream));
 }

@@ -545,23 +545,27 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
     pc[n] = a.cell + (bt0 * ndir + dir) * H + (unit ? j : 0);
     pd[n] = a.dout + bt0 * ndir * H + dir * H + (unit ? j : 0);
   }
+  // Only what depends on the recurrent product of the previous step sits between the two barriers of a step: the point-wise part is
+  // split into FACTORS that depend on the saved forward values alone -- computed a step ahead, inside the FMA stream of the previous
+  // step's product, together with the global stores of d(pre-activation), the cp.async prefetch and the pointer updates -- and five
+  // multiplies that need dh_rec (tools/lstm_trace.py for the forward kernel: a step is issue bound, its serial tail is what is left to cut).
+  //   dh = dy + dh_rec;  dct = dh * A + dc;  d_i = dct Ki;  d_f = dct Kf;  d_g = dct Kg;  d_o = dh Ko;  dc = dct Gf
+  //   A = go (1 - tanh^2 c),  Ki = gg gi (1 - gi),  Kf = c_prev gf (1 - gf),  Kg = gi (1 - gg^2),  Ko = tanh c  go (1 - go),  Gf = gf
   float* ring_t = ring + (tid & 127);
+  const int ju = unit ? j : 0;
   auto prefetch = [&](int s, int sl) {
-    if (unit) {
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        if (s < len[n]) {
-          float* dst = ring_t + (sl * NB + n) * 7 * 128;
+    for (int n = 0; n < NB; ++n) {
+      const bool p = unit && s < len[n];
+      float* dst = ring_t + (sl * NB + n) * 7 * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) cp_async4(dst + g * 128, pg[n] + g * H);
-          cp_async4(dst + 4 * 128, pc[n]);                                    // c_t
-          if (s + 1 < len[n]) cp_async4(dst + 5 * 128, pc[n] + o_stride);     // c of the previous forward step
-          cp_async4(dst + 6 * 128, pd[n]);                                    // d out
-        }
-        pg[n] += g_stride;
-        pc[n] += o_stride;
-        pd[n] += o_stride;
-      }
+      for (int g = 0; g < 4; ++g) cp_async4_if(dst + g * 128, pg[n] + g * H, p);
+      cp_async4_if(dst + 4 * 128, pc[n], p);                                    // c_t
+      cp_async4_if(dst + 5 * 128, pc[n] + o_stride, p && s + 1 < len[n]);       // c of the previous forward step
+      cp_async4_if(dst + 6 * 128, pd[n], p);                                    // d out
+      pg[n] += g_stride;
+      pc[n] += o_stride;
+      pd[n] += o_stride;
     }
     cp_async_commit();
   };
@@ -574,47 +578,60 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
     dh_rec[n] = (unit && seq[n] >= 0 && a.dh_n) ? a.dh_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
     dc[n] = (unit && seq[n] >= 0 && a.dc_n) ? a.dc_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
   }
+  struct Factors { float A, Ki, Kf, Kg, Ko, Gf, Dy; };
+  auto factors = [&](int s, int sl, int n) {       // of backward step s, from ring slot sl (all zero past the sequence's end)
+    Factors f{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* rs = ring_t + (sl * NB + n) * 7 * 128;
+    const float gi = rs[0], gf = rs[128], gg = rs[2 * 128], go = rs[3 * 128], ct = rs[4 * 128], dy = rs[6 * 128];
+    const float cprev = s + 1 < len[n] ? rs[5 * 128] : 0.f;
+    const float tc = tanh_fast(ct);
+    const bool on = s < len[n];
+    f.A = on ? go * (1.f - tc * tc) : 0.f;
+    f.Ki = on ? gg * gi * (1.f - gi) : 0.f;
+    f.Kf = on ? cprev * gf * (1.f - gf) : 0.f;
+    f.Kg = on ? gi * (1.f - gg * gg) : 0.f;
+    f.Ko = on ? tc * go * (1.f - go) : 0.f;
+    f.Gf = on ? gf : 0.f;
+    f.Dy = on ? dy : 0.f;
+    return f;
+  };
+  cp_async_wait<RING - 2>();                       // the first step's slot has landed (each thread reads what it copied itself)
+  Factors fc[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) fc[n] = factors(0, 0, n);
   __syncthreads();
   int sl = 0;
 
 #pragma unroll 1
   for (int s = 0; s < max_len; ++s) {
-    prefetch(s + RING - 1, (sl + RING - 1) & (RING - 1));
-    cp_async_wait<RING - 1>();
-
-    // ---- point-wise part: one thread per hidden unit -----------------------------------------------------------------
-    if (unit) {
+    // ---- between the barriers: what needs dh_rec -----------------------------------------------------------------------
+    float dg[NB][4];
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const bool on = s < len[n];
-        const float* rs = ring_t + (sl * NB + n) * 7 * 128;
-        float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
-        if (on) {
-          const float gi = rs[0], gf = rs[128], gg = rs[2 * 128], go = rs[3 * 128], ct = rs[4 * 128], dy = rs[6 * 128];
-          const float cprev = s + 1 < len[n] ? rs[5 * 128] : 0.f;
-          const float dh = dy + dh_rec[n];
-          const float tc = tanh_fast(ct);
-          const float dct = fmaf(dh * go, 1.f - tc * tc, dc[n]);
-          d_i = dct * gg * gi * (1.f - gi);
-          d_f = dct * cprev * gf * (1.f - gf);
-          d_g = dct * gi * (1.f - gg * gg);
-          d_o = dh * tc * go * (1.f - go);
-          dc[n] = dct * gf;
-          gp[n][0] = d_i;
-          gp[n][H] = d_f;
-          gp[n][2 * H] = d_g;
-          gp[n][3 * H] = d_o;
-        }
-        float* dn = da_s + n * 4 * HP + j;
-        dn[0] = d_i;
-        dn[HP] = d_f;
-        dn[2 * HP] = d_g;
-        dn[3 * HP] = d_o;
-        gp[n] += g_stride;
-      }
+    for (int n = 0; n < NB; ++n) {
+      const float dh = fc[n].Dy + dh_rec[n];
+      const float dct = fmaf(dh, fc[n].A, dc[n]);
+      dg[n][0] = dct * fc[n].Ki;
+      dg[n][1] = dct * fc[n].Kf;
+      dg[n][2] = dct * fc[n].Kg;
+      dg[n][3] = dh * fc[n].Ko;
+      dc[n] = dct * fc[n].Gf;
+      float* dn = da_s + n * 4 * HP + ju;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st_shared_if(dn + g * HP, dg[n][g], unit);
     }
     __syncthreads();
-    // ---- dh_rec partials: this warp pair's gate, this thread's two units -------------------------------------------
+    // ---- dh_rec partials: this warp pair's gate, this thread's two units; and, in the same instruction stream, everything of
+    //      this and the next step that does not depend on them ---------------------------------------------------------------
+    prefetch(s + RING - 1, (sl + RING - 1) & (RING - 1));
+    cp_async_wait<RING - 2>();                                       // slot of step s + 1
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      const bool on = unit && s < len[n];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st_global_if(gp[n] + g * H, dg[n][g], on);
+      gp[n] += g_stride;
+      fc[n] = factors(s + 1, (sl + 1) & (RING - 1), n);
+    }
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
       float p0[2] = {0.f, 0.f}, p1[2] = {0.f, 0.f};
@@ -636,12 +653,10 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
       pn[BWD_SL] = p1[0] + p1[1];
     }
     __syncthreads();
-    if (unit) {
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const float* pn = part + n * 4 * 2 * BWD_SL + j;
-        dh_rec[n] = (pn[0] + pn[2 * BWD_SL]) + (pn[4 * BWD_SL] + pn[6 * BWD_SL]);
-      }
+    for (int n = 0; n < NB; ++n) {
+      const float* pn = part + n * 4 * 2 * BWD_SL + ju;
+      dh_rec[n] = (pn[0] + pn[2 * BWD_SL]) + (pn[4 * BWD_SL] + pn[6 * BWD_SL]);
     }
     sl = (sl + 1) & (RING - 1);
   }

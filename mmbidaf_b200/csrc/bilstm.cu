@@ -482,31 +482,35 @@ __global__ void __launch_bounds__(threads_for(KS / 2 + 1)) bilstm_fwd_pair_kerne
 // The recurrent product dh[j] = sum_{g,r} W_hh[g H + r][j] da[g][r] reads FOUR H-vectors from shared memory per step
 // (the forward reads one), and a broadcast LDS.128 costs 2.3 cycles per warp (tools/micro/lds_bcast.cu), so the first
 // version (two lanes per unit, each reading the 2 x H values of its two gates: 52 LDS.128 per thread) spent ~820 of its
-// 1700 cycles per step in the shared-memory pipe.  Here a thread keeps the W_hh^T columns of TWO units restricted to
-// ONE gate (2 x HP weights, the same register budget) and the gate is uniform over a warp pair: 26 LDS.128 per thread,
-// all lanes of a warp on the same address.  The four per-gate partial sums of a unit meet in shared memory; the
-// point-wise part of a step is done by one thread per unit (threads 0..H-1), which also owns the cp.async ring.
-// Measured: 0.87 -> 0.61 us per step.  (The same cut of the FORWARD kernel doubles its shared-memory reads -- it only
-// needs the H values of h -- and adds a barrier: 0.75 us per step against 0.67 for the lane-pair design above.  Packed
-// fma.rn.f32x2 in place of the scalar FMAs halves the instruction count of both loops but is not faster: forward 0.66,
-// backward 0.69 us per step -- the FMA pipe takes an FFMA2 at half rate and the dependent chains get longer.)
-constexpr int BWD_NT = 256, BWD_SL = 64;     // 8 warps = 4 gates x 64 unit slots; a slot covers units slot and slot + 64
+// 1700 cycles per step in the shared-memory pipe.  The second (a thread = TWO units x ONE gate x all r, the gate uniform
+// over a warp pair: 26 LDS.128 per thread, 8 FFMAs per load) ran at 0.61, then 0.53 us per step, with a quarter of all
+// warp-stall samples on FFMAs waiting for their shared-memory operand (ncu, short scoreboard).  Now a thread = FOUR units
+// x ONE gate x HALF of r (the two halves on neighbouring lanes): 13 LDS.128 per thread, 16 FFMAs per load, the same 208
+// weights in registers; the halves meet by one shuffle per unit, the four per-gate partial sums of a unit in shared
+// memory; the point-wise part of a step is done by one thread per unit (threads 0..H-1), which also owns the cp.async
+// ring.  (Packed fma.rn.f32x2 in place of the scalar FMAs halves the instruction count but is not faster: the FMA pipe
+// takes an FFMA2 at half rate and the dependent chains get longer.)
+constexpr int BWD_NT = 256, BWD_SL = 64;     // 8 warps = 4 gates x 2 halves of 32 unit slots; a slot covers units slot + 32 i, i < 4
 
-template <int KS, int NB>
+// KR: r values per half that are real (H <= 2 KR <= 2 KS): the zero padding of a half costs registers and FFMAs (KS = 52, H = 100: 8 each)
+template <int KS, int NB, int KR = KS>
 __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
   constexpr int HP = 2 * KS;                       // >= H, multiple of 4
-  static_assert(HP <= 2 * BWD_SL, "two units per slot cover the hidden size");
+  constexpr int KSP = (KS % 32 == 0) ? KS + 4 : KS;   // row half stride of da_s: the two halves of r on different banks
+  constexpr int DAS = 2 * KSP;                     // row stride of da_s
+  static_assert(HP <= 2 * BWD_SL, "four units per slot cover the hidden size");
   const int H = a.H, L = a.L, ndir = a.ndir;
   const int dir = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp >> 1;                         // the gate whose rows this warp pair multiplies (warp-uniform)
-  const int slot = tid & (BWD_SL - 1);
+  const int rh = lane & 1;                         // this lane's half of r
+  const int slot = (warp & 1) * 16 + (lane >> 1);  // 0..31
   const bool unit = tid < H;                       // point-wise owner of hidden unit j = tid
   const int j = tid;
 
   extern __shared__ __align__(16) float smem[];
-  float* da_s = smem;                              // [NB][4][HP]
-  float* part = da_s + NB * 4 * HP;                // [NB][4][2 * BWD_SL]
+  float* da_s = smem;                              // [NB][4][2][KSP]
+  float* part = da_s + NB * 4 * DAS;               // [NB][4][2 * BWD_SL]
   float* ring = part + NB * 4 * 2 * BWD_SL;        // [RING][NB][7][128]
 
   int seq[NB], len[NB];
@@ -519,18 +523,18 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
     max_len = max(max_len, len[n]);
   }
 
-  float wt[2][HP];                                 // W_hh[q H + r][slot + 64 u]
+  float wt[4][KR];                                 // W_hh[q H + rh KR + r][slot + 32 u]
   {
     const float* wd = a.w_hh + (size_t)dir * 4 * H * H;
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int r = 0; r < HP; ++r) {
-        const int ju = slot + BWD_SL * u;
-        wt[u][r] = (ju < H && r < H) ? wd[(size_t)(q * H + r) * H + ju] : 0.f;
+      for (int rr = 0; rr < KR; ++rr) {
+        const int ju = slot + 32 * u, r = rh * KR + rr;
+        wt[u][rr] = (ju < H && r < H) ? wd[(size_t)(q * H + r) * H + ju] : 0.f;
       }
   }
-  for (int i = tid; i < NB * 4 * HP + NB * 4 * 2 * BWD_SL; i += BWD_NT) da_s[i] = 0.f;
+  for (int i = tid; i < NB * 4 * DAS + NB * 4 * 2 * BWD_SL; i += BWD_NT) da_s[i] = 0.f;
 
   // Backward step s visits the forward steps in reverse: time t = dir ? s : len-1-s.
   const long sign = dir ? 1 : -1;
@@ -615,9 +619,9 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
       dg[n][2] = dct * fc[n].Kg;
       dg[n][3] = dh * fc[n].Ko;
       dc[n] = dct * fc[n].Gf;
-      float* dn = da_s + n * 4 * HP + ju;
+      float* dn = da_s + n * 4 * DAS + (ju / KR) * KSP + (ju % KR);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) st_shared_if(dn + g * HP, dg[n][g], unit);
+      for (int g = 0; g < 4; ++g) st_shared_if(dn + g * DAS, dg[n][g], unit);
     }
     __syncthreads();
     // ---- dh_rec partials: this warp pair's gate, this thread's two units; and, in the same instruction stream, everything of
@@ -634,23 +638,25 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
     }
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
-      float p0[2] = {0.f, 0.f}, p1[2] = {0.f, 0.f};
-      const float* dq = da_s + (n * 4 + q) * HP;
+      float pu[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* dq = da_s + (n * 4 + q) * DAS + rh * KSP;
 #pragma unroll
-      for (int r4 = 0; r4 < HP / 4; ++r4) {
+      for (int r4 = 0; r4 < (KR + 3) / 4; ++r4) {
         const float4 dv = *reinterpret_cast<const float4*>(dq + r4 * 4);
-        p0[0] = fmaf(wt[0][r4 * 4 + 0], dv.x, p0[0]);
-        p1[0] = fmaf(wt[1][r4 * 4 + 0], dv.x, p1[0]);
-        p0[1] = fmaf(wt[0][r4 * 4 + 1], dv.y, p0[1]);
-        p1[1] = fmaf(wt[1][r4 * 4 + 1], dv.y, p1[1]);
-        p0[0] = fmaf(wt[0][r4 * 4 + 2], dv.z, p0[0]);
-        p1[0] = fmaf(wt[1][r4 * 4 + 2], dv.z, p1[0]);
-        p0[1] = fmaf(wt[0][r4 * 4 + 3], dv.w, p0[1]);
-        p1[1] = fmaf(wt[1][r4 * 4 + 3], dv.w, p1[1]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r4 * 4 + 0 < KR) pu[u] = fmaf(wt[u][r4 * 4 + 0], dv.x, pu[u]);
+          if (r4 * 4 + 1 < KR) pu[u] = fmaf(wt[u][r4 * 4 + 1], dv.y, pu[u]);
+          if (r4 * 4 + 2 < KR) pu[u] = fmaf(wt[u][r4 * 4 + 2], dv.z, pu[u]);
+          if (r4 * 4 + 3 < KR) pu[u] = fmaf(wt[u][r4 * 4 + 3], dv.w, pu[u]);
+        }
       }
-      float* pn = part + (n * 4 + q) * 2 * BWD_SL + slot;
-      pn[0] = p0[0] + p0[1];
-      pn[BWD_SL] = p1[0] + p1[1];
+      // the two halves of r meet: the even lane ends with units 0, 1 of the slot, the odd lane with units 2, 3
+      const float s0 = (rh ? pu[2] : pu[0]) + __shfl_xor_sync(0xffffffffu, rh ? pu[0] : pu[2], 1);
+      const float s1 = (rh ? pu[3] : pu[1]) + __shfl_xor_sync(0xffffffffu, rh ? pu[1] : pu[3], 1);
+      float* pn = part + (n * 4 + q) * 2 * BWD_SL + slot + 64 * rh;
+      pn[0] = s0;
+      pn[32] = s1;
     }
     __syncthreads();
 #pragma unroll
@@ -719,7 +725,13 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
     bilstm_fwd_kernel<KS, NB><<<grid, NT, smem, stream>>>(a);
     return check_launch("bilstm_fwd_kernel");
   }
-  const size_t smem = sizeof(float) * (NB * 4 * HP + NB * 4 * 2 * BWD_SL + (size_t)RING * NB * 7 * 128);
+  constexpr int KSP = (KS % 32 == 0) ? KS + 4 : KS;
+  const size_t smem = sizeof(float) * (NB * 4 * 2 * KSP + NB * 4 * 2 * BWD_SL + (size_t)RING * NB * 7 * 128);
+  if (KS == 52 && a.H <= 100) {                    // the model's hidden size: no padded r values in registers
+    MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB, (KS == 52 ? 50 : KS)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bilstm_bwd_kernel<KS, NB, (KS == 52 ? 50 : KS)><<<grid, BWD_NT, smem, stream>>>(a);
+    return check_launch("bilstm_bwd_kernel");
+  }
   MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bilstm_bwd_kernel<KS, NB><<<grid, BWD_NT, smem, stream>>>(a);
   return check_launch("bilstm_bwd_kernel");

@@ -71,6 +71,13 @@ __device__ __forceinline__ void ldg256(const float* p, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
+// two adjacent 16-byte pieces of a pack (rows r, r + 1 of one chunk) as ONE 32-byte store: a whole sector per request instead of two
+// half sectors that L2 has to merge
+__device__ __forceinline__ void stg256_u(void* p, const uint4 a, const uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void stg256(float* p, const float* v) {
   asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -111,7 +118,11 @@ __device__ __forceinline__ void pack_load4(const PackArgs& a, const PackUnit& un
   }
 }
 
-__global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, const int B) {
+__global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, const int B, int* const zero_ints, const int n_zero) {
+  // the main launch may be scheduled as soon as SMs free up (programmatic dependent launch; it waits for this grid before it reads)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (blockIdx.x == 0)                                  // dependency counters / work-queue head of the main launch
+    for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_ints[i] = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_b0 = pp.side[0].LP / 4, per_b1 = pp.side[1].LP / 4;          // units per batch row (LP is a multiple of 128)
   const int units0 = B * per_b0, n_units = units0 + B * per_b1;
@@ -149,6 +160,7 @@ __global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, c
     char* const s_dst = reinterpret_cast<char*>(a.s_pack) + pack_off;
     char* const v_dst = reinterpret_cast<char*>(a.v_pack) + pack_off;
     float dot[4];
+    uint4 vq[4], sq[4];                                 // this lane's four 16-byte pieces of the value pack / the S pack
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int row = un.row0 + r;
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, c
       __nv_bfloat162 vp[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) vp[e] = __floats2bfloat162_rn(v[r][2 * e], v[r][2 * e + 1]);
-      if (two_packs && lane < CHUNKS) *reinterpret_cast<uint4*>(v_dst + r * 16) = lane < CHUNKS - 1 ? *reinterpret_cast<uint4*>(vp) : make_uint4(0u, 0u, 0u, 0u);
+      vq[r] = lane < CHUNKS - 1 ? *reinterpret_cast<uint4*>(vp) : make_uint4(0u, 0u, 0u, 0u);
       if (a.keep) {                                     // dropout (attention.py:66-67): the S operand sees the dropped values
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -179,7 +191,15 @@ __global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, c
         for (int e = 0; e < 4; ++e) sp[e] = __floats2bfloat162_rn(v[r][2 * e], v[r][2 * e + 1]);
       }
       dot[r] = dt;
-      if (lane < CHUNKS - 1) *reinterpret_cast<uint4*>(s_dst + r * 16) = *reinterpret_cast<uint4*>(sp);
+      sq[r] = *reinterpret_cast<uint4*>(sp);
+    }
+    if (two_packs && lane < CHUNKS) {
+      stg256_u(v_dst, vq[0], vq[1]);
+      stg256_u(v_dst + 32, vq[2], vq[3]);
+    }
+    if (lane < CHUNKS - 1) {
+      stg256_u(s_dst, sq[0], sq[1]);
+      stg256_u(s_dst + 32, sq[2], sq[3]);
     }
     // the four row sums at once: two exchange steps halve the number of values a lane carries, three more finish them
     {
@@ -194,6 +214,7 @@ __global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, c
       for (int r = 0; r < 4; ++r) dot[r] = __shfl_sync(0xffffffffu, sm, ((r >> 1) * 16) + ((r & 1) * 8));
     }
     if (lane == CHUNKS - 1) {                           // the K-padding chunk carries the additive term
+      uint4 tq[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const bool in = un.row0 + r < a.L;
@@ -203,8 +224,10 @@ __global__ void __launch_bounds__(128, 4) bidaf_pack_kernel(const PackPair pp, c
         __nv_bfloat16 t[8] = {zero, zero, zero, zero, zero, zero, zero, zero};
         if (a.text_side) { t[0] = in ? hi : zero; t[1] = in ? lo : zero; t[2] = one; t[3] = one; }
         else             { t[0] = one; t[1] = one; t[2] = in ? hi : zero; t[3] = in ? lo : zero; }
-        *reinterpret_cast<uint4*>(s_dst + r * 16) = *reinterpret_cast<uint4*>(t);
+        tq[r] = *reinterpret_cast<uint4*>(t);
       }
+      stg256_u(s_dst, tq[0], tq[1]);
+      stg256_u(s_dst + 32, tq[2], tq[3]);
     }
     // mask words of the 64-row tile this unit starts
     if ((un.row0 & 63) == 0) {
@@ -651,7 +674,7 @@ int bidaf_fwd_tc(const float* text, const float* modality, const uint8_t* text_m
     }
     const int n_units = B * (LcP + LqP) / 4;
     const int blocks = min((n_units + 3) / 4, num_sms * 4);         // 16 warps per SM, each streaming over its units
-    bidaf_pack_kernel<<<blocks, 128, 0, stream>>>(pp, B);
+    bidaf_pack_kernel<<<blocks, 128, 0, stream>>>(pp, B, pk.ready, B + 1);
   }
   if (int rc = check_launch("bidaf_pack_kernel")) return rc;
 

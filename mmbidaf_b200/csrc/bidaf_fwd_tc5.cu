@@ -296,6 +296,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bidaf_tc5_kernel(const Args f) {
 
   if (warp_u == TMA_WARP) {
     // =========================================== scheduler + TMA producer ===========================================
+    // Programmatic dependent launch: this grid may have started while bidaf_pack_kernel was still running (its CTAs are placed as
+    // SMs free up and get here through their prologue); nothing of the pack kernel's output -- the operand packs, the mask words, the
+    // zeroed queue head and dependency counters -- is touched before this wait, and every other role starts from an item published below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t g = 0;                                                 // slots used so far (ring position)
     EvLog ev{(f.ev && blockIdx.x == 0 && lane == 0) ? f.ev + 2 * 2048 : nullptr, 0};
     for (uint32_t n = 0;; ++n) {                                    // n: passes published so far
@@ -720,9 +724,20 @@ int bidaf_fwd_tc5_launch(const BidafPacks& pk, const float* text, const float* b
     MMB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     MMB_CUDA(cudaFuncSetAttribute(bidaf_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
-  MMB_CUDA(cudaMemsetAsync(pk.ready, 0, sizeof(int) * (size_t)(B + 1), stream));
+  // (pk.ready[0 .. B] -- the counters and the queue head -- are zeroed by bidaf_pack_kernel)
   const int n_items = f.n_q2c + 2 * f.n_c2q;
-  bidaf_tc5_kernel<<<n_items < num_sms ? n_items : num_sms, NTHREADS, SMEM_BYTES, stream>>>(f);
+  static const char* pdl_env = getenv("MMB_BIDAF_PDL");                  // 0: plain stream order (A/B switch)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(n_items < num_sms ? n_items : num_sms));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_env && atoi(pdl_env) == 0) ? 0 : 1;
+  MMB_CUDA(cudaLaunchKernelEx(&cfg, bidaf_tc5_kernel, f));
   return check_launch("bidaf_tc5_kernel");
 }
 

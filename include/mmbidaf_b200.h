@@ -221,6 +221,22 @@ MMB_API int mmb_decoder_attn_finish_bwd(const float* d_xcat, int ldx, const floa
                                         float* d_ctx12, float* vec_acc, float* scal_acc, const float* att_cov,
                                         const float* cov_out, const float* g_cov, float* dcov_tot, int B, int Lt, int D,
                                         mmb_stream_t stream);
+/* The whole backward step of layers/attention.py:145-186 as ONE cluster kernel: mmb_decoder_bwd_head, the two text sweeps of
+ * mmb_decoder_attn_bwd and d h = [d_gates | d_hw4] Wh_stack (Wh_stack (4H + 4D, H) = [lstm.weight_hh; W2; W4; W_beta_2; W_beta_4]).
+ * d_gates is a (B, ldg) buffer with ldg >= 4H + 4D: d_hw4 (B, 4D) is written beside d_gates.  d_proj_a / d_proj_i, vec_acc and
+ * scal_acc are accumulated in place; d_cov (B, Lt) and d_h (B, H) are written. */
+MMB_API int mmb_decoder_step_fused_bwd(const float* probs, const float* d_probs, const long long* target, const float* g_nll,
+                                       const float* g_cov, const float* out_w, const float* gates, const float* cell_in,
+                                       const float* cell_out, const float* d_h_out, const float* d_cell_out, const float* Wcat_ctx,
+                                       const float* d_att_cov, const float* d_cov_out, const float* alpha, const float* beta,
+                                       const float* ctx12, const float* pb, const float* hw, const float* vb1, const float* vb2,
+                                       const float* att, const float* cov_out, const float* Wb13, float* d_logits, int ldd,
+                                       float* d_gates, int ldg, float* d_cell, float* datt, float* dcov_tot, float* d_pre_b,
+                                       float* d_ctx12, float* vec_acc, float* scal_acc, const float* proj_a, const float* proj_i,
+                                       const float* enc_a, const float* enc_i, const float* coverage, const float* v1, const float* wc1,
+                                       const float* v2, const float* wc2, float* d_proj_a, float* d_proj_i, float* d_cov,
+                                       const float* Wh_stack, float* d_h, int B, int Lt, int D, int H, int M, mmb_stream_t stream);
+
 MMB_API int mmb_decoder_attn_bwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
                                  const float* hw, const float* coverage, const float* alpha, const float* beta,
                                  const float* datt, const float* d_ctx12, const float* d_cov_out, const float* d_pre_b,

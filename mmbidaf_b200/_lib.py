@@ -41,6 +41,7 @@ SIGNATURES = {
     "mmb_decoder_out_softmax_bwd": [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "mmb_decoder_cell_bwd": [c_void_p] * 7 + [c_int] + [c_void_p] + [c_int] * 2 + [c_void_p],
     "mmb_decoder_attn_finish_bwd": [c_void_p, c_int] + [c_void_p] * 18 + [c_int] * 3 + [c_void_p],
+    "mmb_decoder_step_fused_bwd": [c_void_p] * 25 + [c_int] + [c_void_p] + [c_int] + [c_void_p] * 21 + [c_int] * 5 + [c_void_p],
     "mmb_decoder_attn_bwd": [c_void_p] * 24 + [c_int] + [c_void_p] * 3 + [c_int] * 4 + [c_void_p],
     "mmb_highway_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_highway_bwd": [c_void_p] * 5 + [ctypes.c_longlong, c_int, c_void_p],

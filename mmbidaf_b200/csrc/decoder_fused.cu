@@ -519,6 +519,13 @@ struct HeadArgs {
   float *d_cell, *datt, *dcov_tot, *d_pre_b, *d_ctx12;      // (B,H), (B,Lt), (B,Lt), (2,B,D), (2,B,D)
   float *vec_acc, *scal_acc;                                // (B,6,D), (B,4): accumulated in place (rows 4, 5; columns 2, 3)
   int B, Lt, D, H, M, ldd, ldg, chunk;
+  // the whole step (mmb_decoder_step_fused_bwd): the two sweeps over the text axis and d h follow in the same launch
+  int sweeps;
+  const float *proj_a, *proj_i, *enc_a, *enc_i, *cov;       // (B,Lt,D) x4, (B,Lt) the step's coverage input
+  const float *v1, *wc1, *v2, *wc2;                         // (D)
+  float *d_proj_a, *d_proj_i, *d_cov;                       // (B,Lt,D) accumulated, (B,Lt) written
+  const float* Wh_stack;                                    // (4H + 4D, H): [W_hh; W2; W4; W_beta_2; W_beta_4]
+  float* d_h;                                               // (B,H)
 };
 
 __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
@@ -664,6 +671,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   }
   __syncthreads();
   // ---- 6: d c_k = beta_k d c3 + W_beta_k^T d_pre_k: the 2D outputs split over the ranks --------------------------------------------
+  float* s_dc = s_scr + NT;                             // [2D]  d c_1 | d c_2, gathered (whole-step launch)
   {
     const int per = (2 * D + CL - 1) / CL, o0 = min(2 * D, R * per), o1 = min(2 * D, o0 + per);
     for (int k = 0; k < 2; ++k) {
@@ -672,17 +680,214 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
       block_matvec_t(a.Wb13 + (size_t)k * D * D, D, nullptr, s_dpre + k * D, D, hi - lo, s_scr, [&](int i) { return lo - k * D + i; },
                      [&](int i, float v) {
                        const int dd = lo - k * D + i;
-                       a.d_ctx12[((size_t)k * a.B + b) * D + dd] = fmaf(bk, s_dctx[dd], v);
+                       const float x = fmaf(bk, s_dctx[dd], v);
+                       a.d_ctx12[((size_t)k * a.B + b) * D + dd] = x;
+                       if (a.sweeps)
+                         for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dc, r)[k * D + dd] = x;
                      });
     }
+  }
+  cluster.sync();      // no rank exits while another may still write into its shared memory; s_dc is complete
+  if (!a.sweeps) return;
+
+  // ==== the text sweeps of the step (decoder_step.cu: dec_attn_sweep1 / sweep2 / reduce_video), this rank's rows [t0, t1) ============
+  const int lane = tid & 31, warp = tid >> 5;
+  const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk), n = t1 - t0;
+  auto up4s = [](int v) { return (v + 3) & ~3; };
+  float* s_da = s_dc + up4s(2 * D);                     // [2][chunk]  d alpha_k of this rank's rows
+  float* s_vec = s_da + up4s(2 * a.chunk);              // [6][D]  v1 | wc1 | hw1 | v2 | wc2 | hw2
+  float* s_part = s_vec + up4s(6 * D);                  // [NW][3][D]
+  float* s_row = s_part + up4s(NW * 3 * D);             // [chunk]  d cov accumulation
+  float* s_colp = s_row + up4s(a.chunk);                // [MAXC][2][3][D]  column partials of every rank (written remotely)
+  float* s_in = s_colp + up4s(MAXC * 6 * D);            // [4H + 4D]  d_gates | d (W2 h) | d (W4 h) | d_pre_b
+  constexpr int MAXJ = 8;                               // D <= 256
+  // ---- 7: d alpha_k[t] = beta_k datt[t] + d c_k . enc_k[t];  sum_t alpha d alpha over the cluster ----------------------------------
+  for (int i = tid; i < D; i += NT) {
+    s_vec[i] = a.v1[i];
+    s_vec[D + i] = a.wc1[i];
+    s_vec[2 * D + i] = a.hw[(size_t)b * 4 * D + i];
+    s_vec[3 * D + i] = a.v2[i];
+    s_vec[4 * D + i] = a.wc2[i];
+    s_vec[5 * D + i] = a.hw[(size_t)b * 4 * D + D + i];
+  }
+  for (int i = tid; i < n; i += NT) s_row[i] = a.dcov_tot[(size_t)b * Lt + t0 + i];
+  {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = warp * 2; i < n; i += NW * 2) {
+      float d1[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f};
+      float eav[2][MAXJ], eiv[2][MAXJ];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {                     // loads first (memory-level parallelism)
+        const float* ea = a.enc_a + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
+        const float* ei = a.enc_i + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          eav[u][j] = d < D ? ea[d] : 0.f;
+          eiv[u][j] = d < D ? ei[d] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) {
+            d1[u] = fmaf(s_dc[d], eav[u][j], d1[u]);
+            d2[u] = fmaf(s_dc[D + d], eiv[u][j], d2[u]);
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float x1 = warp_sum(d1[u]), x2 = warp_sum(d2[u]);
+        if (lane == 0 && i + u < n) {
+          const int t = t0 + i + u;
+          const float g = a.datt[(size_t)b * Lt + t];      // (written by this rank in stage 5)
+          const float da1 = x1 + beta1 * g, da2 = x2 + beta2 * g;
+          s_da[i + u] = da1;
+          s_da[a.chunk + i + u] = da2;
+          s1 = fmaf(a.alpha[((size_t)b * 2 + 0) * Lt + t], da1, s1);
+          s2 = fmaf(a.alpha[((size_t)b * 2 + 1) * Lt + t], da2, s2);
+        }
+      }
+    }
+    s1 = block_sum(s1, s_red);
+    s2 = block_sum(s2, s_red);
+    if (tid < CL) {
+      float* dst = cluster.map_shared_rank(s_ex, tid) + R * 4;
+      dst[0] = s1;
+      dst[1] = s2;
+    }
+  }
+  cluster.sync();
+  float stot0 = 0.f, stot1 = 0.f;
+  for (int r = 0; r < CL; ++r) {
+    stot0 += s_ex[r * 4 + 0];
+    stot1 += s_ex[r * 4 + 1];
+  }
+  // ---- 8: soft-max backward, tanh backward, d proj (+=), d cov, column partials ------------------------------------------------------
+  float se_m0 = 0.f, se_m1 = 0.f;
+  for (int m = 0; m < 2; ++m) {
+    const float* proj = (m == 0 ? a.proj_a : a.proj_i) + ((size_t)b * Lt + t0) * D;
+    float* dproj = (m == 0 ? a.d_proj_a : a.d_proj_i) + ((size_t)b * Lt + t0) * D;
+    const float* vv = s_vec + 3 * m * D;
+    const float* wc = vv + D;
+    const float* hwm = vv + 2 * D;
+    const float stm = m == 0 ? stot0 : stot1;
+    float c_dz[MAXJ], c_cov[MAXJ], c_v[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) c_dz[j] = c_cov[j] = c_v[j] = 0.f;
+    float se = 0.f;
+    for (int i0 = warp * 2; i0 < n; i0 += NW * 2) {     // two sentences per warp iteration: every load in flight before the first tanh
+      float cvs[2], dets[2], pv[2][MAXJ], dpv[2][MAXJ];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = min(i0 + u, n - 1), t = t0 + i;
+        cvs[u] = a.cov[(size_t)b * Lt + t];
+        dets[u] = a.alpha[((size_t)b * 2 + m) * Lt + t] * (s_da[m * a.chunk + i] - stm);
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          pv[u][j] = d < D ? proj[(size_t)i * D + d] : 0.f;
+          dpv[u][j] = d < D ? dproj[(size_t)i * D + d] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u;
+        if (i >= n) break;
+        const float cv = cvs[u], det = dets[u];
+        float row = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) {
+            const float tz = tanh_fast((pv[u][j] + hwm[d]) + cv * wc[d]);
+            const float dz = det * vv[d] * (1.f - tz * tz);
+            dproj[(size_t)i * D + d] = dpv[u][j] + dz;
+            c_dz[j] += dz;
+            c_cov[j] = fmaf(dz, cv, c_cov[j]);
+            c_v[j] = fmaf(det, tz, c_v[j]);
+            row = fmaf(dz, wc[d], row);
+          }
+        }
+        row = warp_sum(row);
+        if (lane == 0) {
+          s_row[i] += row;
+          se += det;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int d = lane + 32 * j;
+      if (d < D) {
+        s_part[(warp * 3 + 0) * D + d] = c_dz[j];
+        s_part[(warp * 3 + 1) * D + d] = c_cov[j];
+        s_part[(warp * 3 + 2) * D + d] = c_v[j];
+      }
+    }
+    se = block_sum(se, s_red);                          // (contains the __syncthreads that publishes s_part)
+    if (m == 0) se_m0 = se; else se_m1 = se;
+    for (int i = tid; i < 3 * D; i += NT) {
+      float x = 0.f;
+      for (int w = 0; w < NW; ++w) x += s_part[w * 3 * D + i];
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_colp, r)[(R * 2 + m) * 3 * D + i] = x;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += NT) a.d_cov[(size_t)b * Lt + t0 + i] = s_row[i];
+  if (tid < CL) {
+    float* dst = cluster.map_shared_rank(s_ex, tid) + R * 4;
+    dst[2] = se_m0;
+    dst[3] = se_m1;
+  }
+  cluster.sync();
+  // ---- 9: the column sums over the cluster (fixed order) -> d (W2 h) | d (W4 h), parameter-gradient accumulators; d h -----------------
+  for (int i = tid; i < 2 * D; i += NT) {
+    const int m = i / D, d = i - m * D;
+    float x = 0.f, y = 0.f, z = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* q = s_colp + (r * 2 + m) * 3 * D;
+      x += q[d];
+      y += q[D + d];
+      z += q[2 * D + d];
+    }
+    s_in[4 * H + m * D + d] = x;
+    s_in[4 * H + (2 + m) * D + d] = s_dpre[m * D + d];
+    if (R == 0) {
+      float* o = a.d_gates + (size_t)b * a.ldg + 4 * H;                   // d_hw4 sits beside d_gates
+      o[m * D + d] = x;
+      o[(2 + m) * D + d] = s_dpre[m * D + d];
+      a.vec_acc[((size_t)b * 6 + m) * D + d] += y;                         // d Wc weight
+      a.vec_acc[((size_t)b * 6 + 2 + m) * D + d] += z;                     // d v weight
+    }
+  }
+  for (int i = tid; i < 4 * H; i += NT) s_in[i] = s_dg[i];
+  if (R == 0 && tid < 2) {
+    float sv = 0.f;
+    for (int r = 0; r < CL; ++r) sv += s_ex[r * 4 + 2 + tid];
+    a.scal_acc[b * 4 + tid] += sv;                                         // d v bias (identically 0 up to rounding)
+  }
+  __syncthreads();
+  {
+    const int per = (H + CL - 1) / CL, j0 = min(H, R * per), j1 = min(H, j0 + per);
+    block_matvec_t(a.Wh_stack, H, nullptr, s_in, 4 * H + 4 * D, j1 - j0, s_scr, [&](int i) { return j0 + i; },
+                   [&](int i, float v) { a.d_h[(size_t)b * H + j0 + i] = v; });
   }
   cluster.sync();      // no rank exits while another may still write into its shared memory
 }
 
-static size_t head_smem_bytes(int D, int H, int M, int CL) {
+static size_t g_head_smem_set = 0;   // dynamic shared memory the kernel attribute of dec_bwd_head_kernel allows (both launchers share it)
+
+static size_t head_smem_bytes(int D, int H, int M, int CL, int chunk = 0, bool sweeps = false) {
   auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
   const size_t per_m = (M + CL - 1) / CL;
-  return (up4(per_m) + up4((size_t)MAXC * H) + up4(4 * H) + up4(D) + up4(2 * D) + MAXC * 4 + 32 + NT) * sizeof(float) + 64;
+  size_t floats = up4(per_m) + up4((size_t)MAXC * H) + up4(4 * H) + up4(D) + up4(2 * D) + MAXC * 4 + 32 + NT;
+  if (sweeps)
+    floats += up4(2 * D) + up4(2 * (size_t)chunk) + up4(6 * D) + up4((size_t)NW * 3 * D) + up4(chunk) + up4((size_t)MAXC * 6 * D) +
+              up4(4 * H + 4 * D);
+  return floats * sizeof(float) + 64;
 }
 
 // bytes of dynamic shared memory for the launch below
@@ -773,13 +978,13 @@ extern "C" int mmb_decoder_bwd_head(const float* probs, const float* d_probs, co
   const int CL = (long long)B * 4 * 2 <= 160 ? 8 : 4;
   HeadArgs a{probs, d_probs, target, g_nll, g_cov, out_w, gates, cell_in, cell_out, d_h_out, d_cell_out, Wcat_ctx, d_att_cov, d_cov_out,
              alpha, beta, ctx12, pb, hw, vb1, vb2, att, cov_out, Wb13, d_logits, d_gates, d_cell, datt, dcov_tot, d_pre_b, d_ctx12,
-             vec_acc, scal_acc, B, Lt, D, H, M, ldd, ldg, (Lt + CL - 1) / CL};
+             vec_acc, scal_acc, B, Lt, D, H, M, ldd, ldg, (Lt + CL - 1) / CL,
+             0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const size_t smem = head_smem_bytes(D, H, M, CL);
   MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_bwd_head: %zu B of shared memory", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > g_head_smem_set) {
     MMB_CUDA(cudaFuncSetAttribute(dec_bwd_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+    g_head_smem_set = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * CL));
@@ -795,4 +1000,54 @@ extern "C" int mmb_decoder_bwd_head(const float* probs, const float* d_probs, co
   cfg.numAttrs = 1;
   MMB_CUDA(cudaLaunchKernelEx(&cfg, dec_bwd_head_kernel, a));
   return check_launch("dec_bwd_head_kernel");
+}
+
+// The WHOLE backward step as one cluster kernel: mmb_decoder_bwd_head + the two text sweeps of mmb_decoder_attn_bwd + d h =
+// [d_gates | d_hw4] Wh_stack (a library GEMM before).  d_gates points at a (B, ldg) buffer with ldg >= 4H + 4D: d_hw4 is written beside
+// d_gates.  One launch per backward step instead of four.
+extern "C" int mmb_decoder_step_fused_bwd(const float* probs, const float* d_probs, const long long* target, const float* g_nll,
+                                          const float* g_cov, const float* out_w, const float* gates, const float* cell_in,
+                                          const float* cell_out, const float* d_h_out, const float* d_cell_out, const float* Wcat_ctx,
+                                          const float* d_att_cov, const float* d_cov_out, const float* alpha, const float* beta,
+                                          const float* ctx12, const float* pb, const float* hw, const float* vb1, const float* vb2,
+                                          const float* att, const float* cov_out, const float* Wb13, float* d_logits, int ldd,
+                                          float* d_gates, int ldg, float* d_cell, float* datt, float* dcov_tot, float* d_pre_b,
+                                          float* d_ctx12, float* vec_acc, float* scal_acc, const float* proj_a, const float* proj_i,
+                                          const float* enc_a, const float* enc_i, const float* coverage, const float* v1, const float* wc1,
+                                          const float* v2, const float* wc2, float* d_proj_a, float* d_proj_i, float* d_cov,
+                                          const float* Wh_stack, float* d_h, int B, int Lt, int D, int H, int M, mmb_stream_t stream) {
+  using namespace mmb;
+  MMB_REQUIRE(probs && out_w && gates && cell_in && cell_out && Wcat_ctx && alpha && beta && ctx12 && pb && hw && vb1 && vb2 && Wb13 &&
+                  d_logits && d_gates && d_cell && datt && dcov_tot && d_pre_b && d_ctx12 && vec_acc && scal_acc && proj_a && proj_i &&
+                  enc_a && enc_i && coverage && v1 && wc1 && v2 && wc2 && d_proj_a && d_proj_i && d_cov && Wh_stack && d_h,
+              MMB_ERR_INVALID, "mmb_decoder_step_fused_bwd: null pointer");
+  MMB_REQUIRE((!target || g_nll) && (!g_cov || (att && cov_out)), MMB_ERR_INVALID, "mmb_decoder_step_fused_bwd: loss-term pointers");
+  MMB_REQUIRE(B > 0 && Lt > 0 && D > 0 && D <= 256 && H > 0 && M > 0 && ldd >= M && ldg >= 4 * H + 4 * D && H <= NT, MMB_ERR_INVALID,
+              "mmb_decoder_step_fused_bwd: B=%d Lt=%d D=%d H=%d M=%d ldd=%d ldg=%d", B, Lt, D, H, M, ldd, ldg);
+  const int CL = (long long)B * 4 * 2 <= 160 ? 8 : 4;
+  const int chunk = (Lt + CL - 1) / CL;
+  HeadArgs a{probs, d_probs, target, g_nll, g_cov, out_w, gates, cell_in, cell_out, d_h_out, d_cell_out, Wcat_ctx, d_att_cov, d_cov_out,
+             alpha, beta, ctx12, pb, hw, vb1, vb2, att, cov_out, Wb13, d_logits, d_gates, d_cell, datt, dcov_tot, d_pre_b, d_ctx12,
+             vec_acc, scal_acc, B, Lt, D, H, M, ldd, ldg, chunk,
+             1, proj_a, proj_i, enc_a, enc_i, coverage, v1, wc1, v2, wc2, d_proj_a, d_proj_i, d_cov, Wh_stack, d_h};
+  const size_t smem = head_smem_bytes(D, H, M, CL, chunk, true);
+  MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fused_bwd: %zu B of shared memory (Lt=%d)", smem, Lt);
+  if (smem > g_head_smem_set) {
+    MMB_CUDA(cudaFuncSetAttribute(dec_bwd_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_head_smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMB_CUDA(cudaLaunchKernelEx(&cfg, dec_bwd_head_kernel, a));
+  return check_launch("dec_bwd_head_kernel (whole step)");
 }

@@ -268,6 +268,21 @@ def decoder_step_bwd(seq: DecoderSeq, h, cell, coverage, probs, cell_out, saved,
     cut = os.environ.get("MMB_DECODER_CUT")
     if cut is None:
         cut = "fused" if B * Lt <= 20000 else "chunks"
+    if cut == "fused":
+        # the WHOLE backward step as one cluster kernel (csrc/decoder_fused.cu): head, both text sweeps, d h.  "head" keeps the
+        # round-2 cut (head kernel + chunk-parallel sweeps + library GEMM) as a cross-check.
+        d_cov = torch.empty(B, Lt, **f32)
+        d_h = torch.empty(B, H, **f32)
+        _lib.check(lib.mmb_decoder_step_fused_bwd(
+            p(probs), p(c(d_probs)), p(target if fused else None), p(g[0] if fused else None), p(g[1] if fused else None),
+            p(seq.out_w), p(gates), p(cell), p(cell_out), p(c(d_h_out)), p(c(d_cell_out)), p(seq.Wcat_ctx), p(c(d_att_cov)),
+            p(c(d_cov_out)), p(alpha), p(beta), p(ctx12), p(pb), p(hw), p(seq.vb1), p(seq.vb2), p(att_cov if fused else None),
+            p(cov_out if fused else None), p(seq.Wb13), d_logits_pad.data_ptr(), seq.Mp, gbuf.data_ptr(), 4 * H + 4 * D, p(d_cell),
+            p(datt), p(dcov_tot), p(d_pre_b), p(d_ctx12), p(vec_acc), p(scal_acc), p(seq.proj_a), p(seq.proj_i), p(seq.enc_a),
+            p(seq.enc_i), p(coverage), p(seq.v1), p(seq.wc1), p(seq.v2), p(seq.wc2), p(d_proj_a), p(d_proj_i), p(d_cov),
+            p(seq.Wh_stack), p(d_h), B, Lt, D, H, M, st), "mmb_decoder_step_fused_bwd")
+        _count(1)
+        return d_h, d_cell, d_cov, d_logits, d_gates, d_ctx12, d_hw4, d_pre_b
     if cut != "chunks":
         # everything up to the text sweeps as ONE cluster kernel (csrc/decoder_fused.cu: dec_bwd_head_kernel)
         _lib.check(lib.mmb_decoder_bwd_head(p(probs), p(c(d_probs)), p(target if fused else None), p(g[0] if fused else None),

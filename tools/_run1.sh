@@ -1,9 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_bidaf_gpu.py -x -q -m gpu > gpurun_out/t1.log 2>&1
-tail -3 gpurun_out/t1.log
-for p in 0 1; do
-  echo "PDL=$p" >> gpurun_out/fwd_ab.log
-  MMB_BIDAF_PDL=$p python tools/bidaf_fwd_graph.py >> gpurun_out/fwd_ab.log 2>&1
-  MMB_BIDAF_PDL=$p python tools/bidaf_micro.py --iters 40 >> gpurun_out/fwd_ab.log 2>&1
-done
-cat gpurun_out/fwd_ab.log | grep -v Warn
+timeout 900 python -m pytest tests/test_decoder_gpu.py tests/test_model_gpu.py tests/test_trainer_gpu.py tests/test_reference_dropin_gpu.py -x -q -m gpu > gpurun_out/t1.log 2>&1
+tail -15 gpurun_out/t1.log
+python bench.py --steps 10 --warmup 3 --sections step > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err
+tail -2 gpurun_out/bench_b.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_b.json')); print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, d.get('e2e'))"

@@ -94,6 +94,9 @@ constexpr int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
 //  * the global stores of a step (out, saved gates, cell state) are issued one step LATE, from registers, inside the next step's FMA
 //    stream, and every memory operation is predicated rather than branched around;
 //  * the cp.async ring has a power-of-two slot stride: one add + one and per step for both ring positions.
+// Measured and not kept (round 2, tools/lstm_trace.py): eight accumulator chains instead of four (no change: a warp alone on its
+// scheduler issues an FFMA every ~2 cycles whatever the chain count); packed fma.rn.f32x2 (104 FFMA2 instead of 208 FFMA: a lone warp
+// then needs ~7 cycles per FFMA2, two warps ~4 -- the same FMA rate, 0.518 - 0.535 against 0.532 us per step).
 template <int KS, int NB, bool TRACE = false>
 __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmArgs a) {
   constexpr int HP = 2 * KS;                       // padded hidden size

@@ -285,6 +285,13 @@ MMB_API int mmb_length_plan(const int32_t* lengths, uint8_t* mask, uint8_t* dec_
 MMB_API int mmb_col_sum_blocks(long long n, int p);
 MMB_API int mmb_col_sum(const float* a, float* partial, float* out, long long n, int p, mmb_stream_t stream);
 
+/* train.py:148-155 hands ~110 per-parameter gradients to clip_grad_norm_ / the optimizer; here they are gathered into the flat gradient
+ * buffer the fused update below runs over.  srcs / dst_offsets / sizes are HOST arrays of n_segs entries (device source pointers, element
+ * offsets into dst that are multiples of 4, element counts); a null source zero-fills its segment; every segment is zero-padded up to a
+ * multiple of 4 elements.  One launch per 120 segments; the pointers travel as kernel parameters. */
+MMB_API int mmb_pack_segments(const float* const* srcs, const long long* dst_offsets, const long long* sizes, int n_segs, float* dst,
+                              mmb_stream_t stream);
+
 /* --------------------------------------------------------------------------------------
  * Parameter update of the training step (train.py:154-155 with the optimiser of train.py:110): clip_grad_norm_ followed by
  * one Adadelta step, fused into one pass over flat buffers of n floats (n % 4 == 0, 16-byte aligned):

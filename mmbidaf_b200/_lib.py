@@ -46,6 +46,7 @@ SIGNATURES = {
     "mmb_highway_fwd": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_highway_bwd": [c_void_p] * 5 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_length_plan": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
+    "mmb_pack_segments": [c_void_p] * 3 + [c_int] + [c_void_p] * 2,
     "mmb_col_sum_blocks": [ctypes.c_longlong, c_int],
     "mmb_col_sum": [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_void_p],
     "mmb_adadelta_clip_step": [c_void_p] * 5 + [c_float] * 5 + [ctypes.c_longlong, c_void_p],

@@ -37,8 +37,74 @@ __global__ void __launch_bounds__(256) adadelta_clip_kernel(float4* __restrict__
   }
 }
 
+// Gradient pack: up to PACK_SEGS per-parameter gradient tensors -> their places in the flat gradient buffer, ONE launch; the source
+// pointers travel in the kernel parameters (captured by value in a CUDA graph, nothing to keep alive).  A null source zero-fills.
+// (torch.cat of the ~110 pieces: 40 us for 12.8 MB on the tail of every step.)
+constexpr int PACK_SEGS = 120, PACK_TILE = 4096;     // floats per block
+struct PackSegs {
+  const float* src[PACK_SEGS];
+  long long dst_off[PACK_SEGS];
+  int n[PACK_SEGS];                                  // elements to copy; the destination is zero-padded up to pad[i]
+  int pad[PACK_SEGS];
+};
+static_assert(sizeof(PackSegs) <= 4000, "kernel parameter space");
+
+__global__ void __launch_bounds__(256) pack_segments_kernel(const __grid_constant__ PackSegs s, float* __restrict__ dst) {
+  const int seg = blockIdx.y;
+  const int n = s.n[seg], pad = s.pad[seg];
+  const int t0 = blockIdx.x * PACK_TILE;
+  if (t0 >= pad) return;
+  const float* src = s.src[seg];
+  float* d = dst + s.dst_off[seg];
+  const bool vec = src == nullptr || (reinterpret_cast<uintptr_t>(src) & 15) == 0;      // (dst_off and pad are multiples of 4)
+  const int t1 = min(pad, t0 + PACK_TILE);
+  if (vec) {
+    for (int i = t0 + threadIdx.x * 4; i < t1; i += 256 * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) {
+        if (i + 4 <= n) v = __ldg(reinterpret_cast<const float4*>(src + i));
+        else {
+          float* e = reinterpret_cast<float*>(&v);
+          for (int k = 0; k < 4; ++k) e[k] = i + k < n ? src[i + k] : 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(d + i) = v;
+    }
+  } else {
+    for (int i = t0 + threadIdx.x; i < t1; i += 256) d[i] = i < n ? src[i] : 0.f;
+  }
+}
+
 }  // namespace
 }  // namespace mmb
+
+extern "C" int mmb_pack_segments(const float* const* srcs, const long long* dst_offsets, const long long* sizes, int n_segs, float* dst,
+                                 mmb_stream_t stream) {
+  using namespace mmb;
+  MMB_REQUIRE(srcs && dst_offsets && sizes && dst && n_segs > 0, MMB_ERR_INVALID, "mmb_pack_segments: bad arguments");
+  MMB_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, MMB_ERR_UNSUPPORTED, "mmb_pack_segments: dst must be 16-byte aligned");
+  for (int base = 0; base < n_segs; base += PACK_SEGS) {
+    const int cnt = n_segs - base < PACK_SEGS ? n_segs - base : PACK_SEGS;
+    PackSegs s{};
+    int max_pad = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const long long sz = sizes[base + i];
+      MMB_REQUIRE(sz >= 0 && sz < (1ll << 31) - 8 && dst_offsets[base + i] % 4 == 0, MMB_ERR_INVALID,
+                  "mmb_pack_segments: segment %d: size %lld, offset %lld (offsets must be multiples of 4)", base + i, sz,
+                  dst_offsets[base + i]);
+      s.src[i] = srcs[base + i];
+      s.dst_off[i] = dst_offsets[base + i];
+      s.n[i] = (int)sz;
+      s.pad[i] = (int)((sz + 3) / 4 * 4);
+      max_pad = s.pad[i] > max_pad ? s.pad[i] : max_pad;
+    }
+    if (max_pad == 0) continue;
+    dim3 grid((unsigned)((max_pad + PACK_TILE - 1) / PACK_TILE), (unsigned)cnt);
+    pack_segments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, dst);
+    if (int rc = check_launch("pack_segments_kernel")) return rc;
+  }
+  return MMB_OK;
+}
 
 extern "C" int mmb_adadelta_clip_step(float* param, float* grad, float* square_avg, float* acc_delta, const float* grad_norm,
                                       float max_norm, float lr, float rho, float eps, float weight_decay, long long n,

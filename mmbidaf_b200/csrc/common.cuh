@@ -51,6 +51,26 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + e
 // Branch-free gate non-linearities for the serial LSTM chain: act_k(x) = 1 - k / (1 + e^{kx}) is tanh for
 // k = 2 and the logistic sigmoid for k = 1.  __expf / __fdividef keep the absolute error near 1e-7
 // (measured against the fp64 oracle in tests/test_lstm_gpu.py), which is what the gates need.
+// Counter-based keep mask for dropout applied INSIDE a kernel: element `idx` of a tensor is kept iff hash(idx, key) < keep_prob 2^32.
+// A 32-bit avalanche hash (two multiplies and three xor-shifts around the two key halves): nine integer instructions, the same bits
+// wherever they are recomputed (the forward store, the backward load, mmb_dropout_mask in the tests).  Not ATen's Philox stream:
+// bit-parity of the random stream with the reference is not a goal, parity GIVEN the mask is tested.
+__device__ __forceinline__ bool dropout_keep(uint32_t idx, uint32_t k0, uint32_t k1, uint32_t thresh) {
+  uint32_t x = idx ^ k0;
+  x *= 0x9E3779B1u;
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= k1;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x < thresh;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh(float keep_prob) {
+  const double t = (double)keep_prob * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (t <= 0.0 ? 0u : (uint32_t)t);
+}
+
 __device__ __forceinline__ float gate_act(float x, float k) { return 1.0f - __fdividef(k, 1.0f + __expf(k * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return gate_act(x, 2.0f); }
 

@@ -120,6 +120,21 @@ MMB_API int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, c
                            const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, int B, int L,
                            int H, int ndir, mmb_stream_t stream);
 
+/* Dropout on a recurrent layer's OUTPUT applied inside the recurrence kernels (layers/encoding.py:104 `F.dropout(x, drop_prob, training)`
+ * after the nn.LSTM call, and nn.LSTM's own inter-layer dropout, encoding.py:77-81): the forward kernel writes y = keep ? out / keep_prob : 0
+ * beside the un-dropped `out` (which the recurrence and the weight gradients need); the backward kernel takes d y.  The keep bit of
+ * element i of (B, L, ndir H) is a counter-based hash of (i, *rng_key): no mask tensor, no separate launch.  mmb_dropout_mask writes the
+ * same bits as bytes (tests: parity GIVEN the mask); mmb_rng_next draws n_keys fresh keys from a device-resident state (splitmix64), so a
+ * CUDA-graph replay gets new masks without host involvement.  Not ATen's Philox stream. */
+MMB_API int mmb_bilstm_fwd_dropout(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out, float* y,
+                                   float* h_n, float* c_n, float* cell, const unsigned long long* rng_key, float keep_prob, int B,
+                                   int L, int H, int ndir, int save, mmb_stream_t stream);
+MMB_API int mmb_bilstm_bwd_dropout(float* gates, const float* cell, const float* w_hh, const int32_t* lengths, const int32_t* order,
+                                   const float* dy, const float* dh_n, const float* dc_n, const unsigned long long* rng_key,
+                                   float keep_prob, int B, int L, int H, int ndir, mmb_stream_t stream);
+MMB_API int mmb_dropout_mask(const unsigned long long* rng_key, float keep_prob, long long n, uint8_t* mask, mmb_stream_t stream);
+MMB_API int mmb_rng_next(unsigned long long* state, unsigned long long* key_out, int n_keys, mmb_stream_t stream);
+
 /* --------------------------------------------------------------------------------------
  * Multimodal attention decoder, one step (replaces attention.py:145-186).
  *

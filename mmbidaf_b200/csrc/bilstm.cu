@@ -71,6 +71,12 @@ struct LstmArgs {
   const float* dc_n;       // bwd: (B, ndir, H) or nullptr
   int B, L, H, ndir, save;
   long long* trace;        // debugging aid (MMB_LSTM_TRACE, tools/lstm_trace.py): clock64 stamps of CTA (0, 0), or null
+  // dropout on the layer's OUTPUT (encoding.py:104, nn.LSTM's inter-layer dropout), applied in the kernel: keep bits from
+  // common.cuh::dropout_keep(element index in (B, L, ndir H), key).  fwd: y = keep ? out / keep_prob : 0 is written beside `out`
+  // (the recurrence and the weight gradients keep the un-dropped states); bwd: `dout` is d y.
+  float* y;                            // fwd: (B, L, ndir*H) or null (no dropout)
+  const unsigned long long* rng_key;   // device scalar, or null (no dropout)
+  float keep_prob;
 };
 
 constexpr int threads_for(int KS) { return (4 * KS + 31) / 32 * 32 < 64 ? 64 : (4 * KS + 31) / 32 * 32; }
@@ -97,7 +103,7 @@ constexpr int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
 // Measured and not kept (round 2, tools/lstm_trace.py): eight accumulator chains instead of four (no change: a warp alone on its
 // scheduler issues an FFMA every ~2 cycles whatever the chain count); packed fma.rn.f32x2 (104 FFMA2 instead of 208 FFMA: a lone warp
 // then needs ~7 cycles per FFMA2, two warps ~4 -- the same FMA rate, 0.518 - 0.535 against 0.532 us per step).
-template <int KS, int NB, bool TRACE = false>
+template <int KS, int NB, bool TRACE = false, bool DROP = false>
 __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmArgs a) {
   constexpr int HP = 2 * KS;                       // padded hidden size
   constexpr int NT = threads_for(KS);              // == blockDim.x
@@ -176,6 +182,12 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
   float c_reg[NB], h_reg[NB], a0_reg[NB], a1_reg[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) c_reg[n] = h_reg[n] = a0_reg[n] = a1_reg[n] = 0.f;
+  // output dropout: key halves, threshold, 1 / keep_prob, and the distance from `out` to `y` (one add per store)
+  constexpr bool drop = DROP;                      // (compile time: the loop body must stay one basic block)
+  const unsigned long long key = drop ? a.rng_key[0] : 0ull;
+  const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32), thresh = dropout_thresh(a.keep_prob);
+  const float inv_keep = drop ? 1.f / a.keep_prob : 1.f;
+  const long y_off = drop ? a.y - a.out : 0;
   const float k_first = kp ? 2.0f : 1.0f;          // lane 0: (i, f) both sigmoid; lane 1: (g = tanh, o = sigmoid)
   const float pre_first = k_first * LOG2E_F;
   const bool save = a.save != 0;
@@ -225,6 +237,10 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
       for (int n = 0; n < NB; ++n) {
         const bool on = prev && (NB == 1 || s - 1 < len[n]), on_sv = on && save;
         st_global_if(op[n], h_reg[n], on);
+        if (drop) {                                                 // (uniform)
+          const bool keep = dropout_keep((uint32_t)(op[n] - a.out), key0, key1, thresh);
+          st_global_if(op[n] + y_off, keep ? h_reg[n] * inv_keep : 0.f, on);
+        }
         st_global_if(gp[n], a0_reg[n], on_sv);
         st_global_if(gp[n] + H, a1_reg[n], on_sv);
         st_global_if(cp[n], c_reg[n], on_sv);
@@ -265,6 +281,10 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
   for (int n = 0; n < NB; ++n) {
     const bool on = max_len > 0 && max_len - 1 < len[n], on_sv = on && save;
     st_global_if(op[n], h_reg[n], on);
+    if (drop) {
+      const bool keep = dropout_keep((uint32_t)(op[n] - a.out), key0, key1, thresh);
+      st_global_if(op[n] + y_off, keep ? h_reg[n] * inv_keep : 0.f, on);
+    }
     st_global_if(gp[n], a0_reg[n], on_sv);
     st_global_if(gp[n] + H, a1_reg[n], on_sv);
     st_global_if(cp[n], c_reg[n], on_sv);
@@ -282,6 +302,7 @@ __global__ void __launch_bounds__(threads_for(KS)) bilstm_fwd_kernel(const LstmA
     for (int i = tid; i < (L - len[n]) * H; i += NT) {
       const int t = len[n] + i / H, u = i % H;
       a.out[((size_t)seq[n] * L + t) * ndir * H + dir * H + u] = 0.f;
+      if (drop) a.y[((size_t)seq[n] * L + t) * ndir * H + dir * H + u] = 0.f;
     }
   }
 }
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(threads_for(KS / 2 + 1)) bilstm_fwd_pair_kerne
 constexpr int BWD_NT = 256, BWD_SL = 64;     // 8 warps = 4 gates x 2 halves of 32 unit slots; a slot covers units slot + 32 i, i < 4
 
 // KR: r values per half that are real (H <= 2 KR <= 2 KS): the zero padding of a half costs registers and FFMAs (KS = 52, H = 100: 8 each)
-template <int KS, int NB, int KR = KS>
+template <int KS, int NB, int KR = KS, bool DROP = false>
 __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
   constexpr int HP = 2 * KS;                       // >= H, multiple of 4
   constexpr int KSP = (KS % 32 == 0) ? KS + 4 : KS;   // row half stride of da_s: the two halves of r on different banks
@@ -585,11 +606,22 @@ __global__ void __launch_bounds__(BWD_NT) bilstm_bwd_kernel(const LstmArgs a) {
     dh_rec[n] = (unit && seq[n] >= 0 && a.dh_n) ? a.dh_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
     dc[n] = (unit && seq[n] >= 0 && a.dc_n) ? a.dc_n[((size_t)seq[n] * ndir + dir) * H + j] : 0.f;
   }
+  // output dropout (see LstmArgs): d out = keep ? d y / keep_prob : 0, the keep bit recomputed from the element index
+  constexpr bool drop = DROP;
+  const unsigned long long key = drop ? a.rng_key[0] : 0ull;
+  const uint32_t key0 = (uint32_t)key, key1 = (uint32_t)(key >> 32), thresh = dropout_thresh(a.keep_prob);
+  const float inv_keep = drop ? 1.f / a.keep_prob : 1.f;
+  uint32_t eidx[NB];                               // element index of (seq, t of backward step 0, dir H + j) in (B, L, ndir H)
+#pragma unroll
+  for (int n = 0; n < NB; ++n)
+    eidx[n] = (uint32_t)(((size_t)max(seq[n], 0) * L + (dir ? 0 : max(len[n] - 1, 0))) * ndir * H + dir * H + (unit ? j : 0));
   struct Factors { float A, Ki, Kf, Kg, Ko, Gf, Dy; };
   auto factors = [&](int s, int sl, int n) {       // of backward step s, from ring slot sl (all zero past the sequence's end)
     Factors f{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float* rs = ring_t + (sl * NB + n) * 7 * 128;
-    const float gi = rs[0], gf = rs[128], gg = rs[2 * 128], go = rs[3 * 128], ct = rs[4 * 128], dy = rs[6 * 128];
+    const float gi = rs[0], gf = rs[128], gg = rs[2 * 128], go = rs[3 * 128], ct = rs[4 * 128];
+    float dy = rs[6 * 128];
+    if (drop) dy = dropout_keep(eidx[n] + (uint32_t)(s * (int)o_stride), key0, key1, thresh) ? dy * inv_keep : 0.f;
     const float cprev = s + 1 < len[n] ? rs[5 * 128] : 0.f;
     const float tc = tanh_fast(ct);
     const bool on = s < len[n];
@@ -724,16 +756,32 @@ int launch(const LstmArgs& a, bool backward, cudaStream_t stream) {
       bilstm_fwd_kernel<KS, 1, true><<<grid, NT, smem, stream>>>(a);
       return check_launch("bilstm_fwd_kernel<trace>");
     }
+    if (a.y) {
+      MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_kernel<KS, NB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bilstm_fwd_kernel<KS, NB, false, true><<<grid, NT, smem, stream>>>(a);
+      return check_launch("bilstm_fwd_kernel<dropout>");
+    }
     MMB_CUDA(cudaFuncSetAttribute(bilstm_fwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bilstm_fwd_kernel<KS, NB><<<grid, NT, smem, stream>>>(a);
     return check_launch("bilstm_fwd_kernel");
   }
   constexpr int KSP = (KS % 32 == 0) ? KS + 4 : KS;
   const size_t smem = sizeof(float) * (NB * 4 * 2 * KSP + NB * 4 * 2 * BWD_SL + (size_t)RING * NB * 7 * 128);
+  constexpr int KR50 = KS == 52 ? 50 : KS;
   if (KS == 52 && a.H <= 100) {                    // the model's hidden size: no padded r values in registers
-    MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB, (KS == 52 ? 50 : KS)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bilstm_bwd_kernel<KS, NB, (KS == 52 ? 50 : KS)><<<grid, BWD_NT, smem, stream>>>(a);
+    if (a.rng_key) {
+      MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB, KR50, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bilstm_bwd_kernel<KS, NB, KR50, true><<<grid, BWD_NT, smem, stream>>>(a);
+      return check_launch("bilstm_bwd_kernel<dropout>");
+    }
+    MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB, KR50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bilstm_bwd_kernel<KS, NB, KR50><<<grid, BWD_NT, smem, stream>>>(a);
     return check_launch("bilstm_bwd_kernel");
+  }
+  if (a.rng_key) {
+    MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB, KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bilstm_bwd_kernel<KS, NB, KS, true><<<grid, BWD_NT, smem, stream>>>(a);
+    return check_launch("bilstm_bwd_kernel<dropout>");
   }
   MMB_CUDA(cudaFuncSetAttribute(bilstm_bwd_kernel<KS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bilstm_bwd_kernel<KS, NB><<<grid, BWD_NT, smem, stream>>>(a);
@@ -759,26 +807,98 @@ int dispatch(const LstmArgs& a, bool backward, cudaStream_t stream) {
 }  // namespace
 }  // namespace mmb
 
-extern "C" int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out,
-                              float* h_n, float* c_n, float* cell, int B, int L, int H, int ndir, int save,
-                              mmb_stream_t stream) {
-  MMB_REQUIRE(gates && w_hh && lengths && out && h_n && c_n, MMB_ERR_INVALID, "mmb_bilstm_fwd: null pointer");
-  MMB_REQUIRE(!save || cell, MMB_ERR_INVALID, "mmb_bilstm_fwd: save=1 needs a cell buffer");
-  MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID,
-              "mmb_bilstm_fwd: B=%d L=%d H=%d ndir=%d", B, L, H, ndir);
-  mmb::LstmArgs a{gates, w_hh, lengths, order, out, h_n, c_n, cell, nullptr, nullptr, nullptr, B, L, H, ndir, save, nullptr};
+static int bilstm_fwd_impl(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out, float* y,
+                           float* h_n, float* c_n, float* cell, const unsigned long long* rng_key, float keep_prob, int B, int L, int H,
+                           int ndir, int save, mmb_stream_t stream, const char* who) {
+  MMB_REQUIRE(gates && w_hh && lengths && out && h_n && c_n, MMB_ERR_INVALID, "%s: null pointer", who);
+  MMB_REQUIRE(!save || cell, MMB_ERR_INVALID, "%s: save=1 needs a cell buffer", who);
+  MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID, "%s: B=%d L=%d H=%d ndir=%d", who, B, L, H, ndir);
+  MMB_REQUIRE((y == nullptr) == (rng_key == nullptr), MMB_ERR_INVALID, "%s: y and rng_key go together", who);
+  MMB_REQUIRE(!y || (keep_prob > 0.f && keep_prob <= 1.f && (long long)B * L * ndir * H < (1ll << 32)), MMB_ERR_INVALID,
+              "%s: keep_prob=%g, or more than 2^32 output elements", who, keep_prob);
+  mmb::LstmArgs a{gates, w_hh, lengths, order, out, h_n, c_n, cell, nullptr, nullptr, nullptr, B, L, H, ndir, save, nullptr,
+                  y, rng_key, keep_prob};
   static const char* trace_env = getenv("MMB_LSTM_TRACE");                 // debugging aid (tools/lstm_trace.py)
   a.trace = trace_env ? reinterpret_cast<long long*>(strtoull(trace_env, nullptr, 0)) : nullptr;
   return mmb::dispatch(a, false, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mmb_bilstm_fwd(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out,
+                              float* h_n, float* c_n, float* cell, int B, int L, int H, int ndir, int save,
+                              mmb_stream_t stream) {
+  return bilstm_fwd_impl(gates, w_hh, lengths, order, out, nullptr, h_n, c_n, cell, nullptr, 1.f, B, L, H, ndir, save, stream,
+                         "mmb_bilstm_fwd");
+}
+
+extern "C" int mmb_bilstm_fwd_dropout(float* gates, const float* w_hh, const int32_t* lengths, const int32_t* order, float* out,
+                                      float* y, float* h_n, float* c_n, float* cell, const unsigned long long* rng_key,
+                                      float keep_prob, int B, int L, int H, int ndir, int save, mmb_stream_t stream) {
+  MMB_REQUIRE(y && rng_key, MMB_ERR_INVALID, "mmb_bilstm_fwd_dropout: y / rng_key is null");
+  return bilstm_fwd_impl(gates, w_hh, lengths, order, out, y, h_n, c_n, cell, rng_key, keep_prob, B, L, H, ndir, save, stream,
+                         "mmb_bilstm_fwd_dropout");
+}
+
+static int bilstm_bwd_impl(float* gates, const float* cell, const float* w_hh, const int32_t* lengths, const int32_t* order,
+                           const float* dout, const float* dh_n, const float* dc_n, const unsigned long long* rng_key, float keep_prob,
+                           int B, int L, int H, int ndir, mmb_stream_t stream, const char* who) {
+  MMB_REQUIRE(gates && cell && w_hh && lengths && dout, MMB_ERR_INVALID, "%s: null pointer", who);
+  MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID, "%s: B=%d L=%d H=%d ndir=%d", who, B, L, H, ndir);
+  MMB_REQUIRE(!rng_key || (keep_prob > 0.f && keep_prob <= 1.f && (long long)B * L * ndir * H < (1ll << 32)), MMB_ERR_INVALID,
+              "%s: keep_prob=%g, or more than 2^32 output elements", who, keep_prob);
+  mmb::LstmArgs a{gates, w_hh, lengths, order, nullptr, nullptr, nullptr, const_cast<float*>(cell), dout, dh_n, dc_n,
+                  B, L, H, ndir, 1, nullptr, nullptr, rng_key, keep_prob};
+  return mmb::dispatch(a, true, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mmb_bilstm_bwd(float* gates, const float* cell, const float* w_hh, const int32_t* lengths,
                               const int32_t* order, const float* dout, const float* dh_n, const float* dc_n, int B, int L,
                               int H, int ndir, mmb_stream_t stream) {
-  MMB_REQUIRE(gates && cell && w_hh && lengths && dout, MMB_ERR_INVALID, "mmb_bilstm_bwd: null pointer");
-  MMB_REQUIRE(B > 0 && L > 0 && H > 0 && (ndir == 1 || ndir == 2), MMB_ERR_INVALID,
-              "mmb_bilstm_bwd: B=%d L=%d H=%d ndir=%d", B, L, H, ndir);
-  mmb::LstmArgs a{gates, w_hh, lengths, order, nullptr, nullptr, nullptr, const_cast<float*>(cell), dout, dh_n, dc_n,
-                  B, L, H, ndir, 1, nullptr};
-  return mmb::dispatch(a, true, static_cast<cudaStream_t>(stream));
+  return bilstm_bwd_impl(gates, cell, w_hh, lengths, order, dout, dh_n, dc_n, nullptr, 1.f, B, L, H, ndir, stream, "mmb_bilstm_bwd");
+}
+
+extern "C" int mmb_bilstm_bwd_dropout(float* gates, const float* cell, const float* w_hh, const int32_t* lengths,
+                                      const int32_t* order, const float* dy, const float* dh_n, const float* dc_n,
+                                      const unsigned long long* rng_key, float keep_prob, int B, int L, int H, int ndir,
+                                      mmb_stream_t stream) {
+  MMB_REQUIRE(rng_key, MMB_ERR_INVALID, "mmb_bilstm_bwd_dropout: rng_key is null");
+  return bilstm_bwd_impl(gates, cell, w_hh, lengths, order, dy, dh_n, dc_n, rng_key, keep_prob, B, L, H, ndir, stream,
+                         "mmb_bilstm_bwd_dropout");
+}
+
+// ---- the keep mask itself (tests: parity GIVEN the mask) and the key stream ---------------------------------------------------------
+namespace mmb {
+namespace {
+__global__ void dropout_mask_kernel(const unsigned long long* __restrict__ rng_key, float keep_prob, long long n, uint8_t* __restrict__ mask) {
+  const unsigned long long key = rng_key[0];
+  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), thresh = dropout_thresh(keep_prob);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mask[i] = dropout_keep((uint32_t)i, k0, k1, thresh) ? 1 : 0;
+}
+// splitmix64: key_out = mix(state += golden).  One thread; the state lives on the device so that a CUDA-graph replay draws fresh keys.
+__global__ void rng_next_kernel(unsigned long long* __restrict__ state, unsigned long long* __restrict__ key_out, int n_keys) {
+  unsigned long long s = state[0];
+  for (int i = 0; i < n_keys; ++i) {
+    s += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    key_out[i] = z ^ (z >> 31);
+  }
+  state[0] = s;
+}
+}  // namespace
+}  // namespace mmb
+
+extern "C" int mmb_dropout_mask(const unsigned long long* rng_key, float keep_prob, long long n, uint8_t* mask, mmb_stream_t stream) {
+  MMB_REQUIRE(rng_key && mask && n > 0 && n < (1ll << 32) && keep_prob > 0.f && keep_prob <= 1.f, MMB_ERR_INVALID,
+              "mmb_dropout_mask: bad arguments");
+  const long long blocks = (n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184;
+  mmb::dropout_mask_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rng_key, keep_prob, n, mask);
+  return mmb::check_launch("dropout_mask_kernel");
+}
+
+extern "C" int mmb_rng_next(unsigned long long* state, unsigned long long* key_out, int n_keys, mmb_stream_t stream) {
+  MMB_REQUIRE(state && key_out && n_keys > 0, MMB_ERR_INVALID, "mmb_rng_next: bad arguments");
+  mmb::rng_next_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(state, key_out, n_keys);
+  return mmb::check_launch("rng_next_kernel");
 }

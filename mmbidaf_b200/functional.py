@@ -140,8 +140,9 @@ class _LstmLayer(torch.autograd.Function):
     """One (bi)directional LSTM layer over padded (B, L, in) with per-sample lengths."""
 
     @staticmethod
-    def forward(ctx, x, lengths, order, *weights):
-        # weights = (w_ih, w_hh, b_ih, b_hh) per direction
+    def forward(ctx, x, lengths, order, rng_key, keep_prob, *weights):
+        # weights = (w_ih, w_hh, b_ih, b_hh) per direction; rng_key (device int64 scalar) or None: dropout of the OUTPUT
+        # (encoding.py:104 / nn.LSTM's inter-layer dropout) applied inside the recurrence kernels, keep bits hashed from the key
         ndir = len(weights) // 4
         B, L, fan_in = x.shape
         H = weights[1].shape[1]
@@ -151,12 +152,13 @@ class _LstmLayer(torch.autograd.Function):
         x2d = x.reshape(B * L, fan_in)
         gates = torch.addmm(bias, x2d, w_ih.t())                                            # plain GEMM (cuBLAS)
         save = any(ctx.needs_input_grad)
-        out, h_n, c_n, cell = ops.lstm_layer_fwd(gates, w_hh, lengths, order, B, L, H, ndir, save)
+        out, h_n, c_n, cell, y = ops.lstm_layer_fwd(gates, w_hh, lengths, order, B, L, H, ndir, save, rng_key, keep_prob)
         if save:
-            ctx.save_for_backward(x2d, gates, cell, out, w_ih, w_hh, lengths, order)
+            ctx.save_for_backward(x2d, gates, cell, out, w_ih, w_hh, lengths, order, rng_key)
             ctx.dims = (B, L, H, ndir, fan_in)
+            ctx.keep_prob = keep_prob
         ctx.mark_non_differentiable(c_n)
-        return out, h_n, c_n
+        return (out if y is None else y), h_n, c_n
 
     @staticmethod
     def backward(ctx, d_out, d_h_n, _d_c_n):
@@ -166,11 +168,11 @@ class _LstmLayer(torch.autograd.Function):
             raise RuntimeError("mmbidaf_b200: the LSTM layer's backward ran twice over one forward (retain_graph=True is not "
                                "supported: its saved gates are overwritten in place)")
         ctx.consumed = True
-        x2d, gates, cell, out, w_ih, w_hh, lengths, order = ctx.saved_tensors
+        x2d, gates, cell, out, w_ih, w_hh, lengths, order, rng_key = ctx.saved_tensors
         B, L, H, ndir, fan_in = ctx.dims
         if d_out is None:
             d_out = torch.zeros_like(out)
-        da = ops.lstm_layer_bwd(gates, cell, w_hh, lengths, order, d_out, d_h_n, None, B, L, H, ndir)
+        da = ops.lstm_layer_bwd(gates, cell, w_hh, lengths, order, d_out, d_h_n, None, B, L, H, ndir, rng_key, ctx.keep_prob)
         da2d = da.view(B * L, ndir * 4 * H)
         dx = (da2d @ w_ih).view(B, L, fan_in) if ctx.needs_input_grad[0] else None
         # Weight gradients are reductions over all B*L rows with small outputs (4H x in, 4H x H): as ONE GEMM they are a
@@ -195,14 +197,19 @@ class _LstmLayer(torch.autograd.Function):
                     dw_hh = out.new_zeros(4 * H, H)
             b_d = db[d * 4 * H:(d + 1) * 4 * H]
             grads += [dw_ih[d * 4 * H:(d + 1) * 4 * H], dw_hh, b_d, b_d]
-        return (dx, None, None, *grads)
+        return (dx, None, None, None, None, *grads)
 
 
-def lstm_layer(x: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Tensor], weights
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+def lstm_layer(x: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Tensor], weights,
+               rng_key: Optional[torch.Tensor] = None, drop_prob: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """x (B,L,in) fp32 CUDA; lengths/order int32 CUDA; weights = [w_ih, w_hh, b_ih, b_hh] * ndir.
-    Returns (out (B,L,ndir*H), h_n (B,ndir,H)) in batch order."""
-    out, h_n, _ = _LstmLayer.apply(x.contiguous(), lengths, order, *weights)
+    Returns (out (B,L,ndir*H), h_n (B,ndir,H)) in batch order.  With ``rng_key`` (one key of :func:`ops.rng_next_keys`) and
+    ``drop_prob`` > 0, ``out`` is dropout(out, drop_prob) applied inside the recurrence kernels (no mask tensor, no extra launch)."""
+    if rng_key is None or drop_prob <= 0.0:
+        rng_key, keep_prob = None, 1.0
+    else:
+        keep_prob = 1.0 - float(drop_prob)
+    out, h_n, _ = _LstmLayer.apply(x.contiguous(), lengths, order, rng_key, keep_prob, *weights)
     return out, h_n
 
 

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as Fn
+from .. import ops
 
 __all__ = ["Embedding", "HighwayEncoder", "RNNEncoder", "ImageEmbedding"]
 
@@ -198,12 +199,18 @@ class RNNEncoder(nn.Module):
             raise RuntimeError("mmbidaf_b200.layers.RNNEncoder runs on a B200 only (no CPU fallback)")
         plan = _lengths.get(lengths, x.device)
         finals = []
+        # Dropout of every layer's output -- nn.LSTM's inter-layer dropout (encoding.py:77-81) and F.dropout on the encoder's
+        # output (encoding.py:104) -- happens inside the recurrence kernels: one launch draws the layer keys on the device.
+        p_inter = self.rnn.dropout if self.training else 0.0
+        p_out = self.drop_prob if self.training else 0.0
+        if p_out >= 1.0 or p_inter >= 1.0:
+            raise ValueError("RNNEncoder: drop_prob must be < 1")
+        keys = ops.rng_next_keys(x.device, self.num_layers) if (p_inter > 0.0 or p_out > 0.0) else None
         for k in range(self.num_layers):
-            x, h_n = Fn.lstm_layer(x, plan.len_i32, plan.order_i32, self._layer_weights(k))
+            p = p_inter if k + 1 < self.num_layers else p_out
+            x, h_n = Fn.lstm_layer(x, plan.len_i32, plan.order_i32, self._layer_weights(k),
+                                   None if keys is None else keys[k:k + 1], p)
             finals.append(h_n)
-            if k + 1 < self.num_layers:                       # nn.LSTM's inter-layer dropout
-                x = F.dropout(x, self.rnn.dropout, self.training)
-        x = F.dropout(x, self.drop_prob, self.training)       # encoding.py:104
         x_hidden = torch.cat(finals, dim=1).index_select(0, plan.sort_idx)
         return x, x_hidden
 

@@ -99,11 +99,11 @@ def bidaf_bwd(grad_out: torch.Tensor, text: torch.Tensor, modality: torch.Tensor
 
 
 def lstm_layer_fwd(gates: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor, order: Optional[torch.Tensor],
-                   B: int, L: int, H: int, ndir: int, save: bool
-                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+                   B: int, L: int, H: int, ndir: int, save: bool, rng_key: Optional[torch.Tensor] = None, keep_prob: float = 1.0):
     """Persistent LSTM recurrence of one layer (encoding.py:96).  ``gates`` (B,L,ndir,4H) holds the input
     projection on entry and, when ``save``, the activated gates on exit.  Returns (out (B,L,ndir*H),
-    h_n (B,ndir,H), c_n (B,ndir,H), cell (B,L,ndir,H) or None)."""
+    h_n (B,ndir,H), c_n (B,ndir,H), cell (B,L,ndir,H) or None, y): with ``rng_key`` (a device int64 scalar from :func:`rng_next_keys`)
+    the kernel also writes ``y`` = dropout(out, 1 - keep_prob) (encoding.py:104 / nn.LSTM's inter-layer dropout); else ``y`` is None."""
     lib = _lib.lib()
     assert gates.dtype == torch.float32 and gates.numel() == B * L * ndir * 4 * H
     assert lengths.dtype == torch.int32 and (order is None or order.dtype == torch.int32)
@@ -113,24 +113,72 @@ def lstm_layer_fwd(gates: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tenso
     c_n = torch.empty(B, ndir, H, device=dev, dtype=torch.float32)
     cell = torch.empty(B, L, ndir, H, device=dev, dtype=torch.float32) if save else None
     p = _lib.ptr
-    _lib.check(lib.mmb_bilstm_fwd(p(gates), p(w_hh), p(lengths), p(order), p(out), p(h_n), p(c_n), p(cell),
-                                  B, L, H, ndir, int(save), _lib.stream()), "mmb_bilstm_fwd")
+    if rng_key is None:
+        _lib.check(lib.mmb_bilstm_fwd(p(gates), p(w_hh), p(lengths), p(order), p(out), p(h_n), p(c_n), p(cell),
+                                      B, L, H, ndir, int(save), _lib.stream()), "mmb_bilstm_fwd")
+        y = None
+    else:
+        assert rng_key.dtype == torch.int64 and rng_key.is_cuda
+        y = torch.empty_like(out)
+        _lib.check(lib.mmb_bilstm_fwd_dropout(p(gates), p(w_hh), p(lengths), p(order), p(out), p(y), p(h_n), p(c_n), p(cell),
+                                              p(rng_key), float(keep_prob), B, L, H, ndir, int(save), _lib.stream()),
+                   "mmb_bilstm_fwd_dropout")
     _count(1)
-    return out, h_n, c_n, cell
+    return out, h_n, c_n, cell, y
 
 
 def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor,
                    order: Optional[torch.Tensor], dout: torch.Tensor, dh_n: Optional[torch.Tensor],
-                   dc_n: Optional[torch.Tensor], B: int, L: int, H: int, ndir: int) -> torch.Tensor:
-    """BPTT of :func:`lstm_layer_fwd`; overwrites ``gates`` with d(pre-activation) and returns it."""
+                   dc_n: Optional[torch.Tensor], B: int, L: int, H: int, ndir: int, rng_key: Optional[torch.Tensor] = None,
+                   keep_prob: float = 1.0) -> torch.Tensor:
+    """BPTT of :func:`lstm_layer_fwd`; overwrites ``gates`` with d(pre-activation) and returns it.  With ``rng_key``, ``dout`` is
+    the gradient of the DROPPED output ``y``."""
     lib = _lib.lib()
     p = _lib.ptr
-    _lib.check(lib.mmb_bilstm_bwd(p(gates), p(cell), p(w_hh), p(lengths), p(order), p(dout.contiguous()),
-                                  p(None if dh_n is None else dh_n.contiguous()),
-                                  p(None if dc_n is None else dc_n.contiguous()), B, L, H, ndir, _lib.stream()),
-               "mmb_bilstm_bwd")
+    dh = None if dh_n is None else dh_n.contiguous()
+    dc = None if dc_n is None else dc_n.contiguous()
+    if rng_key is None:
+        _lib.check(lib.mmb_bilstm_bwd(p(gates), p(cell), p(w_hh), p(lengths), p(order), p(dout.contiguous()), p(dh), p(dc),
+                                      B, L, H, ndir, _lib.stream()), "mmb_bilstm_bwd")
+    else:
+        _lib.check(lib.mmb_bilstm_bwd_dropout(p(gates), p(cell), p(w_hh), p(lengths), p(order), p(dout.contiguous()), p(dh), p(dc),
+                                              p(rng_key), float(keep_prob), B, L, H, ndir, _lib.stream()), "mmb_bilstm_bwd_dropout")
     _count(1)
     return gates
+
+
+_rng_state = {}
+
+
+def rng_seed(seed: int, device=None) -> None:
+    """(Re)seed the device-resident key stream of the in-kernel dropout (all devices, or one)."""
+    for dev, st in _rng_state.items():
+        if device is None or dev == torch.device(device):
+            st.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+
+
+def rng_next_keys(device, n: int) -> torch.Tensor:
+    """``n`` fresh dropout keys (int64, on ``device``), drawn ON the device from a resident state: one tiny launch, capturable (a graph
+    replay draws new keys).  The state is seeded from torch's seed at first use."""
+    device = torch.device(device)
+    st = _rng_state.get(device)
+    if st is None:
+        st = _rng_state[device] = torch.full((1,), (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x1234567) & 0x7FFFFFFFFFFFFFFF,
+                                             dtype=torch.int64, device=device)
+    keys = torch.empty(n, dtype=torch.int64, device=device)
+    _lib.check(_lib.lib().mmb_rng_next(_lib.ptr(st), _lib.ptr(keys), n, _lib.stream()), "mmb_rng_next")
+    _count(1)
+    return keys
+
+
+def dropout_mask(rng_key: torch.Tensor, keep_prob: float, shape) -> torch.Tensor:
+    """The keep mask (bool, ``shape``) the kernels derive from ``rng_key`` for a tensor of that shape (tests / debugging)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    mask = torch.empty(n, dtype=torch.uint8, device=rng_key.device)
+    _lib.check(_lib.lib().mmb_dropout_mask(_lib.ptr(rng_key), float(keep_prob), n, _lib.ptr(mask), _lib.stream()), "mmb_dropout_mask")
+    return mask.view(*shape).bool()
 
 
 class DecoderWeights:

@@ -84,3 +84,93 @@ def test_encoder_matches_oracle(cfg, pair, monkeypatch):
              for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
     for nm, w in zip(names, all_w[0]):
         assert grad_err(w.grad, p64[nm].grad) < 5e-5, nm
+
+
+@pytest.mark.parametrize("cfg", [(7, 33, 20, 16, 0.2), (5, 50, 100, 100, 0.2), (40, 19, 100, 100, 0.5), (3, 21, 16, 33, 0.35)])
+def test_in_kernel_dropout_given_the_mask(cfg):
+    """encoding.py:104 `F.dropout(x, drop_prob, training)` (and nn.LSTM's inter-layer dropout) applied INSIDE the recurrence kernels:
+    with the same key the dropped output equals out * mask / keep_prob BIT FOR BIT (mask from mmb_dropout_mask: the same hash), and all
+    gradients equal those of the un-dropped op fed d out = d y * mask / keep_prob.  The stream is not ATen's Philox: parity GIVEN the mask."""
+    from mmbidaf_b200 import functional as Fn, ops
+    bsz, max_len, fan_in, hid, pr = cfg
+    gen = torch.Generator().manual_seed(77 * bsz + max_len)
+    lengths = torch.randint(1, max_len + 1, (bsz,), generator=gen).tolist()
+    lengths[0] = max_len
+    dev = "cuda"
+    ws = [((torch.rand(*shape, generator=gen) - 0.5) * 0.2).to(dev) for _ in range(2)
+          for shape in ((4 * hid, fan_in), (4 * hid, hid), (4 * hid,), (4 * hid,))]
+    x = torch.randn(bsz, max_len, fan_in, generator=gen).to(dev)
+    g_out = torch.randn(bsz, max_len, 2 * hid, generator=gen).to(dev)
+    g_h = torch.randn(bsz, 2, hid, generator=gen).to(dev)
+    len_d = torch.tensor(lengths, dtype=torch.int32, device=dev)
+    ord_d = O.sort_order(lengths).to(torch.int32).to(dev)
+    ops.rng_seed(1234)
+    key = ops.rng_next_keys(dev, 3)[1:2]
+    mask = ops.dropout_mask(key, 1.0 - pr, (bsz, max_len, 2 * hid))
+    frac = mask.float().mean().item()
+    assert abs(frac - (1.0 - pr)) < 4.0 * (pr * (1 - pr) / mask.numel()) ** 0.5 + 1e-3, frac      # the hash is a fair coin of the right bias
+
+    def run(dropped):
+        w = [t.clone().requires_grad_(True) for t in ws]
+        xin = x.clone().requires_grad_(True)
+        if dropped:
+            y, h_n = Fn.lstm_layer(xin, len_d, ord_d, w, key, pr)
+            ((y * g_out).sum() + (h_n * g_h).sum()).backward()
+        else:
+            out, h_n = Fn.lstm_layer(xin, len_d, ord_d, w)
+            y = out * mask / (1.0 - pr)
+            ((y * g_out).sum() + (h_n * g_h).sum()).backward()
+        return y.detach(), h_n.detach(), xin.grad, [t.grad for t in w]
+
+    y1, h1, dx1, dw1 = run(True)
+    y0, h0, dx0, dw0 = run(False)
+    assert torch.equal(h1, h0)
+    assert rel_err(y1, y0) < 1e-6 and torch.equal(y1 == 0, y0 == 0)
+    for b, n in enumerate(lengths):
+        assert (y1[b, n:] == 0).all()
+    assert grad_err(dx1, dx0) < 1e-5
+    for a, b in zip(dw1, dw0):
+        assert grad_err(a, b) < 1e-5
+
+
+def test_in_kernel_dropout_keys_advance_and_encoder_uses_them():
+    """Successive draws give different masks (also inside a replayed CUDA graph: the key state lives on the device); RNNEncoder in
+    training mode drops both the inter-layer and the output activations, in eval mode nothing."""
+    from mmbidaf_b200 import ops
+    from mmbidaf_b200.layers import RNNEncoder
+    dev = "cuda"
+    ops.rng_seed(5)
+    k = ops.rng_next_keys(dev, 2)
+    k2 = ops.rng_next_keys(dev, 2)
+    assert len({int(v) for v in torch.cat([k, k2]).tolist()}) == 4
+    torch.manual_seed(0)
+    enc = RNNEncoder(12, 16, 2, drop_prob=0.3).to(dev)
+    x = torch.randn(6, 20, 12, device=dev)
+    lengths = [20, 3, 17, 9, 20, 1]
+    enc.eval()
+    ref, ref_h = enc(x, lengths)
+    enc.train()
+    y1, h1 = enc(x, lengths)
+    y2, _ = enc(x, lengths)
+    valid = torch.zeros(6, 20, dtype=torch.bool, device=dev)
+    for b, n in enumerate(lengths):
+        valid[b, :n] = True
+    zero1 = (y1 == 0)[valid].float().mean().item()
+    assert 0.2 < zero1 < 0.4, zero1                                # ~30 % of the valid outputs dropped
+    assert not torch.equal(y1 == 0, y2 == 0)                       # a fresh key per call
+    assert not torch.allclose(h1, ref_h)                           # inter-layer dropout reaches layer 2's state
+    assert (y1[~valid] == 0).all() and (ref[~valid] == 0).all()
+    # graph replay: new masks every replay
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        enc(x, lengths)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        yg, _ = enc(x, lengths)
+    g.replay()
+    a = (yg == 0).clone()
+    g.replay()
+    b = (yg == 0).clone()
+    assert not torch.equal(a, b)

@@ -33,7 +33,7 @@ for it in range(a.iters):
     torch.cuda.synchronize()
     e0, e1, e2 = ev(), ev(), ev()
     e0.record()
-    out, h_n, c_n, cell = ops.lstm_layer_fwd(g, w_hh, len_d, order, B, L, H, 2, True)
+    out, h_n, c_n, cell, _ = ops.lstm_layer_fwd(g, w_hh, len_d, order, B, L, H, 2, True)
     e1.record()
     ops.lstm_layer_bwd(g, cell, w_hh, len_d, order, dout, None, None, B, L, H, 2)
     e2.record()

@@ -275,6 +275,50 @@ def bidaf_microbench(device, rounds: int, warmup: int, precision: int, backward:
     return seconds, algo_bytes
 
 
+def lstm_microbench(device, rounds: int = 5):
+    """One bidirectional LSTM layer of the metric's longest recurrence (audio_enc of config 3: B=32, L=1024, in=H=100) through the
+    layer op (input GEMM + persistent recurrence kernel; backward: BPTT kernel + weight-gradient GEMMs), captured into a CUDA graph.
+    SURVEY 8d: the recurrence is serial-latency bound -- reported as us per time step next to its (low) share of the HBM roofline.
+    Algorithmic bytes per layer: activations 4 B L (in + 2H) + weights 2 * 4 (4H in + 4H H + 8H); forward + backward = 2 x."""
+    from mmbidaf_b200 import functional as Fn
+    B, L, H = CFG3["batch"], CFG3["la"], HIDDEN
+    gen = torch.Generator().manual_seed(11)
+    lengths = torch.randint(L // 2, L + 1, (B,), generator=gen)
+    lengths[0] = L
+    len_d = lengths.to(torch.int32).to(device)
+    ord_d = torch.argsort(lengths, descending=True).to(torch.int32).to(device)
+    ws = [((torch.rand(*shape, generator=gen) - 0.5) * 0.2).to(device).requires_grad_(True) for _ in range(2)
+          for shape in ((4 * H, H), (4 * H, H), (4 * H,), (4 * H,))]
+    x = torch.randn(B, L, H, generator=gen).to(device).requires_grad_(True)
+    g_out = torch.randn(B, L, 2 * H, generator=gen).to(device)
+
+    def fwd():
+        with torch.no_grad():
+            return Fn.lstm_layer(x, len_d, ord_d, ws)[0]
+
+    def fwd_bwd():
+        out, _ = Fn.lstm_layer(x, len_d, ord_d, ws)
+        return torch.autograd.grad(out, [x] + ws, g_out)
+
+    res = {}
+    for name, fn in (("fwd", fwd), ("fwd_bwd", fwd_bwd)):
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            keep = fn()
+        graph.replay()
+        res[name] = _event_time(graph.replay, rounds)
+        del keep, graph
+    algo = 4 * B * L * (H + 2 * H) + 2 * 4 * (4 * H * H + 4 * H * H + 8 * H)
+    return res["fwd"], res["fwd_bwd"], algo, (B, L, H)
+
+
 def measured_traffic(name: str):
     """DRAM bytes per launch of the roofline kernel from the committed ncu capture of this round (profiles/*.json written by
     tools/ncu_traffic.py from `ncu --set full`), or None: never a literal in this file."""
@@ -586,6 +630,14 @@ def run_gpu_arm(args):
                 fb = (algo + algo_bwd) / (t_bidaf + t_bwd) / 1e9
                 roof["forward_backward"] = {"us": round((t_bidaf + t_bwd) * 1e6, 1), "algorithmic_bytes": algo + algo_bwd,
                                             "achieved": round(fb, 1), "frac": round(fb / peak, 4)}
+            t_lf, t_lfb, algo_l, (lb, ll, lh) = lstm_microbench(device)
+            roof["lstm"] = {"kernel": f"one bidirectional LSTM layer (input GEMM + bilstm_fwd_kernel; backward: bilstm_bwd_kernel + weight-"
+                                      f"gradient GEMMs), audio_enc of config 3: B={lb}, L={ll}, in=H={lh}",
+                            "bound": "serial latency (SURVEY 8d): one dependent (4H x H) mat-vec + gate non-linearities per time step",
+                            "fwd_us": round(t_lf * 1e6, 1), "fwd_us_per_timestep": round(t_lf * 1e6 / ll, 3),
+                            "fwd_bwd_us": round(t_lfb * 1e6, 1), "fwd_bwd_us_per_timestep": round(t_lfb * 1e6 / ll, 3),
+                            "algorithmic_bytes_fwd": algo_l, "hbm_frac_fwd": round(algo_l / t_lf / 1e9 / peak, 4),
+                            "hbm_frac_fwd_bwd": round(2 * algo_l / t_lfb / 1e9 / peak, 4)}
             line["roofline"] = roof
         if "cfg5" in sections:
             line["cfg5"] = cfg5_timing(device)

@@ -134,6 +134,11 @@ MMB_API int mmb_bilstm_bwd_dropout(float* gates, const float* cell, const float*
                                    float keep_prob, int B, int L, int H, int ndir, mmb_stream_t stream);
 MMB_API int mmb_dropout_mask(const unsigned long long* rng_key, float keep_prob, long long n, uint8_t* mask, mmb_stream_t stream);
 MMB_API int mmb_rng_next(unsigned long long* state, unsigned long long* key_out, int n_keys, mmb_stream_t stream);
+/* layers/encoding.py:26 `F.dropout(x, self.drop_prob, self.training)` on the embedding inputs: y[i] = keep(i) ? x[i] / keep_prob : 0 with
+ * the same counter-based bits (one launch, no mask tensor; y may alias x; x, y 16-byte aligned, n < 2^32).  Its backward is the same call
+ * on the gradient with the same key.  The BiDAF kernels (attention.py:66-67) take mmb_dropout_mask's bytes as keep_text / keep_modality. */
+MMB_API int mmb_dropout_apply(const float* x, float* y, const unsigned long long* rng_key, float keep_prob, long long n,
+                              mmb_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
  * Multimodal attention decoder, one step (replaces attention.py:145-186).

@@ -35,6 +35,7 @@ SIGNATURES = {
     "mmb_bilstm_bwd_dropout": [c_void_p] * 9 + [c_float] + [c_int] * 4 + [c_void_p],
     "mmb_dropout_mask": [c_void_p, c_float, ctypes.c_longlong, c_void_p, c_void_p],
     "mmb_rng_next": [c_void_p, c_void_p, c_int, c_void_p],
+    "mmb_dropout_apply": [c_void_p, c_void_p, c_void_p, c_float, ctypes.c_longlong, c_void_p],
     "mmb_decoder_chunks": [c_int, c_int],
     "mmb_decoder_step_fused_fwd": [c_void_p] * 42 + [c_int] * 6 + [c_void_p],
     "mmb_decoder_bwd_head": [c_void_p] * 25 + [c_int] + [c_void_p] + [c_int] + [c_void_p] * 7 + [c_int] * 5 + [c_void_p],

@@ -136,6 +136,31 @@ def tall_linear_bias(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) 
     return _TallLinearBias.apply(x.reshape(-1, shape[-1]), weight, bias).view(*shape[:-1], weight.shape[0])
 
 
+class _Dropout(torch.autograd.Function):
+    """F.dropout on a plain tensor (the embedding inputs, encoding.py:26) with the library's counter-based keep bits: forward and
+    backward are the same one-launch kernel with the same key; no mask tensor exists."""
+
+    @staticmethod
+    def forward(ctx, x, rng_key, keep_prob):
+        ctx.save_for_backward(rng_key)
+        ctx.keep_prob = keep_prob
+        return ops.dropout_apply(x, rng_key, keep_prob)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (rng_key,) = ctx.saved_tensors
+        return ops.dropout_apply(dy, rng_key, ctx.keep_prob), None, None
+
+
+def dropout(x: torch.Tensor, drop_prob: float, training: bool) -> torch.Tensor:
+    """``F.dropout(x, drop_prob, training)`` as one own launch (fresh key drawn on the device)."""
+    if not training or drop_prob <= 0.0:
+        return x
+    if drop_prob >= 1.0:
+        return torch.zeros_like(x)
+    return _Dropout.apply(x, ops.rng_next_keys(x.device, 1), 1.0 - float(drop_prob))
+
+
 class _LstmLayer(torch.autograd.Function):
     """One (bi)directional LSTM layer over padded (B, L, in) with per-sample lengths."""
 

@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import functional as Fn
 from .. import ops
@@ -45,9 +44,9 @@ class Embedding(nn.Module):
         self.hwy = HighwayEncoder(2, hidden_size)
 
     def forward(self, x):
-        x = F.dropout(x, self.drop_prob, self.training)
         if not x.is_cuda:
             raise RuntimeError("mmbidaf_b200.layers.Embedding runs on a B200 only (no CPU fallback)")
+        x = Fn.dropout(x, self.drop_prob, self.training)         # encoding.py:26, one own launch (counter-based keep bits)
         return self.hwy(Fn.tall_linear(x, self.proj.weight))     # Linear(E -> H, no bias); batched weight gradient
 
 

@@ -171,14 +171,32 @@ def rng_next_keys(device, n: int) -> torch.Tensor:
     return keys
 
 
-def dropout_mask(rng_key: torch.Tensor, keep_prob: float, shape) -> torch.Tensor:
-    """The keep mask (bool, ``shape``) the kernels derive from ``rng_key`` for a tensor of that shape (tests / debugging)."""
+def dropout_mask_u8(rng_key: torch.Tensor, keep_prob: float, shape) -> torch.Tensor:
+    """The keep bits of ``rng_key`` for a tensor of ``shape`` as bytes (uint8 0 / 1): what the BiDAF kernels take as ``keep_text`` /
+    ``keep_modality`` (attention.py:66-67) -- one own launch instead of ATen's bernoulli_."""
     n = 1
     for d in shape:
         n *= int(d)
     mask = torch.empty(n, dtype=torch.uint8, device=rng_key.device)
     _lib.check(_lib.lib().mmb_dropout_mask(_lib.ptr(rng_key), float(keep_prob), n, _lib.ptr(mask), _lib.stream()), "mmb_dropout_mask")
-    return mask.view(*shape).bool()
+    _count(1)
+    return mask.view(*shape)
+
+
+def dropout_mask(rng_key: torch.Tensor, keep_prob: float, shape) -> torch.Tensor:
+    """The keep mask (bool, ``shape``) the kernels derive from ``rng_key`` for a tensor of that shape (tests / debugging)."""
+    return dropout_mask_u8(rng_key, keep_prob, shape).bool()
+
+
+def dropout_apply(x: torch.Tensor, rng_key: torch.Tensor, keep_prob: float) -> torch.Tensor:
+    """dropout(x, 1 - keep_prob) with the keep bits of ``rng_key`` (encoding.py:26): one launch, no mask tensor."""
+    assert x.dtype == torch.float32 and x.is_cuda and rng_key.dtype == torch.int64
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().mmb_dropout_apply(_lib.ptr(x), _lib.ptr(y), _lib.ptr(rng_key), float(keep_prob), x.numel(), _lib.stream()),
+               "mmb_dropout_apply")
+    _count(1)
+    return y
 
 
 class DecoderWeights:

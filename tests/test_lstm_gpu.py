@@ -174,3 +174,35 @@ def test_in_kernel_dropout_keys_advance_and_encoder_uses_them():
     g.replay()
     b = (yg == 0).clone()
     assert not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(3, 7, 10), (32, 409, 300), (5, 3), (1, 1, 1)])
+def test_dropout_apply_and_mask_bytes(shape):
+    """encoding.py:26 `F.dropout(x, drop_prob, training)` as one own launch: y = x * mask / keep_prob bit for bit with the mask of the
+    same key; the backward applies the same mask to the gradient; BiDAFAttention's byte masks are the same bits."""
+    from mmbidaf_b200 import functional as Fn, ops
+    dev = "cuda"
+    torch.manual_seed(3)
+    x = torch.randn(*shape, device=dev, requires_grad=True)
+    key = ops.rng_next_keys(dev, 1)
+    y = Fn._Dropout.apply(x, key, 0.8)
+    mask = ops.dropout_mask(key, 0.8, shape)
+    assert torch.equal(y, torch.where(mask, x.detach() * (1.0 / 0.8), torch.zeros_like(x)))
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert torch.equal(x.grad, torch.where(mask, g * (1.0 / 0.8), torch.zeros_like(g)))
+    assert torch.equal(ops.dropout_mask_u8(key, 0.8, shape).bool(), mask)
+    assert Fn.dropout(x, 0.3, False) is x
+
+
+def test_bidaf_layer_draws_own_masks():
+    from mmbidaf_b200.layers import BiDAFAttention
+    dev = "cuda"
+    torch.manual_seed(1)
+    att = BiDAFAttention(16, drop_prob=0.25).to(dev).train()
+    kc, kq, scale = att._dropout_masks(torch.empty(4, 50, 16, device=dev), torch.empty(4, 30, 16, device=dev))
+    assert kc.dtype == torch.uint8 and kc.shape == (4, 50, 16) and kq.shape == (4, 30, 16) and abs(scale - 1 / 0.75) < 1e-6
+    assert 0.65 < kc.float().mean().item() < 0.85 and 0.65 < kq.float().mean().item() < 0.85
+    assert not torch.equal(kc[:, :30], kq)                       # two keys
+    att.eval()
+    assert att._dropout_masks(torch.empty(1, 2, 16, device=dev), torch.empty(1, 2, 16, device=dev)) == (None, None, 1.0)

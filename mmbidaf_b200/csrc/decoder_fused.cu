@@ -19,7 +19,9 @@
 // FLOP bound (~0.6 MFLOP per video), and fp32 keeps it inside the 1e-5 tier.
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
+#include "tc_common.cuh"     // mbarrier / bulk-copy helpers (mmb::tc)
 
 namespace cg = cooperative_groups;
 
@@ -29,6 +31,12 @@ namespace {
 constexpr int NT = 512;        // 16 warps: the step is a chain of latency-bound stages, one CTA per SM
 constexpr int NW = NT / 32;
 constexpr int MAXC = 8;        // cluster sizes 4 and 8
+
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ long long* g_dec_trace = nullptr;   // debugging aid (MMB_DEC_TRACE): clock64 stamps of block 0 at the stage boundaries
 #define DEC_STAMP(i)                                                          \
@@ -57,6 +65,7 @@ struct FusedArgs {
   // saved for the backward pass (all required)
   float *hw, *alpha, *beta, *ctx12, *pb, *xcat, *gates;     // (B,4D), (B,2,Lt), (B,2), (2,B,D), (2,B,D), (B,D+E+H), (B,4H)
   int B, Lt, D, H, E, M, chunk;
+  int stage_off;   // float offset of the row stage in dynamic shared memory ([2 mbarriers][2][chunk * D]), or 0: rows read from L2
 };
 
 // y[i] = sum_k Wt[k][col_of(i)] x[k] + bias[col_of(i)] for i < n_out, with the weights TRANSPOSED (Wt (K, ldn): consecutive threads read
@@ -158,6 +167,26 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   float* s_e = s_vec + up4(4 * D);          // [2][chunk] energies -> p -> alpha of this rank's rows
   float* s_cpart = s_e + up4(2 * a.chunk);  // [groups][2][D] context partials inside the block; later this rank's logits
 
+  // Row stage (stage_off != 0): this rank's rows of proj_a / proj_i -- contiguous in memory -- are brought into shared memory by two
+  // bulk copies issued NOW, a whole mat-vec stage and a cluster barrier before stage B reads them; when the energies are done the same
+  // buffers take the rows of enc_a / enc_i for the weighted contexts (under the chunk-local soft-max).  Without it stage B was two
+  // rounds of (issue a warp's loads from L2, wait, compute): 17 k cycles for energies whose MUFU floor is ~5 k (profiles/r02_decoder_fused.md).
+  const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk), n = t1 - t0;
+  const bool staged = a.stage_off != 0;
+  float* const s_st0 = smem + a.stage_off + 4;
+  float* const s_st1 = s_st0 + up4(a.chunk * D);
+  const uint32_t bar_proj = tc::smem_u32(smem + a.stage_off), bar_enc = bar_proj + 8;
+  const uint32_t stage_bytes = (uint32_t)(n * D) * 4u;
+  if (staged && tid == 0) {
+    tc::mbar_init(bar_proj, 1);
+    tc::mbar_init(bar_enc, 1);
+    tc::fence_barrier_init();
+    if (n > 0) {
+      tc::mbar_expect_tx(bar_proj, 2 * stage_bytes, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st0), a.proj_a + ((size_t)b * Lt + t0) * D, stage_bytes, bar_proj, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st1), a.proj_i + ((size_t)b * Lt + t0) * D, stage_bytes, bar_proj, 1);
+    }
+  }
   DEC_STAMP(0);
   // ---- stage 0: this video's step inputs -----------------------------------------------------------------------------------
   for (int i = tid; i < H; i += NT) s_x[D + E + i] = a.h[(size_t)b * H + i];
@@ -185,52 +214,93 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   DEC_STAMP(3);
 
   // ---- stage B: energies of this rank's rows, chunk-local soft-max partials and contexts ----------------------------------
-  const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk), n = t1 - t0;
   {
     const float v1b = a.v1b[0], v2b = a.v2b[0];
-    constexpr int MAXJ = 8;                // D <= 256
-    constexpr int RU = 4;                  // rows per warp iteration: all their loads are in flight before the first tanh
-    for (int i = warp * RU; i < n; i += NW * RU) {
-      float s[RU][2];
-      float pav[RU][MAXJ], piv[RU][MAXJ], cvs[RU];
+    // pa0 / pi0: row 0 of this rank's chunk (shared-memory stage or global memory: one instantiation per address space).
+    // The loop is written for the issue slots (round 2: the first version left the `d < D` test as a divergent branch around every
+    // element and re-read its six step constants from shared memory per element -- ~35 instructions and a BSSY / BSYNC pair per two
+    // tanh, 16.8 k cycles for a stage whose MUFU floor is 5.2 k): the constants of a lane's NJ columns live in REGISTERS for the whole
+    // stage, pre-scaled so that the pre-activation is the ex2 argument directly (tanh x = 1 - 2 / (1 + 2^(2 x log2 e))); columns past D
+    // carry v = 0 and a zero row value, so nothing in the body is predicated; ex2 / rcp are the flush-to-zero MUFU forms (no denormal
+    // guard instructions; a flushed 2^x is 0 beside the 1 it is added to).
+    constexpr float K2 = 2.0f * 1.4426950408889634f;
+    auto energies = [&](const float* __restrict__ pa0, const float* __restrict__ pi0, auto nj_tag, auto ru_tag) {
+      constexpr int NJ = decltype(nj_tag)::value, RU = decltype(ru_tag)::value;
+      float va[NJ], ha[NJ], wa[NJ], vi[NJ], hi[NJ], wi[NJ];
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {         // loads first (memory-level parallelism)
-        s[u][0] = s[u][1] = 0.f;
-        const int t = t0 + min(i + u, n - 1);
-        const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
-        const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
-        cvs[u] = a.cov[(size_t)b * Lt + t];
+      for (int j = 0; j < NJ; ++j) {
+        const int d = lane + 32 * j;
+        const bool in = d < D;
+        const int dd = in ? d : 0;
+        va[j] = in ? s_vec[dd] : 0.f;
+        wa[j] = in ? s_vec[D + dd] * K2 : 0.f;
+        ha[j] = in ? s_hw[dd] * K2 : 0.f;
+        vi[j] = in ? s_vec[2 * D + dd] : 0.f;
+        wi[j] = in ? s_vec[3 * D + dd] * K2 : 0.f;
+        hi[j] = in ? s_hw[D + dd] * K2 : 0.f;
+      }
+      const float* const covp = a.cov + (size_t)b * Lt + t0;
+      for (int i = warp * RU; i < n; i += NW * RU) {
+        float s[RU][2];
+        float pav[RU][NJ], piv[RU][NJ], cvs[RU];
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
-          const int d = lane + 32 * j;
-          if (32 * j < D) {                                      // (uniform: D = 200 has no work for j = 7)
+        for (int u = 0; u < RU; ++u) {         // loads first (memory-level parallelism)
+          s[u][0] = s[u][1] = 0.f;
+          const int r = min(i + u, n - 1);
+          const float* pa = pa0 + (size_t)r * D;
+          const float* pi = pi0 + (size_t)r * D;
+          cvs[u] = covp[r];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int d = lane + 32 * j;
             pav[u][j] = d < D ? pa[d] : 0.f;
             piv[u][j] = d < D ? pi[d] : 0.f;
           }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const float cv = cvs[u];
+        for (int u = 0; u < RU; ++u) {
+          const float cv = cvs[u];
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
-          const int d = lane + 32 * j;
-          if (32 * j < D && d < D) {
-            s[u][0] = fmaf(s_vec[d], tanh_fast((pav[u][j] + s_hw[d]) + cv * s_vec[D + d]), s[u][0]);
-            s[u][1] = fmaf(s_vec[2 * D + d], tanh_fast((piv[u][j] + s_hw[D + d]) + cv * s_vec[3 * D + d]), s[u][1]);
+          for (int j = 0; j < NJ; ++j) {
+            const float x1 = fmaf(cv, wa[j], fmaf(pav[u][j], K2, ha[j]));
+            const float x2 = fmaf(cv, wi[j], fmaf(piv[u][j], K2, hi[j]));
+            const float r1 = rcp_ftz(1.0f + tc::fast_exp2(x1)), r2 = rcp_ftz(1.0f + tc::fast_exp2(x2));
+            s[u][0] = fmaf(va[j], fmaf(-2.0f, r1, 1.0f), s[u][0]);
+            s[u][1] = fmaf(vi[j], fmaf(-2.0f, r2, 1.0f), s[u][1]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          const float x1 = warp_sum(s[u][0]), x2 = warp_sum(s[u][1]);
+          if (lane == 0 && i + u < n) {
+            s_e[i + u] = x1 + v1b;
+            s_e[a.chunk + i + u] = x2 + v2b;
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const float x1 = warp_sum(s[u][0]), x2 = warp_sum(s[u][1]);
-        if (lane == 0 && i + u < n) {
-          s_e[i + u] = x1 + v1b;
-          s_e[a.chunk + i + u] = x2 + v2b;
-        }
-      }
+    };
+    const float* const gpa = a.proj_a + ((size_t)b * Lt + t0) * D;
+    const float* const gpi = a.proj_i + ((size_t)b * Lt + t0) * D;
+    using N7 = std::integral_constant<int, 7>;
+    using N8 = std::integral_constant<int, 8>;
+    using R2 = std::integral_constant<int, 2>;
+    using R4 = std::integral_constant<int, 4>;
+    const bool nj7 = D > 192 && D <= 224;      // the model's D = 2 H = 200; any other D <= 256 takes the zero-padded eight
+    if (staged) {
+      if (n > 0) tc::mbar_wait(bar_proj, 0);
+      if (nj7) energies(s_st0, s_st1, N7{}, R2{});
+      else energies(s_st0, s_st1, N8{}, R2{});
+    } else {
+      if (nj7) energies(gpa, gpi, N7{}, R4{});
+      else energies(gpa, gpi, N8{}, R4{});
     }
     __syncthreads();
+    if (staged && tid == 0 && n > 0) {       // every read of the proj rows is behind the barrier: the buffers take the enc rows
+      tc::fence_proxy_async();
+      tc::mbar_expect_tx(bar_enc, 2 * stage_bytes, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st0), a.enc_a + ((size_t)b * Lt + t0) * D, stage_bytes, bar_enc, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st1), a.enc_i + ((size_t)b * Lt + t0) * D, stage_bytes, bar_enc, 1);
+    }
     DEC_STAMP(4);
     float m1 = -INFINITY, m2 = -INFINITY;
     for (int i = tid; i < n; i += NT) {
@@ -252,8 +322,9 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
     __syncthreads();
     DEC_STAMP(5);
     // weighted contexts of this rank's rows
-    const float* ea = a.enc_a + ((size_t)b * Lt + t0) * D;
-    const float* ei = a.enc_i + ((size_t)b * Lt + t0) * D;
+    if (staged && n > 0) tc::mbar_wait(bar_enc, 0);
+    const float* ea = staged ? s_st0 : a.enc_a + ((size_t)b * Lt + t0) * D;
+    const float* ei = staged ? s_st1 : a.enc_i + ((size_t)b * Lt + t0) * D;
     const bool vec4 = (D & 3) == 0;
     const int groups = vec4 ? NT / (D >> 2) : NT / D;
     if (vec4) {
@@ -700,7 +771,11 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   float* s_row = s_part + up4s(NW * 3 * D);             // [chunk]  d cov accumulation
   float* s_colp = s_row + up4s(a.chunk);                // [MAXC][2][3][D]  column partials of every rank (written remotely)
   float* s_in = s_colp + up4s(MAXC * 6 * D);            // [4H + 4D]  d_gates | d (W2 h) | d (W4 h) | d_pre_b
-  constexpr int MAXJ = 8;                               // D <= 256
+  // Both sweeps are written like stage B of the forward kernel (see there): a lane's per-column constants live in registers for the
+  // whole sweep (zero past D, so the arithmetic is unpredicated), NJ = 7 for the model's D = 200 and the zero-padded 8 for any other D.
+  using N7 = std::integral_constant<int, 7>;
+  using N8 = std::integral_constant<int, 8>;
+  const bool nj7 = D > 192 && D <= 224;
   // ---- 7: d alpha_k[t] = beta_k datt[t] + d c_k . enc_k[t];  sum_t alpha d alpha over the cluster ----------------------------------
   for (int i = tid; i < D; i += NT) {
     s_vec[i] = a.v1[i];
@@ -711,17 +786,25 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     s_vec[5 * D + i] = a.hw[(size_t)b * 4 * D + D + i];
   }
   for (int i = tid; i < n; i += NT) s_row[i] = a.dcov_tot[(size_t)b * Lt + t0 + i];
-  {
-    float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  auto sweep7 = [&](auto nj_tag) {
+    constexpr int NJ = decltype(nj_tag)::value;
+    float dca[NJ], dci[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int d = lane + 32 * j;
+      dca[j] = d < D ? s_dc[d] : 0.f;
+      dci[j] = d < D ? s_dc[D + d] : 0.f;
+    }
     for (int i = warp * 2; i < n; i += NW * 2) {
       float d1[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f};
-      float eav[2][MAXJ], eiv[2][MAXJ];
+      float eav[2][NJ], eiv[2][NJ];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {                     // loads first (memory-level parallelism)
         const float* ea = a.enc_a + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
         const float* ei = a.enc_i + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const int d = lane + 32 * j;
           eav[u][j] = d < D ? ea[d] : 0.f;
           eiv[u][j] = d < D ? ei[d] : 0.f;
@@ -730,12 +813,9 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
-          const int d = lane + 32 * j;
-          if (d < D) {
-            d1[u] = fmaf(s_dc[d], eav[u][j], d1[u]);
-            d2[u] = fmaf(s_dc[D + d], eiv[u][j], d2[u]);
-          }
+        for (int j = 0; j < NJ; ++j) {
+          d1[u] = fmaf(dca[j], eav[u][j], d1[u]);
+          d2[u] = fmaf(dci[j], eiv[u][j], d2[u]);
         }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -751,6 +831,9 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
         }
       }
     }
+  };
+  if (nj7) sweep7(N7{}); else sweep7(N8{});
+  {
     s1 = block_sum(s1, s_red);
     s2 = block_sum(s2, s_red);
     if (tid < CL) {
@@ -766,27 +849,34 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     stot1 += s_ex[r * 4 + 1];
   }
   // ---- 8: soft-max backward, tanh backward, d proj (+=), d cov, column partials ------------------------------------------------------
+  constexpr float K2 = 2.0f * 1.4426950408889634f;      // tanh x = 1 - 2 / (1 + 2^(K2 x)), flush-to-zero MUFU forms (no guard instructions)
   float se_m0 = 0.f, se_m1 = 0.f;
-  for (int m = 0; m < 2; ++m) {
+  auto sweep8 = [&](const int m, auto nj_tag) {
+    constexpr int NJ = decltype(nj_tag)::value;
     const float* proj = (m == 0 ? a.proj_a : a.proj_i) + ((size_t)b * Lt + t0) * D;
     float* dproj = (m == 0 ? a.d_proj_a : a.d_proj_i) + ((size_t)b * Lt + t0) * D;
-    const float* vv = s_vec + 3 * m * D;
-    const float* wc = vv + D;
-    const float* hwm = vv + 2 * D;
     const float stm = m == 0 ? stot0 : stot1;
-    float c_dz[MAXJ], c_cov[MAXJ], c_v[MAXJ];
+    float vvr[NJ], wcr[NJ], hwk[NJ];                    // v, Wc, K2 (W h) of this lane's columns
+    float c_dz[NJ], c_cov[NJ], c_v[NJ];
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) c_dz[j] = c_cov[j] = c_v[j] = 0.f;
+    for (int j = 0; j < NJ; ++j) {
+      const int d = lane + 32 * j;
+      const float* vv = s_vec + 3 * m * D;
+      vvr[j] = d < D ? vv[d] : 0.f;
+      wcr[j] = d < D ? vv[D + d] : 0.f;
+      hwk[j] = d < D ? vv[2 * D + d] * K2 : 0.f;
+      c_dz[j] = c_cov[j] = c_v[j] = 0.f;
+    }
     float se = 0.f;
     for (int i0 = warp * 2; i0 < n; i0 += NW * 2) {     // two sentences per warp iteration: every load in flight before the first tanh
-      float cvs[2], dets[2], pv[2][MAXJ], dpv[2][MAXJ];
+      float cvs[2], dets[2], pv[2][NJ], dpv[2][NJ];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int i = min(i0 + u, n - 1), t = t0 + i;
         cvs[u] = a.cov[(size_t)b * Lt + t];
-        dets[u] = a.alpha[((size_t)b * 2 + m) * Lt + t] * (s_da[m * a.chunk + i] - stm);
+        dets[u] = i0 + u < n ? a.alpha[((size_t)b * 2 + m) * Lt + t] * (s_da[m * a.chunk + i] - stm) : 0.f;   // a row past the end: all zero
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const int d = lane + 32 * j;
           pv[u][j] = d < D ? proj[(size_t)i * D + d] : 0.f;
           dpv[u][j] = d < D ? dproj[(size_t)i * D + d] : 0.f;
@@ -795,31 +885,29 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int i = i0 + u;
-        if (i >= n) break;
-        const float cv = cvs[u], det = dets[u];
+        const bool valid = i < n;
+        const float cv = cvs[u], det = dets[u], cvk = cv * K2;
         float row = 0.f;
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const int d = lane + 32 * j;
-          if (d < D) {
-            const float tz = tanh_fast((pv[u][j] + hwm[d]) + cv * wc[d]);
-            const float dz = det * vv[d] * (1.f - tz * tz);
-            dproj[(size_t)i * D + d] = dpv[u][j] + dz;
-            c_dz[j] += dz;
-            c_cov[j] = fmaf(dz, cv, c_cov[j]);
-            c_v[j] = fmaf(det, tz, c_v[j]);
-            row = fmaf(dz, wc[d], row);
-          }
+          const float tz = fmaf(-2.0f, rcp_ftz(1.0f + tc::fast_exp2(fmaf(cvk, wcr[j], fmaf(pv[u][j], K2, hwk[j])))), 1.0f);
+          const float dz = det * vvr[j] * (1.f - tz * tz);
+          if (valid && d < D) dproj[(size_t)i * D + d] = dpv[u][j] + dz;
+          c_dz[j] += dz;
+          c_cov[j] = fmaf(dz, cv, c_cov[j]);
+          c_v[j] = fmaf(det, tz, c_v[j]);
+          row = fmaf(dz, wcr[j], row);
         }
         row = warp_sum(row);
-        if (lane == 0) {
+        if (lane == 0 && valid) {
           s_row[i] += row;
           se += det;
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int d = lane + 32 * j;
       if (d < D) {
         s_part[(warp * 3 + 0) * D + d] = c_dz[j];
@@ -835,6 +923,9 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_colp, r)[(R * 2 + m) * 3 * D + i] = x;
     }
     __syncthreads();
+  };
+  for (int m = 0; m < 2; ++m) {
+    if (nj7) sweep8(m, N7{}); else sweep8(m, N8{});
   }
   for (int i = tid; i < n; i += NT) a.d_cov[(size_t)b * Lt + t0 + i] = s_row[i];
   if (tid < CL) {
@@ -929,9 +1020,22 @@ extern "C" int mmb_decoder_step_fused_fwd(const float* proj_a, const float* proj
   const int CL = (long long)B * 4 * 2 <= 160 ? 8 : 4;
   FusedArgs a{proj_a, proj_i, enc_a, enc_i, Wh4t, bh4, v1, wc1, v2, wc2, v1b, v2b, Wb13t, vb1, vb2, vb1b, vb2b, Wcatt, bcat, out_wt, out_b,
               sent, h, cell, cov, mask, target, probs, h_out, cell_out, att_cov, cov_out, argmax, nll, cov_loss, hw, alpha, beta,
-              ctx12, pb, xcat, gates, B, Lt, D, H, E, M, 0};
-  const size_t smem = fused_smem_bytes(Lt, D, H, E, M, CL, &a.chunk);
+              ctx12, pb, xcat, gates, B, Lt, D, H, E, M, 0, 0};
+  size_t smem = fused_smem_bytes(Lt, D, H, E, M, CL, &a.chunk);
   MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fused_fwd: %zu B of shared memory (Lt=%d)", smem, Lt);
+  {
+    // the row stage (see the kernel): two buffers of chunk x D floats behind two mbarriers, when they fit and bulk copies apply
+    // (16-byte row granularity).  MMB_DEC_STAGE=0 turns it off (A/B measurements, cross-check in tests/test_decoder_gpu.py).
+    static const char* stage_env = getenv("MMB_DEC_STAGE");
+    const size_t base_floats = (smem + 15) / 16 * 4;
+    const size_t stage_floats = 4 + 2 * (((size_t)a.chunk * D + 3) & ~(size_t)3);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(proj_a) | reinterpret_cast<uintptr_t>(proj_i) | reinterpret_cast<uintptr_t>(enc_a) |
+                           reinterpret_cast<uintptr_t>(enc_i)) & 15) == 0;
+    if ((D & 3) == 0 && aligned && (base_floats + stage_floats) * 4 <= 227 * 1024 && !(stage_env && atoi(stage_env) == 0)) {
+      a.stage_off = (int)base_floats;
+      smem = (base_floats + stage_floats) * 4;
+    }
+  }
   static size_t smem_set = 0;
   if (smem > smem_set) {
     MMB_CUDA(cudaFuncSetAttribute(dec_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -38,6 +38,17 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   return y;
 }
 
+// Predicated reduction (no branch around it: the sweeps' loop bodies stay one basic block)
+__device__ __forceinline__ void red_add_f32_if(float* p, float v, bool on) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q red.global.add.f32 [%0], %1;\n\t"
+      "}" ::"l"(p), "f"(v), "r"((int)on)
+      : "memory");
+}
+
 __device__ long long* g_dec_trace = nullptr;   // debugging aid (MMB_DEC_TRACE): clock64 stamps of block 0 at the stage boundaries
 #define DEC_STAMP(i)                                                          \
   do {                                                                        \
@@ -165,7 +176,8 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   float* s_scr = s_red + 32;                // [NT]   K-slice partial sums of the mat-vecs
   float* s_vec = s_scr + NT;                // [4D]   v1 | wc1 | v2 | wc2
   float* s_e = s_vec + up4(4 * D);          // [2][chunk] energies -> p -> alpha of this rank's rows
-  float* s_cpart = s_e + up4(2 * a.chunk);  // [groups][2][D] context partials inside the block; later this rank's logits
+  float* s_cov = s_e + up4(2 * a.chunk);    // [chunk] coverage input of this rank's rows
+  float* s_cpart = s_cov + up4(a.chunk);    // [groups][2][D] context partials inside the block; later this rank's logits
 
   // Row stage (stage_off != 0): this rank's rows of proj_a / proj_i -- contiguous in memory -- are brought into shared memory by two
   // bulk copies issued NOW, a whole mat-vec stage and a cluster barrier before stage B reads them; when the energies are done the same
@@ -189,6 +201,7 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   }
   DEC_STAMP(0);
   // ---- stage 0: this video's step inputs -----------------------------------------------------------------------------------
+  for (int i = tid; i < n; i += NT) s_cov[i] = a.cov[(size_t)b * Lt + t0 + i];      // (read per row by the energies: not a global load there)
   for (int i = tid; i < H; i += NT) s_x[D + E + i] = a.h[(size_t)b * H + i];
   for (int i = tid; i < E; i += NT) s_x[D + i] = a.sent[(size_t)b * E + i];
   for (int i = tid; i < D; i += NT) {
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
         wi[j] = in ? s_vec[3 * D + dd] * K2 : 0.f;
         hi[j] = in ? s_hw[D + dd] * K2 : 0.f;
       }
-      const float* const covp = a.cov + (size_t)b * Lt + t0;
+      const float* const covp = s_cov;
       for (int i = warp * RU; i < n; i += NW * RU) {
         float s[RU][2];
         float pav[RU][NJ], piv[RU][NJ], cvs[RU];
@@ -597,6 +610,7 @@ struct HeadArgs {
   float *d_proj_a, *d_proj_i, *d_cov;                       // (B,Lt,D) accumulated, (B,Lt) written
   const float* Wh_stack;                                    // (4H + 4D, H): [W_hh; W2; W4; W_beta_2; W_beta_4]
   float* d_h;                                               // (B,H)
+  int stage_off;   // whole step: float offset of the row stage ([2 mbarriers][2][chunk * D]) in dynamic shared memory, or 0
 };
 
 __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
@@ -618,6 +632,27 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   float* s_red = s_ex + MAXC * 4;                       // [32]
   float* s_scr = s_red + 32;                            // [NT]
 
+  // Row stage of the whole-step launch (see dec_step_fused_kernel): this rank's rows of enc_a / enc_i come in by two bulk copies issued
+  // NOW, six head stages before sweep 7 reads them; when sweep 7 is done the same buffers take the rows of proj_a / proj_i for sweep 8
+  // (under the block sums and the cluster barrier between the sweeps).  Without it every warp iteration of a sweep began with an L2
+  // round trip (tools/decoder_bwd_trace.py: 11.3 k + 30.5 k cycles for the two sweeps).
+  const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk), n = t1 - t0;
+  const bool staged = a.stage_off != 0;
+  float* const s_st0 = smem + a.stage_off + 4;
+  float* const s_st1 = s_st0 + up4(a.chunk * D);
+  const uint32_t bar_enc = tc::smem_u32(smem + a.stage_off), bar_proj = bar_enc + 8;
+  const uint32_t stage_bytes = (uint32_t)(n * D) * 4u;
+  if (staged && tid == 0) {
+    tc::mbar_init(bar_enc, 1);
+    tc::mbar_init(bar_proj, 1);
+    tc::fence_barrier_init();
+    if (n > 0) {
+      tc::mbar_expect_tx(bar_enc, 2 * stage_bytes, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st0), a.enc_a + ((size_t)b * Lt + t0) * D, stage_bytes, bar_enc, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st1), a.enc_i + ((size_t)b * Lt + t0) * D, stage_bytes, bar_enc, 1);
+    }
+  }
+  DEC_STAMP(18);
   // ---- 1: masked soft-max backward: d_logit = p (dp - sum p dp); masked entries have p = 0 ---------------------------------
   const int m0 = min(M, R * per_m), m1 = min(M, m0 + per_m);
   const int tg = a.target ? (int)a.target[b] : -1;
@@ -644,6 +679,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
       for (int m = M + tid; m < a.ldd; m += NT) a.d_logits[(size_t)b * a.ldd + m] = 0.f;   // row padding (keeps the weight-gradient GEMM aligned)
   }
   __syncthreads();
+  DEC_STAMP(19);
   // ---- 2: d h (from the logits) = d_logits out.weight: this rank's rows of out.weight, all H outputs; partials summed over the ranks
   block_matvec_t(a.out_w + (size_t)m0 * H, H, nullptr, s_dl, m1 - m0, H, s_scr, [](int i) { return i; }, [&](int i, float v) {
     for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dhp, r)[R * H + i] = v;
@@ -651,6 +687,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   if (m1 - m0 <= 0 && tid < H)
     for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dhp, r)[R * H + tid] = 0.f;
   cluster.sync();
+  DEC_STAMP(20);
   // ---- 3: LSTM cell backward (every rank, redundantly: H elements) ------------------------------------------------------------
   if (tid < H) {
     const int j = tid;
@@ -671,6 +708,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     }
   }
   __syncthreads();
+  DEC_STAMP(21);
   // ---- 4: d c3 = d_gates W_ih[:, :D]: outputs split over the ranks, gathered -----------------------------------------------------
   {
     const int per = (D + CL - 1) / CL, d0 = min(D, R * per), d1 = min(D, d0 + per);
@@ -679,6 +717,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     });
   }
   cluster.sync();
+  DEC_STAMP(22);
   // ---- 5: modality soft-max + W_beta tanh backward; datt / dcov_tot of this rank's text rows ---------------------------------------
   const float beta1 = a.beta[b * 2 + 0], beta2 = a.beta[b * 2 + 1];
   {
@@ -741,6 +780,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     }
   }
   __syncthreads();
+  DEC_STAMP(23);
   // ---- 6: d c_k = beta_k d c3 + W_beta_k^T d_pre_k: the 2D outputs split over the ranks --------------------------------------------
   float* s_dc = s_scr + NT;                             // [2D]  d c_1 | d c_2, gathered (whole-step launch)
   {
@@ -763,12 +803,12 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
 
   // ==== the text sweeps of the step (decoder_step.cu: dec_attn_sweep1 / sweep2 / reduce_video), this rank's rows [t0, t1) ============
   const int lane = tid & 31, warp = tid >> 5;
-  const int t0 = min(Lt, R * a.chunk), t1 = min(Lt, t0 + a.chunk), n = t1 - t0;
   auto up4s = [](int v) { return (v + 3) & ~3; };
-  float* s_da = s_dc + up4s(2 * D);                     // [2][chunk]  d alpha_k of this rank's rows
-  float* s_vec = s_da + up4s(2 * a.chunk);              // [6][D]  v1 | wc1 | hw1 | v2 | wc2 | hw2
-  float* s_part = s_vec + up4s(6 * D);                  // [NW][3][D]
-  float* s_row = s_part + up4s(NW * 3 * D);             // [chunk]  d cov accumulation
+  float* s_da = s_dc + up4s(2 * D);                     // [2][chunk]  d alpha_k of this rank's rows, then alpha_k (d alpha_k - sum)
+  float* s_rowc = s_da + up4s(2 * a.chunk);             // [4][chunk]  per-row scalars of this rank's rows: alpha_1 | alpha_2 | datt | cov
+  float* s_vec = s_rowc + up4s(4 * a.chunk);            // [6][D]  v1 | wc1 | hw1 | v2 | wc2 | hw2
+  float* s_part = staged ? s_st0 : s_vec + up4s(6 * D); // [NW][3][D]  (staged: over stage buffer 0, whose rows are dead by then)
+  float* s_row = s_vec + up4s(6 * D) + (staged ? 0 : up4s(NW * 3 * D));   // [chunk]  d cov accumulation
   float* s_colp = s_row + up4s(a.chunk);                // [MAXC][2][3][D]  column partials of every rank (written remotely)
   float* s_in = s_colp + up4s(MAXC * 6 * D);            // [4H + 4D]  d_gates | d (W2 h) | d (W4 h) | d_pre_b
   // Both sweeps are written like stage B of the forward kernel (see there): a lane's per-column constants live in registers for the
@@ -776,6 +816,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   using N7 = std::integral_constant<int, 7>;
   using N8 = std::integral_constant<int, 8>;
   const bool nj7 = D > 192 && D <= 224;
+  DEC_STAMP(24);
   // ---- 7: d alpha_k[t] = beta_k datt[t] + d c_k . enc_k[t];  sum_t alpha d alpha over the cluster ----------------------------------
   for (int i = tid; i < D; i += NT) {
     s_vec[i] = a.v1[i];
@@ -785,9 +826,18 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     s_vec[4 * D + i] = a.wc2[i];
     s_vec[5 * D + i] = a.hw[(size_t)b * 4 * D + D + i];
   }
-  for (int i = tid; i < n; i += NT) s_row[i] = a.dcov_tot[(size_t)b * Lt + t0 + i];
+  // the per-row scalars of both sweeps come in ONCE, here: read inside the sweeps they were dependent global loads at the end (sweep
+  // 7) or in the middle (sweep 8) of every warp iteration -- ~800 exposed cycles each (tools/decoder_bwd_trace.py)
+  for (int i = tid; i < n; i += NT) {
+    s_row[i] = a.dcov_tot[(size_t)b * Lt + t0 + i];
+    s_rowc[i] = a.alpha[((size_t)b * 2 + 0) * Lt + t0 + i];
+    s_rowc[a.chunk + i] = a.alpha[((size_t)b * 2 + 1) * Lt + t0 + i];
+    s_rowc[2 * a.chunk + i] = a.datt[(size_t)b * Lt + t0 + i];      // (written by this rank in stage 5)
+    s_rowc[3 * a.chunk + i] = a.cov[(size_t)b * Lt + t0 + i];
+  }
+  __syncthreads();
   float s1 = 0.f, s2 = 0.f;
-  auto sweep7 = [&](auto nj_tag) {
+  auto sweep7 = [&](const float* __restrict__ ea0, const float* __restrict__ ei0, auto nj_tag) {
     constexpr int NJ = decltype(nj_tag)::value;
     float dca[NJ], dci[NJ];
 #pragma unroll
@@ -801,8 +851,8 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
       float eav[2][NJ], eiv[2][NJ];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {                     // loads first (memory-level parallelism)
-        const float* ea = a.enc_a + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
-        const float* ei = a.enc_i + ((size_t)b * Lt + t0 + min(i + u, n - 1)) * D;
+        const float* ea = ea0 + (size_t)min(i + u, n - 1) * D;
+        const float* ei = ei0 + (size_t)min(i + u, n - 1) * D;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           const int d = lane + 32 * j;
@@ -821,20 +871,32 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
       for (int u = 0; u < 2; ++u) {
         const float x1 = warp_sum(d1[u]), x2 = warp_sum(d2[u]);
         if (lane == 0 && i + u < n) {
-          const int t = t0 + i + u;
-          const float g = a.datt[(size_t)b * Lt + t];      // (written by this rank in stage 5)
+          const float g = s_rowc[2 * a.chunk + i + u];
           const float da1 = x1 + beta1 * g, da2 = x2 + beta2 * g;
           s_da[i + u] = da1;
           s_da[a.chunk + i + u] = da2;
-          s1 = fmaf(a.alpha[((size_t)b * 2 + 0) * Lt + t], da1, s1);
-          s2 = fmaf(a.alpha[((size_t)b * 2 + 1) * Lt + t], da2, s2);
+          s1 = fmaf(s_rowc[i + u], da1, s1);
+          s2 = fmaf(s_rowc[a.chunk + i + u], da2, s2);
         }
       }
     }
   };
-  if (nj7) sweep7(N7{}); else sweep7(N8{});
+  if (staged) {
+    if (n > 0) tc::mbar_wait(bar_enc, 0);
+    if (nj7) sweep7(s_st0, s_st1, N7{}); else sweep7(s_st0, s_st1, N8{});
+  } else {
+    const float* const gea = a.enc_a + ((size_t)b * Lt + t0) * D;
+    const float* const gei = a.enc_i + ((size_t)b * Lt + t0) * D;
+    if (nj7) sweep7(gea, gei, N7{}); else sweep7(gea, gei, N8{});
+  }
   {
     s1 = block_sum(s1, s_red);
+    if (staged && tid == 0 && n > 0) {       // every read of the enc rows is behind block_sum's barriers: the buffers take the proj rows
+      tc::fence_proxy_async();
+      tc::mbar_expect_tx(bar_proj, 2 * stage_bytes, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st0), a.proj_a + ((size_t)b * Lt + t0) * D, stage_bytes, bar_proj, 1);
+      tc::tma_bulk_g2s(tc::smem_u32(s_st1), a.proj_i + ((size_t)b * Lt + t0) * D, stage_bytes, bar_proj, 1);
+    }
     s2 = block_sum(s2, s_red);
     if (tid < CL) {
       float* dst = cluster.map_shared_rank(s_ex, tid) + R * 4;
@@ -848,14 +910,18 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     stot0 += s_ex[r * 4 + 0];
     stot1 += s_ex[r * 4 + 1];
   }
+  DEC_STAMP(25);
+  for (int i = tid; i < n; i += NT) {                   // d e_k[t] = alpha_k (d alpha_k - sum_t alpha_k d alpha_k), in place
+    s_da[i] = s_rowc[i] * (s_da[i] - stot0);
+    s_da[a.chunk + i] = s_rowc[a.chunk + i] * (s_da[a.chunk + i] - stot1);
+  }
+  __syncthreads();
   // ---- 8: soft-max backward, tanh backward, d proj (+=), d cov, column partials ------------------------------------------------------
   constexpr float K2 = 2.0f * 1.4426950408889634f;      // tanh x = 1 - 2 / (1 + 2^(K2 x)), flush-to-zero MUFU forms (no guard instructions)
   float se_m0 = 0.f, se_m1 = 0.f;
-  auto sweep8 = [&](const int m, auto nj_tag) {
+  auto sweep8 = [&](const int m, const float* __restrict__ proj, auto nj_tag) {     // proj: row 0 of this rank's chunk (stage or global)
     constexpr int NJ = decltype(nj_tag)::value;
-    const float* proj = (m == 0 ? a.proj_a : a.proj_i) + ((size_t)b * Lt + t0) * D;
     float* dproj = (m == 0 ? a.d_proj_a : a.d_proj_i) + ((size_t)b * Lt + t0) * D;
-    const float stm = m == 0 ? stot0 : stot1;
     float vvr[NJ], wcr[NJ], hwk[NJ];                    // v, Wc, K2 (W h) of this lane's columns
     float c_dz[NJ], c_cov[NJ], c_v[NJ];
 #pragma unroll
@@ -869,17 +935,16 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     }
     float se = 0.f;
     for (int i0 = warp * 2; i0 < n; i0 += NW * 2) {     // two sentences per warp iteration: every load in flight before the first tanh
-      float cvs[2], dets[2], pv[2][NJ], dpv[2][NJ];
+      float cvs[2], dets[2], pv[2][NJ];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int i = min(i0 + u, n - 1), t = t0 + i;
-        cvs[u] = a.cov[(size_t)b * Lt + t];
-        dets[u] = i0 + u < n ? a.alpha[((size_t)b * 2 + m) * Lt + t] * (s_da[m * a.chunk + i] - stm) : 0.f;   // a row past the end: all zero
+        const int i = min(i0 + u, n - 1);
+        cvs[u] = s_rowc[3 * a.chunk + i];
+        dets[u] = i0 + u < n ? s_da[m * a.chunk + i] : 0.f;          // a row past the end: all zero
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           const int d = lane + 32 * j;
           pv[u][j] = d < D ? proj[(size_t)i * D + d] : 0.f;
-          dpv[u][j] = d < D ? dproj[(size_t)i * D + d] : 0.f;
         }
       }
 #pragma unroll
@@ -893,7 +958,9 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
           const int d = lane + 32 * j;
           const float tz = fmaf(-2.0f, rcp_ftz(1.0f + tc::fast_exp2(fmaf(cvk, wcr[j], fmaf(pv[u][j], K2, hwk[j])))), 1.0f);
           const float dz = det * vvr[j] * (1.f - tz * tz);
-          if (valid && d < D) dproj[(size_t)i * D + d] = dpv[u][j] + dz;
+          // d proj accumulates over the steps of the sequence: a reduction at L2 (one writer per element and step, steps in stream
+          // order: deterministic) instead of a load - add - store round trip through the SM
+          red_add_f32_if(dproj + (size_t)i * D + d, dz, valid && d < D);
           c_dz[j] += dz;
           c_cov[j] = fmaf(dz, cv, c_cov[j]);
           c_v[j] = fmaf(det, tz, c_v[j]);
@@ -906,6 +973,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
         }
       }
     }
+    if (staged && m == 0) __syncthreads();              // s_part lies over stage buffer 0: every warp is done with its proj_a rows
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int d = lane + 32 * j;
@@ -924,8 +992,15 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     }
     __syncthreads();
   };
+  if (staged && n > 0) tc::mbar_wait(bar_proj, 0);
   for (int m = 0; m < 2; ++m) {
-    if (nj7) sweep8(m, N7{}); else sweep8(m, N8{});
+    if (staged) {
+      const float* const sp = m == 0 ? s_st0 : s_st1;
+      if (nj7) sweep8(m, sp, N7{}); else sweep8(m, sp, N8{});
+    } else {
+      const float* const gp = (m == 0 ? a.proj_a : a.proj_i) + ((size_t)b * Lt + t0) * D;
+      if (nj7) sweep8(m, gp, N7{}); else sweep8(m, gp, N8{});
+    }
   }
   for (int i = tid; i < n; i += NT) a.d_cov[(size_t)b * Lt + t0 + i] = s_row[i];
   if (tid < CL) {
@@ -934,6 +1009,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     dst[3] = se_m1;
   }
   cluster.sync();
+  DEC_STAMP(26);
   // ---- 9: the column sums over the cluster (fixed order) -> d (W2 h) | d (W4 h), parameter-gradient accumulators; d h -----------------
   for (int i = tid; i < 2 * D; i += NT) {
     const int m = i / D, d = i - m * D;
@@ -966,6 +1042,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     block_matvec_t(a.Wh_stack, H, nullptr, s_in, 4 * H + 4 * D, j1 - j0, s_scr, [&](int i) { return j0 + i; },
                    [&](int i, float v) { a.d_h[(size_t)b * H + j0 + i] = v; });
   }
+  DEC_STAMP(27);
   cluster.sync();      // no rank exits while another may still write into its shared memory
 }
 
@@ -976,7 +1053,7 @@ static size_t head_smem_bytes(int D, int H, int M, int CL, int chunk = 0, bool s
   const size_t per_m = (M + CL - 1) / CL;
   size_t floats = up4(per_m) + up4((size_t)MAXC * H) + up4(4 * H) + up4(D) + up4(2 * D) + MAXC * 4 + 32 + NT;
   if (sweeps)
-    floats += up4(2 * D) + up4(2 * (size_t)chunk) + up4(6 * D) + up4((size_t)NW * 3 * D) + up4(chunk) + up4((size_t)MAXC * 6 * D) +
+    floats += up4(2 * D) + up4(2 * (size_t)chunk) + up4(4 * (size_t)chunk) + up4(6 * D) + up4((size_t)NW * 3 * D) + up4(chunk) + up4((size_t)MAXC * 6 * D) +
               up4(4 * H + 4 * D);
   return floats * sizeof(float) + 64;
 }
@@ -991,7 +1068,7 @@ static size_t fused_smem_bytes(int Lt, int D, int H, int E, int M, int CL, int* 
   if (cpart < per_m) cpart = per_m;
   auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
   const size_t floats = up4(4 * D) + up4(K) + 2 * up4(2 * D) + up4(H) + up4((size_t)MAXC * (4 + 2 * D)) + MAXC * 8 +
-                        up4(4 * ((H + MAXC / 2 - 1) / (MAXC / 2) + 1)) + 32 + NT + up4(4 * D) + up4(2 * (size_t)chunk) + up4(cpart);
+                        up4(4 * ((H + MAXC / 2 - 1) / (MAXC / 2) + 1)) + 32 + NT + up4(4 * D) + up4(2 * (size_t)chunk) + up4(chunk) + up4(cpart);
   if (chunk_out) *chunk_out = chunk;
   return floats * sizeof(float) + 64;
 }
@@ -1083,7 +1160,7 @@ extern "C" int mmb_decoder_bwd_head(const float* probs, const float* d_probs, co
   HeadArgs a{probs, d_probs, target, g_nll, g_cov, out_w, gates, cell_in, cell_out, d_h_out, d_cell_out, Wcat_ctx, d_att_cov, d_cov_out,
              alpha, beta, ctx12, pb, hw, vb1, vb2, att, cov_out, Wb13, d_logits, d_gates, d_cell, datt, dcov_tot, d_pre_b, d_ctx12,
              vec_acc, scal_acc, B, Lt, D, H, M, ldd, ldg, (Lt + CL - 1) / CL,
-             0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+             0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   const size_t smem = head_smem_bytes(D, H, M, CL);
   MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_bwd_head: %zu B of shared memory", smem);
   if (smem > g_head_smem_set) {
@@ -1133,9 +1210,24 @@ extern "C" int mmb_decoder_step_fused_bwd(const float* probs, const float* d_pro
   HeadArgs a{probs, d_probs, target, g_nll, g_cov, out_w, gates, cell_in, cell_out, d_h_out, d_cell_out, Wcat_ctx, d_att_cov, d_cov_out,
              alpha, beta, ctx12, pb, hw, vb1, vb2, att, cov_out, Wb13, d_logits, d_gates, d_cell, datt, dcov_tot, d_pre_b, d_ctx12,
              vec_acc, scal_acc, B, Lt, D, H, M, ldd, ldg, chunk,
-             1, proj_a, proj_i, enc_a, enc_i, coverage, v1, wc1, v2, wc2, d_proj_a, d_proj_i, d_cov, Wh_stack, d_h};
-  const size_t smem = head_smem_bytes(D, H, M, CL, chunk, true);
+             1, proj_a, proj_i, enc_a, enc_i, coverage, v1, wc1, v2, wc2, d_proj_a, d_proj_i, d_cov, Wh_stack, d_h, 0};
+  size_t smem = head_smem_bytes(D, H, M, CL, chunk, true);
   MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fused_bwd: %zu B of shared memory (Lt=%d)", smem, Lt);
+  {
+    // the row stage (see the kernel): two buffers of chunk x D floats behind two mbarriers; the per-warp column partials then lie over
+    // buffer 0, so their own region is dropped from the layout.  MMB_DEC_STAGE=0 turns it off.
+    static const char* stage_env = getenv("MMB_DEC_STAGE");
+    const size_t part_floats = ((size_t)NW * 3 * D + 3) & ~(size_t)3;
+    const size_t base_floats = (smem - 64) / 4 - part_floats;
+    const size_t stage_floats = 4 + 2 * (((size_t)chunk * D + 3) & ~(size_t)3);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(proj_a) | reinterpret_cast<uintptr_t>(proj_i) | reinterpret_cast<uintptr_t>(enc_a) |
+                           reinterpret_cast<uintptr_t>(enc_i)) & 15) == 0;
+    if ((D & 3) == 0 && aligned && part_floats <= stage_floats / 2 && (base_floats + stage_floats) * 4 + 64 <= 227 * 1024 &&
+        !(stage_env && atoi(stage_env) == 0)) {
+      a.stage_off = (int)base_floats;
+      smem = (base_floats + stage_floats) * 4 + 64;
+    }
+  }
   if (smem > g_head_smem_set) {
     MMB_CUDA(cudaFuncSetAttribute(dec_bwd_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_head_smem_set = smem;

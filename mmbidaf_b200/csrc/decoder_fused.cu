@@ -38,6 +38,13 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   return y;
 }
 
+// Bulk reduction shared -> global (the TMA adds a whole staged block of rows into memory at L2), its group commit / wait
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Predicated reduction (no branch around it: the sweeps' loop bodies stay one basic block)
 __device__ __forceinline__ void red_add_f32_if(float* p, float v, bool on) {
   asm volatile(
@@ -807,10 +814,11 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   float* s_da = s_dc + up4s(2 * D);                     // [2][chunk]  d alpha_k of this rank's rows, then alpha_k (d alpha_k - sum)
   float* s_rowc = s_da + up4s(2 * a.chunk);             // [4][chunk]  per-row scalars of this rank's rows: alpha_1 | alpha_2 | datt | cov
   float* s_vec = s_rowc + up4s(4 * a.chunk);            // [6][D]  v1 | wc1 | hw1 | v2 | wc2 | hw2
-  float* s_part = staged ? s_st0 : s_vec + up4s(6 * D); // [NW][3][D]  (staged: over stage buffer 0, whose rows are dead by then)
-  float* s_row = s_vec + up4s(6 * D) + (staged ? 0 : up4s(NW * 3 * D));   // [chunk]  d cov accumulation
-  float* s_colp = s_row + up4s(a.chunk);                // [MAXC][2][3][D]  column partials of every rank (written remotely)
-  float* s_in = s_colp + up4s(MAXC * 6 * D);            // [4H + 4D]  d_gates | d (W2 h) | d (W4 h) | d_pre_b
+  const int PW = staged ? NW / 2 : NW;                  // warps per pass of the column-partial reduction (staged: half the buffer, two passes)
+  float* s_part = s_vec + up4s(6 * D);                  // [PW][3][D]
+  float* s_row = s_part + up4s(PW * 3 * D);             // [chunk]  d cov accumulation
+  float* s_colp = s_row + up4s(a.chunk);                // [CL][2][3][D]  column partials of every rank (written remotely)
+  float* s_in = s_colp + up4s(CL * 6 * D);              // [4H + 4D]  d_gates | d (W2 h) | d (W4 h) | d_pre_b
   // Both sweeps are written like stage B of the forward kernel (see there): a lane's per-column constants live in registers for the
   // whole sweep (zero past D, so the arithmetic is unpredicated), NJ = 7 for the model's D = 200 and the zero-padded 8 for any other D.
   using N7 = std::integral_constant<int, 7>;
@@ -919,8 +927,13 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   // ---- 8: soft-max backward, tanh backward, d proj (+=), d cov, column partials ------------------------------------------------------
   constexpr float K2 = 2.0f * 1.4426950408889634f;      // tanh x = 1 - 2 / (1 + 2^(K2 x)), flush-to-zero MUFU forms (no guard instructions)
   float se_m0 = 0.f, se_m1 = 0.f;
-  auto sweep8 = [&](const int m, const float* __restrict__ proj, auto nj_tag) {     // proj: row 0 of this rank's chunk (stage or global)
+  // proj: row 0 of this rank's chunk.  STAGED: the rows sit in a stage buffer; d z overwrites them in place and the whole block is added
+  // into d proj by ONE bulk reduction (d proj accumulates over the steps of the sequence: one writer per element and step, steps in
+  // stream order -- deterministic); else d z goes out as predicated L2 reductions (a warp-wide RED per 128 bytes: ~as slow as the load -
+  // add - store round trip it replaced).
+  auto sweep8 = [&](const int m, float* proj, auto nj_tag, auto staged_tag) {
     constexpr int NJ = decltype(nj_tag)::value;
+    constexpr bool STAGED = decltype(staged_tag)::value;
     float* dproj = (m == 0 ? a.d_proj_a : a.d_proj_i) + ((size_t)b * Lt + t0) * D;
     float vvr[NJ], wcr[NJ], hwk[NJ];                    // v, Wc, K2 (W h) of this lane's columns
     float c_dz[NJ], c_cov[NJ], c_v[NJ];
@@ -958,9 +971,11 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
           const int d = lane + 32 * j;
           const float tz = fmaf(-2.0f, rcp_ftz(1.0f + tc::fast_exp2(fmaf(cvk, wcr[j], fmaf(pv[u][j], K2, hwk[j])))), 1.0f);
           const float dz = det * vvr[j] * (1.f - tz * tz);
-          // d proj accumulates over the steps of the sequence: a reduction at L2 (one writer per element and step, steps in stream
-          // order: deterministic) instead of a load - add - store round trip through the SM
-          red_add_f32_if(dproj + (size_t)i * D + d, dz, valid && d < D);
+          if (STAGED) {
+            if (valid && d < D) proj[(size_t)i * D + d] = dz;
+          } else {
+            red_add_f32_if(dproj + (size_t)i * D + d, dz, valid && d < D);
+          }
           c_dz[j] += dz;
           c_cov[j] = fmaf(dz, cv, c_cov[j]);
           c_v[j] = fmaf(det, tz, c_v[j]);
@@ -973,33 +988,51 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
         }
       }
     }
-    if (staged && m == 0) __syncthreads();              // s_part lies over stage buffer 0: every warp is done with its proj_a rows
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int d = lane + 32 * j;
-      if (d < D) {
-        s_part[(warp * 3 + 0) * D + d] = c_dz[j];
-        s_part[(warp * 3 + 1) * D + d] = c_cov[j];
-        s_part[(warp * 3 + 2) * D + d] = c_v[j];
-      }
-    }
-    se = block_sum(se, s_red);                          // (contains the __syncthreads that publishes s_part)
+    if (STAGED) tc::fence_proxy_async();                // this thread's d z stores, before the bulk reduction reads them
+    se = block_sum(se, s_red);                          // (its barriers: every warp is done with its rows)
     if (m == 0) se_m0 = se; else se_m1 = se;
-    for (int i = tid; i < 3 * D; i += NT) {
-      float x = 0.f;
-      for (int w = 0; w < NW; ++w) x += s_part[w * 3 * D + i];
-      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_colp, r)[(R * 2 + m) * 3 * D + i] = x;
+    if (STAGED && tid == 0 && n > 0) {
+      bulk_reduce_add_f32(dproj, tc::smem_u32(proj), stage_bytes);
+      bulk_commit();
     }
-    __syncthreads();
+    // column partials: per-warp rows -> fixed-order sum over the warps (PW warps per pass) -> slot R of every rank
+    float xacc[2] = {0.f, 0.f};                         // outputs tid and tid + NT of the 3 D (D <= 256)
+    for (int w0 = 0; w0 < NW; w0 += PW) {
+      if (warp >= w0 && warp < w0 + PW) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) {
+            s_part[((warp - w0) * 3 + 0) * D + d] = c_dz[j];
+            s_part[((warp - w0) * 3 + 1) * D + d] = c_cov[j];
+            s_part[((warp - w0) * 3 + 2) * D + d] = c_v[j];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = tid + q * NT;
+        if (i < 3 * D)
+          for (int w = 0; w < PW; ++w) xacc[q] += s_part[w * 3 * D + i];
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * NT;
+      if (i < 3 * D)
+        for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_colp, r)[(R * 2 + m) * 3 * D + i] = xacc[q];
+    }
   };
   if (staged && n > 0) tc::mbar_wait(bar_proj, 0);
   for (int m = 0; m < 2; ++m) {
     if (staged) {
-      const float* const sp = m == 0 ? s_st0 : s_st1;
-      if (nj7) sweep8(m, sp, N7{}); else sweep8(m, sp, N8{});
+      float* const sp = m == 0 ? s_st0 : s_st1;
+      if (nj7) sweep8(m, sp, N7{}, std::true_type{}); else sweep8(m, sp, N8{}, std::true_type{});
     } else {
-      const float* const gp = (m == 0 ? a.proj_a : a.proj_i) + ((size_t)b * Lt + t0) * D;
-      if (nj7) sweep8(m, gp, N7{}); else sweep8(m, gp, N8{});
+      float* const gp = const_cast<float*>(m == 0 ? a.proj_a : a.proj_i) + ((size_t)b * Lt + t0) * D;      // (read only on this path)
+      if (nj7) sweep8(m, gp, N7{}, std::false_type{}); else sweep8(m, gp, N8{}, std::false_type{});
     }
   }
   for (int i = tid; i < n; i += NT) a.d_cov[(size_t)b * Lt + t0 + i] = s_row[i];
@@ -1042,18 +1075,19 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     block_matvec_t(a.Wh_stack, H, nullptr, s_in, 4 * H + 4 * D, j1 - j0, s_scr, [&](int i) { return j0 + i; },
                    [&](int i, float v) { a.d_h[(size_t)b * H + j0 + i] = v; });
   }
+  if (staged && tid == 0) bulk_wait_all();              // the stage buffers are read by the bulk reductions until here
   DEC_STAMP(27);
   cluster.sync();      // no rank exits while another may still write into its shared memory
 }
 
 static size_t g_head_smem_set = 0;   // dynamic shared memory the kernel attribute of dec_bwd_head_kernel allows (both launchers share it)
 
-static size_t head_smem_bytes(int D, int H, int M, int CL, int chunk = 0, bool sweeps = false) {
+static size_t head_smem_bytes(int D, int H, int M, int CL, int chunk = 0, bool sweeps = false, int PW = NW) {
   auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
   const size_t per_m = (M + CL - 1) / CL;
   size_t floats = up4(per_m) + up4((size_t)MAXC * H) + up4(4 * H) + up4(D) + up4(2 * D) + MAXC * 4 + 32 + NT;
   if (sweeps)
-    floats += up4(2 * D) + up4(2 * (size_t)chunk) + up4(4 * (size_t)chunk) + up4(6 * D) + up4((size_t)NW * 3 * D) + up4(chunk) + up4((size_t)MAXC * 6 * D) +
+    floats += up4(2 * D) + up4(2 * (size_t)chunk) + up4(4 * (size_t)chunk) + up4(6 * D) + up4((size_t)PW * 3 * D) + up4(chunk) + up4((size_t)CL * 6 * D) +
               up4(4 * H + 4 * D);
   return floats * sizeof(float) + 64;
 }
@@ -1214,16 +1248,15 @@ extern "C" int mmb_decoder_step_fused_bwd(const float* probs, const float* d_pro
   size_t smem = head_smem_bytes(D, H, M, CL, chunk, true);
   MMB_REQUIRE(smem <= 200 * 1024, MMB_ERR_UNSUPPORTED, "mmb_decoder_step_fused_bwd: %zu B of shared memory (Lt=%d)", smem, Lt);
   {
-    // the row stage (see the kernel): two buffers of chunk x D floats behind two mbarriers; the per-warp column partials then lie over
-    // buffer 0, so their own region is dropped from the layout.  MMB_DEC_STAGE=0 turns it off.
+    // the row stage (see the kernel): two buffers of chunk x D floats behind two mbarriers; the column-partial reduction then runs in two
+    // passes over half the buffer.  MMB_DEC_STAGE=0 turns it off.
     static const char* stage_env = getenv("MMB_DEC_STAGE");
-    const size_t part_floats = ((size_t)NW * 3 * D + 3) & ~(size_t)3;
-    const size_t base_floats = (smem - 64) / 4 - part_floats;
+    const size_t base_floats = (head_smem_bytes(D, H, M, CL, chunk, true, NW / 2) - 64) / 4;
     const size_t stage_floats = 4 + 2 * (((size_t)chunk * D + 3) & ~(size_t)3);
     const bool aligned = ((reinterpret_cast<uintptr_t>(proj_a) | reinterpret_cast<uintptr_t>(proj_i) | reinterpret_cast<uintptr_t>(enc_a) |
-                           reinterpret_cast<uintptr_t>(enc_i)) & 15) == 0;
-    if ((D & 3) == 0 && aligned && part_floats <= stage_floats / 2 && (base_floats + stage_floats) * 4 + 64 <= 227 * 1024 &&
-        !(stage_env && atoi(stage_env) == 0)) {
+                           reinterpret_cast<uintptr_t>(enc_i) | reinterpret_cast<uintptr_t>(d_proj_a) |
+                           reinterpret_cast<uintptr_t>(d_proj_i)) & 15) == 0;
+    if ((D & 3) == 0 && aligned && (base_floats + stage_floats) * 4 + 64 <= 227 * 1024 && !(stage_env && atoi(stage_env) == 0)) {
       a.stage_off = (int)base_floats;
       smem = (base_floats + stage_floats) * 4 + 64;
     }

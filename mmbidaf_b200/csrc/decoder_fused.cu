@@ -31,6 +31,9 @@ namespace {
 constexpr int NT = 512;        // 16 warps: the step is a chain of latency-bound stages, one CTA per SM
 constexpr int NW = NT / 32;
 constexpr int MAXC = 8;        // cluster sizes 4 and 8
+constexpr int SCR = 2048;      // floats of mat-vec scratch in the forward kernel: K slices x outputs of a stage
+// hidden units / outputs of a rank: multiples of 4, so that a rank's weight columns start 16-byte aligned (quad form of the mat-vecs)
+__host__ __device__ constexpr int split4(int n, int parts) { return ((n + parts - 1) / parts + 3) & ~3; }
 
 __device__ __forceinline__ float rcp_ftz(float x) {
   float y;
@@ -87,19 +90,70 @@ struct FusedArgs {
 };
 
 // y[i] = sum_k Wt[k][col_of(i)] x[k] + bias[col_of(i)] for i < n_out, with the weights TRANSPOSED (Wt (K, ldn): consecutive threads read
-// consecutive outputs, no shuffle reductions).  The K axis is split over NT / n_out thread groups whose partial sums meet in shared
-// memory (`scratch`, NT floats).  One thread per (output, K slice): K / S independent coalesced loads and FMAs -- the warp-per-output
-// form (row-major weights, 5 shuffle steps per output) cost four times the instructions and the stage was issue bound.
+// consecutive outputs, no shuffle reductions).  The K axis is split over thread groups whose partial sums meet in shared memory
+// (`scratch`, scratch_cap floats).  The stage is a latency problem, not a bandwidth one: every cluster reads the same weights from L2
+// (~1 000 cycles per round trip) and what counts is the BYTES IN FLIGHT per SM.
+//  * scalar form: one thread per (output, K slice), sixteen 4-byte loads in flight per thread (32 KB per SM);
+//  * quad form (`quads`: n_out, ldn and col_of(4 q) are multiples of 4, col_of(4 q + e) = col_of(4 q) + e): one thread per (four outputs,
+//    K slice), eight 16-byte loads in flight per thread and as many K slices as the scratch holds -- 64 KB per SM in flight and a K
+//    slice short enough for one or two round trips (round 2: stage A 5.3 k -> cycles, see profiles/r02_decoder_fused.md).
 template <typename ColOf, typename Emit>
 __device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, const int ldn, const float* __restrict__ bias, const float* x,
-                                               const int K, const int n_out, float* scratch, ColOf col_of, Emit emit) {
+                                               const int K, const int n_out, float* scratch, const int scratch_cap, bool quads,
+                                               ColOf col_of, Emit emit) {
   const int tid = threadIdx.x;
   if (n_out <= 0) return;
-  const int S = max(1, min(NT / n_out, 8));                        // K slices
+  quads = quads && ((ldn | n_out) & 3) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0 && scratch_cap >= 2 * n_out;
+  if (quads) {                                                      // (uniform over the block)
+    const int nq = n_out >> 2;
+    const int S = max(1, min(min(NT / nq, scratch_cap / n_out), K));
+    const int q = tid % nq, sl = tid / nq;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sl < S) {
+      const int per = (K + S - 1) / S, k0 = min(K, sl * per), k1 = min(K, k0 + per);
+      const float4* w = reinterpret_cast<const float4*>(Wt + (size_t)k0 * ldn + col_of(4 * q));
+      const size_t ld4 = (size_t)(ldn >> 2);
+      int k = k0;
+      for (; k + 8 <= k1; k += 8) {                                 // eight independent 16-byte loads in flight per thread
+        float4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + u * ld4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float xv = x[k + u];
+          acc.x = fmaf(wv[u].x, xv, acc.x); acc.y = fmaf(wv[u].y, xv, acc.y);
+          acc.z = fmaf(wv[u].z, xv, acc.z); acc.w = fmaf(wv[u].w, xv, acc.w);
+        }
+        w += 8 * ld4;
+      }
+      if (k < k1) {                                                 // the tail: all of its loads first, too
+        float4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = k + u < k1 ? __ldg(w + u * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float xv = k + u < k1 ? x[k + u] : 0.f;
+          acc.x = fmaf(wv[u].x, xv, acc.x); acc.y = fmaf(wv[u].y, xv, acc.y);
+          acc.z = fmaf(wv[u].z, xv, acc.z); acc.w = fmaf(wv[u].w, xv, acc.w);
+        }
+      }
+    }
+    __syncthreads();                                                // scratch may still be read from the previous use
+    if (sl < S) *reinterpret_cast<float4*>(scratch + sl * n_out + 4 * q) = acc;
+    __syncthreads();
+    if (tid < n_out) {
+      float v = 0.f;
+      for (int p = 0; p < S; ++p) v += scratch[p * n_out + tid];
+      const int c = col_of(tid);
+      emit(tid, v + (bias ? __ldg(bias + c) : 0.f));
+    }
+    return;
+  }
+  const int S = max(1, min(min(NT / n_out, scratch_cap / n_out), 32));   // K slices
   const int i = tid % n_out, sl = tid / n_out;
   float acc = 0.f;
   if (sl < S) {
-    const int per = (K + S - 1) / S, k0 = sl * per, k1 = min(K, k0 + per);
+    const int per = (K + S - 1) / S, k0 = min(K, sl * per), k1 = min(K, k0 + per);
     const float* w = Wt + (size_t)k0 * ldn + col_of(i);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = k0;
@@ -179,9 +233,9 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   float* s_part = s_hn + up4(H);            // [MAXC][4 + 2D] soft-max partials of every rank (written remotely)
   float* s_ex = s_part + up4(MAXC * (4 + 2 * D));   // [MAXC][8] small exchanges: coverage loss, soft-max (max, sum), arg-max (p, index)
   float* s_g = s_ex + MAXC * 8;             // [4][ceil(H / CL) + 1] gate pre-activations of this rank's units
-  float* s_red = s_g + up4(4 * ((H + MAXC / 2 - 1) / (MAXC / 2) + 1));   // [32]   (sized for the smaller cluster)
-  float* s_scr = s_red + 32;                // [NT]   K-slice partial sums of the mat-vecs
-  float* s_vec = s_scr + NT;                // [4D]   v1 | wc1 | v2 | wc2
+  float* s_red = s_g + up4(4 * (split4(H, MAXC / 2) + 1));   // [32]   (sized for the smaller cluster)
+  float* s_scr = s_red + 32;                // [SCR]  K-slice partial sums of the mat-vecs
+  float* s_vec = s_scr + SCR;               // [4D]   v1 | wc1 | v2 | wc2
   float* s_e = s_vec + up4(4 * D);          // [2][chunk] energies -> p -> alpha of this rank's rows
   float* s_cov = s_e + up4(2 * a.chunk);    // [chunk] coverage input of this rank's rows
   float* s_cpart = s_cov + up4(a.chunk);    // [groups][2][D] context partials inside the block; later this rank's logits
@@ -223,7 +277,7 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   // ---- stage A: hw = Wh4 h + bh4, outputs split over the ranks, gathered in every rank ------------------------------------
   {
     const int per = (4 * D + CL - 1) / CL, o0 = R * per, o1 = min(4 * D, o0 + per);
-    block_matvec_t(a.Wh4t, 4 * D, a.bh4, s_x + D + E, H, o1 - o0, s_scr, [&](int i) { return o0 + i; }, [&](int i, float v) {
+    block_matvec_t(a.Wh4t, 4 * D, a.bh4, s_x + D + E, H, o1 - o0, s_scr, SCR, (o0 & 3) == 0, [&](int i) { return o0 + i; }, [&](int i, float v) {
       const int o = o0 + i;
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_hw, r)[o] = v;
       a.hw[(size_t)b * 4 * D + o] = v;
@@ -431,7 +485,8 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
     // outputs below D take c1 (W_beta_1), the others c2 (W_beta_3); a rank's range may straddle the two
     for (int k = 0; k < 2; ++k) {
       const int lo = max(o0, k * D), hi = min(o1, (k + 1) * D);
-      block_matvec_t(a.Wb13t + (size_t)k * D * D, D, nullptr, s_ctx + k * D, D, hi - lo, s_scr, [&](int i) { return lo - k * D + i; },
+      block_matvec_t(a.Wb13t + (size_t)k * D * D, D, nullptr, s_ctx + k * D, D, hi - lo, s_scr, SCR, ((lo - k * D) & 3) == 0,
+                     [&](int i) { return lo - k * D + i; },
                      [&](int i, float v) {
                        const int o = lo + i;
                        for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_pb, r)[o] = v;
@@ -482,8 +537,9 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   DEC_STAMP(11);
   // ---- stage D: LSTM gates of this rank's hidden units, cell update; h' gathered -------------------------------------------
   {
-    const int per = (H + CL - 1) / CL, j0 = R * per, j1 = min(H, j0 + per), nj = max(0, j1 - j0);
-    block_matvec_t(a.Wcatt, 4 * H, a.bcat, s_x, K, 4 * nj, s_scr, [&](int i) { return (i / nj) * H + j0 + (i % nj); },
+    // (units per rank: a multiple of 4 -- the four gate segments of a rank start 16-byte aligned and hold whole quads)
+    const int per = split4(H, CL), j0 = R * per, j1 = min(H, j0 + per), nj = max(0, j1 - j0);
+    block_matvec_t(a.Wcatt, 4 * H, a.bcat, s_x, K, 4 * nj, s_scr, SCR, ((H | nj) & 3) == 0, [&](int i) { return (i / nj) * H + j0 + (i % nj); },
                    [&](int i, float v) { s_g[(i / nj) * (per + 1) + (i % nj)] = v; });
     __syncthreads();
     if (tid < nj) {
@@ -512,7 +568,7 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
   {
     const int per = (M + CL - 1) / CL, m0 = min(M, R * per), m1 = min(M, m0 + per);
     float* const lg = s_cpart;                                   // this rank's logits (the context partials are dead)
-    block_matvec_t(a.out_wt, M, a.out_b, s_hn, H, m1 - m0, s_scr, [&](int i) { return m0 + i; }, [&](int i, float v) { lg[i] = v; });
+    block_matvec_t(a.out_wt, M, a.out_b, s_hn, H, m1 - m0, s_scr, SCR, (m0 & 3) == 0, [&](int i) { return m0 + i; }, [&](int i, float v) { lg[i] = v; });
     __syncthreads();
     for (int m = m0 + tid; m < m1; m += NT)
       if (!a.mask[(size_t)b * M + m]) lg[m - m0] = kNegFill;     // attention.py:184 (masked_softmax)
@@ -638,6 +694,10 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   float* s_ex = s_dpre + up4(2 * D);                    // [MAXC][4] scalar exchanges
   float* s_red = s_ex + MAXC * 4;                       // [32]
   float* s_scr = s_red + 32;                            // [NT]
+  // mat-vec scratch: the whole-step launch lends the (then dead) column-partial buffer of sweep 8 -- room for the quad form's K slices
+  const int mv_cap = a.sweeps ? (a.stage_off != 0 ? NW / 2 : NW) * 3 * D : NT;
+  float* const mv_scr = a.sweeps ? s_scr + NT + up4(2 * D) + up4(2 * a.chunk) + up4(4 * a.chunk) + up4(6 * D) : s_scr;
+  const bool mv_quads = a.sweeps != 0;
 
   // Row stage of the whole-step launch (see dec_step_fused_kernel): this rank's rows of enc_a / enc_i come in by two bulk copies issued
   // NOW, six head stages before sweep 7 reads them; when sweep 7 is done the same buffers take the rows of proj_a / proj_i for sweep 8
@@ -688,7 +748,7 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   __syncthreads();
   DEC_STAMP(19);
   // ---- 2: d h (from the logits) = d_logits out.weight: this rank's rows of out.weight, all H outputs; partials summed over the ranks
-  block_matvec_t(a.out_w + (size_t)m0 * H, H, nullptr, s_dl, m1 - m0, H, s_scr, [](int i) { return i; }, [&](int i, float v) {
+  block_matvec_t(a.out_w + (size_t)m0 * H, H, nullptr, s_dl, m1 - m0, H, mv_scr, mv_cap, mv_quads, [](int i) { return i; }, [&](int i, float v) {
     for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dhp, r)[R * H + i] = v;
   });
   if (m1 - m0 <= 0 && tid < H)
@@ -718,8 +778,8 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   DEC_STAMP(21);
   // ---- 4: d c3 = d_gates W_ih[:, :D]: outputs split over the ranks, gathered -----------------------------------------------------
   {
-    const int per = (D + CL - 1) / CL, d0 = min(D, R * per), d1 = min(D, d0 + per);
-    block_matvec_t(a.Wcat_ctx, D, nullptr, s_dg, 4 * H, d1 - d0, s_scr, [&](int i) { return d0 + i; }, [&](int i, float v) {
+    const int per = split4(D, CL), d0 = min(D, R * per), d1 = min(D, d0 + per);
+    block_matvec_t(a.Wcat_ctx, D, nullptr, s_dg, 4 * H, d1 - d0, mv_scr, mv_cap, mv_quads, [&](int i) { return d0 + i; }, [&](int i, float v) {
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_dctx, r)[d0 + i] = v;
     });
   }
@@ -795,7 +855,8 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
     for (int k = 0; k < 2; ++k) {
       const int lo = max(o0, k * D), hi = min(o1, (k + 1) * D);
       const float bk = k == 0 ? beta1 : beta2;
-      block_matvec_t(a.Wb13 + (size_t)k * D * D, D, nullptr, s_dpre + k * D, D, hi - lo, s_scr, [&](int i) { return lo - k * D + i; },
+      block_matvec_t(a.Wb13 + (size_t)k * D * D, D, nullptr, s_dpre + k * D, D, hi - lo, mv_scr, mv_cap, mv_quads && ((lo - k * D) & 3) == 0,
+                     [&](int i) { return lo - k * D + i; },
                      [&](int i, float v) {
                        const int dd = lo - k * D + i;
                        const float x = fmaf(bk, s_dctx[dd], v);
@@ -1071,8 +1132,8 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   }
   __syncthreads();
   {
-    const int per = (H + CL - 1) / CL, j0 = min(H, R * per), j1 = min(H, j0 + per);
-    block_matvec_t(a.Wh_stack, H, nullptr, s_in, 4 * H + 4 * D, j1 - j0, s_scr, [&](int i) { return j0 + i; },
+    const int per = split4(H, CL), j0 = min(H, R * per), j1 = min(H, j0 + per);
+    block_matvec_t(a.Wh_stack, H, nullptr, s_in, 4 * H + 4 * D, j1 - j0, mv_scr, mv_cap, mv_quads, [&](int i) { return j0 + i; },
                    [&](int i, float v) { a.d_h[(size_t)b * H + j0 + i] = v; });
   }
   if (staged && tid == 0) bulk_wait_all();              // the stage buffers are read by the bulk reductions until here
@@ -1102,7 +1163,7 @@ static size_t fused_smem_bytes(int Lt, int D, int H, int E, int M, int CL, int* 
   if (cpart < per_m) cpart = per_m;
   auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
   const size_t floats = up4(4 * D) + up4(K) + 2 * up4(2 * D) + up4(H) + up4((size_t)MAXC * (4 + 2 * D)) + MAXC * 8 +
-                        up4(4 * ((H + MAXC / 2 - 1) / (MAXC / 2) + 1)) + 32 + NT + up4(4 * D) + up4(2 * (size_t)chunk) + up4(chunk) + up4(cpart);
+                        up4(4 * (split4(H, MAXC / 2) + 1)) + 32 + SCR + up4(4 * D) + up4(2 * (size_t)chunk) + up4(chunk) + up4(cpart);
   if (chunk_out) *chunk_out = chunk;
   return floats * sizeof(float) + 64;
 }

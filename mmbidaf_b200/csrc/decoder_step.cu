@@ -14,6 +14,7 @@
 // Backward: out_softmax_bwd -> [GEMM] -> cell_bwd -> [GEMM] -> attn_finish_bwd -> [GEMM] -> sweep1 -> sweep2
 //           -> attn_reduce -> [GEMM]
 // W1.enc / W3.enc are step invariant and arrive pre-multiplied (proj_a / proj_i).
+#include <type_traits>
 #include "common.cuh"
 
 namespace mmb {
@@ -21,6 +22,17 @@ namespace {
 
 constexpr int NT = 256;
 constexpr int NW = NT / 32;
+// flush-to-zero MUFU forms (no denormal guard instructions around them)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -122,45 +134,66 @@ __global__ void __launch_bounds__(NT) dec_attn_partial_kernel(const PartialArgs 
   }
   __syncthreads();
   const float v1b = a.v1b[0], v2b = a.v2b[0];
-  // two sentences per warp iteration: all loads of both rows are in flight before the first tanh
-  constexpr int MAXJ = 8;                // D <= 256
-  for (int i = warp * 2; i < n; i += NW * 2) {
-    float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    float pav[2][MAXJ], piv[2][MAXJ], cvs[2];
+  // Two sentences per warp iteration: all loads of both rows are in flight before the first tanh.  Written for the issue slots like
+  // stage B of the one-kernel step (decoder_fused.cu): a lane's per-column constants live in registers for the whole chunk, pre-scaled
+  // so that the pre-activation is the ex2 argument (tanh x = 1 - 2 / (1 + 2^(2 x log2 e))); columns past D carry v = 0, so nothing in
+  // the body is predicated (the first version branched around every element and re-read six constants from shared memory per element).
+  constexpr float K2 = 2.0f * 1.4426950408889634f;
+  auto energies = [&](auto nj_tag) {
+    constexpr int NJ = decltype(nj_tag)::value;
+    float va[NJ], ha[NJ], wa[NJ], vi[NJ], hi[NJ], wi[NJ];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {          // loads first (memory-level parallelism)
-      const int t = t0 + min(i + u, n - 1);
-      const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
-      const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
-      cvs[u] = a.cov[(size_t)b * Lt + t];
-#pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {
-        const int d = lane + 32 * j;
-        pav[u][j] = d < D ? pa[d] : 0.f;
-        piv[u][j] = d < D ? pi[d] : 0.f;
-      }
+    for (int j = 0; j < NJ; ++j) {
+      const int d = lane + 32 * j;
+      const bool in = d < D;
+      const int dd = in ? d : 0;
+      va[j] = in ? vec[dd] : 0.f;
+      wa[j] = in ? vec[D + dd] * K2 : 0.f;
+      ha[j] = in ? vec[2 * D + dd] * K2 : 0.f;
+      vi[j] = in ? vec[3 * D + dd] : 0.f;
+      wi[j] = in ? vec[4 * D + dd] * K2 : 0.f;
+      hi[j] = in ? vec[5 * D + dd] * K2 : 0.f;
     }
+    for (int i = warp * 2; i < n; i += NW * 2) {
+      float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+      float pav[2][NJ], piv[2][NJ], cvs[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float cv = cvs[u];
+      for (int u = 0; u < 2; ++u) {          // loads first (memory-level parallelism)
+        const int t = t0 + min(i + u, n - 1);
+        const float* pa = a.proj_a + ((size_t)b * Lt + t) * D;
+        const float* pi = a.proj_i + ((size_t)b * Lt + t) * D;
+        cvs[u] = a.cov[(size_t)b * Lt + t];
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {
-        const int d = lane + 32 * j;
-        if (d < D) {
-          s[u][0] = fmaf(vec[d], tanh_fast((pav[u][j] + vec[2 * D + d]) + cv * vec[D + d]), s[u][0]);
-          s[u][1] = fmaf(vec[3 * D + d], tanh_fast((piv[u][j] + vec[5 * D + d]) + cv * vec[4 * D + d]), s[u][1]);
+        for (int j = 0; j < NJ; ++j) {
+          const int d = lane + 32 * j;
+          pav[u][j] = d < D ? pa[d] : 0.f;
+          piv[u][j] = d < D ? pi[d] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float cv = cvs[u];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float x1 = fmaf(cv, wa[j], fmaf(pav[u][j], K2, ha[j]));
+          const float x2 = fmaf(cv, wi[j], fmaf(piv[u][j], K2, hi[j]));
+          const float r1 = rcp_ftz(1.0f + ex2_ftz(x1)), r2 = rcp_ftz(1.0f + ex2_ftz(x2));
+          s[u][0] = fmaf(va[j], fmaf(-2.0f, r1, 1.0f), s[u][0]);
+          s[u][1] = fmaf(vi[j], fmaf(-2.0f, r2, 1.0f), s[u][1]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float x1 = warp_sum(s[u][0]), x2 = warp_sum(s[u][1]);
+        if (lane == 0 && i + u < n) {
+          e[i + u] = x1 + v1b;
+          e[a.chunk + i + u] = x2 + v2b;
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float x1 = warp_sum(s[u][0]), x2 = warp_sum(s[u][1]);
-      if (lane == 0 && i + u < n) {
-        e[i + u] = x1 + v1b;
-        e[a.chunk + i + u] = x2 + v2b;
-      }
-    }
-  }
+  };
+  if (D > 192 && D <= 224) energies(std::integral_constant<int, 7>{});      // the model's D = 2 H = 200
+  else energies(std::integral_constant<int, 8>{});                          // any other D <= 256: zero padded
   __syncthreads();
   float m1 = -INFINITY, m2 = -INFINITY;
   for (int i = tid; i < n; i += NT) {

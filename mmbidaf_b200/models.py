@@ -9,6 +9,8 @@ next inputs with device-side indexing instead of ``B x T`` ``int(tensor)`` host 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -45,6 +47,8 @@ class MMBiDAF(nn.Module):
     # that their latency-bound recurrences overlap on the 148 SMs.  autograd replays each backward op on
     # the stream of its forward op, so the overlap carries over to the backward pass.
     use_streams = True
+    # the text / image encoders start behind the audio embedding (the audio chain is the critical path); MMB_NO_STAGGER=1: A/B measurements
+    stagger_encoders = os.environ.get("MMB_NO_STAGGER", "0") != "1"
 
     def _fork_join(self, jobs, meanwhile=None):
         """Run ``jobs`` on side streams and join them into the current stream.  ``meanwhile`` (optional) is issued on the
@@ -167,13 +171,24 @@ class MMBiDAF(nn.Module):
 
             for st in self._streams:
                 st.wait_stream(main)
+            # The audio chain (embedding -> 1024-step recurrence) is the critical path of the forward pass and the other two encoders
+            # have ~250 us of slack: they start when the audio EMBEDDING is done, so that its five small GEMMs / point-wise kernels do not
+            # share the chip with theirs (tools/step_timeline.py: 178 us from the start of the step to the start of the audio recurrence
+            # with all three chains launched together).
             with torch.cuda.stream(s_audio):
-                branch["audio"] = audio_branch()[0]
+                audio_emb = self.a_emb(embedded_audio)
+                audio_emb_done = torch.cuda.Event()
+                audio_emb_done.record(s_audio)
+                branch["audio"] = self.audio_enc(audio_emb, original_audio_lengths)[0]
             with torch.cuda.stream(s_text):
+                if self.stagger_encoders:
+                    s_text.wait_event(audio_emb_done)
                 branch["text"] = text_branch()[1]
                 text_done = torch.cuda.Event()
                 text_done.record(s_text)
             with torch.cuda.stream(s_image):
+                if self.stagger_encoders:
+                    s_image.wait_event(audio_emb_done)
                 branch["image"] = image_branch()[1]
             make_masks()                          # on the main stream, beside the encoders: needs only the lengths
             # ... and so do the keep-masks of the two BiDAF blocks (shapes only): two mask draws less between the audio recurrence and

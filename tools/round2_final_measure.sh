@@ -13,6 +13,8 @@ python tools/bidaf_micro.py --bwd --iters 40 >> $O/f_bidaf.log 2>&1
 python tools/bidaf_micro.py --bwd --dropout --iters 40 >> $O/f_bidaf.log 2>&1
 python tools/bidaf_micro.py --shape 32 409 1024 --iters 40 >> $O/f_bidaf.log 2>&1
 python tools/bidaf_micro.py --shape 32 409 128 --iters 40 >> $O/f_bidaf.log 2>&1
+python tools/decoder_fused_trace.py > $O/f_decoder.log 2>&1
+python tools/decoder_bwd_trace.py >> $O/f_decoder.log 2>&1
 python tools/step_timeline.py --min-us 30 --csv $O/f_step_timeline.csv > $O/f_step_timeline.log 2>&1
 python bench.py > $O/f_bench.json 2> $O/f_bench.err; tail -1 $O/f_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/f_bench_ref.json 2> $O/f_bench_ref.err

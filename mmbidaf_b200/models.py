@@ -159,9 +159,11 @@ class MMBiDAF(nn.Module):
             # behind a join of all three encoders (which is what two successive fork-joins did: 160 us on the critical path).
             main = torch.cuda.current_stream()
             if getattr(self, "_streams", None) is None or self._streams[0].device != main.device:
-                # stream 0 carries the critical path (audio): high priority, so that its 64 CTAs are never queued behind the others
-                object.__setattr__(self, "_streams", [torch.cuda.Stream(device=main.device, priority=-1 if i == 0 else 0)
-                                                      for i in range(3)])
+                # stream 0 carries the critical path (audio): highest priority, so that its 64 CTAs are never queued behind the others;
+                # the text / image chains rank above the weight-gradient lanes (functional.leaf_lanes: default priority), which share the
+                # tail of the backward pass with them
+                prio = [int(v) for v in os.environ.get("MMB_STREAM_PRIO", "-3,-2,-2").split(",")]
+                object.__setattr__(self, "_streams", [torch.cuda.Stream(device=main.device, priority=prio[i]) for i in range(3)])
             s_audio, s_text, s_image = self._streams
             capturing = torch.cuda.is_current_stream_capturing()
 

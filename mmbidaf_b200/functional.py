@@ -161,6 +161,25 @@ def dropout(x: torch.Tensor, drop_prob: float, training: bool) -> torch.Tensor:
     return _Dropout.apply(x, ops.rng_next_keys(x.device, 1), 1.0 - float(drop_prob))
 
 
+def _stacked(parts, shape):
+    """``parts`` concatenated along dim 0 and viewed as ``shape``: a VIEW of the first part's storage when the parts are contiguous
+    and adjacent in one storage (no launch), else a copy."""
+    first = parts[0]
+    end = first.storage_offset() + first.numel()
+    adjacent = first.is_contiguous()
+    for t in parts[1:]:
+        adjacent = (adjacent and t.is_contiguous() and t.dtype == first.dtype and t.storage_offset() == end
+                    and t.untyped_storage().data_ptr() == first.untyped_storage().data_ptr())
+        end += t.numel()
+    if adjacent:
+        strides, acc = [], 1
+        for n in reversed(shape):
+            strides.append(acc)
+            acc *= n
+        return torch.as_strided(first.detach(), shape, tuple(reversed(strides)), first.storage_offset())
+    return torch.cat([t.reshape(-1) for t in parts]).view(shape)
+
+
 class _LstmLayer(torch.autograd.Function):
     """One (bi)directional LSTM layer over padded (B, L, in) with per-sample lengths."""
 
@@ -171,9 +190,14 @@ class _LstmLayer(torch.autograd.Function):
         ndir = len(weights) // 4
         B, L, fan_in = x.shape
         H = weights[1].shape[1]
-        w_ih = torch.cat([weights[4 * d] for d in range(ndir)], dim=0)                       # (ndir*4H, in)
-        w_hh = torch.stack([weights[4 * d + 1] for d in range(ndir)], dim=0).contiguous()    # (ndir, 4H, H)
-        bias = torch.cat([weights[4 * d + 2] + weights[4 * d + 3] for d in range(ndir)], dim=0)
+        # The two directions' weights stacked: views when the parameters already lie side by side in memory (trainer.FlatState puts
+        # the forward / reverse tensors of every nn.LSTM layer next to each other for exactly this), else three small copies --
+        # five launches per layer in front of the input GEMM, on the serial chain of the step
+        w_ih = _stacked([weights[4 * d] for d in range(ndir)], (ndir * 4 * H, fan_in))       # (ndir*4H, in)
+        w_hh = _stacked([weights[4 * d + 1] for d in range(ndir)], (ndir, 4 * H, H))         # (ndir, 4H, H)
+        b_ih = _stacked([weights[4 * d + 2] for d in range(ndir)], (ndir * 4 * H,))
+        b_hh = _stacked([weights[4 * d + 3] for d in range(ndir)], (ndir * 4 * H,))
+        bias = b_ih + b_hh
         x2d = x.reshape(B * L, fan_in)
         gates = torch.addmm(bias, x2d, w_ih.t())                                            # plain GEMM (cuBLAS)
         save = any(ctx.needs_input_grad)

@@ -42,12 +42,33 @@ def shard_batch(batch: Batch, rank: int, world: int) -> Batch:
                  batch.images[sel, :max(il)].contiguous(), il, batch.targets[sel].contiguous(), gl, batch.max_dec_len)
 
 
+def _lstm_directions_adjacent(params: List[torch.nn.Parameter]) -> List[torch.nn.Parameter]:
+    """nn.LSTM registers a bidirectional layer as (w_ih, w_hh, b_ih, b_hh, w_ih_reverse, w_hh_reverse, b_ih_reverse, b_hh_reverse).
+    Re-ordered here to (w_ih, w_ih_reverse, w_hh, w_hh_reverse, ...): in the flat buffer the two directions of every tensor are then
+    contiguous, and the recurrence's stacked operands are views instead of per-step concatenations (functional._stacked).  Groups are
+    recognised by shape: eight consecutive parameters with shapes (a, b, c, c, a, b, c, c), c one-dimensional, every size a multiple of
+    four (no padding between them).  Anything else keeps its place; the order is the same on every rank."""
+    out, i = [], 0
+    while i < len(params):
+        g = params[i:i + 8]
+        if (len(g) == 8 and g[0].dim() == 2 and g[1].dim() == 2 and g[2].dim() == 1 and g[2].shape == g[3].shape
+                and all(g[k].shape == g[k + 4].shape for k in range(4)) and g[0].shape[0] == g[2].shape[0] == g[1].shape[0]
+                and all(t.numel() % 4 == 0 for t in g)):
+            out += [g[0], g[4], g[1], g[5], g[2], g[6], g[3], g[7]]
+            i += 8
+        else:
+            out.append(params[i])
+            i += 1
+    return out
+
+
 class FlatState:
     """All trainable parameters AND their gradients as views into two contiguous buffers: one all-reduce,
     one norm, one scale, and an optimiser that is five element-wise ops instead of 60 small-tensor updates."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.params = _lstm_directions_adjacent(self.params)
         pad = lambda n: (n + 3) // 4 * 4                 # every parameter stays 16-byte aligned (kernels use float4)
         self.offsets, total = [], 0
         for p in self.params:

@@ -114,3 +114,38 @@ def test_flat_adadelta_matches_torch_optimizer():
         ref.step()
     for p, q in zip(a.parameters(), b.parameters()):
         assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+
+
+def test_flat_state_puts_lstm_directions_side_by_side():
+    """trainer.FlatState orders the two directions of every nn.LSTM tensor next to each other, so that the recurrence's stacked
+    operands (functional._stacked) are views of the flat parameter buffer -- and stay copies for parameters that are not adjacent."""
+    import torch.nn as nn
+    from mmbidaf_b200.functional import _stacked
+    from mmbidaf_b200.trainer import FlatState
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.head = nn.Linear(12, 7)
+            self.rnn = nn.LSTM(12, 8, 2, batch_first=True, bidirectional=True)
+            self.tail = nn.Linear(3, 5)
+
+    torch.manual_seed(0)
+    net = Net()
+    before = {k: v.detach().clone() for k, v in net.named_parameters()}
+    state = FlatState(net.parameters())
+    for k, v in net.named_parameters():
+        assert torch.equal(v, before[k])                         # values kept, every parameter a view of the flat buffer
+        assert v.untyped_storage().data_ptr() == state.flat_param.untyped_storage().data_ptr()
+    for layer, fan_in in ((0, 12), (1, 16)):
+        f, r = getattr(net.rnn, f"weight_ih_l{layer}"), getattr(net.rnn, f"weight_ih_l{layer}_reverse")
+        w = _stacked([f, r], (2 * 32, fan_in))
+        assert w.data_ptr() == f.data_ptr() and torch.equal(w, torch.cat([f, r]))          # a view, same values
+        hf, hr = getattr(net.rnn, f"weight_hh_l{layer}"), getattr(net.rnn, f"weight_hh_l{layer}_reverse")
+        wh = _stacked([hf, hr], (2, 32, 8))
+        assert wh.data_ptr() == hf.data_ptr() and torch.equal(wh, torch.stack([hf, hr]))
+        bf, br = getattr(net.rnn, f"bias_hh_l{layer}"), getattr(net.rnn, f"bias_hh_l{layer}_reverse")
+        assert _stacked([bf, br], (64,)).data_ptr() == bf.data_ptr()
+    a, b = torch.randn(4, 3), torch.randn(4, 3)                    # unrelated tensors: a copy
+    c = _stacked([a, b], (8, 3))
+    assert c.data_ptr() != a.data_ptr() and torch.equal(c, torch.cat([a, b]))

@@ -137,6 +137,9 @@ class MMBiDAF(nn.Module):
             start["cov"] = embedded_text.new_zeros(B, Lt, 1)
             start["rows"] = torch.arange(B, device=embedded_text.device)
             start["targets"] = batch_target_indices.reshape(B, -1).to(embedded_text.device).long()   # int(tensor), models.py:168
+            # (steps, B): a step's targets are one contiguous row (a column of (B, T) cost a strided-copy launch between every two
+            # decoder steps -- ~2 us on the serial chain, 12 times)
+            start["targets_t"] = start["targets"].t().contiguous()
             if self.training:
                 # teacher forcing (models.py:173): every step's next input is known up front -- one gather for the whole
                 # sequence, laid out (steps, B, E) so that a step's slice is contiguous, instead of a gather per step
@@ -227,12 +230,12 @@ class MMBiDAF(nn.Module):
         # models.py:143-149 (the hidden-state rows are in descending-length order: reference quirk Q3)
         decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)
         decoder_cell_state, decoder_input, coverage_vec = start["cell"], start["input"], start["cov"]
-        rows, targets = start["rows"], start["targets"]
+        rows, targets, targets_t = start["rows"], start["targets"], start["targets_t"]
         out_distributions, step_losses = [], []
         if self.training:
             next_inputs = start["next"]
         for idx in range(steps):
-            tgt = targets[:, idx]
+            tgt = targets_t[idx] if idx < targets_t.size(0) else targets[:, idx]
             # the decoder kernels also emit this step's loss terms: -log(p[target] + 1e-12) (models.py:168-170)
             # and sum(min(att_cov_dist, coverage_vec)) (models.py:177), one value per video
             out_distribution, decoder_hidden, decoder_cell_state, att_cov_dist, coverage_vec, step_loss = \

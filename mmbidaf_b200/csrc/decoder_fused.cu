@@ -95,8 +95,9 @@ struct FusedArgs {
 // (~1 000 cycles per round trip) and what counts is the BYTES IN FLIGHT per SM.
 //  * scalar form: one thread per (output, K slice), sixteen 4-byte loads in flight per thread (32 KB per SM);
 //  * quad form (`quads`: n_out, ldn and col_of(4 q) are multiples of 4, col_of(4 q + e) = col_of(4 q) + e): one thread per (four outputs,
-//    K slice), eight 16-byte loads in flight per thread and as many K slices as the scratch holds -- 64 KB per SM in flight and a K
-//    slice short enough for one or two round trips (round 2: stage A 5.3 k -> cycles, see profiles/r02_decoder_fused.md).
+//    K slice), sixteen 16-byte loads in flight per thread and as many K slices as the scratch holds.  Measured (stamps inside stage D,
+//    profiles/r02_decoder_fused.md): a batch of 129 KB per SM takes ~2 900 cycles = 44 B/clk, close to what the L1 / L2 path of one SM
+//    delivers -- the stages are bound by the BYTES a CTA pulls (every cluster re-reads the step's weights), not by latency or width.
 template <typename ColOf, typename Emit>
 __device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, const int ldn, const float* __restrict__ bias, const float* x,
                                                const int K, const int n_out, float* scratch, const int scratch_cap, bool quads,
@@ -113,29 +114,19 @@ __device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, con
       const int per = (K + S - 1) / S, k0 = min(K, sl * per), k1 = min(K, k0 + per);
       const float4* w = reinterpret_cast<const float4*>(Wt + (size_t)k0 * ldn + col_of(4 * q));
       const size_t ld4 = (size_t)(ldn >> 2);
-      int k = k0;
-      for (; k + 8 <= k1; k += 8) {                                 // eight independent 16-byte loads in flight per thread
-        float4 wv[8];
+      // sixteen independent 16-byte loads in flight per thread, ALL issued before the first FMA: a K slice of up to sixteen rows (the
+      // usual case: the slices are as many as the scratch holds) is ONE L2 round trip -- a batch of eight plus a tail was two
+      for (int k = k0; k < k1; k += 16) {
+        float4 wv[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + u * ld4);
+        for (int u = 0; u < 16; ++u) wv[u] = k + u < k1 ? __ldcg(w + u * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float xv = x[k + u];
-          acc.x = fmaf(wv[u].x, xv, acc.x); acc.y = fmaf(wv[u].y, xv, acc.y);
-          acc.z = fmaf(wv[u].z, xv, acc.z); acc.w = fmaf(wv[u].w, xv, acc.w);
-        }
-        w += 8 * ld4;
-      }
-      if (k < k1) {                                                 // the tail: all of its loads first, too
-        float4 wv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = k + u < k1 ? __ldg(w + u * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const float xv = k + u < k1 ? x[k + u] : 0.f;
           acc.x = fmaf(wv[u].x, xv, acc.x); acc.y = fmaf(wv[u].y, xv, acc.y);
           acc.z = fmaf(wv[u].z, xv, acc.z); acc.w = fmaf(wv[u].w, xv, acc.w);
         }
+        w += 16 * ld4;
       }
     }
     __syncthreads();                                                // scratch may still be read from the previous use
@@ -160,7 +151,7 @@ __device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, con
     for (; k + 16 <= k1; k += 16) {                                 // sixteen independent loads in flight per thread
       float wv[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (size_t)u * ldn);
+      for (int u = 0; u < 16; ++u) wv[u] = __ldcg(w + (size_t)u * ldn);
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
         a0 = fmaf(wv[u], x[k + u], a0); a1 = fmaf(wv[u + 1], x[k + u + 1], a1);
@@ -171,7 +162,7 @@ __device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, con
     if (k + 8 <= k1) {
       float wv[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)u * ldn);
+      for (int u = 0; u < 8; ++u) wv[u] = __ldcg(w + (size_t)u * ldn);
 #pragma unroll
       for (int u = 0; u < 8; u += 4) {
         a0 = fmaf(wv[u], x[k + u], a0); a1 = fmaf(wv[u + 1], x[k + u + 1], a1);
@@ -181,7 +172,7 @@ __device__ __forceinline__ void block_matvec_t(const float* __restrict__ Wt, con
       k += 8;
     }
     for (; k < k1; ++k) {
-      a0 = fmaf(__ldg(w), x[k], a0);
+      a0 = fmaf(__ldcg(w), x[k], a0);
       w += ldn;
     }
     acc = (a0 + a1) + (a2 + a3);

@@ -150,8 +150,12 @@ def lstm_layer_bwd(gates: torch.Tensor, cell: torch.Tensor, w_hh: torch.Tensor, 
 _rng_state = {}
 
 
+_rng_seed_override = {"seed": None}
+
+
 def rng_seed(seed: int, device=None) -> None:
-    """(Re)seed the device-resident key stream of the in-kernel dropout (all devices, or one)."""
+    """(Re)seed the device-resident key stream of the in-kernel dropout (all devices, or one); states created later start from it too."""
+    _rng_seed_override["seed"] = int(seed)
     for dev, st in _rng_state.items():
         if device is None or dev == torch.device(device):
             st.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
@@ -163,8 +167,16 @@ def rng_next_keys(device, n: int) -> torch.Tensor:
     device = torch.device(device)
     st = _rng_state.get(device)
     if st is None:
-        st = _rng_state[device] = torch.full((1,), (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x1234567) & 0x7FFFFFFFFFFFFFFF,
-                                             dtype=torch.int64, device=device)
+        if torch.cuda.is_current_stream_capturing():
+            # created inside a capture, the state's initial fill would be replayed too: the same masks on every replay
+            raise RuntimeError("mmbidaf_b200: the dropout key state must exist before a CUDA-graph capture (run one eager step, as "
+                               "Trainer.capture does, or call ops.rng_next_keys once)")
+        # (every rank of a data-parallel job draws its own masks: the rank is mixed into the seed)
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        st = _rng_state[device] = torch.full((1,), (((torch.initial_seed() if _rng_seed_override["seed"] is None else _rng_seed_override["seed"]) + 0x51ED27 * rank)
+                                              * 0x9E3779B97F4A7C15 + 0x1234567)
+                                             & 0x7FFFFFFFFFFFFFFF, dtype=torch.int64, device=device)
     keys = torch.empty(n, dtype=torch.int64, device=device)
     _lib.check(_lib.lib().mmb_rng_next(_lib.ptr(st), _lib.ptr(keys), n, _lib.stream()), "mmb_rng_next")
     _count(1)

@@ -158,6 +158,26 @@ class MultimodalAttentionDecoder(nn.Module):
             params = {name: self._param_of(name) for name in _lib_fields()}
             self._prepared = ops.DecoderWeights(params, self.output_size)
 
+    def hoist(self, which, enc):
+        """Optional: compute the step-invariant projection of one encoder output NOW, on the current stream -- ``which`` = "a"
+        (``W1 enc_a``, attention.py:152) or "i" (``W3 enc_i``, attention.py:157).  A caller that runs the two modality chains on
+        their own streams (mmbidaf_b200/models.py) calls it at the end of each chain: the GEMM of the chain that finishes first is
+        off the serial path in front of the first decoder step, and the two gradient GEMMs behind the last step run side by side
+        (autograd replays a backward op on the stream of its forward).  The next new sequence over the same tensor picks the
+        result up (once)."""
+        lin = self.W1 if which == "a" else self.W3
+        proj = Fn.tall_linear_bias(enc, lin.weight, lin.bias)
+        if getattr(self, "_hoisted", None) is None:
+            self._hoisted = {}
+        self._hoisted[which] = (weakref.ref(enc), enc._version, torch.is_grad_enabled(), proj)
+        return proj
+
+    def _hoisted_or_new(self, which, enc, lin):
+        hit = (getattr(self, "_hoisted", None) or {}).pop(which, None)
+        if hit is not None and hit[0]() is enc and hit[1] == enc._version and hit[2] == torch.is_grad_enabled():
+            return hit[3]
+        return Fn.tall_linear_bias(enc, lin.weight, lin.bias)
+
     # ---- per-sequence state: step-invariant projections (+ the autograd tape when training) ----------------
     def _sequence(self, enc_a, enc_i):
         grad = torch.is_grad_enabled()
@@ -165,8 +185,8 @@ class MultimodalAttentionDecoder(nn.Module):
         if c is not None and c["a"]() is enc_a and c["i"]() is enc_i and c["key"] == (enc_a._version, enc_i._version, grad):
             return c
         # hoisted: the reference recomputes them per step (attention.py:152, 157)
-        proj_a = Fn.tall_linear_bias(enc_a, self.W1.weight, self.W1.bias)
-        proj_i = Fn.tall_linear_bias(enc_i, self.W3.weight, self.W3.bias)
+        proj_a = self._hoisted_or_new("a", enc_a, self.W1)
+        proj_i = self._hoisted_or_new("i", enc_i, self.W3)
         c = {"a": weakref.ref(enc_a), "i": weakref.ref(enc_i), "key": (enc_a._version, enc_i._version, grad),
              "proj_a": proj_a, "proj_i": proj_i, "seq": None, "tape": None, "token": None, "last_h": None}
         params = {name: self._param_of(name) for name in _lib_fields()}

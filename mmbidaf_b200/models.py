@@ -120,13 +120,23 @@ class MMBiDAF(nn.Module):
             masks["audio"] = self.get_mask(embedded_audio, original_audio_lengths)
             masks["image"] = self.get_mask(transformed_images, original_image_lengths)     # (B, Li, ...): same (B, Li)
 
+        side = {}                                    # made at the end of a chain, on its stream, for the decoder's start
+
         def audio_aware():
             att = self.bidaf_att_audio(branch["text"], branch["audio"], masks["text"], masks["audio"])
-            return self.mod_t_a(att, original_text_lengths)
+            out = self.mod_t_a(att, original_text_lengths)
+            if self.use_streams and out[0].is_cuda:
+                side["proj_a"] = self.multimodal_att_decoder.hoist("a", out[0])      # the decoder's hoisted W1 enc_a
+                side["hid_a"] = out[1].sum(1)                                        # models.py:143
+            return out
 
         def image_aware():
             att = self.bidaf_att_image(branch["text"], branch["image"], masks["text"], masks["image"])
-            return self.mod_t_i(att, original_text_lengths)
+            out = self.mod_t_i(att, original_text_lengths)
+            if self.use_streams and out[0].is_cuda:
+                side["proj_i"] = self.multimodal_att_decoder.hoist("i", out[0])      # ... W3 enc_i: this chain ends ~200 us earlier
+                side["hid_i"] = out[1].sum(1)
+            return out
 
         steps = batch_target_indices.size(1) if self.training else max_dec_len
         start = {}
@@ -223,12 +233,16 @@ class MMBiDAF(nn.Module):
             for m in masks.values():
                 keep(m, s_audio)
                 keep(m, s_image)
-            for t in (mod_text_audio, text_audio_hidden, mod_text_image, text_img_hidden, branch["text"], branch["audio"], branch["image"]):
+            for t in (mod_text_audio, text_audio_hidden, mod_text_image, text_img_hidden, branch["text"], branch["audio"], branch["image"],
+                      *side.values()):
                 keep(t, main)
         decoder_mask = masks["decoder"]
 
         # models.py:143-149 (the hidden-state rows are in descending-length order: reference quirk Q3)
-        decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)
+        if "hid_a" in side and "hid_i" in side:
+            decoder_hidden = (side["hid_a"] + side["hid_i"]).unsqueeze(1)
+        else:
+            decoder_hidden = (text_audio_hidden.sum(1) + text_img_hidden.sum(1)).unsqueeze(1)
         decoder_cell_state, decoder_input, coverage_vec = start["cell"], start["input"], start["cov"]
         rows, targets, targets_t = start["rows"], start["targets"], start["targets_t"]
         out_distributions, step_losses = [], []

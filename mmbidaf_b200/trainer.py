@@ -56,6 +56,12 @@ def _lstm_directions_adjacent(params: List[torch.nn.Parameter]) -> List[torch.nn
                 and all(t.numel() % 4 == 0 for t in g)):
             out += [g[0], g[4], g[1], g[5], g[2], g[6], g[3], g[7]]
             i += 8
+        elif (len(g) == 8 and all(g[k].dim() == 2 and g[k].shape == g[0].shape and g[k].shape[0] == g[k].shape[1] for k in (0, 2, 4, 6))
+              and all(g[k].dim() == 1 and g[k].shape[0] == g[0].shape[0] for k in (1, 3, 5, 7)) and g[0].shape[0] % 4 == 0):
+            # a two-layer HighwayEncoder: transforms (W, b) x 2 then gates (W, b) x 2 (layers/encoding.py) -> per layer gate and
+            # transform side by side, weights then biases: the stacked (2H, H) operand of a layer's one GEMM is a view
+            out += [g[4], g[0], g[5], g[1], g[6], g[2], g[7], g[3]]
+            i += 8
         else:
             out.append(params[i])
             i += 1

@@ -146,6 +146,15 @@ def test_flat_state_puts_lstm_directions_side_by_side():
         assert wh.data_ptr() == hf.data_ptr() and torch.equal(wh, torch.stack([hf, hr]))
         bf, br = getattr(net.rnn, f"bias_hh_l{layer}"), getattr(net.rnn, f"bias_hh_l{layer}_reverse")
         assert _stacked([bf, br], (64,)).data_ptr() == bf.data_ptr()
+    # a two-layer highway encoder: gate and transform of a layer side by side (weights, then biases)
+    from mmbidaf_b200.layers import HighwayEncoder
+    hwy = HighwayEncoder(2, 8)
+    FlatState(hwy.parameters())
+    for k in range(2):
+        gw, tw, gb, tb = hwy.gates[k].weight, hwy.transforms[k].weight, hwy.gates[k].bias, hwy.transforms[k].bias
+        w = _stacked([gw, tw], (16, 8))
+        assert w.data_ptr() == gw.data_ptr() and torch.equal(w, torch.cat([gw, tw]))
+        assert _stacked([gb, tb], (16,)).data_ptr() == gb.data_ptr()
     a, b = torch.randn(4, 3), torch.randn(4, 3)                    # unrelated tensors: a copy
     c = _stacked([a, b], (8, 3))
     assert c.data_ptr() != a.data_ptr() and torch.equal(c, torch.cat([a, b]))

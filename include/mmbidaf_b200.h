@@ -170,6 +170,10 @@ MMB_API int mmb_decoder_chunks(int B, int Lt);
  * [lstm.weight_ih | lstm.weight_hh]^T with bcat = b_ih + b_hh, out_wt (H,M) = out.weight^T.
  * Writes the step's outputs and everything mmb_decoder_*_bwd wants saved: hw (B,4D), alpha (B,2,Lt), beta (B,2), ctx12 (2,B,D),
  * pb (2,B,D), xcat (B,D+E+H) = [c3 | sent | h], gates (B,4H) activated.  argmax, target / nll and cov_loss may be NULL.
+ * When D is a multiple of 4 and proj / enc are 16-byte aligned, each CTA stages its rows of proj_a / proj_i (then enc_a / enc_i) in shared
+ * memory by bulk copies issued at kernel start (two buffers of ceil(Lt / cluster) x D floats; skipped when they do not fit in 227 KB, and
+ * with MMB_DEC_STAGE=0): same results, fewer L2 round trips.  mmb_decoder_step_fused_bwd stages enc then proj the same way and adds its
+ * d z rows into d_proj_a / d_proj_i with one bulk reduction per modality (d_proj_* must then be 16-byte aligned too).
  */
 MMB_API int mmb_decoder_step_fused_fwd(const float* proj_a, const float* proj_i, const float* enc_a, const float* enc_i,
                                        const float* Wh4t, const float* bh4, const float* v1, const float* wc1, const float* v2,

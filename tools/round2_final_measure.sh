@@ -21,6 +21,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/f_bench_ref.json 2> $
 # ncu: DRAM traffic of one forward / one backward (third call of tools/bidaf_one_call.py)
 ncu --set full --cache-control none --clock-control none --import-source on -k regex:bidaf -s 4 -c 2 -f -o $O/f_fwd python tools/bidaf_one_call.py > $O/f_ncu_fwd.log 2>&1
 ncu --set full --cache-control none --clock-control none --import-source on -k regex:bidaf -s 12 -c 3 -f -o $O/f_bwd python tools/bidaf_one_call.py --bwd > $O/f_ncu_bwd.log 2>&1
+# ncu: the two decoder step kernels, warm caches (profiles/r02_decoder_fused.md; read with `ncu -i ... --page raw --csv`)
+ncu --set full --cache-control none --clock-control none --import-source on -k regex:dec_ -s 2 -c 4 -f -o $O/f_dec python tools/decoder_bwd_trace.py > $O/f_ncu_dec.log 2>&1
 # ncu: launch list of one step launched kernel by kernel
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/f_launches.csv python bench.py --steps 1 --warmup 3 --no-graph --sections step --no-cpu-baseline > $O/f_ncu_launch.log 2>&1
 gzip -f $O/f_launches.csv

@@ -625,7 +625,8 @@ __global__ void __launch_bounds__(NT) dec_step_fused_kernel(const FusedArgs a) {
     }
   }
   DEC_STAMP(16);
-  cluster.sync();      // no rank exits while another may still write into its shared memory
+  // (No barrier before the exit: every rank's LAST store into another rank's shared memory -- the soft-max statistics or the arg-max
+  // candidates -- lies before a cluster barrier it has passed, so nothing can still be written into a rank that leaves here.)
   DEC_STAMP(17);
 }
 
@@ -1129,7 +1130,8 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   }
   if (staged && tid == 0) bulk_wait_all();              // the stage buffers are read by the bulk reductions until here
   DEC_STAMP(27);
-  cluster.sync();      // no rank exits while another may still write into its shared memory
+  // (No barrier before the exit: the last stores into another rank's shared memory -- the column partials of sweep 8 -- lie before
+  // the cluster barrier in front of stage 9.)
 }
 
 static size_t g_head_smem_set = 0;   // dynamic shared memory the kernel attribute of dec_bwd_head_kernel allows (both launchers share it)

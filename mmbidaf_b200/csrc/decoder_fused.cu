@@ -716,17 +716,18 @@ __global__ void __launch_bounds__(NT) dec_bwd_head_kernel(const HeadArgs a) {
   const int m0 = min(M, R * per_m), m1 = min(M, m0 + per_m);
   const int tg = a.target ? (int)a.target[b] : -1;
   const float dp_t = a.target ? -a.g_nll[b] / (a.probs[(size_t)b * M + tg] + 1e-12f) : 0.f;   // d(-log(p_tgt + eps)) at the target column
+  if (a.d_probs) {      // (uniform over the cluster.  With the fused loss terms alone -- a training step -- sum p dp has the target's term
+                        // only, which every rank forms by itself: no exchange, no cluster barrier)
+    float dot = 0.f;
+    for (int m = m0 + tid; m < m1; m += NT) dot = fmaf(a.probs[(size_t)b * M + m], a.d_probs[(size_t)b * M + m], dot);
+    dot = block_sum(dot, s_red);
+    if (tid < CL) cluster.map_shared_rank(s_ex, tid)[R * 4 + 0] = dot;
+    cluster.sync();
+  }
   {
     float dot = 0.f;
     if (a.d_probs)
-      for (int m = m0 + tid; m < m1; m += NT) dot = fmaf(a.probs[(size_t)b * M + m], a.d_probs[(size_t)b * M + m], dot);
-    dot = block_sum(dot, s_red);
-    if (tid < CL) cluster.map_shared_rank(s_ex, tid)[R * 4 + 0] = dot;
-  }
-  cluster.sync();
-  {
-    float dot = 0.f;
-    for (int r = 0; r < CL; ++r) dot += s_ex[r * 4 + 0];
+      for (int r = 0; r < CL; ++r) dot += s_ex[r * 4 + 0];
     if (a.target) dot = fmaf(a.probs[(size_t)b * M + tg], dp_t, dot);
     for (int m = m0 + tid; m < m1; m += NT) {
       const float dp = (a.d_probs ? a.d_probs[(size_t)b * M + m] : 0.f) + (m == tg ? dp_t : 0.f);
